@@ -1,0 +1,7 @@
+"""rgfm-b200: B200-native ratio-guided coupled Euler sampler (drop-in for the reference's sampling path)."""
+from .sampler import (sample_bimodal_guided, sample_bimodal_guided_mnist_svhn, shard_bounds, gather_pairs,
+                      clear_plan_cache)
+from .synthetic import synthetic_module, state_dict as synthetic_state_dict, StateDictModule
+
+__all__ = ["sample_bimodal_guided", "sample_bimodal_guided_mnist_svhn", "shard_bounds", "gather_pairs",
+           "clear_plan_cache", "synthetic_module", "synthetic_state_dict", "StateDictModule"]

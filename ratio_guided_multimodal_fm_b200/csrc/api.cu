@@ -1,0 +1,168 @@
+// extern "C" boundary of librgfm.so (include/rgfm.h).  Exceptions stop here: every entry point returns an int
+// status and stores the message for rgfm_last_error().
+#include "net.h"
+#include <cstring>
+
+namespace rgfm {
+struct Sampler;
+Sampler* sampler_create(const rgfm_sampler_desc*, const rgfm_weights*, const rgfm_weights*, const rgfm_weights*);
+void sampler_destroy(Sampler*);
+void sampler_run(Sampler*, const float*, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
+void sampler_run_host(Sampler*, const float*, const float*, const float*, const float*, float*, float*, float*);
+void sampler_get_bank(Sampler*, float*, float*, float*, cudaStream_t);
+int64_t sampler_launches(const Sampler*);
+}  // namespace rgfm
+
+static thread_local std::string g_err;
+
+#define RGFM_API_BEGIN try {
+#define RGFM_API_END                          \
+  }                                           \
+  catch (const std::exception& e) {           \
+    g_err = e.what();                         \
+    return 1;                                 \
+  }                                           \
+  catch (...) {                               \
+    g_err = "unknown error";                  \
+    return 1;                                 \
+  }                                           \
+  return 0;
+
+struct rgfm_net {
+  std::unique_ptr<rgfm::Net> net;
+  float* scores = nullptr;  // ratio scratch
+  int device = 0;
+};
+
+extern "C" {
+
+const char* rgfm_last_error(void) { return g_err.c_str(); }
+int rgfm_abi_version(void) { return RGFM_ABI_VERSION; }
+
+int rgfm_sampler_create(const rgfm_sampler_desc* desc, const rgfm_weights* fm_x, const rgfm_weights* fm_y,
+                        const rgfm_weights* ratio, rgfm_sampler** out) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(out != nullptr, "rgfm_sampler_create: null out");
+  *out = reinterpret_cast<rgfm_sampler*>(rgfm::sampler_create(desc, fm_x, fm_y, ratio));
+  RGFM_API_END
+}
+
+int rgfm_sampler_run(rgfm_sampler* s, const float* x0, const float* y0, const float* mc_x0, const float* mc_y0,
+                     float* x1, float* y1, float* diag, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(s != nullptr, "rgfm_sampler_run: null plan");
+  rgfm::sampler_run(reinterpret_cast<rgfm::Sampler*>(s), x0, y0, mc_x0, mc_y0, x1, y1, diag, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_sampler_run_host(rgfm_sampler* s, const float* x0, const float* y0, const float* mc_x0, const float* mc_y0,
+                          float* x1, float* y1, float* diag) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(s != nullptr, "rgfm_sampler_run_host: null plan");
+  rgfm::sampler_run_host(reinterpret_cast<rgfm::Sampler*>(s), x0, y0, mc_x0, mc_y0, x1, y1, diag);
+  RGFM_API_END
+}
+
+int rgfm_sampler_get_bank(rgfm_sampler* s, float* mc_x, float* mc_y, float* mc_ratios, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(s != nullptr, "rgfm_sampler_get_bank: null plan");
+  rgfm::sampler_get_bank(reinterpret_cast<rgfm::Sampler*>(s), mc_x, mc_y, mc_ratios, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int64_t rgfm_sampler_launch_count(const rgfm_sampler* s) {
+  return s ? rgfm::sampler_launches(reinterpret_cast<const rgfm::Sampler*>(s)) : 0;
+}
+
+void rgfm_sampler_destroy(rgfm_sampler* s) {
+  if (s) rgfm::sampler_destroy(reinterpret_cast<rgfm::Sampler*>(s));
+}
+
+int rgfm_net_create(int32_t net_kind, const rgfm_weights* w, int32_t max_batch, int32_t precision, int32_t device,
+                    rgfm_net** out) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(out != nullptr, "rgfm_net_create: null out");
+  std::unique_ptr<rgfm_net> n(new rgfm_net());
+  n->device = device;
+  n->net.reset(new rgfm::Net(net_kind, w, max_batch, precision, device));
+  *out = n.release();
+  RGFM_API_END
+}
+
+int rgfm_unet_forward(rgfm_net* net, const float* x, float t, int32_t batch, float* v, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(net && net->net->is_unet(), "rgfm_unet_forward: not a U-Net");
+  RGFM_CUDA(cudaSetDevice(net->device));
+  RGFM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // the time-bias row is rewritten synchronously
+  net->net->set_times({t});
+  net->net->forward((cudaStream_t)stream, batch, x, nullptr, v, rgfm::OUT_NCHW, 0.f, nullptr);
+  RGFM_API_END
+}
+
+int rgfm_ratio_log_ratio(rgfm_net* net, const float* x, const float* y, int32_t batch, int32_t loss_type,
+                         float* log_ratio, float* scores, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(net && (net->net->kind() == RGFM_NET_RATIO28 || net->net->kind() == RGFM_NET_RATIO_MNIST_SVHN),
+             "rgfm_ratio_log_ratio: not a ratio estimator");
+  // unknown loss_type -> error, as ratio_estimator.py:190-191 raises ValueError
+  RGFM_CHECK(loss_type == RGFM_LOSS_DISC || loss_type == RGFM_LOSS_RULSIF, "Unknown loss_type");
+  RGFM_CUDA(cudaSetDevice(net->device));
+  float* sc = scores;
+  if (!sc) {
+    RGFM_CUDA(cudaMalloc(&sc, (size_t)batch * sizeof(float)));
+  }
+  net->net->forward((cudaStream_t)stream, batch, x, y, sc, 0, 0.f, nullptr);
+  rgfm::launch_ratio_head(sc, loss_type, log_ratio, nullptr, batch, (cudaStream_t)stream);
+  if (!scores) {
+    RGFM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    RGFM_CUDA(cudaFree(sc));
+  }
+  RGFM_API_END
+}
+
+int rgfm_classifier_logits(rgfm_net*, const float*, int32_t, float*, void*) {
+  g_err = "rgfm_classifier_logits: not implemented in this build";
+  return 1;
+}
+
+void rgfm_net_destroy(rgfm_net* net) { delete net; }
+
+int rgfm_mc_feng_step(int32_t batch, int32_t n_mc, int32_t dx, int32_t dy, const float* x, const float* y,
+                      const float* v_x, const float* v_y, const float* mc_x, const float* mc_y,
+                      const float* mc_ratios, double t, double dt, double gamma, float* x_out, float* y_out,
+                      float* g_x, float* g_y, float* weights, void* stream) {
+  RGFM_API_BEGIN
+  using namespace rgfm;
+  RGFM_CHECK(batch >= 1 && n_mc >= 1, "rgfm_mc_feng_step: sizes");
+  const double eps = 1e-3, sigma = 1.0 - t + eps;
+  StepScalars h{};
+  h.t = (float)t; h.sig2 = (float)(sigma * sigma); h.sigma = (float)sigma; h.inv_sigma = (float)(1.0 / sigma);
+  h.one_minus_gamma = (float)(1.0 - gamma); h.gamma = (float)gamma; h.dt = (float)dt;
+  McfArgs a{};
+  a.B = batch; a.N = n_mc; a.Dx = dx; a.Dy = dy;
+  a.x = x; a.y = y; a.vx = v_x; a.vy = v_y; a.mcx = mc_x; a.mcy = mc_y; a.ratios = mc_ratios;
+  a.x_out = x_out; a.y_out = y_out; a.gx = g_x; a.gy = g_y; a.w = weights;
+  const size_t nf = mcf_scratch_floats(batch, n_mc, dx, dy, &a.ksplit_x, &a.ksplit_y);
+  float* scratch = nullptr;
+  StepScalars* dsc = nullptr;
+  RGFM_CUDA(cudaMalloc(&scratch, nf * sizeof(float)));
+  RGFM_CUDA(cudaMalloc(&dsc, sizeof(StepScalars)));
+  RGFM_CUDA(cudaMemcpy(dsc, &h, sizeof(h), cudaMemcpyHostToDevice));
+  a.sc = dsc; a.step = nullptr;
+  a.logits = scratch;
+  a.wbuf = scratch + (size_t)(a.ksplit_x + a.ksplit_y) * batch * n_mc;
+  a.zbuf = a.wbuf + (size_t)batch * n_mc;
+  try {
+    launch_mcf(a, (cudaStream_t)stream);
+    RGFM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  } catch (...) {
+    cudaFree(scratch);
+    cudaFree(dsc);
+    throw;
+  }
+  cudaFree(scratch);
+  cudaFree(dsc);
+  RGFM_API_END
+}
+
+}  // extern "C"

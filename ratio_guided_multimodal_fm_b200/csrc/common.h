@@ -1,0 +1,197 @@
+// Shared declarations for librgfm.so (B200 / sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <map>
+#include <memory>
+#include <cstdio>
+
+namespace rgfm {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define RGFM_CUDA(expr)                                                                                  \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      throw ::rgfm::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ +  \
+                          ":" + std::to_string(__LINE__) + ")");                                         \
+  } while (0)
+
+#define RGFM_CHECK(cond, msg)                                                                     \
+  do {                                                                                            \
+    if (!(cond)) throw ::rgfm::Error(std::string(msg) + " [" #cond "] (" + __FILE__ + ":" +       \
+                                     std::to_string(__LINE__) + ")");                             \
+  } while (0)
+
+constexpr int TM = 128;  // output pixels per conv tile (one tcgen05 M=128 accumulator)
+
+// Tiling of an H x W output image into <=128-pixel tiles of whole rows (or several whole images per tile when
+// H*W < 128).  Shared by every conv implementation so per-tile GroupNorm partial sums have one layout.
+struct TileGeom {
+  int H, W;    // output spatial size
+  int th;      // rows per tile
+  int imgs;    // images per tile (1 unless H*W*2 <= TM)
+  int parts;   // tiles per image (1 when imgs > 1)
+  __host__ __device__ int tiles(int nimg) const { return imgs == 1 ? nimg * parts : (nimg + imgs - 1) / imgs; }
+};
+
+inline TileGeom make_geom(int H, int W) {
+  TileGeom g;
+  g.H = H;
+  g.W = W;
+  if (H * W >= TM) {
+    g.th = TM / W;
+    g.imgs = 1;
+    g.parts = (H + g.th - 1) / g.th;
+  } else {
+    g.th = H;
+    g.imgs = TM / (H * W);
+    g.parts = 1;
+  }
+  return g;
+}
+
+// Row r of tile `tile` -> (n, ho, wo, part); returns validity.
+__host__ __device__ inline bool tile_row(const TileGeom& g, int tile, int r, int nimg, int& n, int& ho, int& wo,
+                                         int& part) {
+  if (g.imgs == 1) {
+    n = tile / g.parts;
+    part = tile - n * g.parts;
+    if (r >= g.th * g.W) return false;
+    int rr = r / g.W;
+    ho = part * g.th + rr;
+    wo = r - rr * g.W;
+    return ho < g.H && n < nimg;
+  }
+  int hw = g.H * g.W;
+  int il = r / hw;
+  if (il >= g.imgs) return false;
+  n = tile * g.imgs + il;
+  part = 0;
+  int q = r - il * hw;
+  ho = q / g.W;
+  wo = q - ho * g.W;
+  return n < nimg;
+}
+
+// Raw (pre-norm) activation: fp32 NHWC plus optional per-(image, part, channel) {sum, sumsq} partials.
+struct Act {
+  float* p = nullptr;
+  int H = 0, W = 0, C = 0;
+  float* stats = nullptr;  // [n][parts][C][2]
+  int parts = 0;
+  size_t elems_per_img() const { return (size_t)H * W * C; }
+};
+
+// Normalised/activated conv operand: NHWC, fp32 (SIMT path) or bf16 (tcgen05 path)
+struct Packed {
+  void* p = nullptr;
+  int H = 0, W = 0, C = 0;
+  bool bf16 = false;
+};
+
+enum NormMode { NORM_NONE = 0, NORM_GN = 1, NORM_AFFINE = 2 };
+enum SpatialMode { SP_ID = 0, SP_UP2 = 1, SP_POOL2 = 2 };
+enum OutMode { OUT_RAW = 0, OUT_NCHW = 1, OUT_EULER = 2 };
+enum ActMode { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2 };
+
+// ---- kernel launch descriptors (plain structs passed by value) ----
+struct PackSrc {
+  const float* p;      // raw NHWC
+  const float* stats;  // may be null when norm != GN
+  int C, parts;
+};
+
+struct PackArgs {
+  PackSrc src[2];
+  int nsrc;
+  int Hs, Ws;           // source spatial
+  int Ho, Wo;           // output spatial
+  int C;                // total channels
+  int norm, act, spatial;
+  const float* gamma;   // GN: gamma[C]; AFFINE: scale[C]
+  const float* beta;    // GN: beta[C];  AFFINE: shift[C]
+  int groups;
+  void* out;
+  int out_bf16;
+  int nimg;
+};
+
+struct ConvArgs {
+  const void* in;  // packed NHWC (fp32 for SIMT, bf16 for TC)
+  int Hin, Win, Cin;
+  const float* w;  // SIMT: [ks*ks][Cin][CoutP]
+  const float* bias;  // [CoutP]
+  const float* temb;  // time-bias table [rows][temb_stride] or null
+  int temb_stride, temb_off;
+  const int* step;    // device step index (row of temb)
+  const float* res;   // raw NHWC [n][Ho][Wo][Cout] or null
+  int CoutP;          // padded Cout (multiple of 32)
+  int Cout;           // real Cout
+  int ks, stride, pad;
+  TileGeom g;
+  int nimg;
+  int out_mode;
+  float* out;         // OUT_RAW: NHWC [n][Ho][Wo][Cout]; OUT_NCHW: v[n][Cout][Ho][Wo]; OUT_EULER: x[n][Cout][Ho][Wo] += dt*val
+  float* stats;       // [n][parts][Cout][2] or null
+  float dt;
+};
+
+// ops_simt.cu
+void launch_pack(const PackArgs& a, cudaStream_t s);
+void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, int out_bf16, int nimg, cudaStream_t s);
+void launch_conv_simt(const ConvArgs& a, cudaStream_t s);
+void launch_gap_fc(const float* in, int HW, int C, const float* w, const float* b, int Cout, float* out, int ld,
+                   int nimg, cudaStream_t s);
+struct MlpLayer {
+  const float* w;   // [out][in]
+  const float* b;
+  const float* ln_g;  // null => no LayerNorm/SiLU (final layer)
+  const float* ln_b;
+  int in, out, act;
+};
+void launch_mlp(const float* in, int ld_in, const MlpLayer* layers, int nlayers, float* out, int ld_out, int nimg,
+                cudaStream_t s);
+void launch_ratio_head(const float* scores, int loss_type, float* log_ratio, float* ratios, int n, cudaStream_t s);
+void launch_step_inc(int* step, cudaStream_t s);
+void launch_euler(float* x, const float* v, float dt, size_t n, cudaStream_t s);
+
+// guidance.cu
+struct StepScalars {  // per Euler step, computed on the host in double then rounded like the reference
+  float t, sig2, inv_sigma, sigma, one_minus_gamma, gamma, dt, pad;
+};
+struct McfArgs {
+  int B, N, Dx, Dy;
+  const float *x, *y, *vx, *vy, *mcx, *mcy, *ratios;
+  const StepScalars* sc;  // table
+  const int* step;        // index into sc (null => 0)
+  float *x_out, *y_out;   // may alias x, y
+  float *gx, *gy, *w;     // optional
+  float* logits;          // scratch [ksplit][B][N]
+  float* wbuf;            // scratch [B][N]
+  float* zbuf;            // scratch [B][4]: Z_bar, w_min, w_max
+  int ksplit_x, ksplit_y;
+};
+size_t mcf_scratch_floats(int B, int N, int Dx, int Dy, int* ksx, int* ksy);
+void launch_mcf(const McfArgs& a, cudaStream_t s);
+struct DiagArgs {
+  int B, Dx, Dy, N;
+  const float *vx, *vy, *gx, *gy, *zbuf;
+  const StepScalars* sc;
+  const int* step;
+  int diag_step;
+  float* diag;
+};
+void launch_diag(const DiagArgs& a, cudaStream_t s);
+void launch_ratio_stats(const float* ratios, int n, float* diag3, cudaStream_t s);
+
+extern thread_local int64_t g_launch_counter;  // incremented by every launch_* (graph build-time kernel count)
+
+}  // namespace rgfm

@@ -1,0 +1,105 @@
+// Op programs for the networks on the hot path: three U-Net velocity fields and two ratio estimators
+// (SURVEY.md section 8a), built once from a reference state_dict and run on chunks of images.
+#pragma once
+#include "common.h"
+#include "rgfm.h"
+#include <functional>
+
+namespace rgfm {
+
+// name -> host tensor view of the caller's state_dict
+struct WeightMap {
+  std::map<std::string, std::pair<const float*, int64_t>> m;
+  explicit WeightMap(const rgfm_weights* w);
+  const float* get(const std::string& name, int64_t numel) const;
+  bool has(const std::string& name) const { return m.count(name) != 0; }
+};
+
+// Device memory for a plan: bump allocations that live as long as the plan, plus a free-list for activations.
+class DevPool {
+ public:
+  ~DevPool();
+  void* alloc(size_t bytes);     // reuse a released block of sufficient size or cudaMalloc
+  void release(void* p);         // return a block to the free list (plan-build time liveness)
+  void* persistent(size_t bytes);
+  template <typename T>
+  T* upload(const std::vector<T>& h) {
+    T* d = (T*)persistent(h.size() * sizeof(T));
+    RGFM_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+  }
+  size_t total_bytes() const { return total_; }
+
+ private:
+  struct Block { void* p; size_t bytes; bool free; };
+  std::vector<Block> blocks_;
+  std::vector<void*> persist_;
+  size_t total_ = 0;
+};
+
+struct RunCtx {
+  cudaStream_t s;
+  int nimg;            // images in this chunk
+  const float* x;      // chunk input, NCHW fp32 (U-Net: x_t; ratio: x)
+  const float* y;      // ratio: y
+  float* out;          // U-Net: v (OUT_NCHW) or x to update (OUT_EULER); ratio: scores
+  int out_mode;
+  float dt;
+  const int* step;     // device step index selecting the time-bias row (null = row 0)
+};
+
+struct TcConv;  // conv_tc.cu
+struct TcDeleter { void operator()(TcConv* p) const; };
+using TcPtr = std::unique_ptr<TcConv, TcDeleter>;
+
+class Net {
+ public:
+  Net(int kind, const rgfm_weights* w, int chunk, int precision, int device);
+  ~Net();
+  int kind() const { return kind_; }
+  bool is_unet() const { return kind_ <= RGFM_NET_UNET_SVHN; }
+  int in_ch() const { return in_ch_; }
+  int img() const { return img_; }
+  int chunk() const { return chunk_; }
+  size_t dim() const { return (size_t)in_ch_ * img_ * img_; }
+
+  // U-Net: precompute the per-step time-bias rows for times ts (fp32 values of step*dt).
+  // reference: timestep_embedding + time_embed + every ResBlock.time_mlp (unet.py:228-229,88)
+  void set_times(const std::vector<float>& ts);
+
+  // Run on `nimg` images (looping over chunks).  U-Net: out_mode OUT_NCHW writes v, OUT_EULER does x += dt*v
+  // in place on `out`.  Ratio: x, y -> scores[nimg].
+  void forward(cudaStream_t s, int nimg, const float* x, const float* y, float* out, int out_mode, float dt,
+               const int* step);
+
+ private:
+  friend struct Builder;
+  int kind_, chunk_, precision_, device_;
+  int in_ch_ = 0, img_ = 0, in_ch_y_ = 0;
+  DevPool pool_;
+  std::vector<std::function<void(const RunCtx&)>> ops_;
+  std::vector<TcPtr> tc_;
+  // time embedding (host copies)
+  int model_ch_ = 0, temb_dim_ = 0, temb_C_ = 0;
+  std::vector<float> te0_w_, te0_b_, te2_w_, te2_b_;
+  struct TimeMlp { std::vector<float> w, b; int cout, off; };
+  std::vector<TimeMlp> tmlps_;
+  float* d_temb_ = nullptr;
+  int temb_rows_ = 0;
+};
+
+// conv_tc.cu -- tcgen05 implicit-GEMM convolution (bf16 operands, fp32 accumulate in TMEM)
+struct TcConvDesc {
+  int Hin, Win, Cin;     // operand (bf16 NHWC) geometry
+  int Cout, CoutP;       // real / padded output channels
+  int ks;                // 1 or 3 (stride 1, pad ks/2)
+  int chunk;             // max images
+  const void* in;        // bf16 NHWC operand buffer
+  const float* w_oihw;   // host weights, torch layout [Cout][Cin_real][ks][ks]
+  int Cin_real;
+};
+TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool);
+void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s);
+bool tc_available();
+
+}  // namespace rgfm

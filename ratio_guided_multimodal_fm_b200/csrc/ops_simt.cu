@@ -1,0 +1,501 @@
+// fp32 CUDA-core kernels: operand packing (GroupNorm/BatchNorm-affine + SiLU + pool/upsample + concat), the
+// exact-fp32 implicit-GEMM convolution used by the fp32 precision mode, and the small dense heads.
+// The bf16 tensor-core convolution lives in conv_tc.cu and plugs into the same op program.
+#include "common.h"
+
+namespace rgfm {
+
+thread_local int64_t g_launch_counter = 0;
+
+static inline void post_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw Error(std::string(what) + " launch failed: " + cudaGetErrorString(e));
+  ++g_launch_counter;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_SILU) return silu_f(x);
+  if (act == ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCHW fp32 image -> NHWC operand with channels zero-padded to Cp (input conv operand)
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void pack_nchw_kernel(const float* __restrict__ x, int C, int HW, int Cp, void* __restrict__ out,
+                                 size_t total_px) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total_px) return;
+  size_t n = p / HW;
+  int q = (int)(p - n * HW);
+  const float* src = x + n * (size_t)C * HW + q;
+  for (int c = 0; c < Cp; c += 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (c + j < C) ? __ldg(src + (size_t)(c + j) * HW) : 0.0f;
+    if (BF16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + p * Cp + c) = u;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + p * Cp + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, int out_bf16, int nimg,
+                      cudaStream_t s) {
+  size_t total = (size_t)nimg * H * W;
+  int threads = 256;
+  unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  if (out_bf16)
+    pack_nchw_kernel<true><<<blocks, threads, 0, s>>>(x, C, H * W, Cp, out, total);
+  else
+    pack_nchw_kernel<false><<<blocks, threads, 0, s>>>(x, C, H * W, Cp, out, total);
+  post_launch("pack_nchw");
+}
+
+// ------------------------------------------------------------------------------------------------
+// PACK: raw NHWC (1 or 2 concatenated sources) -> normalised + activated (+pooled / upsampled) conv operand.
+// GroupNorm statistics come from the producers' per-tile {sum, sumsq} partials; they are combined here in
+// double, in a fixed order (deterministic).  reference: F.group_norm at unet.py:83,91,274;
+// BatchNorm(eval)/max_pool2d at ratio_flexible.py:217-226.
+// ------------------------------------------------------------------------------------------------
+constexpr int PACK_PIX = 32;
+constexpr int PACK_MAXC = 512;
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
+  __shared__ float s_scale[PACK_MAXC];
+  __shared__ float s_shift[PACK_MAXC];
+  __shared__ float s_mean[32];
+  __shared__ float s_rstd[32];
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int C0 = a.src[0].C;
+
+  if (a.norm == NORM_GN) {
+    const int cpg = a.C / a.groups;
+    if (tid < a.groups) {
+      double s = 0.0, ss = 0.0;
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+        const int si = (c < C0) ? 0 : 1;
+        const int cl = si ? c - C0 : c;
+        const int Cs = a.src[si].C, parts = a.src[si].parts;
+        const float* st = a.src[si].stats + (size_t)n * parts * Cs * 2;
+        for (int p = 0; p < parts; ++p) {
+          s += (double)st[((size_t)p * Cs + cl) * 2];
+          ss += (double)st[((size_t)p * Cs + cl) * 2 + 1];
+        }
+      }
+      const double cnt = (double)cpg * a.Hs * a.Ws;
+      const double mean = s / cnt;
+      double var = ss / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[tid] = (float)mean;
+      s_rstd[tid] = (float)(1.0 / sqrt(var + 1e-5));
+    }
+    __syncthreads();
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      const int g = c / cpg;
+      const float sc = s_rstd[g] * a.gamma[c];
+      s_scale[c] = sc;
+      s_shift[c] = a.beta[c] - s_mean[g] * sc;
+    }
+  } else if (a.norm == NORM_AFFINE) {
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      s_scale[c] = a.gamma[c];
+      s_shift[c] = a.beta[c];
+    }
+  } else {
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      s_scale[c] = 1.0f;
+      s_shift[c] = 0.0f;
+    }
+  }
+  __syncthreads();
+
+  const int C4 = a.C >> 2;
+  const int npix = a.Ho * a.Wo;
+  const int p0 = blockIdx.x * PACK_PIX;
+  const bool plain = (a.norm == NORM_NONE && a.act == ACT_NONE);
+  for (int i = tid; i < PACK_PIX * C4; i += blockDim.x) {
+    const int p = p0 + i / C4;
+    if (p >= npix) break;
+    const int c = (i % C4) << 2;
+    const int ho = p / a.Wo, wo = p - ho * a.Wo;
+    const int si = (c < C0) ? 0 : 1;
+    const int cl = si ? c - C0 : c;
+    const int Cs = a.src[si].C;
+    const float* base = a.src[si].p + (size_t)n * a.Hs * a.Ws * Cs + cl;
+    float4 r;
+    if (a.spatial == SP_POOL2) {
+      r = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(base + ((size_t)(2 * ho + dy) * a.Ws + (2 * wo + dx)) * Cs));
+          v.x = apply_act(v.x * s_scale[c] + s_shift[c], a.act);
+          v.y = apply_act(v.y * s_scale[c + 1] + s_shift[c + 1], a.act);
+          v.z = apply_act(v.z * s_scale[c + 2] + s_shift[c + 2], a.act);
+          v.w = apply_act(v.w * s_scale[c + 3] + s_shift[c + 3], a.act);
+          r.x = fmaxf(r.x, v.x); r.y = fmaxf(r.y, v.y); r.z = fmaxf(r.z, v.z); r.w = fmaxf(r.w, v.w);
+        }
+    } else {
+      const int hs = (a.spatial == SP_UP2) ? (ho >> 1) : ho;
+      const int ws = (a.spatial == SP_UP2) ? (wo >> 1) : wo;
+      r = __ldg(reinterpret_cast<const float4*>(base + ((size_t)hs * a.Ws + ws) * Cs));
+      if (!plain) {
+        r.x = apply_act(r.x * s_scale[c] + s_shift[c], a.act);
+        r.y = apply_act(r.y * s_scale[c + 1] + s_shift[c + 1], a.act);
+        r.z = apply_act(r.z * s_scale[c + 2] + s_shift[c + 2], a.act);
+        r.w = apply_act(r.w * s_scale[c + 3] + s_shift[c + 3], a.act);
+      }
+    }
+    const size_t o = ((size_t)n * npix + p) * a.C + c;
+    if (BF16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(r.z, r.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o) = u;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o) = r;
+    }
+  }
+}
+
+void launch_pack(const PackArgs& a, cudaStream_t s) {
+  RGFM_CHECK(a.C <= PACK_MAXC && a.C % 4 == 0, "pack: channel count");
+  RGFM_CHECK(a.groups <= 32, "pack: groups");
+  dim3 grid((a.Ho * a.Wo + PACK_PIX - 1) / PACK_PIX, a.nimg);
+  if (a.out_bf16)
+    pack_kernel<true><<<grid, 256, 0, s>>>(a);
+  else
+    pack_kernel<false><<<grid, 256, 0, s>>>(a);
+  post_launch("pack");
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 implicit-GEMM convolution (3x3 / 1x1, stride 1 / 2) on CUDA cores: the exact-fp32 precision mode.
+// M = 128 output pixels (TileGeom), N = TN output channels, K = taps x Cin in chunks of 16.
+// Epilogue: + bias + per-step time bias + residual, raw NHWC store (or NCHW velocity / fused Euler update),
+// per-tile GroupNorm partial sums.  reference ops: nn.Conv2d at unet.py:55,66,70,104,115,164,210.
+// ------------------------------------------------------------------------------------------------
+template <int TN>
+__global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
+  constexpr int KC = 16;
+  constexpr int CPT = TN / 16;
+  __shared__ __align__(16) float As[KC][TM + 4];
+  __shared__ __align__(16) float Bs[KC][TN];
+  __shared__ float Ts[TM][TN + 1];
+
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int n0 = blockIdx.y * TN;
+  const int pg = tid >> 4, cg = tid & 15;
+  const float* in = reinterpret_cast<const float*>(a.in);
+
+  // A-operand load assignment: two (pixel, channel-quad) items per thread
+  int ln[2], lh[2], lw[2];
+  bool lv[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int idx = tid + j * 256;
+    int n, ho, wo, part;
+    lv[j] = tile_row(a.g, tile, idx >> 2, a.nimg, n, ho, wo, part);
+    ln[j] = n;
+    lh[j] = ho * a.stride - a.pad;
+    lw[j] = wo * a.stride - a.pad;
+  }
+
+  float acc[8][CPT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[i][j] = 0.0f;
+
+  const int ntaps = a.ks * a.ks;
+  for (int tap = 0; tap < ntaps; ++tap) {
+    const int ky = tap / a.ks, kx = tap - ky * a.ks;
+    for (int c0 = 0; c0 < a.Cin; c0 += KC) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int idx = tid + j * 256;
+        const int px = idx >> 2, c4 = idx & 3;
+        const int hi = lh[j] + ky, wi = lw[j] + kx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lv[j] && hi >= 0 && hi < a.Hin && wi >= 0 && wi < a.Win)
+          v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)ln[j] * a.Hin + hi) * a.Win + wi) * a.Cin + c0 + c4 * 4));
+        As[c4 * 4 + 0][px] = v.x;
+        As[c4 * 4 + 1][px] = v.y;
+        As[c4 * 4 + 2][px] = v.z;
+        As[c4 * 4 + 3][px] = v.w;
+      }
+      if (tid < KC * TN / 4) {
+        const int k = tid / (TN / 4), c4b = tid % (TN / 4);
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(a.w + ((size_t)tap * a.Cin + c0 + k) * a.CoutP + n0 + c4b * 4));
+        *reinterpret_cast<float4*>(&Bs[k][c4b * 4]) = wv;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[k][pg * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[k][pg * 8 + 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float bv[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) bv[j] = Bs[k][cg * CPT + j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+  const float* tb = a.temb ? a.temb + (size_t)(a.step ? *a.step : 0) * a.temb_stride + a.temb_off : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int px = pg * 8 + i;
+    int n, ho, wo, part;
+    const bool valid = tile_row(a.g, tile, px, a.nimg, n, ho, wo, part);
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int co = n0 + cg * CPT + j;
+      float val = 0.0f;
+      if (valid && co < a.Cout) {
+        val = acc[i][j] + a.bias[co];
+        if (tb) val += tb[co];
+        const size_t o = (((size_t)n * a.g.H + ho) * a.g.W + wo) * a.Cout + co;
+        if (a.res) val += a.res[o];
+        if (a.out_mode == OUT_RAW) {
+          a.out[o] = val;
+        } else {
+          const size_t oc = (((size_t)n * a.Cout + co) * a.g.H + ho) * a.g.W + wo;
+          if (a.out_mode == OUT_NCHW)
+            a.out[oc] = val;
+          else
+            a.out[oc] = __fadd_rn(a.out[oc], __fmul_rn(val, a.dt));
+        }
+      }
+      Ts[px][cg * CPT + j] = val;
+    }
+  }
+  if (a.stats == nullptr) return;
+  __syncthreads();
+  const int hw = a.g.H * a.g.W;
+  for (int item = tid; item < a.g.imgs * TN; item += 256) {
+    const int il = item / TN, c = item - il * TN;
+    const int r0 = (a.g.imgs == 1) ? 0 : il * hw;
+    const int r1 = (a.g.imgs == 1) ? a.g.th * a.g.W : r0 + hw;
+    float s = 0.f, ss = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float v = Ts[r][c];
+      s += v;
+      ss = fmaf(v, v, ss);
+    }
+    const int n = (a.g.imgs == 1) ? tile / a.g.parts : tile * a.g.imgs + il;
+    const int part = (a.g.imgs == 1) ? tile % a.g.parts : 0;
+    const int co = n0 + c;
+    if (n < a.nimg && co < a.Cout) {
+      float* st = a.stats + (((size_t)n * a.g.parts + part) * a.Cout + co) * 2;
+      st[0] = s;
+      st[1] = ss;
+    }
+  }
+}
+
+void launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
+  RGFM_CHECK(a.Cin % 16 == 0, "conv_simt: Cin must be a multiple of 16");
+  RGFM_CHECK(a.CoutP % 32 == 0, "conv_simt: padded Cout must be a multiple of 32");
+  const int tiles = a.g.tiles(a.nimg);
+  if (a.CoutP % 64 == 0) {
+    dim3 grid(tiles, a.CoutP / 64);
+    conv_simt_kernel<64><<<grid, 256, 0, s>>>(a);
+  } else {
+    dim3 grid(tiles, a.CoutP / 32);
+    conv_simt_kernel<32><<<grid, 256, 0, s>>>(a);
+  }
+  post_launch("conv_simt");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Global average pool + Linear: one CTA per image.  reference: ratio_estimator.py:86-91, ratio_flexible.py:228-230
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gap_fc_kernel(const float* __restrict__ in, int HW, int C,
+                                                     const float* __restrict__ w, const float* __restrict__ b,
+                                                     int Cout, float* __restrict__ out, int ld) {
+  __shared__ float m[PACK_MAXC];
+  const int n = blockIdx.x;
+  const float* src = in + (size_t)n * HW * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += src[(size_t)p * C + c];
+    m[c] = s / (float)HW;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < Cout; j += 8) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w[(size_t)j * C + c], m[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[(size_t)n * ld + j] = s + b[j];
+  }
+}
+
+void launch_gap_fc(const float* in, int HW, int C, const float* w, const float* b, int Cout, float* out, int ld,
+                   int nimg, cudaStream_t s) {
+  RGFM_CHECK(C <= PACK_MAXC, "gap_fc: C");
+  gap_fc_kernel<<<nimg, 256, 0, s>>>(in, HW, C, w, b, Cout, out, ld);
+  post_launch("gap_fc");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense head: up to 4 x (Linear [-> LayerNorm -> SiLU] | [-> ReLU]); one CTA per sample.
+// reference: score_net at ratio_estimator.py:125-135, ratio_flexible.py:332-345
+// ------------------------------------------------------------------------------------------------
+struct MlpPack {
+  MlpLayer l[4];
+  int n;
+};
+constexpr int MLP_MAXW = 8192;
+
+__global__ void __launch_bounds__(256) mlp_kernel(const float* __restrict__ in, int ld_in, MlpPack mp,
+                                                  float* __restrict__ out, int ld_out) {
+  extern __shared__ float sm[];  // two ping-pong activation vectors
+  __shared__ float red[2];
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* cur = sm;
+  float* nxt = sm + MLP_MAXW;
+  for (int i = tid; i < mp.l[0].in; i += 256) cur[i] = in[(size_t)n * ld_in + i];
+  __syncthreads();
+  for (int li = 0; li < mp.n; ++li) {
+    const MlpLayer L = mp.l[li];
+    for (int j = warp; j < L.out; j += 8) {
+      const float* wr = L.w + (size_t)j * L.in;
+      float s = 0.f;
+      for (int c = lane; c < L.in; c += 32) s = fmaf(wr[c], cur[c], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) nxt[j] = s + L.b[j];
+    }
+    __syncthreads();
+    if (L.ln_g) {
+      if (warp == 0) {
+        float s = 0.f;
+        for (int c = lane; c < L.out; c += 32) s += nxt[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)L.out;
+        float v = 0.f;
+        for (int c = lane; c < L.out; c += 32) {
+          const float d = nxt[c] - mean;
+          v = fmaf(d, d, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+          red[0] = mean;
+          red[1] = rsqrtf(v / (float)L.out + 1e-5f);
+        }
+      }
+      __syncthreads();
+      for (int c = tid; c < L.out; c += 256) nxt[c] = (nxt[c] - red[0]) * red[1] * L.ln_g[c] + L.ln_b[c];
+      __syncthreads();
+    }
+    if (L.act != ACT_NONE) {
+      for (int c = tid; c < L.out; c += 256) nxt[c] = apply_act(nxt[c], L.act);
+      __syncthreads();
+    }
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  const int nout = mp.l[mp.n - 1].out;
+  for (int c = tid; c < nout; c += 256) out[(size_t)n * ld_out + c] = cur[c];
+}
+
+void launch_mlp(const float* in, int ld_in, const MlpLayer* layers, int nlayers, float* out, int ld_out, int nimg,
+                cudaStream_t s) {
+  RGFM_CHECK(nlayers >= 1 && nlayers <= 4, "mlp: layer count");
+  MlpPack mp;
+  mp.n = nlayers;
+  for (int i = 0; i < nlayers; ++i) {
+    mp.l[i] = layers[i];
+    RGFM_CHECK(layers[i].in <= MLP_MAXW && layers[i].out <= MLP_MAXW, "mlp: width");
+  }
+  static bool attr_set = false;
+  const size_t smem = 2 * MLP_MAXW * sizeof(float);
+  if (!attr_set) {
+    RGFM_CUDA(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  mlp_kernel<<<nimg, 256, smem, s>>>(in, ld_in, mp, out, ld_out);
+  post_launch("mlp");
+}
+
+// log r = logsigmoid(T) - logsigmoid(-T) (disc) | log(softplus(T) + 1e-8) (rulsif); r = exp(log r)
+// reference: ratio_estimator.py:182-189, flow_utils.py:256-257
+__global__ void ratio_head_kernel(const float* __restrict__ scores, int loss_type, float* __restrict__ lr,
+                                  float* __restrict__ r, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float T = scores[i];
+  float v;
+  if (loss_type == 0) {
+    const float l1p = log1pf(expf(-fabsf(T)));
+    const float a = fminf(T, 0.f) - l1p;
+    const float b = fminf(-T, 0.f) - l1p;
+    v = a - b;
+  } else {
+    const float sp = (T > 20.f) ? T : log1pf(expf(T));
+    v = logf(sp + 1e-8f);
+  }
+  if (lr) lr[i] = v;
+  if (r) r[i] = expf(v);
+}
+
+void launch_ratio_head(const float* scores, int loss_type, float* log_ratio, float* ratios, int n, cudaStream_t s) {
+  ratio_head_kernel<<<(n + 127) / 128, 128, 0, s>>>(scores, loss_type, log_ratio, ratios, n);
+  post_launch("ratio_head");
+}
+
+__global__ void step_inc_kernel(int* step) { *step += 1; }
+void launch_step_inc(int* step, cudaStream_t s) {
+  step_inc_kernel<<<1, 1, 0, s>>>(step);
+  post_launch("step_inc");
+}
+
+// x <- x + v*dt, rounded like the reference (mul then add, no FMA).  reference: flow_utils.py:372-373
+__global__ void euler_kernel(float* __restrict__ x, const float* __restrict__ v, float dt, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<float4*>(x)[i];
+  const float4 b = __ldg(reinterpret_cast<const float4*>(v) + i);
+  a.x = __fadd_rn(a.x, __fmul_rn(b.x, dt));
+  a.y = __fadd_rn(a.y, __fmul_rn(b.y, dt));
+  a.z = __fadd_rn(a.z, __fmul_rn(b.z, dt));
+  a.w = __fadd_rn(a.w, __fmul_rn(b.w, dt));
+  reinterpret_cast<float4*>(x)[i] = a;
+}
+void launch_euler(float* x, const float* v, float dt, size_t n, cudaStream_t s) {
+  RGFM_CHECK(n % 4 == 0, "euler: n % 4");
+  size_t n4 = n / 4;
+  euler_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(x, v, dt, n4);
+  post_launch("euler");
+}
+
+}  // namespace rgfm

@@ -1,0 +1,276 @@
+// The coupled guided Euler sampler as a plan: MC pre-pass, ratio forward, N-step main loop, all captured as
+// per-step CUDA graphs driven by a device-side step counter (no host synchronisation inside the loop).
+// reference: flow_utils.py:178-375 (28x28 pair), sample_mnist_svhn.py:39-177 (MNIST32 <-> SVHN).
+#include "net.h"
+#include <cmath>
+#include <algorithm>
+
+namespace rgfm {
+
+struct Graph {
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t e = nullptr;
+  int64_t kernels = 0;
+  ~Graph() {
+    if (e) cudaGraphExecDestroy(e);
+    if (g) cudaGraphDestroy(g);
+  }
+};
+
+struct Sampler {
+  rgfm_sampler_desc d;
+  std::unique_ptr<Net> fx, fy, fr;
+  int Dx = 0, Dy = 0, B = 0, N = 0, steps = 0;
+  bool guided = false;
+  float dtf = 0.f;
+  DevPool pool;
+  float *x = nullptr, *y = nullptr, *vx = nullptr, *vy = nullptr, *gx = nullptr, *gy = nullptr;
+  float *mcx = nullptr, *mcy = nullptr, *scores = nullptr, *ratios = nullptr, *scratch = nullptr;
+  float* diag = nullptr;
+  int* step = nullptr;
+  StepScalars* sc = nullptr;
+  int first_guided = 0;  // first step with t > eps
+  int ksx = 1, ksy = 1;
+  cudaStream_t cap = nullptr;
+  Graph g_pre_x, g_pre_y, g_ratio, g_plain, g_guided;
+  int64_t launches = 0;
+  float *hx = nullptr, *hy = nullptr, *hmx = nullptr, *hmy = nullptr;  // pinned staging for run_host
+  std::vector<float*> stage;  // device staging for run_host
+
+  ~Sampler() {
+    cudaSetDevice(d.device);
+    if (cap) cudaStreamDestroy(cap);
+    if (hx) cudaFreeHost(hx);
+    if (hy) cudaFreeHost(hy);
+    if (hmx) cudaFreeHost(hmx);
+    if (hmy) cudaFreeHost(hmy);
+  }
+
+  template <typename F>
+  void capture(Graph& G, F&& body) {
+    const int64_t before = g_launch_counter;
+    RGFM_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    try {
+      body(cap);
+    } catch (...) {
+      cudaGraph_t junk = nullptr;
+      cudaStreamEndCapture(cap, &junk);
+      if (junk) cudaGraphDestroy(junk);
+      throw;
+    }
+    RGFM_CUDA(cudaStreamEndCapture(cap, &G.g));
+    RGFM_CUDA(cudaGraphInstantiate(&G.e, G.g, 0));
+    G.kernels = g_launch_counter - before;
+  }
+
+  void build(const rgfm_weights* wx, const rgfm_weights* wy, const rgfm_weights* wr) {
+    RGFM_CHECK(d.abi_version == RGFM_ABI_VERSION, "rgfm_sampler_desc.abi_version mismatch");
+    RGFM_CHECK(d.num_samples >= 1 && d.num_steps >= 1, "num_samples and num_steps must be positive");
+    RGFM_CUDA(cudaSetDevice(d.device));
+    B = d.num_samples;
+    N = d.mc_batch_size;
+    steps = d.num_steps;
+    // Unknown methods, or mc_feng without a ratio estimator, silently degrade to unguided exactly like the
+    // reference (flow_utils.py:231,273).
+    guided = (d.guidance == RGFM_GUIDE_MC_FENG) && wr != nullptr && N >= 1;
+    RGFM_CHECK(d.guidance != RGFM_GUIDE_GRAD_LOG_RATIO, "grad_log_ratio guidance is not implemented in this build");
+    int kx, ky, kr;
+    if (d.pair == RGFM_PAIR_28) {
+      kx = ky = RGFM_NET_UNET_MNIST28;
+      kr = RGFM_NET_RATIO28;
+    } else if (d.pair == RGFM_PAIR_MNIST_SVHN) {
+      kx = RGFM_NET_UNET_MNIST32;
+      ky = RGFM_NET_UNET_SVHN;
+      kr = RGFM_NET_RATIO_MNIST_SVHN;
+    } else {
+      throw Error("unknown pair kind");
+    }
+    int chunk = d.chunk > 0 ? d.chunk : 256;
+    chunk = std::min(chunk, std::max(B, guided ? N : 1));
+    fx.reset(new Net(kx, wx, chunk, d.precision, d.device));
+    fy.reset(new Net(ky, wy, chunk, d.precision, d.device));
+    if (guided) fr.reset(new Net(kr, wr, std::min(chunk, N), d.precision, d.device));
+    Dx = (int)fx->dim();
+    Dy = (int)fy->dim();
+
+    // per-step scalars, computed in double like the reference's Python floats and rounded once to fp32
+    const double dt = 1.0 / steps, eps = 1e-3;
+    dtf = (float)dt;
+    std::vector<float> ts(steps);
+    std::vector<StepScalars> hs(steps);
+    first_guided = steps;
+    for (int s = 0; s < steps; ++s) {
+      const double t = s * dt;
+      ts[s] = (float)t;  // torch.full((B,), t) -> fp32
+      const double sigma = 1.0 - t + eps;
+      hs[s].t = (float)t;
+      hs[s].sig2 = (float)(sigma * sigma);
+      hs[s].sigma = (float)sigma;
+      hs[s].inv_sigma = (float)(1.0 / sigma);
+      hs[s].one_minus_gamma = (float)(1.0 - d.guidance_strength);
+      hs[s].gamma = (float)d.guidance_strength;
+      hs[s].dt = (float)dt;
+      hs[s].pad = 0.f;
+      if (t > eps && first_guided == steps) first_guided = s;
+    }
+    fx->set_times(ts);
+    fy->set_times(ts);
+    sc = pool.upload(hs);
+    step = (int*)pool.persistent(sizeof(int));
+    diag = (float*)pool.persistent(RGFM_DIAG_FLOATS * sizeof(float));
+    x = (float*)pool.persistent((size_t)B * Dx * sizeof(float));
+    y = (float*)pool.persistent((size_t)B * Dy * sizeof(float));
+    if (guided) {
+      vx = (float*)pool.persistent((size_t)B * Dx * sizeof(float));
+      vy = (float*)pool.persistent((size_t)B * Dy * sizeof(float));
+      gx = (float*)pool.persistent((size_t)B * Dx * sizeof(float));
+      gy = (float*)pool.persistent((size_t)B * Dy * sizeof(float));
+      mcx = (float*)pool.persistent((size_t)N * Dx * sizeof(float));
+      mcy = (float*)pool.persistent((size_t)N * Dy * sizeof(float));
+      scores = (float*)pool.persistent((size_t)N * sizeof(float));
+      ratios = (float*)pool.persistent((size_t)N * sizeof(float));
+      const size_t nf = mcf_scratch_floats(B, N, Dx, Dy, &ksx, &ksy);
+      scratch = (float*)pool.persistent(nf * sizeof(float));
+    }
+    RGFM_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+
+    // ---- graphs ----
+    if (guided) {
+      capture(g_pre_x, [&](cudaStream_t s) {  // mc_x += fm_x(mc_x, t) * dt   (flow_utils.py:236-241)
+        fx->forward(s, N, mcx, nullptr, mcx, OUT_EULER, dtf, step);
+        launch_step_inc(step, s);
+      });
+      capture(g_pre_y, [&](cudaStream_t s) {
+        fy->forward(s, N, mcy, nullptr, mcy, OUT_EULER, dtf, step);
+        launch_step_inc(step, s);
+      });
+      capture(g_ratio, [&](cudaStream_t s) {  // mc_ratios = exp(log_ratio(mc_x, mc_y))  (flow_utils.py:255-258)
+        fr->forward(s, N, mcx, mcy, scores, 0, 0.f, nullptr);
+        launch_ratio_head(scores, d.loss_type, nullptr, ratios, N, s);
+        launch_ratio_stats(ratios, N, diag + 9, s);
+      });
+      capture(g_guided, [&](cudaStream_t s) {
+        fx->forward(s, B, x, nullptr, vx, OUT_NCHW, dtf, step);
+        fy->forward(s, B, y, nullptr, vy, OUT_NCHW, dtf, step);
+        McfArgs a{};
+        a.B = B; a.N = N; a.Dx = Dx; a.Dy = Dy;
+        a.x = x; a.y = y; a.vx = vx; a.vy = vy; a.mcx = mcx; a.mcy = mcy; a.ratios = ratios;
+        a.sc = sc; a.step = step; a.x_out = x; a.y_out = y; a.gx = gx; a.gy = gy; a.w = nullptr;
+        a.logits = scratch;
+        a.wbuf = scratch + (size_t)(ksx + ksy) * B * N;
+        a.zbuf = a.wbuf + (size_t)B * N;
+        a.ksplit_x = ksx; a.ksplit_y = ksy;
+        launch_mcf(a, s);
+        DiagArgs da{B, Dx, Dy, N, vx, vy, gx, gy, a.zbuf, sc, step, (int)(0.3 * steps), diag};
+        launch_diag(da, s);
+        launch_step_inc(step, s);
+      });
+    }
+    capture(g_plain, [&](cudaStream_t s) {  // x += fm_x(x, t) * dt ; y += fm_y(y, t) * dt
+      fx->forward(s, B, x, nullptr, x, OUT_EULER, dtf, step);
+      fy->forward(s, B, y, nullptr, y, OUT_EULER, dtf, step);
+      launch_step_inc(step, s);
+    });
+    RGFM_CUDA(cudaStreamSynchronize(cap));
+    launches = 0;
+    if (guided) launches += (int64_t)steps * (g_pre_x.kernels + g_pre_y.kernels) + g_ratio.kernels;
+    for (int s = 0; s < steps; ++s) launches += (guided && s >= first_guided) ? g_guided.kernels : g_plain.kernels;
+  }
+
+  void run(const float* x0, const float* y0, const float* mx0, const float* my0, float* x1, float* y1,
+           float* diag_out, cudaStream_t s) {
+    RGFM_CHECK(x0 && y0 && x1 && y1, "rgfm_sampler_run: null state pointer");
+    RGFM_CUDA(cudaSetDevice(d.device));
+    RGFM_CUDA(cudaMemcpyAsync(x, x0, (size_t)B * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    RGFM_CUDA(cudaMemcpyAsync(y, y0, (size_t)B * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    RGFM_CUDA(cudaMemsetAsync(diag, 0, RGFM_DIAG_FLOATS * sizeof(float), s));
+    if (guided) {
+      RGFM_CHECK(mx0 && my0, "rgfm_sampler_run: mc_feng needs mc_x0 and mc_y0");
+      RGFM_CUDA(cudaMemcpyAsync(mcx, mx0, (size_t)N * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      RGFM_CUDA(cudaMemcpyAsync(mcy, my0, (size_t)N * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      RGFM_CUDA(cudaMemsetAsync(step, 0, sizeof(int), s));
+      for (int i = 0; i < steps; ++i) RGFM_CUDA(cudaGraphLaunch(g_pre_x.e, s));
+      RGFM_CUDA(cudaMemsetAsync(step, 0, sizeof(int), s));
+      for (int i = 0; i < steps; ++i) RGFM_CUDA(cudaGraphLaunch(g_pre_y.e, s));
+      RGFM_CUDA(cudaGraphLaunch(g_ratio.e, s));
+    }
+    RGFM_CUDA(cudaMemsetAsync(step, 0, sizeof(int), s));
+    for (int i = 0; i < steps; ++i)
+      RGFM_CUDA(cudaGraphLaunch((guided && i >= first_guided) ? g_guided.e : g_plain.e, s));
+    RGFM_CUDA(cudaMemcpyAsync(x1, x, (size_t)B * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    RGFM_CUDA(cudaMemcpyAsync(y1, y, (size_t)B * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (diag_out) RGFM_CUDA(cudaMemcpyAsync(diag_out, diag, RGFM_DIAG_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+};
+
+// ---- C-ABI glue (api.cu calls these) ----
+Sampler* sampler_create(const rgfm_sampler_desc* d, const rgfm_weights* wx, const rgfm_weights* wy, const rgfm_weights* wr) {
+  RGFM_CHECK(d && wx && wy, "rgfm_sampler_create: null argument");
+  std::unique_ptr<Sampler> s(new Sampler());
+  s->d = *d;
+  s->build(wx, wy, wr);
+  return s.release();
+}
+void sampler_destroy(Sampler* s) { delete s; }
+void sampler_run(Sampler* s, const float* x0, const float* y0, const float* mx0, const float* my0, float* x1, float* y1,
+                 float* diag, cudaStream_t st) {
+  s->run(x0, y0, mx0, my0, x1, y1, diag, st);
+}
+int64_t sampler_launches(const Sampler* s) { return s->launches; }
+
+void sampler_run_host(Sampler* s, const float* x0, const float* y0, const float* mx0, const float* my0, float* x1,
+                      float* y1, float* diag) {
+  RGFM_CUDA(cudaSetDevice(s->d.device));
+  const size_t bx = (size_t)s->B * s->Dx * sizeof(float), by = (size_t)s->B * s->Dy * sizeof(float);
+  const size_t mx = (size_t)s->N * s->Dx * sizeof(float), my = (size_t)s->N * s->Dy * sizeof(float);
+  if (!s->hx) {
+    RGFM_CUDA(cudaMallocHost(&s->hx, bx));
+    RGFM_CUDA(cudaMallocHost(&s->hy, by));
+    if (s->guided) {
+      RGFM_CUDA(cudaMallocHost(&s->hmx, mx));
+      RGFM_CUDA(cudaMallocHost(&s->hmy, my));
+    }
+  }
+  // staging in device memory: reuse v buffers' worth of fresh allocations (kept for the plan's lifetime)
+  auto& st = s->stage;
+  if (st.empty()) {
+    st.resize(5, nullptr);
+    st[0] = (float*)s->pool.persistent(bx);
+    st[1] = (float*)s->pool.persistent(by);
+    if (s->guided) {
+      st[2] = (float*)s->pool.persistent(mx);
+      st[3] = (float*)s->pool.persistent(my);
+    }
+    st[4] = (float*)s->pool.persistent(RGFM_DIAG_FLOATS * sizeof(float));
+  }
+  cudaStream_t cs = s->cap;
+  memcpy(s->hx, x0, bx);
+  memcpy(s->hy, y0, by);
+  RGFM_CUDA(cudaMemcpyAsync(st[0], s->hx, bx, cudaMemcpyHostToDevice, cs));
+  RGFM_CUDA(cudaMemcpyAsync(st[1], s->hy, by, cudaMemcpyHostToDevice, cs));
+  if (s->guided) {
+    RGFM_CHECK(mx0 && my0, "rgfm_sampler_run_host: mc_feng needs mc_x0 and mc_y0");
+    memcpy(s->hmx, mx0, mx);
+    memcpy(s->hmy, my0, my);
+    RGFM_CUDA(cudaMemcpyAsync(st[2], s->hmx, mx, cudaMemcpyHostToDevice, cs));
+    RGFM_CUDA(cudaMemcpyAsync(st[3], s->hmy, my, cudaMemcpyHostToDevice, cs));
+  }
+  s->run(st[0], st[1], st[2], st[3], st[0], st[1], st[4], cs);
+  RGFM_CUDA(cudaMemcpyAsync(s->hx, st[0], bx, cudaMemcpyDeviceToHost, cs));
+  RGFM_CUDA(cudaMemcpyAsync(s->hy, st[1], by, cudaMemcpyDeviceToHost, cs));
+  float hd[RGFM_DIAG_FLOATS];
+  RGFM_CUDA(cudaMemcpyAsync(hd, st[4], sizeof(hd), cudaMemcpyDeviceToHost, cs));
+  RGFM_CUDA(cudaStreamSynchronize(cs));
+  memcpy(x1, s->hx, bx);
+  memcpy(y1, s->hy, by);
+  if (diag) memcpy(diag, hd, sizeof(hd));
+}
+
+void sampler_get_bank(Sampler* s, float* mx, float* my, float* r, cudaStream_t st) {
+  RGFM_CHECK(s->guided, "rgfm_sampler_get_bank: plan is unguided");
+  if (mx) RGFM_CUDA(cudaMemcpyAsync(mx, s->mcx, (size_t)s->N * s->Dx * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (my) RGFM_CUDA(cudaMemcpyAsync(my, s->mcy, (size_t)s->N * s->Dy * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (r) RGFM_CUDA(cudaMemcpyAsync(r, s->ratios, (size_t)s->N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+}  // namespace rgfm

@@ -1,0 +1,156 @@
+"""Drop-in Python entry points of the ratio-guided coupled Euler sampler.
+
+Same names, arguments, defaults, RNG consumption and return values as the reference:
+  sample_bimodal_guided             /root/reference/src/utils/flow_utils.py:178-375
+  sample_bimodal_guided_mnist_svhn  /root/reference/src/sample_mnist_svhn.py:39-177
+The body is one call into librgfm.so (C ABI, include/rgfm.h).  Optional keyword-only
+extras (precision, shard, plan cache) never have to be passed.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_PLAN_CACHE: Dict[tuple, "_lib.SamplerPlan"] = {}
+_PLAN_CACHE_MAX = 4
+
+
+def default_precision() -> str:
+    return os.environ.get("RGFM_PRECISION", "fp32")
+
+
+def _fingerprint(module) -> tuple:
+    if module is None:
+        return ()
+    sd = module.state_dict()
+    return tuple((k, v.data_ptr(), getattr(v, "_version", 0)) for k, v in sd.items() if torch.is_tensor(v))
+
+
+def _get_plan(pair, fm_x, fm_y, ratio, method, gamma, B, steps, N, loss_type, precision, device, chunk):
+    key = (pair, _fingerprint(fm_x), _fingerprint(fm_y), _fingerprint(ratio), method, float(gamma), B, steps, N,
+           loss_type, precision, str(device), chunk)
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE))).close()
+        plan = _lib.SamplerPlan(pair, fm_x.state_dict(), fm_y.state_dict(),
+                                ratio.state_dict() if ratio is not None else None,
+                                guidance_method=method, guidance_strength=gamma, num_samples=B, num_steps=steps,
+                                mc_batch_size=N, loss_type=loss_type, precision=precision, device=device, chunk=chunk)
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
+def clear_plan_cache():
+    for p in _PLAN_CACHE.values():
+        p.close()
+    _PLAN_CACHE.clear()
+
+
+def shard_bounds(num_samples: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous partition of the batch: the first `rem` ranks get one extra sample."""
+    base, rem = divmod(num_samples, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_pairs(x_local: torch.Tensor, y_local: torch.Tensor, num_samples: int, group=None):
+    """all_gather of finished pairs in rank-major order (the only data-path collective; NCCL on GPUs)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    bounds = [shard_bounds(num_samples, world, r) for r in range(world)]
+    nmax = max(hi - lo for lo, hi in bounds)
+
+    def gather(t):
+        pad = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        out = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(out, pad, group=group)
+        return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, bounds)], dim=0)
+
+    return gather(x_local), gather(y_local)
+
+
+def _sample(pair, shape_x, shape_y, fm_x, fm_y, ratio_estimator, guidance_method, guidance_strength, num_samples,
+            num_steps, device, mc_batch_size, precision, shard, group, chunk, verbose, noise=None):
+    fm_x.eval()
+    fm_y.eval()
+    if ratio_estimator is not None:
+        ratio_estimator.eval()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.RgfmError("rgfm samplers run on CUDA devices only; there is no CPU fallback")
+    precision = precision or default_precision()
+    guided = guidance_method == "mc_feng" and ratio_estimator is not None
+    loss_type = getattr(ratio_estimator, "loss_type", "disc") if ratio_estimator is not None else "disc"
+    if guided and loss_type not in _lib.LOSS:
+        raise ValueError(f"Unknown loss_type: {loss_type}")
+
+    # The reference consumes the device's global RNG with exactly these draws, in this order
+    # (flow_utils.py:220-221,235,244).  Every rank of a sharded run draws the FULL batch and slices its rows, so
+    # the gathered result equals the single-device one.
+    if noise is None:
+        x0 = torch.randn(num_samples, *shape_x, device=device)
+        y0 = torch.randn(num_samples, *shape_y, device=device)
+        mc_x0 = mc_y0 = None
+        if guided:
+            if verbose:
+                print(f"  Generating {mc_batch_size} independent MC samples from flows...")
+            mc_x0 = torch.randn(mc_batch_size, *shape_x, device=device)
+            mc_y0 = torch.randn(mc_batch_size, *shape_y, device=device)
+    else:
+        x0, y0, mc_x0, mc_y0 = noise
+
+    lo, hi = 0, num_samples
+    if shard:
+        import torch.distributed as dist
+        lo, hi = shard_bounds(num_samples, dist.get_world_size(group), dist.get_rank(group))
+    n_local = hi - lo
+    if n_local > 0:
+        plan = _get_plan(pair, fm_x, fm_y, ratio_estimator if guided else None, guidance_method if guided else "none",
+                         guidance_strength, n_local, num_steps, mc_batch_size, loss_type, precision, device, chunk)
+        x1, y1, diag = plan.run(x0[lo:hi], y0[lo:hi], mc_x0, mc_y0, want_diag=True)
+    else:
+        x1 = torch.empty((0,) + shape_x, device=device)
+        y1 = torch.empty((0,) + shape_y, device=device)
+        diag = torch.zeros(_lib.DIAG_FLOATS, device=device)
+
+    if verbose and guided:
+        d = diag.tolist()  # one D2H after the whole loop (the reference syncs mid-loop)
+        print(f"  Generated MC samples: x shape={torch.Size((mc_batch_size,) + shape_x)}, "
+              f"y shape={torch.Size((mc_batch_size,) + shape_y)}")
+        print(f"  MC ratios: min={d[9]:.4f}, max={d[10]:.4f}, mean={d[11]:.4f}")
+        if pair == "pair28" and d[1] != 0.0:
+            print(f"\n[MC Guidance Diagnostics at t={d[0]:.2f}]")
+            print(f"  sigma_t={d[1]:.4f}")
+            print(f"  ||v_x||={d[2]:.4f}, ||v_y||={d[3]:.4f}")
+            print(f"  ||g_x||={d[4]:.4f}, ||g_y||={d[5]:.4f}")
+            print(f"  weights: min={d[6]:.6f}, max={d[7]:.6f}")
+            print(f"  Z_bar: {d[8]:.4f}")
+    if shard:
+        x1, y1 = gather_pairs(x1, y1, num_samples, group)
+    return x1, y1
+
+
+def sample_bimodal_guided(fm_x, fm_y, ratio_estimator=None, guidance_method='none', guidance_strength=0.0,
+                          num_samples=16, num_steps=100, device='cuda', mc_batch_size=64, *,
+                          precision: Optional[str] = None, shard: bool = False, group=None, chunk: int = 0,
+                          verbose: bool = True, _noise=None):
+    """(MNIST, transformed-MNIST) 1x28x28 pairs.  Returns (samples_x [N,1,28,28], samples_y [N,1,28,28])."""
+    return _sample("pair28", (1, 28, 28), (1, 28, 28), fm_x, fm_y, ratio_estimator, guidance_method,
+                   guidance_strength, num_samples, num_steps, device, mc_batch_size, precision, shard, group, chunk,
+                   verbose, _noise)
+
+
+def sample_bimodal_guided_mnist_svhn(fm_mnist, fm_svhn, ratio_estimator=None, guidance_method='none',
+                                     guidance_strength=0.0, num_samples=16, num_steps=100, device='cuda',
+                                     mc_batch_size=64, *, precision: Optional[str] = None, shard: bool = False,
+                                     group=None, chunk: int = 0, verbose: bool = True, _noise=None):
+    """(MNIST 1x32x32, SVHN 3x32x32) pairs.  Returns (samples_mnist [N,1,32,32], samples_svhn [N,3,32,32])."""
+    return _sample("mnist_svhn", (1, 32, 32), (3, 32, 32), fm_mnist, fm_svhn, ratio_estimator, guidance_method,
+                   guidance_strength, num_samples, num_steps, device, mc_batch_size, precision, shard, group, chunk,
+                   verbose, _noise)

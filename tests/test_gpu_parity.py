@@ -1,0 +1,220 @@
+"""GPU parity: the CUDA path, called through the C ABI (librgfm.so via ctypes), against the oracle and the
+fixtures generated from the live reference.  Tolerances follow BASELINE.json's north_star: final x1, y1 within
+max-abs 1e-3 (fp32 mode) / 1e-2 (bf16 mode) of the reference sampler on identical weights and noise."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, T
+from oracle import rgfm_oracle as O  # checker only
+from ratio_guided_multimodal_fm_b200 import _lib, synthetic
+from ratio_guided_multimodal_fm_b200 import sample_bimodal_guided, sample_bimodal_guided_mnist_svhn
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+PRECS = ["fp32", "bf16"]
+TOL_FINAL = {"fp32": 1e-3, "bf16": 1e-2}
+# single forward passes: velocities are O(1) per element
+TOL_FWD = {"fp32": 2e-4, "bf16": 6e-2}
+
+
+def maxabs(a, b):
+    return (torch.as_tensor(a).float().cpu() - torch.as_tensor(b).float().cpu()).abs().max().item()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    _lib.lib()  # fail loudly if the extension is missing
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("kind", ["unet_mnist28", "unet_mnist32", "unet_svhn"])
+def test_unet_forward(kind, prec, synth):
+    g = load_golden(f"{kind}_forward")
+    sd = synth(kind, g["seed"])
+    net = _lib.Net(kind, sd, max_batch=2, precision=prec, device=DEV)  # chunk 2 < batch 3: ragged last chunk
+    x = T(g["x"]).to(DEV)
+    for i, t in enumerate(g["t"]):
+        v = net.unet_forward(x, float(t))
+        torch.cuda.synchronize()
+        ref = T(g["v"])[i]
+        # the golden forward uses a per-sample t; row i of our uniform-t forward must match row i of the golden
+        err = maxabs(v[i], ref)
+        scale = ref.abs().max().item()
+        assert err <= TOL_FWD[prec] * max(1.0, scale), f"{kind} t={t}: max-abs {err} (scale {scale})"
+    net.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("kind", ["ratio28", "ratio_mnist_svhn"])
+def test_ratio_log_ratio(kind, prec, synth):
+    g = load_golden(f"{kind}_forward")
+    sd = synth(kind, g["seed"])
+    net = _lib.Net(kind, sd, max_batch=3, precision=prec, device=DEV)
+    x, y = T(g["x"]).to(DEV), T(g["y"]).to(DEV)
+    tol = 2e-4 if prec == "fp32" else 3e-2
+    lr, sc = net.log_ratio(x, y, "disc", return_scores=True)
+    assert maxabs(sc, g["scores"]) <= tol
+    assert maxabs(lr, g["log_ratio_disc"]) <= tol
+    assert maxabs(net.log_ratio(x, y, "rulsif"), g["log_ratio_rulsif"]) <= tol
+    with pytest.raises(ValueError):
+        net.log_ratio(x, y, "nope")
+    net.close()
+
+
+def test_mc_feng_block():
+    """fp32 guidance block vs the reference arithmetic at early, middle and saturated times."""
+    g = load_golden("mc_feng_block")
+    mcx, mcy, r = (T(g[k]).to(DEV) for k in ("mc_x", "mc_y", "mc_ratios"))
+    gen = torch.Generator().manual_seed(9)
+    for i in range(5):
+        t = float(g[f"t{i}"])
+        x, y = T(g[f"x{i}"]).to(DEV), T(g[f"y{i}"]).to(DEV)
+        vx = torch.randn(x.shape, generator=gen).to(DEV)
+        vy = torch.randn(y.shape, generator=gen).to(DEV)
+        gamma, dt = 0.5, 0.01
+        xo, yo, gx, gy, w = _lib.mc_feng_step(x, y, vx, vy, mcx, mcy, r, t, dt, gamma)
+        torch.cuda.synchronize()
+        assert maxabs(w, g[f"w{i}"]) <= 2e-5, f"weights at t={t}"
+        gscale = max(1.0, float(np.abs(g[f"gx{i}"]).max()))
+        assert maxabs(gx, g[f"gx{i}"]) <= 1e-4 * gscale, f"g_x at t={t}"
+        assert maxabs(gy, g[f"gy{i}"]) <= 1e-4 * gscale, f"g_y at t={t}"
+        x_ref = T(g[f"x{i}"]) + ((1 - gamma) * vx.cpu() + gamma * T(g[f"gx{i}"])) * dt
+        y_ref = T(g[f"y{i}"]) + ((1 - gamma) * vy.cpu() + gamma * T(g[f"gy{i}"])) * dt
+        assert maxabs(xo, x_ref) <= 1e-5 * gscale and maxabs(yo, y_ref) <= 1e-5 * gscale
+
+
+def _run_golden_sampler(name, prec, synth, chunk=0, host=False):
+    g = load_golden(name)
+    pair = str(g["pair"])
+    kx, ky, kr, _, _ = O.PAIR_KINDS[pair]
+    sx, sy, sr = (int(s) for s in g["seeds"])
+    method = str(g["method"])
+    guided = method == "mc_feng"
+    plan = _lib.SamplerPlan(pair, synth(kx, sx), synth(ky, sy), synth(kr, sr) if guided else None,
+                            guidance_method=method, guidance_strength=float(g["gamma"]), num_samples=int(g["B"]),
+                            num_steps=int(g["steps"]), mc_batch_size=int(g["N_mc"]), loss_type=str(g["loss_type"]),
+                            precision=prec, device=DEV, chunk=chunk)
+    if host:
+        x1, y1, diag = plan.run_host(g["x0"], g["y0"], g["mc_x0"] if guided else None, g["mc_y0"] if guided else None)
+        x1, y1, diag = T(x1), T(y1), T(diag)
+    else:
+        a = [T(g["x0"]).to(DEV), T(g["y0"]).to(DEV)]
+        a += [T(g["mc_x0"]).to(DEV), T(g["mc_y0"]).to(DEV)] if guided else [None, None]
+        keep = [t.clone() if t is not None else None for t in a]
+        x1, y1, diag = plan.run(*a, want_diag=True)
+        torch.cuda.synchronize()
+        for t, k in zip(a, keep):
+            assert t is None or torch.equal(t, k), "inputs must not be mutated"
+    assert plan.launch_count > 0
+    res = dict(ex=maxabs(x1, g["x1"]), ey=maxabs(y1, g["y1"]), diag=diag.cpu(), g=g, plan=plan)
+    if guided and not host:
+        mx, my, r = plan.bank()
+        res.update(emx=maxabs(mx, g["mc_x"]), emy=maxabs(my, g["mc_y"]), er=maxabs(r, g["mc_ratios"]))
+    return res
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", ["sampler_pair28_small", "sampler_pair28_rulsif", "sampler_pair28_none",
+                                  "sampler_mnist_svhn_small", "sampler_mnist_svhn_g2"])
+def test_sampler_short(name, prec, synth):
+    r = _run_golden_sampler(name, prec, synth)
+    assert r["ex"] <= TOL_FINAL[prec] and r["ey"] <= TOL_FINAL[prec], (r["ex"], r["ey"])
+    if "emx" in r:
+        assert r["emx"] <= TOL_FINAL[prec] and r["emy"] <= TOL_FINAL[prec]
+        assert r["er"] <= (1e-4 if prec == "fp32" else 2e-2)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_sampler_pair28_cfg0_100_steps(prec, synth):
+    """BASELINE.json configs[0] at full size: B=64, N_mc=128, 100 steps, mc_feng gamma=0.5, disc."""
+    r = _run_golden_sampler("sampler_pair28_cfg0", prec, synth)
+    print(f"cfg0[{prec}]: max|dx|={r['ex']:.3e} max|dy|={r['ey']:.3e} bank {r['emx']:.3e}/{r['emy']:.3e} r {r['er']:.3e}")
+    assert r["ex"] <= TOL_FINAL[prec] and r["ey"] <= TOL_FINAL[prec]
+    # the diagnostics the reference prints at step int(0.3*steps) (flow_utils.py:349-363)
+    out = str(r["g"]["ref_stdout"])
+    d = r["diag"].tolist()
+    tol = 2e-3 if prec == "fp32" else 5e-2
+    for key, val in (("sigma_t=", d[1]), ("||v_x||=", d[2]), ("||g_x||=", d[4]), ("Z_bar: ", d[8])):
+        ref = float(out.split(key)[1].split(",")[0].split()[0])
+        assert abs(ref - val) <= tol * max(1.0, abs(ref)), (key, ref, val)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_sampler_mnist_svhn_100_steps(prec, synth):
+    """configs[1] shape (MNIST32 <-> SVHN, 3.3M-param ratio net) at reduced batch, full 100 steps."""
+    r = _run_golden_sampler("sampler_mnist_svhn_100", prec, synth, chunk=8)
+    print(f"ms100[{prec}]: max|dx|={r['ex']:.3e} max|dy|={r['ey']:.3e} bank {r['emx']:.3e}/{r['emy']:.3e} r {r['er']:.3e}")
+    assert r["ex"] <= TOL_FINAL[prec] and r["ey"] <= TOL_FINAL[prec]
+
+
+def test_host_buffer_call_matches_device_call(synth):
+    a = _run_golden_sampler("sampler_mnist_svhn_small", "fp32", synth)
+    b = _run_golden_sampler("sampler_mnist_svhn_small", "fp32", synth, host=True)
+    assert abs(a["ex"] - b["ex"]) < 1e-6 and b["ex"] <= 1e-3 and b["ey"] <= 1e-3
+
+
+def test_ragged_batches_and_chunks(synth):
+    """B=1, B not a multiple of the chunk, N_mc not a multiple of 4: same answers as the oracle."""
+    sdx, sdy, sdr = synth("unet_mnist28", 11), synth("unet_mnist28", 14), synth("ratio28", 21)
+    gen = torch.Generator().manual_seed(123)
+    for B, N, chunk in ((1, 3, 0), (5, 6, 2), (7, 5, 4)):
+        x0, y0 = torch.randn(B, 1, 28, 28, generator=gen), torch.randn(B, 1, 28, 28, generator=gen)
+        m0, n0 = torch.randn(N, 1, 28, 28, generator=gen), torch.randn(N, 1, 28, 28, generator=gen)
+        ox, oy = O.sample_pair(sdx, sdy, sdr, "pair28", "mc_feng", 0.5, 4, x0, y0, m0, n0, "disc")
+        plan = _lib.SamplerPlan("pair28", sdx, sdy, sdr, guidance_method="mc_feng", guidance_strength=0.5,
+                                num_samples=B, num_steps=4, mc_batch_size=N, precision="fp32", device=DEV, chunk=chunk)
+        x1, y1 = plan.run(x0.to(DEV), y0.to(DEV), m0.to(DEV), n0.to(DEV))
+        assert maxabs(x1, ox) <= 1e-3 and maxabs(y1, oy) <= 1e-3, (B, N, chunk)
+        plan.close()
+
+
+def test_public_api_draws_reference_noise_order(synth, capsys):
+    """The drop-in functions consume the device RNG with the reference's four draws, in order, and print the
+    reference's progress lines."""
+    fx = synthetic.StateDictModule("unet_mnist32", synth("unet_mnist32", 12))
+    fy = synthetic.StateDictModule("unet_svhn", synth("unet_svhn", 13))
+    fr = synthetic.StateDictModule("ratio_mnist_svhn", synth("ratio_mnist_svhn", 22), loss_type="disc")
+    B, N, steps = 4, 6, 4
+    torch.manual_seed(7); torch.cuda.manual_seed_all(7)
+    x1, y1 = sample_bimodal_guided_mnist_svhn(fx, fy, fr, guidance_method="mc_feng", guidance_strength=0.5,
+                                              num_samples=B, num_steps=steps, device=DEV, mc_batch_size=N,
+                                              precision="fp32")
+    out = capsys.readouterr().out
+    assert "Generating 6 independent MC samples from flows..." in out and "MC ratios: min=" in out
+    torch.manual_seed(7); torch.cuda.manual_seed_all(7)
+    x0 = torch.randn(B, 1, 32, 32, device=DEV); y0 = torch.randn(B, 3, 32, 32, device=DEV)
+    m0 = torch.randn(N, 1, 32, 32, device=DEV); n0 = torch.randn(N, 3, 32, 32, device=DEV)
+    ox, oy = O.sample_pair(fx.state_dict(), fy.state_dict(), fr.state_dict(), "mnist_svhn", "mc_feng", 0.5, steps,
+                           x0.cpu(), y0.cpu(), m0.cpu(), n0.cpu(), "disc")
+    assert x1.shape == (B, 1, 32, 32) and y1.shape == (B, 3, 32, 32) and x1.dtype == torch.float32
+    assert maxabs(x1, ox) <= 1e-3 and maxabs(y1, oy) <= 1e-3
+    # silent degradation to unguided: unknown method / missing estimator (flow_utils.py:231,273)
+    torch.manual_seed(7); torch.cuda.manual_seed_all(7)
+    a = sample_bimodal_guided_mnist_svhn(fx, fy, None, guidance_method="mc_feng", guidance_strength=0.5,
+                                         num_samples=B, num_steps=steps, device=DEV, precision="fp32")
+    ux, uy = O.sample_pair(fx.state_dict(), fy.state_dict(), None, "mnist_svhn", "none", 0.0, steps, x0.cpu(), y0.cpu())
+    assert maxabs(a[0], ux) <= 1e-3 and maxabs(a[1], uy) <= 1e-3
+
+
+def test_full_size_properties(synth):
+    """BASELINE configs[1] batch (1024 pairs, N_mc=256) at a few steps: size-independent properties --
+    gamma=0 guided == unguided; batch rows are independent (a sub-batch reproduces its rows)."""
+    sdx, sdy, sdr = synth("unet_mnist32", 12), synth("unet_svhn", 13), synth("ratio_mnist_svhn", 22)
+    B, N, steps = 1024, 256, 3
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x0 = torch.randn(B, 1, 32, 32, device=DEV, generator=gen); y0 = torch.randn(B, 3, 32, 32, device=DEV, generator=gen)
+    m0 = torch.randn(N, 1, 32, 32, device=DEV, generator=gen); n0 = torch.randn(N, 3, 32, 32, device=DEV, generator=gen)
+    mk = lambda method, gamma, b, sdr_: _lib.SamplerPlan("mnist_svhn", sdx, sdy, sdr_, guidance_method=method,
+                                                         guidance_strength=gamma, num_samples=b, num_steps=steps,
+                                                         mc_batch_size=N, precision="fp32", device=DEV)
+    pg0 = mk("mc_feng", 0.0, B, sdr); pn = mk("none", 0.0, B, None); pg = mk("mc_feng", 0.5, B, sdr)
+    a = pg0.run(x0, y0, m0, n0); b = pn.run(x0, y0); c = pg.run(x0, y0, m0, n0)
+    assert maxabs(a[0], b[0]) <= 1e-5 and maxabs(a[1], b[1]) <= 1e-5
+    assert torch.isfinite(c[0]).all() and torch.isfinite(c[1]).all()
+    assert maxabs(c[0], b[0]) > 1e-3  # guidance does something
+    ps = mk("mc_feng", 0.5, 96, sdr)
+    d = ps.run(x0[300:396], y0[300:396], m0, n0)
+    assert maxabs(d[0], c[0][300:396]) <= 1e-4 and maxabs(d[1], c[1][300:396]) <= 1e-4

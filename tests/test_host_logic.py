@@ -1,0 +1,85 @@
+"""CPU: host-side logic -- synthetic state_dict shapes/param counts, batch sharding, world_size-2 gloo gather."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ratio_guided_multimodal_fm_b200 import synthetic, shard_bounds, gather_pairs
+
+
+def nparams(sd):
+    return sum(v.numel() for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k)
+
+
+def test_param_counts_match_survey():
+    # SURVEY.md D7 (measured from the reference modules)
+    assert nparams(synthetic.state_dict("unet_mnist28", 0)) == 901121
+    assert nparams(synthetic.state_dict("unet_mnist32", 0)) == 901121
+    assert nparams(synthetic.state_dict("unet_svhn", 0)) == 6074371
+    assert nparams(synthetic.state_dict("ratio28", 0)) == 943745
+    assert nparams(synthetic.state_dict("ratio_mnist_svhn", 0)) == 3327617
+    assert len(synthetic.state_dict("unet_svhn", 0)) == 208
+    assert len(synthetic.state_dict("ratio_mnist_svhn", 0)) == 102
+    assert len(synthetic.state_dict("ratio28", 0)) == 46
+
+
+def test_out_conv_is_not_zero():
+    sd = synthetic.state_dict("unet_svhn", 3)
+    assert sd["out_conv.weight"].abs().sum() > 0
+
+
+@pytest.mark.parametrize("n,world", [(65536, 8), (16384, 8), (10, 4), (3, 8), (1, 2), (7, 3)])
+def test_shard_bounds_partition(n, world):
+    spans = [shard_bounds(n, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    for (a, b), (c, d) in zip(spans, spans[1:]):
+        assert b == c and b >= a
+    sizes = [b - a for a, b in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank draws the FULL batch with the same seed and takes its rows
+        torch.manual_seed(42)
+        x0 = torch.randn(n, 1, 4, 4)
+        y0 = torch.randn(n, 3, 4, 4)
+        lo, hi = shard_bounds(n, world, rank)
+        xl, yl = x0[lo:hi] * 2 + 1, y0[lo:hi] * 3 - 1  # stand-in for the per-rank sampler
+        xg, yg = gather_pairs(xl, yl, n)
+        ok = torch.equal(xg, x0 * 2 + 1) and torch.equal(yg, y0 * 3 - 1)
+        # coherence count all_reduce
+        cnt = torch.tensor([hi - lo], dtype=torch.int64)
+        dist.all_reduce(cnt)
+        ok = ok and int(cnt) == n
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [8, 5, 1])
+def test_gloo_world2_gather_equals_single_device(n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
