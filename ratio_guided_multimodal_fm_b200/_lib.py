@@ -46,12 +46,17 @@ class _SamplerDesc(C.Structure):
                 ("chunk", C.c_int32)]
 
 
+class _ProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double),
+                ("launches", C.c_int64)]
+
+
 _lib = None
 
 # every symbol include/rgfm.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     "rgfm_last_error", "rgfm_abi_version", "rgfm_sampler_create", "rgfm_sampler_run", "rgfm_sampler_run_host",
-    "rgfm_sampler_get_bank", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
+    "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
     "rgfm_unet_forward", "rgfm_ratio_log_ratio", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
 ]
 
@@ -72,6 +77,7 @@ def lib() -> C.CDLL:
     L.rgfm_sampler_run.argtypes = [vp] + [vp] * 7 + [vp]
     L.rgfm_sampler_run_host.argtypes = [vp] + [vp] * 7
     L.rgfm_sampler_get_bank.argtypes = [vp, vp, vp, vp, vp]
+    L.rgfm_sampler_profile_step.argtypes = [vp, C.POINTER(_ProfEntry), C.c_int32, C.POINTER(C.c_int32)]
     L.rgfm_sampler_launch_count.argtypes = [vp]
     L.rgfm_sampler_launch_count.restype = C.c_int64
     L.rgfm_sampler_destroy.argtypes = [vp]
@@ -228,6 +234,14 @@ class SamplerPlan:
         p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
         check(lib().rgfm_sampler_run_host(self.h, p(x0), p(y0), p(mc_x0), p(mc_y0), p(x1), p(y1), p(diag)))
         return x1, y1, diag
+
+    def profile_step(self):
+        """{kernel family: dict(ms, flops, bytes, launches)} for one main-loop step, CUDA-event timed."""
+        buf = (_ProfEntry * 32)()
+        n = C.c_int32(0)
+        check(lib().rgfm_sampler_profile_step(self.h, buf, 32, C.byref(n)))
+        return {buf[i].name.decode(): dict(ms=buf[i].ms, flops=buf[i].flops, bytes=buf[i].bytes,
+                                           launches=int(buf[i].launches)) for i in range(n.value)}
 
     def bank(self):
         mx = torch.empty((self.N,) + self.shape_x, device=self.device)

@@ -11,6 +11,7 @@ void sampler_run(Sampler*, const float*, const float*, const float*, const float
 void sampler_run_host(Sampler*, const float*, const float*, const float*, const float*, float*, float*, float*);
 void sampler_get_bank(Sampler*, float*, float*, float*, cudaStream_t);
 int64_t sampler_launches(const Sampler*);
+int sampler_profile(Sampler*, rgfm_prof_entry*, int);
 }  // namespace rgfm
 
 static thread_local std::string g_err;
@@ -67,6 +68,13 @@ int rgfm_sampler_get_bank(rgfm_sampler* s, float* mc_x, float* mc_y, float* mc_r
   RGFM_API_BEGIN
   RGFM_CHECK(s != nullptr, "rgfm_sampler_get_bank: null plan");
   rgfm::sampler_get_bank(reinterpret_cast<rgfm::Sampler*>(s), mc_x, mc_y, mc_ratios, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_sampler_profile_step(rgfm_sampler* s, rgfm_prof_entry* out, int32_t max_entries, int32_t* n_entries) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(s && out && n_entries, "rgfm_sampler_profile_step: null argument");
+  *n_entries = rgfm::sampler_profile(reinterpret_cast<rgfm::Sampler*>(s), out, max_entries);
   RGFM_API_END
 }
 

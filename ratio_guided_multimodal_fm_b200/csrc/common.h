@@ -163,6 +163,29 @@ void launch_ratio_head(const float* scores, int loss_type, float* log_ratio, flo
 void launch_step_inc(int* step, cudaStream_t s);
 void launch_euler(float* x, const float* v, float dt, size_t n, cudaStream_t s);
 
+struct ProfRec {  // one timed op launch (CUDA events on the launching stream)
+  const char* kind;
+  cudaEvent_t e0, e1;
+  double flops, bytes;
+};
+struct ProfScope {  // brackets a launch with events when profiling is on
+  std::vector<ProfRec>* prof;
+  cudaStream_t s;
+  ProfRec r;
+  ProfScope(std::vector<ProfRec>* p, cudaStream_t st, const char* kind, double flops, double bytes) : prof(p), s(st) {
+    if (!prof) return;
+    r = ProfRec{kind, nullptr, nullptr, flops, bytes};
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, s);
+  }
+  ~ProfScope() {
+    if (!prof) return;
+    cudaEventRecord(r.e1, s);
+    prof->push_back(r);
+  }
+};
+
 // guidance.cu
 struct StepScalars {  // per Euler step, computed on the host in double then rounded like the reference
   float t, sig2, inv_sigma, sigma, one_minus_gamma, gamma, dt, pad;
@@ -180,7 +203,7 @@ struct McfArgs {
   int ksplit_x, ksplit_y;
 };
 size_t mcf_scratch_floats(int B, int N, int Dx, int Dy, int* ksx, int* ksy);
-void launch_mcf(const McfArgs& a, cudaStream_t s);
+void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof = nullptr);
 struct DiagArgs {
   int B, Dx, Dy, N;
   const float *vx, *vy, *gx, *gy, *zbuf;

@@ -256,22 +256,34 @@ size_t mcf_scratch_floats(int B, int N, int Dx, int Dy, int* ksx, int* ksy) {
   return (size_t)(kx + ky) * B * N + (size_t)B * N + (size_t)B * 4;
 }
 
-void launch_mcf(const McfArgs& a, cudaStream_t s) {
+void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof) {
   RGFM_CHECK(a.Dx % DK == 0 && a.Dy % DK == 0, "mc_feng: D must be a multiple of 16");
   RGFM_CHECK(a.N * sizeof(float) <= 48 * 1024, "mc_feng: mc_batch_size too large (max 12288)");
-  dim3 g1((a.B + DT - 1) / DT, (a.N + DT - 1) / DT, a.ksplit_x + a.ksplit_y);
-  mcf_dist_kernel<<<g1, 256, 0, s>>>(a);
-  post_launch("mcf_dist");
-  mcf_weights_kernel<<<a.B, 128, a.N * sizeof(float), s>>>(a);
-  post_launch("mcf_weights");
-  ApplyArgs ax{a.B, a.N, a.Dx, a.x, a.vx, a.mcx, a.wbuf, a.sc, a.step, a.x_out, a.gx};
-  dim3 g3x((a.B + DT - 1) / DT, (a.Dx + DT - 1) / DT);
-  mcf_apply_kernel<<<g3x, 256, 0, s>>>(ax);
-  post_launch("mcf_apply_x");
-  ApplyArgs ay{a.B, a.N, a.Dy, a.y, a.vy, a.mcy, a.wbuf, a.sc, a.step, a.y_out, a.gy};
-  dim3 g3y((a.B + DT - 1) / DT, (a.Dy + DT - 1) / DT);
-  mcf_apply_kernel<<<g3y, 256, 0, s>>>(ay);
-  post_launch("mcf_apply_y");
+  const double BN = (double)a.B * a.N, D = (double)a.Dx + a.Dy;
+  {
+    // algorithmic: 3 flops per (b, i, d); reads x, y once and the bank once, writes the partial sums
+    ProfScope ps(prof, s, "mcf_dist", 3.0 * BN * D, 4.0 * (a.B * D + a.N * D + BN * (a.ksplit_x + a.ksplit_y)));
+    dim3 g1((a.B + DT - 1) / DT, (a.N + DT - 1) / DT, a.ksplit_x + a.ksplit_y);
+    mcf_dist_kernel<<<g1, 256, 0, s>>>(a);
+    post_launch("mcf_dist");
+  }
+  {
+    ProfScope ps(prof, s, "mcf_weights", 10.0 * BN, 4.0 * BN * (a.ksplit_x + a.ksplit_y + 1));
+    mcf_weights_kernel<<<a.B, 128, a.N * sizeof(float), s>>>(a);
+    post_launch("mcf_weights");
+  }
+  {
+    // fused guidance-sum + blend + Euler update: algorithmic bytes = read x, v, write x (+ bank and weights once)
+    ProfScope ps(prof, s, "mcf_apply", 2.0 * BN * D, 4.0 * (3.0 * a.B * D + a.N * D + BN));
+    ApplyArgs ax{a.B, a.N, a.Dx, a.x, a.vx, a.mcx, a.wbuf, a.sc, a.step, a.x_out, a.gx};
+    dim3 g3x((a.B + DT - 1) / DT, (a.Dx + DT - 1) / DT);
+    mcf_apply_kernel<<<g3x, 256, 0, s>>>(ax);
+    post_launch("mcf_apply_x");
+    ApplyArgs ay{a.B, a.N, a.Dy, a.y, a.vy, a.mcy, a.wbuf, a.sc, a.step, a.y_out, a.gy};
+    dim3 g3y((a.B + DT - 1) / DT, (a.Dy + DT - 1) / DT);
+    mcf_apply_kernel<<<g3y, 256, 0, s>>>(ay);
+    post_launch("mcf_apply_y");
+  }
 }
 
 // Diagnostics of the 28x28 reference sampler (flow_utils.py:349-363), written to a device buffer at

@@ -123,9 +123,9 @@ struct Builder {
   Packed pack_input(int C, int H, int Wd, int Cp, bool from_y) {
     Packed p = new_packed(H, Wd, Cp, false);
     void* out = p.p;
-    net.ops_.push_back([=](const RunCtx& c) {
+    net.ops_.push_back({[=](const RunCtx& c) {
       launch_pack_nchw(from_y ? c.y : c.x, C, H, Wd, Cp, out, 0, c.nimg, c.s);
-    });
+    }, "pack_nchw", 0.0, (double)H * Wd * (C * 4.0 + Cp * 4.0)});
     return p;
   }
 
@@ -148,11 +148,12 @@ struct Builder {
     a.gamma = gamma; a.beta = beta; a.groups = 8;
     Packed p = new_packed(a.Ho, a.Wo, C, out_bf16);
     a.out = p.p; a.out_bf16 = out_bf16 ? 1 : 0;
-    net.ops_.push_back([a](const RunCtx& c) {
+    const double bytes = (double)a.Hs * a.Ws * C * 4.0 * (spatial == SP_POOL2 ? 1.0 : 1.0) + (double)a.Ho * a.Wo * C * (out_bf16 ? 2.0 : 4.0);
+    net.ops_.push_back({[a](const RunCtx& c) {
       PackArgs b = a;
       b.nimg = c.nimg;
       launch_pack(b, c.s);
-    });
+    }, "pack", 0.0, bytes});
     return p;
   }
 
@@ -189,7 +190,9 @@ struct Builder {
     }
     const bool has_temb = temb_off >= 0;
     Net* np = &net;
-    net.ops_.push_back([a, tcp, final, has_temb, np](const RunCtx& c) {
+    const double flops = 2.0 * Ho * Wo * (double)cout * cin_real * ks * ks;
+    const double bytes = (double)in.H * in.W * in.C * (in.bf16 ? 2.0 : 4.0) + (double)Ho * Wo * cout * 4.0 * (res ? 2.0 : 1.0);
+    net.ops_.push_back({[a, tcp, final, has_temb, np](const RunCtx& c) {
       ConvArgs b = a;
       b.nimg = c.nimg;
       if (has_temb) {
@@ -206,7 +209,7 @@ struct Builder {
         launch_conv_tc(*tcp, b, c.s);
       else
         launch_conv_simt(b, c.s);
-    });
+    }, use_tc ? "conv_tc" : "conv_simt", flops, bytes});
     return o;
   }
 
@@ -364,7 +367,8 @@ struct Builder {
     const float* fb = vec(pre + "fc.bias", 256);
     const float* src = (const float*)cur.p;
     const int HW = cur.H * cur.W, C = cur.C;
-    net.ops_.push_back([=](const RunCtx& c) { launch_gap_fc(src, HW, C, fw, fb, 256, feat + feat_off, feat_ld, c.nimg, c.s); });
+    net.ops_.push_back({[=](const RunCtx& c) { launch_gap_fc(src, HW, C, fw, fb, 256, feat + feat_off, feat_ld, c.nimg, c.s); },
+                        "gap_fc", 2.0 * 256 * C, (double)HW * C * 4.0});
     release(cur);
   }
 
@@ -385,7 +389,10 @@ struct Builder {
     const std::string a = "score_net." + std::to_string(last);
     f.in = in; f.out = 1; f.w = vec(a + ".weight", in); f.b = vec(a + ".bias", 1); f.act = ACT_NONE;
     layers.push_back(f);
-    net.ops_.push_back([=](const RunCtx& c) { launch_mlp(feat, 512, layers.data(), (int)layers.size(), c.out, 1, c.nimg, c.s); });
+    double mf = 0;
+    for (auto& l : layers) mf += 2.0 * l.in * l.out;
+    net.ops_.push_back({[=](const RunCtx& c) { launch_mlp(feat, 512, layers.data(), (int)layers.size(), c.out, 1, c.nimg, c.s); },
+                        "mlp", mf, 512 * 4.0});
   }
 
   void build_ratio28() {  // reference: ratio_estimator.py:34-158
@@ -479,7 +486,7 @@ void Net::set_times(const std::vector<float>& ts) {
 }
 
 void Net::forward(cudaStream_t s, int nimg, const float* x, const float* y, float* out, int out_mode, float dt,
-                  const int* step) {
+                  const int* step, std::vector<ProfRec>* prof) {
   const size_t dx = (size_t)in_ch_ * img_ * img_;
   const size_t dy = (size_t)in_ch_y_ * img_ * img_;
   for (int c0 = 0; c0 < nimg; c0 += chunk_) {
@@ -492,7 +499,20 @@ void Net::forward(cudaStream_t s, int nimg, const float* x, const float* y, floa
     c.out_mode = out_mode;
     c.dt = dt;
     c.step = step;
-    for (auto& op : ops_) op(c);
+    c.prof = prof;
+    for (auto& op : ops_) {
+      if (prof) {
+        ProfRec r{op.kind, nullptr, nullptr, op.flops_per_img * c.nimg, op.bytes_per_img * c.nimg};
+        RGFM_CUDA(cudaEventCreate(&r.e0));
+        RGFM_CUDA(cudaEventCreate(&r.e1));
+        RGFM_CUDA(cudaEventRecord(r.e0, s));
+        op.fn(c);
+        RGFM_CUDA(cudaEventRecord(r.e1, s));
+        prof->push_back(r);
+      } else {
+        op.fn(c);
+      }
+    }
   }
 }
 

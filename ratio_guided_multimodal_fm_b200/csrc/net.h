@@ -38,6 +38,7 @@ class DevPool {
 };
 
 struct RunCtx {
+  std::vector<ProfRec>* prof = nullptr;  // when set, every op is bracketed by events
   cudaStream_t s;
   int nimg;            // images in this chunk
   const float* x;      // chunk input, NCHW fp32 (U-Net: x_t; ratio: x)
@@ -70,14 +71,20 @@ class Net {
   // Run on `nimg` images (looping over chunks).  U-Net: out_mode OUT_NCHW writes v, OUT_EULER does x += dt*v
   // in place on `out`.  Ratio: x, y -> scores[nimg].
   void forward(cudaStream_t s, int nimg, const float* x, const float* y, float* out, int out_mode, float dt,
-               const int* step);
+               const int* step, std::vector<ProfRec>* prof = nullptr);
 
  private:
   friend struct Builder;
   int kind_, chunk_, precision_, device_;
   int in_ch_ = 0, img_ = 0, in_ch_y_ = 0;
   DevPool pool_;
-  std::vector<std::function<void(const RunCtx&)>> ops_;
+  struct Op {
+    std::function<void(const RunCtx&)> fn;
+    const char* kind;       // kernel family, e.g. "conv_simt"
+    double flops_per_img;   // algorithmic FLOPs (2*MACs of the reference op)
+    double bytes_per_img;   // algorithmic bytes: operands read once + result written once
+  };
+  std::vector<Op> ops_;
   std::vector<TcPtr> tc_;
   // time embedding (host copies)
   int model_ch_ = 0, temb_dim_ = 0, temb_C_ = 0;

@@ -46,6 +46,38 @@ struct Sampler {
     if (hmy) cudaFreeHost(hmy);
   }
 
+  McfArgs mcf_args() const {
+    McfArgs a{};
+    a.B = B; a.N = N; a.Dx = Dx; a.Dy = Dy;
+    a.x = x; a.y = y; a.vx = vx; a.vy = vy; a.mcx = mcx; a.mcy = mcy; a.ratios = ratios;
+    a.sc = sc; a.step = step; a.x_out = x; a.y_out = y; a.gx = gx; a.gy = gy; a.w = nullptr;
+    a.logits = scratch;
+    a.wbuf = scratch + (size_t)(ksx + ksy) * B * N;
+    a.zbuf = a.wbuf + (size_t)B * N;
+    a.ksplit_x = ksx; a.ksplit_y = ksy;
+    return a;
+  }
+
+  // One main-loop step run eagerly with every kernel bracketed by CUDA events on the launching stream.
+  // Destroys the plan's transient state (the next run() re-initialises it); call after a run().
+  std::vector<ProfRec> profile_step() {
+    RGFM_CUDA(cudaSetDevice(d.device));
+    std::vector<ProfRec> recs;
+    const int st = std::min(steps - 1, std::max(first_guided, steps / 2));
+    RGFM_CUDA(cudaMemcpyAsync(step, &st, sizeof(int), cudaMemcpyHostToDevice, cap));
+    RGFM_CUDA(cudaStreamSynchronize(cap));
+    if (guided && st >= first_guided) {
+      fx->forward(cap, B, x, nullptr, vx, OUT_NCHW, dtf, step, &recs);
+      fy->forward(cap, B, y, nullptr, vy, OUT_NCHW, dtf, step, &recs);
+      launch_mcf(mcf_args(), cap, &recs);
+    } else {
+      fx->forward(cap, B, x, nullptr, x, OUT_EULER, dtf, step, &recs);
+      fy->forward(cap, B, y, nullptr, y, OUT_EULER, dtf, step, &recs);
+    }
+    RGFM_CUDA(cudaStreamSynchronize(cap));
+    return recs;
+  }
+
   template <typename F>
   void capture(Graph& G, F&& body) {
     const int64_t before = g_launch_counter;
@@ -152,14 +184,7 @@ struct Sampler {
       capture(g_guided, [&](cudaStream_t s) {
         fx->forward(s, B, x, nullptr, vx, OUT_NCHW, dtf, step);
         fy->forward(s, B, y, nullptr, vy, OUT_NCHW, dtf, step);
-        McfArgs a{};
-        a.B = B; a.N = N; a.Dx = Dx; a.Dy = Dy;
-        a.x = x; a.y = y; a.vx = vx; a.vy = vy; a.mcx = mcx; a.mcy = mcy; a.ratios = ratios;
-        a.sc = sc; a.step = step; a.x_out = x; a.y_out = y; a.gx = gx; a.gy = gy; a.w = nullptr;
-        a.logits = scratch;
-        a.wbuf = scratch + (size_t)(ksx + ksy) * B * N;
-        a.zbuf = a.wbuf + (size_t)B * N;
-        a.ksplit_x = ksx; a.ksplit_y = ksy;
+        McfArgs a = mcf_args();
         launch_mcf(a, s);
         DiagArgs da{B, Dx, Dy, N, vx, vy, gx, gy, a.zbuf, sc, step, (int)(0.3 * steps), diag};
         launch_diag(da, s);
@@ -264,6 +289,32 @@ void sampler_run_host(Sampler* s, const float* x0, const float* y0, const float*
   memcpy(x1, s->hx, bx);
   memcpy(y1, s->hy, by);
   if (diag) memcpy(diag, hd, sizeof(hd));
+}
+
+int sampler_profile(Sampler* s, rgfm_prof_entry* out, int max_entries) {
+  std::vector<ProfRec> recs = s->profile_step();
+  std::vector<rgfm_prof_entry> agg;
+  for (auto& r : recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    size_t k = 0;
+    for (; k < agg.size(); ++k)
+      if (std::string(agg[k].name) == r.kind) break;
+    if (k == agg.size()) {
+      rgfm_prof_entry e{};
+      snprintf(e.name, sizeof(e.name), "%s", r.kind);
+      agg.push_back(e);
+    }
+    agg[k].ms += ms;
+    agg[k].flops += r.flops;
+    agg[k].bytes += r.bytes;
+    agg[k].launches += 1;
+  }
+  const int n = std::min<int>((int)agg.size(), max_entries);
+  for (int i = 0; i < n; ++i) out[i] = agg[i];
+  return n;
 }
 
 void sampler_get_bank(Sampler* s, float* mx, float* my, float* r, cudaStream_t st) {

