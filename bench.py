@@ -256,7 +256,7 @@ def run_gpu(args):
         cpu_v, cpu_sample, _ = cpu_sample_throughput(budget_s=15.0)
         line = dict(metric=METRIC, value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype={"fp32": "f32", "bf16": "bf16", "tf32": "tf32"}[prec], data="synthetic",
+                    dtype={"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[prec], data="synthetic",
                     config=dict(workload=f"BASELINE configs[1]: MNIST32-SVHN mc_feng gamma={GAMMA}, B={B_PER_GPU}/GPU, N_mc={N_MC}, "
                                          f"{EULER_STEPS} Euler steps, RatioEstimatorMNISTSVHN(disc), incl. MC pre-pass",
                                 precision=prec, l2="256 MiB flush between timed iterations", sharding=f"batch x{world}, all_gather of pairs"),
@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="rgfm", choices=["rgfm", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("RGFM_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("RGFM_PRECISION", "fp16"))
     ap.add_argument("--chunk", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -24,7 +24,7 @@ NET_KINDS = {"unet_mnist28": 0, "unet_mnist32": 1, "unet_svhn": 2, "ratio28": 3,
 PAIRS = {"pair28": 0, "mnist_svhn": 1}
 GUIDANCE = {"none": 0, "mc_feng": 1, "grad_log_ratio": 2}
 LOSS = {"disc": 0, "rulsif": 1}
-PRECISION = {"fp32": 0, "bf16": 1, "tf32": 2}
+PRECISION = {"fp32": 0, "bf16": 1, "tf32": 2, "fp16": 3}
 
 
 class RgfmError(RuntimeError):

@@ -72,9 +72,10 @@ struct Builder {
   const WeightMap& W;
   DevPool& pool;
   int chunk;
-  bool tc;  // bf16 tensor-core convs
+  bool tc;    // 16-bit tensor-core convs
+  bool fp16;  // 16-bit operand format: fp16 (true) or bf16
 
-  Builder(Net& n, const WeightMap& w) : net(n), W(w), pool(n.pool_), chunk(n.chunk_), tc(n.precision_ == RGFM_PREC_BF16) {}
+  Builder(Net& n, const WeightMap& w) : net(n), W(w), pool(n.pool_), chunk(n.chunk_), tc(n.precision_ == RGFM_PREC_BF16 || n.precision_ == RGFM_PREC_FP16), fp16(n.precision_ == RGFM_PREC_FP16) {}
 
   Act new_act(int H, int Wd, int C, int parts) {
     Act a;
@@ -147,7 +148,7 @@ struct Builder {
     a.C = C; a.norm = norm; a.act = act; a.spatial = spatial;
     a.gamma = gamma; a.beta = beta; a.groups = 8;
     Packed p = new_packed(a.Ho, a.Wo, C, out_bf16);
-    a.out = p.p; a.out_bf16 = out_bf16 ? 1 : 0;
+    a.out = p.p; a.out_bf16 = out_bf16 ? (fp16 ? 2 : 1) : 0;
     const double bytes = (double)a.Hs * a.Ws * C * 4.0 * (spatial == SP_POOL2 ? 1.0 : 1.0) + (double)a.Ho * a.Wo * C * (out_bf16 ? 2.0 : 4.0);
     net.ops_.push_back({[a](const RunCtx& c) {
       PackArgs b = a;
@@ -157,12 +158,20 @@ struct Builder {
     return p;
   }
 
+  static bool tc_stats_ok(int H, int Wd) {
+    const TileGeom g = make_geom(H, Wd);
+    return g.imgs == 1 || (g.imgs == 2 && H * Wd == 64);
+  }
+
   // generic conv; returns raw activation (or none when `final`)
   Act conv(const Packed& in, const std::string& wname, int cin_real, int cout, int ks, int stride, int temb_off,
            const float* res, bool stats, bool final) {
     const int pad = ks / 2;
     const int Ho = (in.H + 2 * pad - ks) / stride + 1, Wo = (in.W + 2 * pad - ks) / stride + 1;
-    const int coutP = (cout + 31) / 32 * 32;
+    const bool use_tc = tc && in.bf16;
+    // the tcgen05 kernel walks the operand (stride-1) space and stores stride-2 outputs subsampled
+    const TileGeom g = use_tc ? make_geom(in.H, in.W) : make_geom(Ho, Wo);
+    const int coutP = (use_tc && final) ? 16 : (cout + 31) / 32 * 32;
     ConvArgs a{};
     a.in = in.p; a.Hin = in.H; a.Win = in.W; a.Cin = in.C;
     a.bias = vec(wname + ".bias", cout, coutP);
@@ -173,15 +182,14 @@ struct Builder {
     a.out_mode = OUT_RAW;
     Act o;
     if (!final) {
-      o = new_act(Ho, Wo, cout, stats ? a.g.parts : 0);
+      o = new_act(Ho, Wo, cout, stats ? g.parts : 0);
       a.out = o.p;
       a.stats = o.stats;
     }
-    const bool use_tc = tc && in.bf16;
     TcConv* tcp = nullptr;
     if (use_tc) {
-      RGFM_CHECK(stride == 1, "tensor-core conv: stride 1 only (stride-2 convs are packed by the caller)");
-      TcConvDesc d{in.H, in.W, in.C, cout, coutP, ks, chunk, in.p, W.get(wname + ".weight", (int64_t)cout * cin_real * ks * ks), cin_real};
+      if (stats) RGFM_CHECK(tc_stats_ok(in.H, in.W), "tensor-core conv: unsupported GroupNorm tile geometry");
+      TcConvDesc d{in.H, in.W, in.C, cout, coutP, ks, chunk, in.p, W.get(wname + ".weight", (int64_t)cout * cin_real * ks * ks), cin_real, fp16};
       net.tc_.push_back(make_tc_conv(d, pool));
       tcp = net.tc_.back().get();
     } else {
@@ -284,12 +292,16 @@ struct Builder {
       if (level + 1 < mult.size()) {
         // Downsample: conv3x3 stride 2 on the raw activation (unet.py:99-107); exact fp32 path handles the stride
         const std::string p = "downsamplers." + std::to_string(di++) + ".conv";
-        Packed op;
-        op.p = h.p; op.H = h.H; op.W = h.W; op.C = h.C; op.bf16 = false;
-        const bool s2 = tc;
-        tc = false;
-        h = conv(op, p, h.C, h.C, 3, 2, -1, nullptr, true, false);
-        tc = s2;
+        Act dsrc = h;
+        if (tc) {
+          Packed op = pack({dsrc}, NORM_NONE, nullptr, nullptr, ACT_NONE, SP_ID, true);
+          h = conv(op, p, dsrc.C, dsrc.C, 3, 2, -1, nullptr, true, false);
+          release(op);
+        } else {
+          Packed op;
+          op.p = dsrc.p; op.H = dsrc.H; op.W = dsrc.W; op.C = dsrc.C; op.bf16 = false;
+          h = conv(op, p, dsrc.C, dsrc.C, 3, 2, -1, nullptr, true, false);
+        }
         hs.push_back(h);
       }
     }
@@ -346,10 +358,19 @@ struct Builder {
                float* feat, int feat_ld, int feat_off, int fc_in) {
     Packed cur = pack_input(in_ch, img, img, 16, from_y);
     const bool tc_saved = tc;
+    // spatial size seen by each conv, and whether it can run on the tensor cores
+    std::vector<int> sp(L.size());
+    std::vector<bool> ltc(L.size());
+    int hcur = img;
+    for (size_t i = 0; i < L.size(); ++i) {
+      sp[i] = hcur;
+      ltc[i] = tc_saved && i > 0 && (!gn || tc_stats_ok(hcur, hcur));
+      if (L[i].pool) hcur /= 2;
+    }
     for (size_t i = 0; i < L.size(); ++i) {
       const EncLayer& l = L[i];
-      const bool first = (i == 0), last = (i + 1 == L.size());
-      if (first) tc = false;  // K = 9/27 input conv on CUDA cores
+      const bool last = (i + 1 == L.size());
+      tc = ltc[i];  // layer 0 (K = 9/27) and odd GroupNorm geometries stay on the exact fp32 path
       Act h = conv(cur, pre + l.conv, l.cin, l.cout, 3, 1, -1, nullptr, gn, false);
       tc = tc_saved;
       release(cur);
@@ -360,7 +381,7 @@ struct Builder {
       } else {
         bn_affine(pre + l.norm, l.cout, &g, &b);
       }
-      cur = pack({h}, gn ? NORM_GN : NORM_AFFINE, g, b, ACT_SILU, l.pool ? SP_POOL2 : SP_ID, last ? false : tc);
+      cur = pack({h}, gn ? NORM_GN : NORM_AFFINE, g, b, ACT_SILU, l.pool ? SP_POOL2 : SP_ID, last ? false : (bool)ltc[i + 1]);
       release(h);
     }
     const float* fw = vec(pre + "fc.weight", 256 * fc_in);
@@ -421,9 +442,10 @@ struct Builder {
 Net::Net(int kind, const rgfm_weights* w, int chunk, int precision, int device)
     : kind_(kind), chunk_(chunk), precision_(precision), device_(device) {
   RGFM_CHECK(chunk >= 1, "net: chunk");
-  RGFM_CHECK(precision == RGFM_PREC_FP32 || precision == RGFM_PREC_BF16, "net: precision must be fp32 or bf16");
+  RGFM_CHECK(precision == RGFM_PREC_FP32 || precision == RGFM_PREC_BF16 || precision == RGFM_PREC_FP16,
+             "net: precision must be fp32, bf16 or fp16");
   RGFM_CUDA(cudaSetDevice(device));
-  if (precision == RGFM_PREC_BF16) RGFM_CHECK(tc_available(), "bf16 precision needs an sm_100 device");
+  if (precision != RGFM_PREC_FP32) RGFM_CHECK(tc_available(), "16-bit tensor-core precision needs an sm_100 device");
   WeightMap W(w);
   Builder b(*this, W);
   switch (kind) {

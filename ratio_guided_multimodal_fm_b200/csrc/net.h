@@ -104,6 +104,7 @@ struct TcConvDesc {
   const void* in;        // bf16 NHWC operand buffer
   const float* w_oihw;   // host weights, torch layout [Cout][Cin_real][ks][ks]
   int Cin_real;
+  bool fp16;             // operand format: fp16 (true) or bf16 (false); fp32 accumulate either way
 };
 TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool);
 void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s);

@@ -2,6 +2,7 @@
 // exact-fp32 implicit-GEMM convolution used by the fp32 precision mode, and the small dense heads.
 // The bf16 tensor-core convolution lives in conv_tc.cu and plugs into the same op program.
 #include "common.h"
+#include <cuda_fp16.h>
 
 namespace rgfm {
 
@@ -21,10 +22,32 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// store 4 consecutive operand values as fp32 (FMT 0), bf16 (FMT 1) or fp16 (FMT 2)
+template <int FMT>
+__device__ __forceinline__ void store4(void* out, size_t idx, float a, float b, float c, float d) {
+  if (FMT == 0) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + idx) = make_float4(a, b, c, d);
+  } else if (FMT == 1) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + idx) = u;
+  } else {
+    const float L = 65504.f;  // saturate instead of overflowing to inf
+    __half2 lo = __floats2half2_rn(fminf(fmaxf(a, -L), L), fminf(fmaxf(b, -L), L));
+    __half2 hi = __floats2half2_rn(fminf(fmaxf(c, -L), L), fminf(fmaxf(d, -L), L));
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + idx) = u;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // NCHW fp32 image -> NHWC operand with channels zero-padded to Cp (input conv operand)
 // ------------------------------------------------------------------------------------------------
-template <bool BF16>
+template <int FMT>
 __global__ void pack_nchw_kernel(const float* __restrict__ x, int C, int HW, int Cp, void* __restrict__ out,
                                  size_t total_px) {
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,16 +59,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, int C, int HW, int
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = (c + j < C) ? __ldg(src + (size_t)(c + j) * HW) : 0.0f;
-    if (BF16) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]);
-      __nv_bfloat162 hi = __floats2bfloat162_rn(v[2], v[3]);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&lo);
-      u.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + p * Cp + c) = u;
-    } else {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + p * Cp + c) = make_float4(v[0], v[1], v[2], v[3]);
-    }
+    store4<FMT>(out, p * Cp + c, v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -54,10 +68,12 @@ void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, in
   size_t total = (size_t)nimg * H * W;
   int threads = 256;
   unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  if (out_bf16)
-    pack_nchw_kernel<true><<<blocks, threads, 0, s>>>(x, C, H * W, Cp, out, total);
+  if (out_bf16 == 1)
+    pack_nchw_kernel<1><<<blocks, threads, 0, s>>>(x, C, H * W, Cp, out, total);
+  else if (out_bf16 == 2)
+    pack_nchw_kernel<2><<<blocks, threads, 0, s>>>(x, C, H * W, Cp, out, total);
   else
-    pack_nchw_kernel<false><<<blocks, threads, 0, s>>>(x, C, H * W, Cp, out, total);
+    pack_nchw_kernel<0><<<blocks, threads, 0, s>>>(x, C, H * W, Cp, out, total);
   post_launch("pack_nchw");
 }
 
@@ -70,7 +86,7 @@ void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, in
 constexpr int PACK_PIX = 32;
 constexpr int PACK_MAXC = 512;
 
-template <bool BF16>
+template <int FMT>
 __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
   __shared__ float s_scale[PACK_MAXC];
   __shared__ float s_shift[PACK_MAXC];
@@ -160,16 +176,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
       }
     }
     const size_t o = ((size_t)n * npix + p) * a.C + c;
-    if (BF16) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y);
-      __nv_bfloat162 hi = __floats2bfloat162_rn(r.z, r.w);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&lo);
-      u.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.out) + o) = u;
-    } else {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + o) = r;
-    }
+    store4<FMT>(a.out, o, r.x, r.y, r.z, r.w);
   }
 }
 
@@ -177,10 +184,12 @@ void launch_pack(const PackArgs& a, cudaStream_t s) {
   RGFM_CHECK(a.C <= PACK_MAXC && a.C % 4 == 0, "pack: channel count");
   RGFM_CHECK(a.groups <= 32, "pack: groups");
   dim3 grid((a.Ho * a.Wo + PACK_PIX - 1) / PACK_PIX, a.nimg);
-  if (a.out_bf16)
-    pack_kernel<true><<<grid, 256, 0, s>>>(a);
+  if (a.out_bf16 == 1)
+    pack_kernel<1><<<grid, 256, 0, s>>>(a);
+  else if (a.out_bf16 == 2)
+    pack_kernel<2><<<grid, 256, 0, s>>>(a);
   else
-    pack_kernel<false><<<grid, 256, 0, s>>>(a);
+    pack_kernel<0><<<grid, 256, 0, s>>>(a);
   post_launch("pack");
 }
 

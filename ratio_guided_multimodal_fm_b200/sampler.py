@@ -20,7 +20,7 @@ _PLAN_CACHE_MAX = 4
 
 
 def default_precision() -> str:
-    return os.environ.get("RGFM_PRECISION", "fp32")
+    return os.environ.get("RGFM_PRECISION", "fp16")
 
 
 def _fingerprint(module) -> tuple:
