@@ -94,7 +94,8 @@ struct Act {
 struct Packed {
   void* p = nullptr;
   int H = 0, W = 0, C = 0;
-  bool bf16 = false;
+  bool bf16 = false;    // 16-bit operand (bf16 or fp16 per the net's precision)
+  bool padded = false;  // padded-linear layout [slot][C] (tcgen05 path), see pack_padded_kernel
 };
 
 enum NormMode { NORM_NONE = 0, NORM_GN = 1, NORM_AFFINE = 2 };
@@ -120,8 +121,9 @@ struct PackArgs {
   const float* beta;    // GN: beta[C];  AFFINE: shift[C]
   int groups;
   void* out;
-  int out_bf16;
+  int out_bf16;         // 0 = fp32, 1 = bf16, 2 = fp16
   int nimg;
+  int Cpad;             // padded-linear layout only: channels of the operand tensor (multiple of 64, zero filled)
 };
 
 struct ConvArgs {
@@ -146,6 +148,8 @@ struct ConvArgs {
 
 // ops_simt.cu
 void launch_pack(const PackArgs& a, cudaStream_t s);
+void launch_pack_padded(const PackArgs& a, cudaStream_t s);
+void launch_gn_stats(const float* x, int HW, int C, float* stats, int nimg, cudaStream_t s);
 void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, int out_bf16, int nimg, cudaStream_t s);
 void launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 void launch_gap_fc(const float* in, int HW, int C, const float* w, const float* b, int Cout, float* out, int ld,

@@ -29,24 +29,25 @@ static inline void post_launch(const char* what) {
   ++g_launch_counter;
 }
 
-constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 64 + 2 * 128;  // producer warp, MMA warp, two epilogue groups of 4 warps
+constexpr int TC_SUPER = 256;             // output slots per super-tile (two M=128 accumulators sharing every B tile)
 
 struct TcArgs {
-  ConvArgs c;       // epilogue description; c.g is the tile geometry of the operand (= stride-1 output) space
-  int nkb;          // K-blocks = taps * cblocks
-  int cblocks;      // Cin / BK
-  int BK;           // 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
-  int ks, pad;
-  int stages;
-  uint32_t a_bytes; // TMA box bytes of one A stage (rows actually loaded)
-  uint32_t a_stage; // reserved bytes per A stage (128 rows)
-  uint32_t b_bytes; // bytes of one B stage
-  uint32_t layout;  // UMMA layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-  uint32_t sbo;     // stride between 8-row groups in bytes
+  ConvArgs c;        // epilogue description (bias, time bias, residual, output, stats, nimg, out_mode, dt)
+  int H, W, P;       // operand image geometry and padded pitch P = W + 2
+  int cblocks;       // operand channels / 64
+  int ntaps;         // 9 (3x3) or 1 (1x1)
+  int tap_shift[9];  // row shift of each tap inside the A tile: ky*P + kx
+  int a_box_rows;    // rows per TMA box; an A tile is two boxes
+  uint32_t a_slot;   // bytes of one A slot (2 * a_box_rows * 128)
+  uint32_t b_bytes;  // bytes of one B stage (CoutP * 128)
+  int b_stages;
+  int nbuf;          // TMEM double buffering (2) when 4 * CoutP <= 512 columns, else 1
   uint32_t idesc;
   uint32_t tmem_cols;
-  int sub;          // stride-2: store rows with even (ho, wo) only
+  int sub;           // stride-2: store rows with even (h, w) only
+  int out_H, out_W;  // output spatial size (H, W or halved when sub)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -83,6 +84,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
@@ -144,33 +151,45 @@ __device__ __forceinline__ float transpose_reduce32(float* f, int lane) {
   return f[0];
 }
 
+
+// decode padded-linear output index m' -> (image, h, w); valid iff a real pixel of an image < nimg
+__device__ __forceinline__ bool slot_pixel(int m, int H, int P, int nimg, int& n, int& h, int& w) {
+  const int hv = m / P;
+  w = m - hv * P;
+  n = hv / (H + 1);
+  h = hv - n * (H + 1);
+  return (w < P - 2) && (h < H) && (n < nimg);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2];
+  __shared__ __align__(8) uint64_t b_full[TC_MAX_STAGES], b_empty[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[256];
-  __shared__ float s_part[2][4][256][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = p.a_stage + p.b_bytes;
+  const uint32_t smem_b = smem_base + 2u * p.a_slot;
   const ConvArgs& a = p.c;
-  const int tiles = a.g.tiles(a.nimg);
+  const int N = a.CoutP;
+  const int total_rows = a.nimg * (p.H + 1) * p.P;
+  const int supers = (total_rows + TC_SUPER - 1) / TC_SUPER;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 256);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 128);
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -181,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp >= 2) {
     // bias + this step's time bias: identical for every tile of the launch (t is uniform over the batch)
     const float* tb = a.temb ? a.temb + (size_t)(a.step ? *a.step : 0) * a.temb_stride + a.temb_off : nullptr;
-    for (int c = threadIdx.x - 64; c < a.CoutP; c += TC_THREADS - 64) {
+    for (int c = threadIdx.x - 64; c < N; c += TC_THREADS - 64) {
       float b = a.bias[c];
       if (tb && c < a.Cout) b += tb[c];
       s_bias[c] = b;
@@ -195,77 +214,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
-      uint32_t g = 0;  // running K-block counter across tiles (ring position)
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        int n0, h0;
-        if (a.g.imgs == 1) {
-          n0 = tile / a.g.parts;
-          h0 = (tile - n0 * a.g.parts) * a.g.th;
-        } else {
-          n0 = tile * a.g.imgs;
-          h0 = 0;
-        }
-        for (int kb = 0; kb < p.nkb; ++kb, ++g) {
-          const uint32_t s = g % p.stages;
-          const uint32_t ph = (g / p.stages) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-          const int ky = tap / p.ks, kx = tap - ky * p.ks;
-          mbar_expect_tx(&full_bar[s], p.a_bytes + p.b_bytes);
-          const uint32_t sa = smem_base + s * stage_bytes;
-          tma_load_4d(sa, &tmA, &full_bar[s], cb * p.BK, kx - p.pad, h0 + ky - p.pad, n0);
-          tma_load_3d(sa + p.a_stage, &tmB, &full_bar[s], cb * p.BK, 0, tap);
+      uint32_t ga = 0, gb = 0;  // ring positions, running across super-tiles
+      for (int st = blockIdx.x; st < supers; st += gridDim.x) {
+        const int row0 = st * TC_SUPER;
+        for (int cb = 0; cb < p.cblocks; ++cb, ++ga) {
+          const uint32_t as = ga & 1u;
+          mbar_wait(&a_empty[as], ((ga >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&a_full[as], p.a_slot);
+          const uint32_t sa = smem_base + as * p.a_slot;
+          tma_load_2d(sa, &tmA, &a_full[as], cb * 64, row0);
+          tma_load_2d(sa + (p.a_slot >> 1), &tmA, &a_full[as], cb * 64, row0 + p.a_box_rows);
+          for (int tap = 0; tap < p.ntaps; ++tap, ++gb) {
+            const uint32_t bs = gb % p.b_stages;
+            mbar_wait(&b_empty[bs], ((gb / p.b_stages) & 1u) ^ 1u);
+            mbar_expect_tx(&b_full[bs], p.b_bytes);
+            tma_load_3d(smem_b + bs * p.b_bytes, &tmB, &b_full[bs], cb * 64, 0, tap);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
     if (lane == 0) {
-      uint32_t g = 0;
+      uint32_t ga = 0, gb = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&tmem_empty_bar[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+      for (int st = blockIdx.x; st < supers; st += gridDim.x, ++it) {
+        const int buf = (p.nbuf == 2) ? (it & 1) : 0;
+        const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+        mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // both epilogue groups drained this accumulator pair
         tc_fence_after();
-        const uint32_t td = tmem_d + (uint32_t)(buf * a.CoutP);
-        for (int kb = 0; kb < p.nkb; ++kb, ++g) {
-          const uint32_t s = g % p.stages;
-          const uint32_t ph = (g / p.stages) & 1u;
-          mbar_wait(&full_bar[s], ph);
+        const uint32_t td0 = tmem_d + (uint32_t)(buf * 2 * N);
+        for (int cb = 0; cb < p.cblocks; ++cb, ++ga) {
+          const uint32_t as = ga & 1u;
+          mbar_wait(&a_full[as], (ga >> 1) & 1u);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * stage_bytes;
-          const uint64_t da = make_desc(sa, p.sbo, p.layout);
-          const uint64_t db = make_desc(sa + p.a_stage, p.sbo, p.layout);
-          const int nk = p.BK >> 4;
-          for (int k = 0; k < nk; ++k)  // advance 16 elements = 32 bytes inside the swizzle atom: +2 in the >>4 address field
-            tc_mma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (uint32_t)((kb | k) != 0));
-          tc_commit(&empty_bar[s]);
+          const uint32_t sa = smem_base + as * p.a_slot;
+          for (int tap = 0; tap < p.ntaps; ++tap, ++gb) {
+            const uint32_t bs = gb % p.b_stages;
+            mbar_wait(&b_full[bs], (gb / p.b_stages) & 1u);
+            tc_fence_after();
+            // the tap is a ROW SHIFT of the shared A tile: descriptor start = tile base + shift * 128 B
+            const uint32_t a0 = sa + (uint32_t)p.tap_shift[tap] * 128u;
+            const uint64_t db = make_desc(smem_b + bs * p.b_bytes, 1024u, 2u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 64 channels = 4 x K16; +32 bytes per step inside the swizzle atom
+              const uint32_t acc = (uint32_t)((cb | tap | k) != 0);
+              tc_mma_bf16(td0, make_desc(a0 + k * 32u, 1024u, 2u), db + (uint64_t)(2 * k), p.idesc, acc);
+              tc_mma_bf16(td0 + (uint32_t)N, make_desc(a0 + 128u * 128u + k * 32u, 1024u, 2u), db + (uint64_t)(2 * k), p.idesc, acc);
+            }
+            tc_commit(&b_empty[bs]);
+          }
+          tc_commit(&a_empty[as]);
         }
         tc_commit(&tmem_full_bar[buf]);
       }
     }
     __syncwarp();
   } else {
-    // ------------------------------- epilogue: two groups of 4 warps, one per accumulator -------------------------------
-    const int eg = (warp - 2) >> 2;  // epilogue group == TMEM accumulator index
-    const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
-    const int et = threadIdx.x - 64 - eg * 128;  // thread index within the group
-    int it = eg;
-    for (int tile = blockIdx.x + eg * gridDim.x; tile < tiles; tile += 2 * gridDim.x, it += 2) {
-      int n, ho, wo, part;
-      bool valid = tile_row(a.g, tile, r, a.nimg, n, ho, wo, part);
-      int Ho = a.g.H, Wo = a.g.W;
+    // ---------------- epilogue: group eg owns rows [128*eg, 128*eg+128) of every super-tile ----------------
+    const int eg = (warp - 2) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int st = blockIdx.x; st < supers; st += gridDim.x, ++it) {
+      const int buf = (p.nbuf == 2) ? (it & 1) : 0;
+      const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+      const int unit = st * 2 + eg;          // 128-row unit index
+      const int m = unit * 128 + q * 32 + lane;
+      int n, h, w;
+      bool valid = slot_pixel(m, p.H, p.P, a.nimg, n, h, w);
       if (p.sub) {
-        valid = valid && !(ho & 1) && !(wo & 1);
-        ho >>= 1; wo >>= 1; Ho >>= 1; Wo >>= 1;
+        valid = valid && !(h & 1) && !(w & 1);
+        h >>= 1; w >>= 1;
       }
-      mbar_wait(&tmem_full_bar[eg], ((uint32_t)it >> 1) & 1u);
+      mbar_wait(&tmem_full_bar[buf], use & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(eg * a.CoutP);
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + eg) * N);
       if (a.out_mode == OUT_RAW) {
-        const size_t o = valid ? (((size_t)n * Ho + ho) * Wo + wo) * a.Cout : 0;
-        for (int c0 = 0; c0 < a.CoutP; c0 += 32) {
+        const size_t o = valid ? (((size_t)n * p.out_H + h) * p.out_W + w) * a.Cout : 0;
+        for (int c0 = 0; c0 < N; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
@@ -284,60 +310,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(a.out + o + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           }
-          if (a.stats) {
-            float sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              f[j] = valid ? f[j] : 0.f;
-              sq[j] = f[j] * f[j];
-            }
-            const float s1 = transpose_reduce32(f, lane);
-            const float s2 = transpose_reduce32(sq, lane);
-            s_part[eg][q][c0 + lane][0] = s1;
-            s_part[eg][q][c0 + lane][1] = s2;
-          }
         }
-        // accumulator fully read: hand it back to the MMA warp before the (global-memory) statistics tail
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[eg]);
-        if (a.stats) {
-          if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-          else asm volatile("bar.sync 2, 128;" ::: "memory");
-          for (int c = et; c < a.Cout; c += 128) {
-            if (a.g.imgs == 1) {
-              const int ni = tile / a.g.parts, pi = tile - ni * a.g.parts;
-              if (ni < a.nimg) {
-                float* st = a.stats + (((size_t)ni * a.g.parts + pi) * a.Cout + c) * 2;
-                st[0] = (s_part[eg][0][c][0] + s_part[eg][1][c][0]) + (s_part[eg][2][c][0] + s_part[eg][3][c][0]);
-                st[1] = (s_part[eg][0][c][1] + s_part[eg][1][c][1]) + (s_part[eg][2][c][1] + s_part[eg][3][c][1]);
-              }
-            } else {  // two 64-pixel images per tile: quarters {0,1} and {2,3}
-#pragma unroll
-              for (int il = 0; il < 2; ++il) {
-                const int ni = tile * 2 + il;
-                if (ni < a.nimg) {
-                  float* st = a.stats + ((size_t)ni * a.Cout + c) * 2;
-                  st[0] = s_part[eg][2 * il][c][0] + s_part[eg][2 * il + 1][c][0];
-                  st[1] = s_part[eg][2 * il][c][1] + s_part[eg][2 * il + 1][c][1];
-                }
-              }
-            }
-          }
-          // s_part[eg] is rewritten by the next tile of this group: wait until everyone has read it
-          if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-          else asm volatile("bar.sync 2, 128;" ::: "memory");
-        }
+        mbar_arrive(&tmem_empty_bar[buf]);
       } else {
         // output conv: Cout <= 16 real channels -> NCHW velocity, or fused Euler update x += dt * v
         uint32_t v[16];
         tmem_ld16(taddr, v);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[eg]);
+        mbar_arrive(&tmem_empty_bar[buf]);
         if (valid) {
           for (int c = 0; c < a.Cout; ++c) {
             const float val = __uint_as_float(v[c]) + s_bias[c];
-            const size_t oc = (((size_t)n * a.Cout + c) * Ho + ho) * Wo + wo;
+            const size_t oc = (((size_t)n * a.Cout + c) * p.out_H + h) * p.out_W + w;
             if (a.out_mode == OUT_NCHW)
               a.out[oc] = val;
             else
@@ -387,40 +373,46 @@ bool tc_available() {
   return pr.major == 10;
 }
 
+size_t tc_operand_slots(int H, int W, int chunk) { return (size_t)(1 + (size_t)chunk * (H + 1)) * (W + 2); }
+int tc_stats_parts(int H, int W) { return ((H + 1) * (W + 2) - 1) / 128 + 2; }
+
 TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
-  RGFM_CHECK(d.Cin % 32 == 0, "tc conv: operand channels must be a multiple of 32");
+  RGFM_CHECK(d.Cin % 64 == 0, "tc conv: operand channels must be a multiple of 64");
   RGFM_CHECK(d.CoutP % 16 == 0 && d.CoutP >= 16 && d.CoutP <= 256, "tc conv: padded Cout must be 16..256, multiple of 16");
   RGFM_CHECK(d.ks == 1 || d.ks == 3, "tc conv: 1x1 or 3x3");
+  RGFM_CHECK(d.Win + 2 <= 39, "tc conv: image width must be <= 37");
   TcPtr t(new TcConv());
   TcArgs& p = t->p;
   std::memset(&p, 0, sizeof(p));
-  const int BK = (d.Cin % 64 == 0) ? 64 : 32;
-  const TileGeom g = make_geom(d.Hin, d.Win);
-  p.BK = BK;
-  p.cblocks = d.Cin / BK;
-  p.ks = d.ks;
-  p.pad = d.ks / 2;
-  p.nkb = d.ks * d.ks * p.cblocks;
-  p.a_stage = TM * BK * 2;
-  p.a_bytes = (uint32_t)(g.W * g.th * g.imgs) * BK * 2;
-  p.b_bytes = (uint32_t)d.CoutP * BK * 2;
-  p.layout = BK == 64 ? 2u : 4u;
-  p.sbo = 8u * BK * 2;
+  const int P = d.Win + 2;
+  p.H = d.Hin; p.W = d.Win; p.P = P;
+  p.cblocks = d.Cin / 64;
+  p.ntaps = d.ks * d.ks;
+  if (d.ks == 3) {
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) p.tap_shift[ky * 3 + kx] = ky * P + kx;
+  } else {
+    p.tap_shift[0] = P + 1;
+  }
+  const int rows_needed = TC_SUPER + 2 * P + 2;
+  p.a_box_rows = ((rows_needed + 1) / 2 + 7) / 8 * 8;
+  RGFM_CHECK(p.a_box_rows <= 256, "tc conv: A box too tall");
+  p.a_slot = 2u * p.a_box_rows * 128u;
+  p.b_bytes = (uint32_t)d.CoutP * 128u;
   const uint32_t fmt = d.fp16 ? 0u : 1u;  // UMMA F16F32Format: 0 = F16, 1 = BF16
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(d.CoutP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(d.CoutP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.nbuf = (4 * d.CoutP <= 512) ? 2 : 1;
   uint32_t cols = 32;
-  while (cols < 2u * (uint32_t)d.CoutP) cols <<= 1;  // two accumulators (MMA of tile i+1 overlaps the epilogue of tile i)
+  while (cols < (uint32_t)(2 * p.nbuf * d.CoutP)) cols <<= 1;
   p.tmem_cols = cols;
-  const uint32_t stage = p.a_stage + p.b_bytes;
-  int stages = (int)((176u * 1024u) / stage);  // one persistent CTA per SM
-  if (stages < 3) stages = 3;
+  int stages = (int)((196u * 1024u - 2u * p.a_slot) / p.b_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  if (stages > p.nkb) stages = p.nkb;
-  p.stages = stages;
-  t->smem = (size_t)stages * stage + 1024;
+  RGFM_CHECK(stages >= 2, "tc conv: not enough shared memory for the weight ring");
+  p.b_stages = stages;
+  t->smem = 2 * (size_t)p.a_slot + (size_t)stages * p.b_bytes + 1024;
 
-  // weights: torch [Cout][Cin_real][ks][ks] fp32 -> [tap][CoutP][Cin] bf16 (zero padded)
-  const int taps = d.ks * d.ks;
+  // weights: torch [Cout][Cin_real][ks][ks] fp32 -> [tap][CoutP][Cin] 16-bit (zero padded)
+  const int taps = p.ntaps;
   std::vector<uint16_t> hw((size_t)taps * d.CoutP * d.Cin, 0);
   for (int o = 0; o < d.Cout; ++o)
     for (int c = 0; c < d.Cin_real; ++c)
@@ -428,36 +420,34 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
         const float wv = d.w_oihw[((size_t)o * d.Cin_real + c) * taps + tp];
         uint16_t bits;
         if (d.fp16) {
-          const __half h = __float2half_rn(wv);
-          std::memcpy(&bits, &h, 2);
+          const __half hv = __float2half_rn(wv);
+          std::memcpy(&bits, &hv, 2);
         } else {
-          const __nv_bfloat16 h = __float2bfloat16(wv);
-          std::memcpy(&bits, &h, 2);
+          const __nv_bfloat16 hv = __float2bfloat16(wv);
+          std::memcpy(&bits, &hv, 2);
         }
         hw[((size_t)tp * d.CoutP + o) * d.Cin + c] = bits;
       }
   t->w = pool.upload(hw);
 
   const CUtensorMapDataType dt16 = d.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.Win, (cuuint64_t)d.Hin, (cuuint64_t)d.chunk};
-    cuuint64_t strides[3] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.Win * d.Cin * 2, (cuuint64_t)d.Hin * d.Win * d.Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)g.W, (cuuint32_t)g.th, (cuuint32_t)g.imgs};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = encode_fn()(&t->tmA, dt16, 4, const_cast<void*>(d.in), dims, strides, box, es,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // operand: 2-D [slots][Cin]; out-of-range rows of the last tile are zero-filled by TMA
+    cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)tc_operand_slots(d.Hin, d.Win, d.chunk)};
+    cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.a_box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(&t->tmA, dt16, 2, const_cast<void*>(d.in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RGFM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed with code " + std::to_string((int)r));
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)d.CoutP, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.CoutP * d.Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)d.CoutP, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)d.CoutP, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encode_fn()(&t->tmB, dt16, 3, t->w, dims, strides, box, es,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode_fn()(&t->tmB, dt16, 3, t->w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RGFM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with code " + std::to_string((int)r));
   }
   static bool attr = false;
@@ -472,18 +462,20 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
   TcArgs p = tc.p;
   p.c = a;
   p.sub = (a.stride == 2) ? 1 : 0;
-  p.c.g = make_geom(a.Hin, a.Win);  // tiles walk the operand (stride-1 output) space
-  if (a.stats) RGFM_CHECK(p.c.g.imgs == 1 || (p.c.g.imgs == 2 && !p.sub), "tc conv: GroupNorm partials need <=2 images per tile");
+  p.out_H = p.sub ? p.H / 2 : p.H;
+  p.out_W = p.sub ? p.W / 2 : p.W;
+  RGFM_CHECK(a.stats == nullptr, "tc conv: GroupNorm statistics are computed by the consumer pack, not here");
   if (a.out_mode != OUT_RAW) RGFM_CHECK(a.CoutP == 16, "tc conv: the output conv uses a 16-column accumulator");
   else RGFM_CHECK(a.CoutP % 32 == 0 && a.Cout == a.CoutP, "tc conv: raw outputs need Cout % 32 == 0");
-  const int tiles = p.c.g.tiles(a.nimg);
+  const int total_rows = a.nimg * (p.H + 1) * p.P;
+  const int supers = (total_rows + TC_SUPER - 1) / TC_SUPER;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     RGFM_CUDA(cudaGetDevice(&dev));
     RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = tiles < num_sms ? tiles : num_sms;  // persistent: one CTA per SM, static round-robin over tiles
+  const int grid = supers < num_sms ? supers : num_sms;  // persistent: one CTA per SM, static round-robin
   conv_tc_kernel<<<grid, TC_THREADS, tc.smem, s>>>(tc.tmA, tc.tmB, p);
   post_launch("conv_tc");
 }

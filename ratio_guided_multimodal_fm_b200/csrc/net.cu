@@ -94,8 +94,15 @@ struct Builder {
   }
   Packed new_packed(int H, int Wd, int C, bool bf16) {
     Packed p;
-    p.H = H; p.W = Wd; p.C = C; p.bf16 = bf16;
-    p.p = pool.alloc((size_t)chunk * H * Wd * C * (bf16 ? 2 : 4));
+    p.H = H; p.W = Wd; p.bf16 = bf16;
+    if (bf16) {  // tcgen05 operand: padded-linear layout, channels padded to a multiple of 64
+      p.padded = true;
+      p.C = (C + 63) / 64 * 64;
+      p.p = pool.alloc(tc_operand_slots(H, Wd, chunk) * p.C * 2);
+    } else {
+      p.C = C;
+      p.p = pool.alloc((size_t)chunk * H * Wd * C * 4);
+    }
     return p;
   }
   void release(Packed& p) {
@@ -136,9 +143,20 @@ struct Builder {
     a.nsrc = (int)srcs.size();
     RGFM_CHECK(a.nsrc >= 1 && a.nsrc <= 2, "pack: 1 or 2 sources");
     int C = 0;
+    std::vector<float*> tmp_stats;
     for (int i = 0; i < a.nsrc; ++i) {
       a.src[i] = PackSrc{srcs[i].p, srcs[i].stats, srcs[i].C, srcs[i].parts};
-      if (norm == NORM_GN) RGFM_CHECK(srcs[i].stats != nullptr, "pack: GroupNorm source without statistics");
+      if (norm == NORM_GN && !out_bf16 && srcs[i].stats == nullptr) {
+        // fp32-operand pack after a producer without GroupNorm partials (tcgen05 conv): compute them here
+        float* st = (float*)pool.alloc((size_t)chunk * srcs[i].C * 2 * sizeof(float));
+        tmp_stats.push_back(st);
+        const float* src = srcs[i].p;
+        const int HW = srcs[i].H * srcs[i].W, Cs = srcs[i].C;
+        net.ops_.push_back({[=](const RunCtx& c) { launch_gn_stats(src, HW, Cs, st, c.nimg, c.s); }, "gn_stats", 0.0,
+                            (double)HW * Cs * 4.0});
+        a.src[i].stats = st;
+        a.src[i].parts = 1;
+      }
       C += srcs[i].C;
     }
     if (a.nsrc == 1) a.src[1] = a.src[0];
@@ -149,19 +167,20 @@ struct Builder {
     a.gamma = gamma; a.beta = beta; a.groups = 8;
     Packed p = new_packed(a.Ho, a.Wo, C, out_bf16);
     a.out = p.p; a.out_bf16 = out_bf16 ? (fp16 ? 2 : 1) : 0;
-    const double bytes = (double)a.Hs * a.Ws * C * 4.0 * (spatial == SP_POOL2 ? 1.0 : 1.0) + (double)a.Ho * a.Wo * C * (out_bf16 ? 2.0 : 4.0);
-    net.ops_.push_back({[a](const RunCtx& c) {
+    a.Cpad = p.C;
+    const double bytes = (double)a.Hs * a.Ws * C * 4.0 + (double)a.Ho * a.Wo * C * (out_bf16 ? 2.0 : 4.0);
+    const bool padded = p.padded;
+    net.ops_.push_back({[a, padded](const RunCtx& c) {
       PackArgs b = a;
       b.nimg = c.nimg;
-      launch_pack(b, c.s);
-    }, "pack", 0.0, bytes});
+      if (padded) launch_pack_padded(b, c.s);
+      else launch_pack(b, c.s);
+    }, padded ? "pack_padded" : "pack", 0.0, bytes});
+    for (float* st : tmp_stats) pool.release(st);
     return p;
   }
 
-  static bool tc_stats_ok(int H, int Wd) {
-    const TileGeom g = make_geom(H, Wd);
-    return g.imgs == 1 || (g.imgs == 2 && H * Wd == 64);
-  }
+  static bool tc_stats_ok(int H, int Wd) { return (H + 1) * (Wd + 2) >= 64; }
 
   // generic conv; returns raw activation (or none when `final`)
   Act conv(const Packed& in, const std::string& wname, int cin_real, int cout, int ks, int stride, int temb_off,
@@ -170,7 +189,8 @@ struct Builder {
     const int Ho = (in.H + 2 * pad - ks) / stride + 1, Wo = (in.W + 2 * pad - ks) / stride + 1;
     const bool use_tc = tc && in.bf16;
     // the tcgen05 kernel walks the operand (stride-1) space and stores stride-2 outputs subsampled
-    const TileGeom g = use_tc ? make_geom(in.H, in.W) : make_geom(Ho, Wo);
+    if (use_tc) stats = false;  // consumers compute GroupNorm statistics themselves (pack_padded / gn_stats)
+    const int stat_parts = make_geom(Ho, Wo).parts;
     const int coutP = (use_tc && final) ? 16 : (cout + 31) / 32 * 32;
     ConvArgs a{};
     a.in = in.p; a.Hin = in.H; a.Win = in.W; a.Cin = in.C;
@@ -182,13 +202,12 @@ struct Builder {
     a.out_mode = OUT_RAW;
     Act o;
     if (!final) {
-      o = new_act(Ho, Wo, cout, stats ? g.parts : 0);
+      o = new_act(Ho, Wo, cout, stats ? stat_parts : 0);
       a.out = o.p;
       a.stats = o.stats;
     }
     TcConv* tcp = nullptr;
     if (use_tc) {
-      if (stats) RGFM_CHECK(tc_stats_ok(in.H, in.W), "tensor-core conv: unsupported GroupNorm tile geometry");
       TcConvDesc d{in.H, in.W, in.C, cout, coutP, ks, chunk, in.p, W.get(wname + ".weight", (int64_t)cout * cin_real * ks * ks), cin_real, fp16};
       net.tc_.push_back(make_tc_conv(d, pool));
       tcp = net.tc_.back().get();
@@ -279,7 +298,7 @@ struct Builder {
     Packed pin = pack_input(in_ch, img, img, 16, false);
     const bool tc_saved = tc;
     tc = false;
-    Act h = conv(pin, "input_conv", in_ch, mc, 3, 1, -1, nullptr, true, false);
+    Act h = conv(pin, "input_conv", in_ch, mc, 3, 1, -1, nullptr, !tc_saved, false);
     tc = tc_saved;
     release(pin);
     std::vector<Act> hs{h};
@@ -329,9 +348,10 @@ struct Builder {
         h = o;
       }
     }
+    const int out_cin = h.C;
     Packed po = pack({h}, NORM_GN, vec("out_norm.weight", h.C), vec("out_norm.bias", h.C), ACT_SILU, SP_ID, tc);
     release(h);
-    conv(po, "out_conv", po.C, in_ch, 3, 1, -1, nullptr, false, true);
+    conv(po, "out_conv", out_cin, in_ch, 3, 1, -1, nullptr, false, true);
     release(po);
   }
 
@@ -364,14 +384,16 @@ struct Builder {
     int hcur = img;
     for (size_t i = 0; i < L.size(); ++i) {
       sp[i] = hcur;
-      ltc[i] = tc_saved && i > 0 && (!gn || tc_stats_ok(hcur, hcur));
+      ltc[i] = tc_saved && i > 0;
       if (L[i].pool) hcur /= 2;
     }
     for (size_t i = 0; i < L.size(); ++i) {
       const EncLayer& l = L[i];
       const bool last = (i + 1 == L.size());
       tc = ltc[i];  // layer 0 (K = 9/27) and odd GroupNorm geometries stay on the exact fp32 path
-      Act h = conv(cur, pre + l.conv, l.cin, l.cout, 3, 1, -1, nullptr, gn, false);
+      // GroupNorm partials are only needed when the following pack writes an fp32 operand from a SIMT producer
+      const bool next_padded = !last && ltc[i + 1];
+      Act h = conv(cur, pre + l.conv, l.cin, l.cout, 3, 1, -1, nullptr, gn && !next_padded, false);
       tc = tc_saved;
       release(cur);
       const float *g, *b;

@@ -97,11 +97,11 @@ class Net {
 
 // conv_tc.cu -- tcgen05 implicit-GEMM convolution (bf16 operands, fp32 accumulate in TMEM)
 struct TcConvDesc {
-  int Hin, Win, Cin;     // operand (bf16 NHWC) geometry
+  int Hin, Win, Cin;     // operand geometry; Cin = padded channel count of the padded-linear operand tensor
   int Cout, CoutP;       // real / padded output channels
   int ks;                // 1 or 3 (stride 1, pad ks/2)
   int chunk;             // max images
-  const void* in;        // bf16 NHWC operand buffer
+  const void* in;        // 16-bit padded-linear operand buffer [slots][Cin]
   const float* w_oihw;   // host weights, torch layout [Cout][Cin_real][ks][ks]
   int Cin_real;
   bool fp16;             // operand format: fp16 (true) or bf16 (false); fp32 accumulate either way
@@ -109,5 +109,7 @@ struct TcConvDesc {
 TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool);
 void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s);
 bool tc_available();
+size_t tc_operand_slots(int H, int W, int chunk);  // rows of the padded-linear operand tensor
+int tc_stats_parts(int H, int W);                  // GroupNorm partial-sum slots per image written by the tcgen05 conv
 
 }  // namespace rgfm

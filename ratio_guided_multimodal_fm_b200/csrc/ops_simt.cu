@@ -180,6 +180,194 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// PACK (padded-linear layout) for the tcgen05 convolution.  The operand is a 2-D tensor [slot][Cpad] of 16-bit
+// values where slot = (1 + n*(H+1) + h) * P + (w + 1), P = W + 2: every image row carries one zero pixel on each
+// side and every image is followed by one zero row (row 0 is zero too), so the nine taps of a 3x3 convolution are
+// nine ROW SHIFTS (ky*P + kx) of one shared-memory tile and the conv's zero padding is physically in memory.
+// This kernel writes the pad slots (zeros) together with the valid pixels, so arena blocks can be recycled.
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float fast_act(float x, int act) {
+  if (act == ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
+  if (act == ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (FMT == 1) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  const float L = 65504.f;
+  __half2 v = __floats2half2_rn(fminf(fmaxf(a, -L), L), fminf(fmaxf(b, -L), L));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// One CTA per image.  GroupNorm statistics are computed HERE, on the concatenated view of the (one or two) fp32
+// sources: pass A accumulates per-channel sum / sum-of-squares (fp32 per thread, combined in double), pass B
+// normalises, activates and writes the 16-bit padded-linear operand.  The second read of the image hits L2.
+template <int FMT>
+__global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
+  __shared__ float s_scale[PACK_MAXC];
+  __shared__ float s_shift[PACK_MAXC];
+  __shared__ float s_red[2][PACK_MAXC];   // per-channel sum / sumsq
+  __shared__ double s_grp[32][2];
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int C0 = a.src[0].C;
+  const int C8 = a.C >> 3;
+  const int HWs = a.Hs * a.Ws;
+
+  if (a.norm == NORM_GN) {
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      s_red[0][c] = 0.f;
+      s_red[1][c] = 0.f;
+    }
+    __syncthreads();
+    const int PL = blockDim.x / C8;  // pixel lanes
+    const int co = tid % C8, pl = tid / C8;
+    if (pl < PL) {
+      const int c = co << 3;
+      const int si = (c < C0) ? 0 : 1;
+      const int cl = si ? c - C0 : c;
+      const int Cs = a.src[si].C;
+      const float* base = a.src[si].p + (size_t)n * HWs * Cs + cl;
+      float s1[8], s2[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+      for (int p = pl; p < HWs; p += PL) {
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * Cs));
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * Cs + 4));
+        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += xv[j];
+          s2[j] = fmaf(xv[j], xv[j], s2[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&s_red[0][c + j], s1[j]);
+        atomicAdd(&s_red[1][c + j], s2[j]);
+      }
+    }
+    __syncthreads();
+    const int cpg = a.C / a.groups;
+    if (tid < a.groups) {
+      double s = 0.0, ss = 0.0;
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+        s += (double)s_red[0][c];
+        ss += (double)s_red[1][c];
+      }
+      const double cnt = (double)cpg * HWs;
+      const double mean = s / cnt;
+      double var = ss / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_grp[tid][0] = mean;
+      s_grp[tid][1] = 1.0 / sqrt(var + 1e-5);
+    }
+    __syncthreads();
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      const int g = c / cpg;
+      const float sc = (float)s_grp[g][1] * a.gamma[c];
+      s_scale[c] = sc;
+      s_shift[c] = a.beta[c] - (float)s_grp[g][0] * sc;
+    }
+  } else {
+    for (int c = tid; c < a.C; c += blockDim.x) {
+      s_scale[c] = a.norm == NORM_AFFINE ? a.gamma[c] : 1.0f;
+      s_shift[c] = a.norm == NORM_AFFINE ? a.beta[c] : 0.0f;
+    }
+  }
+  __syncthreads();
+
+  const int P = a.Wo + 2;
+  const int CP8 = a.Cpad >> 3;
+  const int slots_img = (a.Ho + 1) * P;
+  uint4* out = reinterpret_cast<uint4*>(a.out);
+  if (n == 0)  // the leading zero row
+    for (int i = tid; i < P * CP8; i += blockDim.x) out[i] = make_uint4(0u, 0u, 0u, 0u);
+  const bool plain = (a.norm == NORM_NONE && a.act == ACT_NONE);
+  const size_t slot0 = (size_t)(1 + n * (a.Ho + 1)) * P;
+  for (int i = tid; i < slots_img * CP8; i += blockDim.x) {
+    const int pp = i / CP8;
+    const int c = (i - pp * CP8) << 3;
+    const int ho = pp / P, ww = pp - ho * P;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (ho < a.Ho && ww >= 1 && ww <= a.Wo && c < a.C) {
+      const int wo = ww - 1;
+      const int si = (c < C0) ? 0 : 1;
+      const int cl = si ? c - C0 : c;
+      const int Cs = a.src[si].C;
+      const float* base = a.src[si].p + (size_t)n * HWs * Cs + cl;
+      float v[8];
+      if (a.spatial == SP_POOL2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = -INFINITY;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const float* q = base + ((size_t)(2 * ho + dy) * a.Ws + (2 * wo + dx)) * Cs;
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(q));
+            const float4 x1 = __ldg(reinterpret_cast<const float4*>(q + 4));
+            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], fast_act(fmaf(xv[j], s_scale[c + j], s_shift[c + j]), a.act));
+          }
+      } else {
+        const int hs = (a.spatial == SP_UP2) ? (ho >> 1) : ho;
+        const int ws = (a.spatial == SP_UP2) ? (wo >> 1) : wo;
+        const float* q = base + ((size_t)hs * a.Ws + ws) * Cs;
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(q));
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(q + 4));
+        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = plain ? xv[j] : fast_act(fmaf(xv[j], s_scale[c + j], s_shift[c + j]), a.act);
+      }
+      o.x = pack2<FMT>(v[0], v[1]);
+      o.y = pack2<FMT>(v[2], v[3]);
+      o.z = pack2<FMT>(v[4], v[5]);
+      o.w = pack2<FMT>(v[6], v[7]);
+    }
+    out[(slot0 + pp) * CP8 + (c >> 3)] = o;
+  }
+}
+
+void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
+  RGFM_CHECK(a.C <= PACK_MAXC && a.C % 8 == 0 && a.Cpad % 8 == 0 && a.Cpad >= a.C, "pack_padded: channel counts");
+  RGFM_CHECK(a.src[0].C % 8 == 0, "pack_padded: first source channels must be a multiple of 8");
+  RGFM_CHECK(a.out_bf16 == 1 || a.out_bf16 == 2, "pack_padded: 16-bit output only");
+  if (a.out_bf16 == 1)
+    pack_padded_kernel<1><<<a.nimg, 256, 0, s>>>(a);
+  else
+    pack_padded_kernel<2><<<a.nimg, 256, 0, s>>>(a);
+  post_launch("pack_padded");
+}
+
+// Per-(image, channel) {sum, sumsq} of a raw NHWC fp32 tensor, one CTA per image (used where an fp32-operand pack
+// follows a producer that does not emit GroupNorm partials, i.e. the tcgen05 conv).
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int HW, int C, float* __restrict__ stats) {
+  const int n = blockIdx.x;
+  const float* src = x + (size_t)n * HW * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int p = 0; p < HW; ++p) {
+      const float v = src[(size_t)p * C + c];
+      s += v;
+      ss = fmaf(v, v, ss);
+    }
+    stats[((size_t)n * C + c) * 2] = s;
+    stats[((size_t)n * C + c) * 2 + 1] = ss;
+  }
+}
+void launch_gn_stats(const float* x, int HW, int C, float* stats, int nimg, cudaStream_t s) {
+  gn_stats_kernel<<<nimg, 256, 0, s>>>(x, HW, C, stats);
+  post_launch("gn_stats");
+}
+
 void launch_pack(const PackArgs& a, cudaStream_t s) {
   RGFM_CHECK(a.C <= PACK_MAXC && a.C % 4 == 0, "pack: channel count");
   RGFM_CHECK(a.groups <= 32, "pack: groups");
