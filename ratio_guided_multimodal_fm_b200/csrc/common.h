@@ -82,9 +82,16 @@ __host__ __device__ inline bool tile_row(const TileGeom& g, int tile, int r, int
 }
 
 // Raw (pre-norm) activation: fp32 NHWC plus optional per-(image, part, channel) {sum, sumsq} partials.
+// Pixel (n, h, w) of a raw activation -> element offset of its channel 0.  Dense NHWC, or the padded-linear layout
+// the tcgen05 conv stores with TMA: row index = GEMM row m' = (n*(H+1) + h)*(W+2) + w (pad rows/columns hold garbage).
+__host__ __device__ inline size_t raw_offset(int padded, int n, int h, int w, int H, int W, int C) {
+  return padded ? ((size_t)((size_t)n * (H + 1) + h) * (W + 2) + w) * C : (((size_t)n * H + h) * W + w) * C;
+}
+
 struct Act {
   float* p = nullptr;
   int H = 0, W = 0, C = 0;
+  bool padded = false;     // padded-linear layout (tcgen05 path)
   float* stats = nullptr;  // [n][parts][C][2]
   int parts = 0;
   size_t elems_per_img() const { return (size_t)H * W * C; }
@@ -108,6 +115,7 @@ struct PackSrc {
   const float* p;      // raw NHWC
   const float* stats;  // may be null when norm != GN
   int C, parts;
+  int padded;          // source layout (see raw_offset)
 };
 
 struct PackArgs {
@@ -123,6 +131,7 @@ struct PackArgs {
   void* out;
   int out_bf16;         // 0 = fp32, 1 = bf16, 2 = fp16
   int nimg;
+  void* out2;           // padded-linear layout only: optional second output, the un-normalised 16-bit copy of the sources
   int Cpad;             // padded-linear layout only: channels of the operand tensor (multiple of 64, zero filled)
 };
 
@@ -144,12 +153,13 @@ struct ConvArgs {
   float* out;         // OUT_RAW: NHWC [n][Ho][Wo][Cout]; OUT_NCHW: v[n][Cout][Ho][Wo]; OUT_EULER: x[n][Cout][Ho][Wo] += dt*val
   float* stats;       // [n][parts][Cout][2] or null
   float dt;
+  int out_padded;     // OUT_RAW: write the padded-linear layout (see raw_offset)
 };
 
 // ops_simt.cu
 void launch_pack(const PackArgs& a, cudaStream_t s);
 void launch_pack_padded(const PackArgs& a, cudaStream_t s);
-void launch_gn_stats(const float* x, int HW, int C, float* stats, int nimg, cudaStream_t s);
+void launch_gn_stats(const float* x, int H, int W, int C, int padded, float* stats, int nimg, cudaStream_t s);
 void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, int out_bf16, int nimg, cudaStream_t s);
 void launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 void launch_gap_fc(const float* in, int HW, int C, const float* w, const float* b, int Cout, float* out, int ld,

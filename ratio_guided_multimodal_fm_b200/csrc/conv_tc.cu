@@ -31,23 +31,26 @@ static inline void post_launch(const char* what) {
 
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_THREADS = 64 + 2 * 128;  // producer warp, MMA warp, two epilogue groups of 4 warps
-constexpr int TC_SUPER = 256;             // output slots per super-tile (two M=128 accumulators sharing every B tile)
+constexpr int TC_SUPER = 256;             // output rows per super-tile (two M=128 accumulators sharing every B tile)
+constexpr uint32_t TC_STAGE_BYTES = 128 * 128;  // epilogue staging buffer: 128 rows x 32 fp32, 128B-swizzled
 
 struct TcArgs {
-  ConvArgs c;        // epilogue description (bias, time bias, residual, output, stats, nimg, out_mode, dt)
-  int H, W, P;       // operand image geometry and padded pitch P = W + 2
-  int cblocks;       // operand channels / 64
-  int ntaps;         // 9 (3x3) or 1 (1x1)
-  int tap_shift[9];  // row shift of each tap inside the A tile: ky*P + kx
-  int a_box_rows;    // rows per TMA box; an A tile is two boxes
-  uint32_t a_slot;   // bytes of one A slot (2 * a_box_rows * 128)
-  uint32_t b_bytes;  // bytes of one B stage (CoutP * 128)
+  ConvArgs c;           // epilogue description (bias, time bias, output, nimg, out_mode, dt)
+  int H, W, P;          // operand image geometry and padded pitch P = W + 2
+  int nseg;             // K segments: [0] the conv proper, [1] the folded 1x1 skip conv / identity residual
+  int cblocks[2];       // operand channels / 64 per segment
+  int ntaps[2];         // 9 (3x3) or 1 (1x1)
+  int tap_shift[2][9];  // row shift of each tap inside the A tile: ky*P + kx (3x3), P+1 (1x1)
+  int a_box_rows;       // rows per TMA box; an A tile is two boxes
+  uint32_t a_slot;      // bytes of one A slot (2 * a_box_rows * 128)
+  uint32_t b_bytes;     // bytes of one B stage (CoutP * 128)
   int b_stages;
-  int nbuf;          // TMEM double buffering (2) when 4 * CoutP <= 512 columns, else 1
+  int nbuf;             // TMEM double buffering (2) when 4 * CoutP <= 512 columns, else 1
   uint32_t idesc;
   uint32_t tmem_cols;
-  int sub;           // stride-2: store rows with even (h, w) only
-  int out_H, out_W;  // output spatial size (H, W or halved when sub)
+  int sub;              // stride-2: store rows with even (h, w) only
+  int tma_store;        // raw output leaves through swizzled smem staging + TMA store (fully coalesced)
+  int out_H, out_W;     // output spatial size (H, W or halved when sub)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -152,6 +155,11 @@ __device__ __forceinline__ float transpose_reduce32(float* f, int lane) {
 }
 
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
 // decode padded-linear output index m' -> (image, h, w); valid iff a real pixel of an image < nimg
 __device__ __forceinline__ bool slot_pixel(int m, int H, int P, int nimg, int& n, int& h, int& w) {
   const int hv = m / P;
@@ -162,7 +170,9 @@ __device__ __forceinline__ bool slot_pixel(int m, int H, int P, int nimg, int& n
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmO, const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2];
   __shared__ __align__(8) uint64_t b_full[TC_MAX_STAGES], b_empty[TC_MAX_STAGES];
@@ -172,15 +182,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_b = smem_base + 2u * p.a_slot;
+  const uint32_t smem_stage = smem_base + 2u * p.a_slot;                       // epilogue staging (if tma_store)
+  const uint32_t smem_b = smem_stage + (p.tma_store ? 4u * TC_STAGE_BYTES : 0u);  // weight ring
   const ConvArgs& a = p.c;
   const int N = a.CoutP;
   const int total_rows = a.nimg * (p.H + 1) * p.P;
   const int supers = (total_rows + TC_SUPER - 1) / TC_SUPER;
 
   if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB0)) : "memory");
+    if (p.nseg > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA1)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB1)) : "memory");
+    }
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
@@ -217,18 +233,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ga = 0, gb = 0;  // ring positions, running across super-tiles
       for (int st = blockIdx.x; st < supers; st += gridDim.x) {
         const int row0 = st * TC_SUPER;
-        for (int cb = 0; cb < p.cblocks; ++cb, ++ga) {
-          const uint32_t as = ga & 1u;
-          mbar_wait(&a_empty[as], ((ga >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(&a_full[as], p.a_slot);
-          const uint32_t sa = smem_base + as * p.a_slot;
-          tma_load_2d(sa, &tmA, &a_full[as], cb * 64, row0);
-          tma_load_2d(sa + (p.a_slot >> 1), &tmA, &a_full[as], cb * 64, row0 + p.a_box_rows);
-          for (int tap = 0; tap < p.ntaps; ++tap, ++gb) {
-            const uint32_t bs = gb % p.b_stages;
-            mbar_wait(&b_empty[bs], ((gb / p.b_stages) & 1u) ^ 1u);
-            mbar_expect_tx(&b_full[bs], p.b_bytes);
-            tma_load_3d(smem_b + bs * p.b_bytes, &tmB, &b_full[bs], cb * 64, 0, tap);
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const CUtensorMap* tA = seg ? &tmA1 : &tmA0;
+          const CUtensorMap* tB = seg ? &tmB1 : &tmB0;
+          for (int cb = 0; cb < p.cblocks[seg]; ++cb, ++ga) {
+            const uint32_t as = ga & 1u;
+            mbar_wait(&a_empty[as], ((ga >> 1) & 1u) ^ 1u);
+            mbar_expect_tx(&a_full[as], p.a_slot);
+            const uint32_t sa = smem_base + as * p.a_slot;
+            tma_load_2d(sa, tA, &a_full[as], cb * 64, row0);
+            tma_load_2d(sa + (p.a_slot >> 1), tA, &a_full[as], cb * 64, row0 + p.a_box_rows);
+            for (int tap = 0; tap < p.ntaps[seg]; ++tap, ++gb) {
+              const uint32_t bs = gb % p.b_stages;
+              mbar_wait(&b_empty[bs], ((gb / p.b_stages) & 1u) ^ 1u);
+              mbar_expect_tx(&b_full[bs], p.b_bytes);
+              tma_load_3d(smem_b + bs * p.b_bytes, tB, &b_full[bs], cb * 64, 0, tap);
+            }
           }
         }
       }
@@ -244,27 +264,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // both epilogue groups drained this accumulator pair
         tc_fence_after();
         const uint32_t td0 = tmem_d + (uint32_t)(buf * 2 * N);
-        for (int cb = 0; cb < p.cblocks; ++cb, ++ga) {
-          const uint32_t as = ga & 1u;
-          mbar_wait(&a_full[as], (ga >> 1) & 1u);
-          tc_fence_after();
-          const uint32_t sa = smem_base + as * p.a_slot;
-          for (int tap = 0; tap < p.ntaps; ++tap, ++gb) {
-            const uint32_t bs = gb % p.b_stages;
-            mbar_wait(&b_full[bs], (gb / p.b_stages) & 1u);
+        uint32_t first = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          for (int cb = 0; cb < p.cblocks[seg]; ++cb, ++ga) {
+            const uint32_t as = ga & 1u;
+            mbar_wait(&a_full[as], (ga >> 1) & 1u);
             tc_fence_after();
-            // the tap is a ROW SHIFT of the shared A tile: descriptor start = tile base + shift * 128 B
-            const uint32_t a0 = sa + (uint32_t)p.tap_shift[tap] * 128u;
-            const uint64_t db = make_desc(smem_b + bs * p.b_bytes, 1024u, 2u);
+            const uint32_t sa = smem_base + as * p.a_slot;
+            for (int tap = 0; tap < p.ntaps[seg]; ++tap, ++gb) {
+              const uint32_t bs = gb % p.b_stages;
+              mbar_wait(&b_full[bs], (gb / p.b_stages) & 1u);
+              tc_fence_after();
+              // the tap is a ROW SHIFT of the shared A tile: descriptor start = tile base + shift * 128 B
+              const uint32_t a0 = sa + (uint32_t)p.tap_shift[seg][tap] * 128u;
+              const uint64_t db = make_desc(smem_b + bs * p.b_bytes, 1024u, 2u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 64 channels = 4 x K16; +32 bytes per step inside the swizzle atom
-              const uint32_t acc = (uint32_t)((cb | tap | k) != 0);
-              tc_mma_bf16(td0, make_desc(a0 + k * 32u, 1024u, 2u), db + (uint64_t)(2 * k), p.idesc, acc);
-              tc_mma_bf16(td0 + (uint32_t)N, make_desc(a0 + 128u * 128u + k * 32u, 1024u, 2u), db + (uint64_t)(2 * k), p.idesc, acc);
+              for (int k = 0; k < 4; ++k) {  // 64 channels = 4 x K16; +32 bytes per step inside the swizzle atom
+                tc_mma_bf16(td0, make_desc(a0 + k * 32u, 1024u, 2u), db + (uint64_t)(2 * k), p.idesc, first);
+                tc_mma_bf16(td0 + (uint32_t)N, make_desc(a0 + 128u * 128u + k * 32u, 1024u, 2u), db + (uint64_t)(2 * k), p.idesc, first);
+                first = 1;
+              }
+              tc_commit(&b_empty[bs]);
             }
-            tc_commit(&b_empty[bs]);
+            tc_commit(&a_empty[as]);
           }
-          tc_commit(&a_empty[as]);
         }
         tc_commit(&tmem_full_bar[buf]);
       }
@@ -274,12 +297,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------- epilogue: group eg owns rows [128*eg, 128*eg+128) of every super-tile ----------------
     const int eg = (warp - 2) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64 - eg * 128;
+    const int r = q * 32 + lane;  // row inside the 128-row unit
+    uint32_t sc = 0;              // staging-buffer use counter of this group
     int it = 0;
     for (int st = blockIdx.x; st < supers; st += gridDim.x, ++it) {
       const int buf = (p.nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
-      const int unit = st * 2 + eg;          // 128-row unit index
-      const int m = unit * 128 + q * 32 + lane;
+      const int unit = st * 2 + eg;  // 128-row unit index
+      const int m = unit * 128 + r;
       int n, h, w;
       bool valid = slot_pixel(m, p.H, p.P, a.nimg, n, h, w);
       if (p.sub) {
@@ -290,7 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + eg) * N);
       if (a.out_mode == OUT_RAW) {
-        const size_t o = valid ? (((size_t)n * p.out_H + h) * p.out_W + w) * a.Cout : 0;
+        const size_t o = valid ? raw_offset(a.out_padded, n, h, w, p.out_H, p.out_W, a.Cout) : 0;
         for (int c0 = 0; c0 < N; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
@@ -298,14 +324,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
-          if (valid) {
-            if (a.res) {
+          if (p.tma_store) {
+            // registers -> 128B-swizzled staging tile -> one TMA store of [128 rows x 32 channels]
+            const uint32_t stg = smem_stage + (uint32_t)(eg * 2 + (sc & 1u)) * TC_STAGE_BYTES;
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer free again?
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 rv = *reinterpret_cast<const float4*>(a.res + o + c0 + j);
-                f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
-              }
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t dst = stg + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                           "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (et == 0) {
+              tma_store_2d(&tmO, stg, c0, unit * 128);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++sc;
+          } else if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(a.out + o + c0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -332,6 +371,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if (p.tma_store && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the stores
   }
   tc_fence_before();
   __syncthreads();
@@ -359,10 +399,9 @@ static EncodeTiledFn encode_fn() {
 }
 
 struct TcConv {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA[2], tmB[2], tmO;
   TcArgs p;
   size_t smem;
-  uint16_t* w = nullptr;
 };
 void TcDeleter::operator()(TcConv* p) const { delete p; }
 
@@ -374,26 +413,29 @@ bool tc_available() {
 }
 
 size_t tc_operand_slots(int H, int W, int chunk) { return (size_t)(1 + (size_t)chunk * (H + 1)) * (W + 2); }
-int tc_stats_parts(int H, int W) { return ((H + 1) * (W + 2) - 1) / 128 + 2; }
+size_t tc_raw_rows(int H, int W, int chunk) { return (size_t)chunk * (H + 1) * (W + 2); }
+
+static void encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner, uint64_t rows,
+                      uint32_t box_inner, uint32_t box_rows, const char* what) {
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * esize};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(tm, dt, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RGFM_CHECK(r == CUDA_SUCCESS, std::string("cuTensorMapEncodeTiled(") + what + ") failed with code " + std::to_string((int)r));
+}
 
 TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
-  RGFM_CHECK(d.Cin % 64 == 0, "tc conv: operand channels must be a multiple of 64");
   RGFM_CHECK(d.CoutP % 16 == 0 && d.CoutP >= 16 && d.CoutP <= 256, "tc conv: padded Cout must be 16..256, multiple of 16");
-  RGFM_CHECK(d.ks == 1 || d.ks == 3, "tc conv: 1x1 or 3x3");
   RGFM_CHECK(d.Win + 2 <= 39, "tc conv: image width must be <= 37");
+  RGFM_CHECK(d.nseg == 1 || d.nseg == 2, "tc conv: one or two K segments");
   TcPtr t(new TcConv());
   TcArgs& p = t->p;
   std::memset(&p, 0, sizeof(p));
   const int P = d.Win + 2;
   p.H = d.Hin; p.W = d.Win; p.P = P;
-  p.cblocks = d.Cin / 64;
-  p.ntaps = d.ks * d.ks;
-  if (d.ks == 3) {
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) p.tap_shift[ky * 3 + kx] = ky * P + kx;
-  } else {
-    p.tap_shift[0] = P + 1;
-  }
+  p.nseg = d.nseg;
   const int rows_needed = TC_SUPER + 2 * P + 2;
   p.a_box_rows = ((rows_needed + 1) / 2 + 7) / 8 * 8;
   RGFM_CHECK(p.a_box_rows <= 256, "tc conv: A box too tall");
@@ -405,51 +447,65 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.nbuf * d.CoutP)) cols <<= 1;
   p.tmem_cols = cols;
-  int stages = (int)((196u * 1024u - 2u * p.a_slot) / p.b_bytes);
+  p.tma_store = (d.out != nullptr && d.CoutP <= 128 && d.Cout == d.CoutP && d.Cout % 32 == 0) ? 1 : 0;
+  const uint32_t fixed = 2u * p.a_slot + (p.tma_store ? 4u * TC_STAGE_BYTES : 0u);
+  int stages = (int)((198u * 1024u - fixed) / p.b_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   RGFM_CHECK(stages >= 2, "tc conv: not enough shared memory for the weight ring");
   p.b_stages = stages;
-  t->smem = 2 * (size_t)p.a_slot + (size_t)stages * p.b_bytes + 1024;
-
-  // weights: torch [Cout][Cin_real][ks][ks] fp32 -> [tap][CoutP][Cin] 16-bit (zero padded)
-  const int taps = p.ntaps;
-  std::vector<uint16_t> hw((size_t)taps * d.CoutP * d.Cin, 0);
-  for (int o = 0; o < d.Cout; ++o)
-    for (int c = 0; c < d.Cin_real; ++c)
-      for (int tp = 0; tp < taps; ++tp) {
-        const float wv = d.w_oihw[((size_t)o * d.Cin_real + c) * taps + tp];
-        uint16_t bits;
-        if (d.fp16) {
-          const __half hv = __float2half_rn(wv);
-          std::memcpy(&bits, &hv, 2);
-        } else {
-          const __nv_bfloat16 hv = __float2bfloat16(wv);
-          std::memcpy(&bits, &hv, 2);
-        }
-        hw[((size_t)tp * d.CoutP + o) * d.Cin + c] = bits;
-      }
-  t->w = pool.upload(hw);
+  t->smem = (size_t)fixed + (size_t)stages * p.b_bytes + 1024;
 
   const CUtensorMapDataType dt16 = d.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  {
+  for (int sg = 0; sg < d.nseg; ++sg) {
+    const TcSegment& S = d.seg[sg];
+    RGFM_CHECK(S.Cin % 64 == 0, "tc conv: operand channels must be a multiple of 64");
+    RGFM_CHECK(S.ks == 1 || S.ks == 3, "tc conv: 1x1 or 3x3");
+    p.cblocks[sg] = S.Cin / 64;
+    p.ntaps[sg] = S.ks * S.ks;
+    if (S.ks == 3) {
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) p.tap_shift[sg][ky * 3 + kx] = ky * P + kx;
+    } else {
+      p.tap_shift[sg][0] = P + 1;
+    }
+    // weights: torch [Cout][Cin_real][ks][ks] fp32 (or identity when w_oihw == nullptr) -> [tap][CoutP][Cin] 16-bit
+    const int taps = p.ntaps[sg];
+    std::vector<uint16_t> hw((size_t)taps * d.CoutP * S.Cin, 0);
+    for (int o = 0; o < d.Cout; ++o)
+      for (int c = 0; c < S.Cin_real; ++c)
+        for (int tp = 0; tp < taps; ++tp) {
+          const float wv = S.w_oihw ? S.w_oihw[((size_t)o * S.Cin_real + c) * taps + tp] : (o == c ? 1.0f : 0.0f);
+          uint16_t bits;
+          if (d.fp16) {
+            const __half hv = __float2half_rn(wv);
+            std::memcpy(&bits, &hv, 2);
+          } else {
+            const __nv_bfloat16 hv = __float2bfloat16(wv);
+            std::memcpy(&bits, &hv, 2);
+          }
+          hw[((size_t)tp * d.CoutP + o) * S.Cin + c] = bits;
+        }
+    uint16_t* dw = pool.upload(hw);
     // operand: 2-D [slots][Cin]; out-of-range rows of the last tile are zero-filled by TMA
-    cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)tc_operand_slots(d.Hin, d.Win, d.chunk)};
-    cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)p.a_box_rows};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = encode_fn()(&t->tmA, dt16, 2, const_cast<void*>(d.in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RGFM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed with code " + std::to_string((int)r));
+    encode_2d(&t->tmA[sg], dt16, 2, S.in, (uint64_t)S.Cin, tc_operand_slots(d.Hin, d.Win, d.chunk), 64, (uint32_t)p.a_box_rows, "A");
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)S.Cin, (cuuint64_t)d.CoutP, (cuuint64_t)taps};
+      cuuint64_t strides[2] = {(cuuint64_t)S.Cin * 2, (cuuint64_t)d.CoutP * S.Cin * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)d.CoutP, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult r = encode_fn()(&t->tmB[sg], dt16, 3, dw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      RGFM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with code " + std::to_string((int)r));
+    }
   }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)d.CoutP, (cuuint64_t)taps};
-    cuuint64_t strides[2] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.CoutP * d.Cin * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)d.CoutP, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encode_fn()(&t->tmB, dt16, 3, t->w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RGFM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with code " + std::to_string((int)r));
+  if (d.nseg == 1) {
+    t->tmA[1] = t->tmA[0];
+    t->tmB[1] = t->tmB[0];
   }
+  if (p.tma_store)
+    encode_2d(&t->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out, (uint64_t)d.Cout, tc_raw_rows(d.Hin, d.Win, d.chunk), 32, 128, "out");
+  else
+    t->tmO = t->tmA[0];
   static bool attr = false;
   if (!attr) {
     RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -464,9 +520,14 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
   p.sub = (a.stride == 2) ? 1 : 0;
   p.out_H = p.sub ? p.H / 2 : p.H;
   p.out_W = p.sub ? p.W / 2 : p.W;
-  RGFM_CHECK(a.stats == nullptr, "tc conv: GroupNorm statistics are computed by the consumer pack, not here");
-  if (a.out_mode != OUT_RAW) RGFM_CHECK(a.CoutP == 16, "tc conv: the output conv uses a 16-column accumulator");
-  else RGFM_CHECK(a.CoutP % 32 == 0 && a.Cout == a.CoutP, "tc conv: raw outputs need Cout % 32 == 0");
+  if (p.sub) p.tma_store = 0;
+  RGFM_CHECK(a.stats == nullptr && a.res == nullptr, "tc conv: statistics and residuals are handled by pack / the folded K segment");
+  if (a.out_mode != OUT_RAW) {
+    RGFM_CHECK(a.CoutP == 16, "tc conv: the output conv uses a 16-column accumulator");
+    p.tma_store = 0;
+  } else {
+    RGFM_CHECK(a.CoutP % 32 == 0 && a.Cout == a.CoutP && a.out_padded, "tc conv: raw outputs need Cout % 32 == 0 and the padded-linear layout");
+  }
   const int total_rows = a.nimg * (p.H + 1) * p.P;
   const int supers = (total_rows + TC_SUPER - 1) / TC_SUPER;
   static int num_sms = 0;
@@ -476,7 +537,7 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = supers < num_sms ? supers : num_sms;  // persistent: one CTA per SM, static round-robin
-  conv_tc_kernel<<<grid, TC_THREADS, tc.smem, s>>>(tc.tmA, tc.tmB, p);
+  conv_tc_kernel<<<grid, TC_THREADS, tc.smem, s>>>(tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmO, p);
   post_launch("conv_tc");
 }
 

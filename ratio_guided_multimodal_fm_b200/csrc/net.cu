@@ -72,15 +72,18 @@ struct Builder {
   const WeightMap& W;
   DevPool& pool;
   int chunk;
-  bool tc;    // 16-bit tensor-core convs
-  bool fp16;  // 16-bit operand format: fp16 (true) or bf16
+  bool tc;       // route the NEXT conv to the tensor cores (toggled off around the K=9/27 input convs)
+  bool tc_mode;  // the net runs in a 16-bit tensor-core precision
+  bool fp16;     // 16-bit operand format: fp16 (true) or bf16
 
-  Builder(Net& n, const WeightMap& w) : net(n), W(w), pool(n.pool_), chunk(n.chunk_), tc(n.precision_ == RGFM_PREC_BF16 || n.precision_ == RGFM_PREC_FP16), fp16(n.precision_ == RGFM_PREC_FP16) {}
+  Builder(Net& n, const WeightMap& w) : net(n), W(w), pool(n.pool_), chunk(n.chunk_), tc(n.precision_ == RGFM_PREC_BF16 || n.precision_ == RGFM_PREC_FP16), tc_mode(tc), fp16(n.precision_ == RGFM_PREC_FP16) {}
 
   Act new_act(int H, int Wd, int C, int parts) {
     Act a;
     a.H = H; a.W = Wd; a.C = C;
-    a.p = (float*)pool.alloc((size_t)chunk * H * Wd * C * sizeof(float));
+    a.padded = tc_mode;  // every raw activation of a tensor-core net lives in the padded-linear layout
+    const size_t rows = a.padded ? tc_raw_rows(H, Wd, chunk) : (size_t)chunk * H * Wd;
+    a.p = (float*)pool.alloc(rows * C * sizeof(float));
     if (parts > 0) {
       a.parts = parts;
       a.stats = (float*)pool.alloc((size_t)chunk * parts * C * 2 * sizeof(float));
@@ -138,22 +141,22 @@ struct Builder {
   }
 
   Packed pack(const std::vector<Act>& srcs, int norm, const float* gamma, const float* beta, int act, int spatial,
-              bool out_bf16) {
+              bool out_bf16, Packed* raw16 = nullptr) {
     PackArgs a{};
     a.nsrc = (int)srcs.size();
     RGFM_CHECK(a.nsrc >= 1 && a.nsrc <= 2, "pack: 1 or 2 sources");
     int C = 0;
     std::vector<float*> tmp_stats;
     for (int i = 0; i < a.nsrc; ++i) {
-      a.src[i] = PackSrc{srcs[i].p, srcs[i].stats, srcs[i].C, srcs[i].parts};
+      a.src[i] = PackSrc{srcs[i].p, srcs[i].stats, srcs[i].C, srcs[i].parts, srcs[i].padded ? 1 : 0};
       if (norm == NORM_GN && !out_bf16 && srcs[i].stats == nullptr) {
         // fp32-operand pack after a producer without GroupNorm partials (tcgen05 conv): compute them here
         float* st = (float*)pool.alloc((size_t)chunk * srcs[i].C * 2 * sizeof(float));
         tmp_stats.push_back(st);
         const float* src = srcs[i].p;
-        const int HW = srcs[i].H * srcs[i].W, Cs = srcs[i].C;
-        net.ops_.push_back({[=](const RunCtx& c) { launch_gn_stats(src, HW, Cs, st, c.nimg, c.s); }, "gn_stats", 0.0,
-                            (double)HW * Cs * 4.0});
+        const int Hh = srcs[i].H, Ww = srcs[i].W, Cs = srcs[i].C, pd = srcs[i].padded ? 1 : 0;
+        net.ops_.push_back({[=](const RunCtx& c) { launch_gn_stats(src, Hh, Ww, Cs, pd, st, c.nimg, c.s); }, "gn_stats", 0.0,
+                            (double)Hh * Ww * Cs * 4.0});
         a.src[i].stats = st;
         a.src[i].parts = 1;
       }
@@ -168,7 +171,13 @@ struct Builder {
     Packed p = new_packed(a.Ho, a.Wo, C, out_bf16);
     a.out = p.p; a.out_bf16 = out_bf16 ? (fp16 ? 2 : 1) : 0;
     a.Cpad = p.C;
-    const double bytes = (double)a.Hs * a.Ws * C * 4.0 + (double)a.Ho * a.Wo * C * (out_bf16 ? 2.0 : 4.0);
+    a.out2 = nullptr;
+    if (raw16) {
+      RGFM_CHECK(out_bf16 && spatial == SP_ID, "pack: the raw 16-bit copy needs a padded 16-bit pack without resampling");
+      *raw16 = new_packed(a.Ho, a.Wo, C, true);
+      a.out2 = raw16->p;
+    }
+    const double bytes = (double)a.Hs * a.Ws * C * 4.0 + (double)a.Ho * a.Wo * C * (out_bf16 ? 2.0 : 4.0) * (raw16 ? 2.0 : 1.0);
     const bool padded = p.padded;
     net.ops_.push_back({[a, padded](const RunCtx& c) {
       PackArgs b = a;
@@ -183,8 +192,11 @@ struct Builder {
   static bool tc_stats_ok(int H, int Wd) { return (H + 1) * (Wd + 2) >= 64; }
 
   // generic conv; returns raw activation (or none when `final`)
+  // `skip` (tensor-core path only): a second K segment accumulated into the same tile -- the ResBlock's 1x1 skip conv
+  // over the raw 16-bit copy of the block input (weights `skip_w`), or the identity residual when skip_w is empty.
   Act conv(const Packed& in, const std::string& wname, int cin_real, int cout, int ks, int stride, int temb_off,
-           const float* res, bool stats, bool final) {
+           const float* res, bool stats, bool final, const Packed* skip = nullptr, const std::string& skip_w = "",
+           int skip_cin_real = 0) {
     const int pad = ks / 2;
     const int Ho = (in.H + 2 * pad - ks) / stride + 1, Wo = (in.W + 2 * pad - ks) / stride + 1;
     const bool use_tc = tc && in.bf16;
@@ -194,7 +206,16 @@ struct Builder {
     const int coutP = (use_tc && final) ? 16 : (cout + 31) / 32 * 32;
     ConvArgs a{};
     a.in = in.p; a.Hin = in.H; a.Win = in.W; a.Cin = in.C;
-    a.bias = vec(wname + ".bias", cout, coutP);
+    if (skip && !skip_w.empty()) {  // conv bias + folded skip-conv bias
+      const float* b0 = W.get(wname + ".bias", cout);
+      const float* b1 = W.get(skip_w + ".bias", cout);
+      std::vector<float> bs(coutP, 0.f);
+      for (int i = 0; i < cout; ++i) bs[i] = b0[i] + b1[i];
+      a.bias = pool.upload(bs);
+    } else {
+      a.bias = vec(wname + ".bias", cout, coutP);
+    }
+    a.out_padded = tc_mode ? 1 : 0;
     a.temb_off = temb_off < 0 ? 0 : temb_off;
     a.res = res;
     a.CoutP = coutP; a.Cout = cout; a.ks = ks; a.stride = stride; a.pad = pad;
@@ -208,16 +229,25 @@ struct Builder {
     }
     TcConv* tcp = nullptr;
     if (use_tc) {
-      TcConvDesc d{in.H, in.W, in.C, cout, coutP, ks, chunk, in.p, W.get(wname + ".weight", (int64_t)cout * cin_real * ks * ks), cin_real, fp16};
+      TcConvDesc d{};
+      d.Hin = in.H; d.Win = in.W; d.Cout = cout; d.CoutP = coutP; d.chunk = chunk; d.fp16 = fp16;
+      d.nseg = skip ? 2 : 1;
+      d.seg[0] = TcSegment{in.p, in.C, cin_real, ks, W.get(wname + ".weight", (int64_t)cout * cin_real * ks * ks)};
+      if (skip) {
+        RGFM_CHECK(skip->padded && skip->H == in.H && skip->W == in.W, "conv: skip operand geometry");
+        const float* sw = skip_w.empty() ? nullptr : W.get(skip_w + ".weight", (int64_t)cout * skip_cin_real);
+        d.seg[1] = TcSegment{skip->p, skip->C, skip_cin_real, 1, sw};
+      }
+      d.out = (final || stride != 1) ? nullptr : o.p;
       net.tc_.push_back(make_tc_conv(d, pool));
       tcp = net.tc_.back().get();
     } else {
-      RGFM_CHECK(!in.bf16, "SIMT conv needs an fp32 operand");
+      RGFM_CHECK(!in.bf16 && !skip, "SIMT conv needs an fp32 operand and has no folded skip segment");
       a.w = conv_w_simt(wname + ".weight", cout, cin_real, ks, in.C, coutP);
     }
     const bool has_temb = temb_off >= 0;
     Net* np = &net;
-    const double flops = 2.0 * Ho * Wo * (double)cout * cin_real * ks * ks;
+    const double flops = 2.0 * Ho * Wo * (double)cout * (cin_real * ks * ks + (skip && !skip_w.empty() ? skip_cin_real : 0));
     const double bytes = (double)in.H * in.W * in.C * (in.bf16 ? 2.0 : 4.0) + (double)Ho * Wo * cout * 4.0 * (res ? 2.0 : 1.0);
     net.ops_.push_back({[a, tcp, final, has_temb, np](const RunCtx& c) {
       ConvArgs b = a;
@@ -258,6 +288,23 @@ struct Builder {
     net.tmlps_.push_back(std::move(tm));
     const int toff = net.tmlps_.back().off;
 
+    if (tc) {
+      // tensor-core path: 2 packs + 2 convs.  The first pack also emits the raw 16-bit copy of x, which conv2 consumes
+      // as a second K segment (1x1 skip conv, or identity weights for the plain residual) -- no separate skip
+      // kernel, no residual read in the epilogue.
+      Packed x16;
+      Packed a1 = pack(x, NORM_GN, vec(p + "norm1.weight", cin), vec(p + "norm1.bias", cin), ACT_SILU, SP_ID, true, &x16);
+      Act h1 = conv(a1, p + "conv1", cin, cout, 3, 1, toff, nullptr, false, false);
+      release(a1);
+      Packed a2 = pack({h1}, NORM_GN, vec(p + "norm2.weight", cout), vec(p + "norm2.bias", cout), ACT_SILU, SP_ID, true);
+      release(h1);
+      const bool has_skip = W.has(p + "skip.weight");
+      if (!has_skip) RGFM_CHECK(cin == cout, "resblock: identity skip needs matching channels");
+      Act out = conv(a2, p + "conv2", cout, cout, 3, 1, -1, nullptr, false, false, &x16, has_skip ? p + "skip" : std::string(), cin);
+      release(a2);
+      release(x16);
+      return out;
+    }
     Packed a1 = pack(x, NORM_GN, vec(p + "norm1.weight", cin), vec(p + "norm1.bias", cin), ACT_SILU, SP_ID, tc);
     Act h1 = conv(a1, p + "conv1", cin, cout, 3, 1, toff, nullptr, true, false);
     release(a1);

@@ -95,21 +95,27 @@ class Net {
   int temb_rows_ = 0;
 };
 
-// conv_tc.cu -- tcgen05 implicit-GEMM convolution (bf16 operands, fp32 accumulate in TMEM)
-struct TcConvDesc {
-  int Hin, Win, Cin;     // operand geometry; Cin = padded channel count of the padded-linear operand tensor
-  int Cout, CoutP;       // real / padded output channels
-  int ks;                // 1 or 3 (stride 1, pad ks/2)
-  int chunk;             // max images
+// conv_tc.cu -- tcgen05 implicit-GEMM convolution (16-bit operands, fp32 accumulate in TMEM)
+struct TcSegment {
   const void* in;        // 16-bit padded-linear operand buffer [slots][Cin]
-  const float* w_oihw;   // host weights, torch layout [Cout][Cin_real][ks][ks]
+  int Cin;               // operand channels (multiple of 64, zero padded)
   int Cin_real;
+  int ks;                // 1 or 3
+  const float* w_oihw;   // host weights, torch layout [Cout][Cin_real][ks][ks]; nullptr = identity (folded residual)
+};
+struct TcConvDesc {
+  int Hin, Win;          // operand image geometry (stride-1 output geometry)
+  int Cout, CoutP;       // real / padded output channels
+  int chunk;             // max images
+  int nseg;              // 1, or 2 when a 1x1 skip conv / identity residual is folded in as extra K
+  TcSegment seg[2];
+  float* out;            // raw padded-linear fp32 output buffer (TMA store) or nullptr
   bool fp16;             // operand format: fp16 (true) or bf16 (false); fp32 accumulate either way
 };
 TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool);
 void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s);
 bool tc_available();
-size_t tc_operand_slots(int H, int W, int chunk);  // rows of the padded-linear operand tensor
-int tc_stats_parts(int H, int W);                  // GroupNorm partial-sum slots per image written by the tcgen05 conv
+size_t tc_operand_slots(int H, int W, int chunk);  // rows of a padded-linear operand tensor
+size_t tc_raw_rows(int H, int W, int chunk);       // rows of a padded-linear raw activation tensor
 
 }  // namespace rgfm

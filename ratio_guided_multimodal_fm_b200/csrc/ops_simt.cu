@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     const int si = (c < C0) ? 0 : 1;
     const int cl = si ? c - C0 : c;
     const int Cs = a.src[si].C;
-    const float* base = a.src[si].p + (size_t)n * a.Hs * a.Ws * Cs + cl;
+    const float* base = a.src[si].p + cl;
+    const int spad = a.src[si].padded;
     float4 r;
     if (a.spatial == SP_POOL2) {
       r = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-          float4 v = __ldg(reinterpret_cast<const float4*>(base + ((size_t)(2 * ho + dy) * a.Ws + (2 * wo + dx)) * Cs));
+          float4 v = __ldg(reinterpret_cast<const float4*>(base + raw_offset(spad, n, 2 * ho + dy, 2 * wo + dx, a.Hs, a.Ws, Cs)));
           v.x = apply_act(v.x * s_scale[c] + s_shift[c], a.act);
           v.y = apply_act(v.y * s_scale[c + 1] + s_shift[c + 1], a.act);
           v.z = apply_act(v.z * s_scale[c + 2] + s_shift[c + 2], a.act);
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     } else {
       const int hs = (a.spatial == SP_UP2) ? (ho >> 1) : ho;
       const int ws = (a.spatial == SP_UP2) ? (wo >> 1) : wo;
-      r = __ldg(reinterpret_cast<const float4*>(base + ((size_t)hs * a.Ws + ws) * Cs));
+      r = __ldg(reinterpret_cast<const float4*>(base + raw_offset(spad, n, hs, ws, a.Hs, a.Ws, Cs)));
       if (!plain) {
         r.x = apply_act(r.x * s_scale[c] + s_shift[c], a.act);
         r.y = apply_act(r.y * s_scale[c + 1] + s_shift[c + 1], a.act);
@@ -233,13 +234,16 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
       const int si = (c < C0) ? 0 : 1;
       const int cl = si ? c - C0 : c;
       const int Cs = a.src[si].C;
-      const float* base = a.src[si].p + (size_t)n * HWs * Cs + cl;
+      const float* base = a.src[si].p + cl;
+      const int spad = a.src[si].padded;
       float s1[8], s2[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
       for (int p = pl; p < HWs; p += PL) {
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * Cs));
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * Cs + 4));
+        const int ph = p / a.Ws, pw = p - ph * a.Ws;
+        const float* q = base + raw_offset(spad, n, ph, pw, a.Hs, a.Ws, Cs);
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(q));
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(q + 4));
         const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -287,21 +291,26 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
   const int CP8 = a.Cpad >> 3;
   const int slots_img = (a.Ho + 1) * P;
   uint4* out = reinterpret_cast<uint4*>(a.out);
+  uint4* out2 = reinterpret_cast<uint4*>(a.out2);
   if (n == 0)  // the leading zero row
-    for (int i = tid; i < P * CP8; i += blockDim.x) out[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < P * CP8; i += blockDim.x) {
+      out[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (out2) out2[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
   const bool plain = (a.norm == NORM_NONE && a.act == ACT_NONE);
   const size_t slot0 = (size_t)(1 + n * (a.Ho + 1)) * P;
   for (int i = tid; i < slots_img * CP8; i += blockDim.x) {
     const int pp = i / CP8;
     const int c = (i - pp * CP8) << 3;
     const int ho = pp / P, ww = pp - ho * P;
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u), o2 = o;
     if (ho < a.Ho && ww >= 1 && ww <= a.Wo && c < a.C) {
       const int wo = ww - 1;
       const int si = (c < C0) ? 0 : 1;
       const int cl = si ? c - C0 : c;
       const int Cs = a.src[si].C;
-      const float* base = a.src[si].p + (size_t)n * HWs * Cs + cl;
+      const float* base = a.src[si].p + cl;
+      const int spad = a.src[si].padded;
       float v[8];
       if (a.spatial == SP_POOL2) {
 #pragma unroll
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
           for (int dx = 0; dx < 2; ++dx) {
-            const float* q = base + ((size_t)(2 * ho + dy) * a.Ws + (2 * wo + dx)) * Cs;
+            const float* q = base + raw_offset(spad, n, 2 * ho + dy, 2 * wo + dx, a.Hs, a.Ws, Cs);
             const float4 x0 = __ldg(reinterpret_cast<const float4*>(q));
             const float4 x1 = __ldg(reinterpret_cast<const float4*>(q + 4));
             const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
@@ -320,12 +329,18 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
       } else {
         const int hs = (a.spatial == SP_UP2) ? (ho >> 1) : ho;
         const int ws = (a.spatial == SP_UP2) ? (wo >> 1) : wo;
-        const float* q = base + ((size_t)hs * a.Ws + ws) * Cs;
+        const float* q = base + raw_offset(spad, n, hs, ws, a.Hs, a.Ws, Cs);
         const float4 x0 = __ldg(reinterpret_cast<const float4*>(q));
         const float4 x1 = __ldg(reinterpret_cast<const float4*>(q + 4));
         const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = plain ? xv[j] : fast_act(fmaf(xv[j], s_scale[c + j], s_shift[c + j]), a.act);
+        if (out2) {  // second output: the raw (un-normalised) 16-bit copy, operand of the folded skip / identity segment
+          o2.x = pack2<FMT>(xv[0], xv[1]);
+          o2.y = pack2<FMT>(xv[2], xv[3]);
+          o2.z = pack2<FMT>(xv[4], xv[5]);
+          o2.w = pack2<FMT>(xv[6], xv[7]);
+        }
       }
       o.x = pack2<FMT>(v[0], v[1]);
       o.y = pack2<FMT>(v[2], v[3]);
@@ -333,6 +348,7 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
       o.w = pack2<FMT>(v[6], v[7]);
     }
     out[(slot0 + pp) * CP8 + (c >> 3)] = o;
+    if (out2) out2[(slot0 + pp) * CP8 + (c >> 3)] = o2;
   }
 }
 
@@ -349,13 +365,13 @@ void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
 
 // Per-(image, channel) {sum, sumsq} of a raw NHWC fp32 tensor, one CTA per image (used where an fp32-operand pack
 // follows a producer that does not emit GroupNorm partials, i.e. the tcgen05 conv).
-__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int HW, int C, float* __restrict__ stats) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int H, int W, int C, int padded,
+                                                       float* __restrict__ stats) {
   const int n = blockIdx.x;
-  const float* src = x + (size_t)n * HW * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f, ss = 0.f;
-    for (int p = 0; p < HW; ++p) {
-      const float v = src[(size_t)p * C + c];
+    for (int p = 0; p < H * W; ++p) {
+      const float v = x[raw_offset(padded, n, p / W, p % W, H, W, C) + c];
       s += v;
       ss = fmaf(v, v, ss);
     }
@@ -363,8 +379,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     stats[((size_t)n * C + c) * 2 + 1] = ss;
   }
 }
-void launch_gn_stats(const float* x, int HW, int C, float* stats, int nimg, cudaStream_t s) {
-  gn_stats_kernel<<<nimg, 256, 0, s>>>(x, HW, C, stats);
+void launch_gn_stats(const float* x, int H, int W, int C, int padded, float* stats, int nimg, cudaStream_t s) {
+  gn_stats_kernel<<<nimg, 256, 0, s>>>(x, H, W, C, padded, stats);
   post_launch("gn_stats");
 }
 
@@ -477,7 +493,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
         const size_t o = (((size_t)n * a.g.H + ho) * a.g.W + wo) * a.Cout + co;
         if (a.res) val += a.res[o];
         if (a.out_mode == OUT_RAW) {
-          a.out[o] = val;
+          a.out[a.out_padded ? raw_offset(1, n, ho, wo, a.g.H, a.g.W, a.Cout) + co : o] = val;
         } else {
           const size_t oc = (((size_t)n * a.Cout + co) * a.g.H + ho) * a.g.W + wo;
           if (a.out_mode == OUT_NCHW)
