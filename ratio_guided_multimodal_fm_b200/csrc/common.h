@@ -179,6 +179,7 @@ void launch_euler(float* x, const float* v, float dt, size_t n, cudaStream_t s);
 
 struct ProfRec {  // one timed op launch (CUDA events on the launching stream)
   const char* kind;
+  const char* label = nullptr;  // optional per-op description (RGFM_PROFILE_VERBOSE)
   cudaEvent_t e0, e1;
   double flops, bytes;
 };
@@ -188,7 +189,7 @@ struct ProfScope {  // brackets a launch with events when profiling is on
   ProfRec r;
   ProfScope(std::vector<ProfRec>* p, cudaStream_t st, const char* kind, double flops, double bytes) : prof(p), s(st) {
     if (!prof) return;
-    r = ProfRec{kind, nullptr, nullptr, flops, bytes};
+    r = ProfRec{kind, nullptr, nullptr, nullptr, flops, bytes};
     cudaEventCreate(&r.e0);
     cudaEventCreate(&r.e1);
     cudaEventRecord(r.e0, s);

@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstring>
+#include <cstdlib>
 
 namespace rgfm {
 
@@ -29,8 +30,8 @@ static inline void post_launch(const char* what) {
   ++g_launch_counter;
 }
 
-constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 64 + 2 * 128;  // producer warp, MMA warp, two epilogue groups of 4 warps
+constexpr int TC_MAX_STAGES = 12;
+constexpr int TC_THREADS = 96 + 2 * 128;  // producer warp, two MMA warps (one per accumulator half), two epilogue groups of 4 warps
 constexpr int TC_SUPER = 256;             // output rows per super-tile (two M=128 accumulators sharing every B tile)
 constexpr uint32_t TC_STAGE_BYTES = 128 * 128;  // epilogue staging buffer: 128 rows x 32 fp32, 128B-swizzled
 
@@ -43,7 +44,9 @@ struct TcArgs {
   int tap_shift[2][9];  // row shift of each tap inside the A tile: ky*P + kx (3x3), P+1 (1x1)
   int a_box_rows;       // rows per TMA box; an A tile is two boxes
   uint32_t a_slot;      // bytes of one A slot (2 * a_box_rows * 128)
-  uint32_t b_bytes;     // bytes of one B stage (CoutP * 128)
+  uint32_t b_bytes;     // bytes of one weight tap tile (CoutP * 128)
+  uint32_t b_stage;     // bytes of one weight-ring stage (taps_per_stage * b_bytes)
+  int tps[2];           // taps per weight-ring stage, per segment: barrier round trips are amortised over tps*4 MMAs
   int b_stages;
   int nbuf;             // TMEM double buffering (2) when 4 * CoutP <= 512 columns, else 1
   uint32_t idesc;
@@ -51,6 +54,7 @@ struct TcArgs {
   int sub;              // stride-2: store rows with even (h, w) only
   int tma_store;        // raw output leaves through swizzled smem staging + TMA store (fully coalesced)
   int out_H, out_W;     // output spatial size (H, W or halved when sub)
+  int dbg;              // experiment switches (RGFM_TC_DBG): 1 = epilogue does no work, 2 = producer loads nothing
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -101,6 +105,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -113,6 +122,15 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_acc(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
@@ -183,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_stage = smem_base + 2u * p.a_slot;                       // epilogue staging (if tma_store)
-  const uint32_t smem_b = smem_stage + (p.tma_store ? 4u * TC_STAGE_BYTES : 0u);  // weight ring
+  const uint32_t smem_b = smem_stage + (p.tma_store ? 2u * TC_STAGE_BYTES : 0u);  // weight ring
   const ConvArgs& a = p.c;
   const int N = a.CoutP;
   const int total_rows = a.nimg * (p.H + 1) * p.P;
@@ -199,13 +217,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);
-      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&a_empty[s], 2);         // both MMA warps
+      mbar_init(&tmem_full_bar[s], 2);   // both MMA warps
       mbar_init(&tmem_empty_bar[s], 256);
     }
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], 2);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -213,10 +231,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2) {
+  if (warp >= 3) {
     // bias + this step's time bias: identical for every tile of the launch (t is uniform over the batch)
     const float* tb = a.temb ? a.temb + (size_t)(a.step ? *a.step : 0) * a.temb_stride + a.temb_off : nullptr;
-    for (int c = threadIdx.x - 64; c < N; c += TC_THREADS - 64) {
+    for (int c = threadIdx.x - 96; c < N; c += TC_THREADS - 96) {
       float b = a.bias[c];
       if (tb && c < a.Cout) b += tb[c];
       s_bias[c] = b;
@@ -229,75 +247,114 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
-      uint32_t ga = 0, gb = 0;  // ring positions, running across super-tiles
-      for (int st = blockIdx.x; st < supers; st += gridDim.x) {
-        const int row0 = st * TC_SUPER;
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          const CUtensorMap* tA = seg ? &tmA1 : &tmA0;
-          const CUtensorMap* tB = seg ? &tmB1 : &tmB0;
-          for (int cb = 0; cb < p.cblocks[seg]; ++cb, ++ga) {
-            const uint32_t as = ga & 1u;
-            mbar_wait(&a_empty[as], ((ga >> 1) & 1u) ^ 1u);
-            mbar_expect_tx(&a_full[as], p.a_slot);
-            const uint32_t sa = smem_base + as * p.a_slot;
-            tma_load_2d(sa, tA, &a_full[as], cb * 64, row0);
-            tma_load_2d(sa + (p.a_slot >> 1), tA, &a_full[as], cb * 64, row0 + p.a_box_rows);
-            for (int tap = 0; tap < p.ntaps[seg]; ++tap, ++gb) {
-              const uint32_t bs = gb % p.b_stages;
-              mbar_wait(&b_empty[bs], ((gb / p.b_stages) & 1u) ^ 1u);
-              mbar_expect_tx(&b_full[bs], p.b_bytes);
-              tma_load_3d(smem_b + bs * p.b_bytes, tB, &b_full[bs], cb * 64, 0, tap);
+    // The whole warp runs the (warp-uniform) loop; one elected lane issues.  Ring positions are kept as
+    // (index, phase) counters: no divisions on the critical path.
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+    for (int st = blockIdx.x; st < supers; st += gridDim.x) {
+      const int row0 = st * TC_SUPER;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        const CUtensorMap* tA = seg ? &tmA1 : &tmA0;
+        const CUtensorMap* tB = seg ? &tmB1 : &tmB0;
+        const int ncb = p.cblocks[seg], ntp = p.ntaps[seg];
+        for (int cb = 0; cb < ncb; ++cb) {
+          mbar_wait(&a_empty[as], aph ^ 1u);
+          if (elect_one()) {
+            if (p.dbg & 2) {
+              mbar_arrive(&a_full[as]);
+            } else {
+              mbar_expect_tx(&a_full[as], p.a_slot);
+              const uint32_t sa = smem_base + as * p.a_slot;
+              tma_load_2d(sa, tA, &a_full[as], cb * 64, row0);
+              tma_load_2d(sa + (p.a_slot >> 1), tA, &a_full[as], cb * 64, row0 + p.a_box_rows);
+            }
+          }
+          __syncwarp();
+          as ^= 1u;
+          if (as == 0u) aph ^= 1u;
+          const int tps = p.tps[seg];
+          for (int tap = 0; tap < ntp; tap += tps) {
+            mbar_wait(&b_empty[bs], bph ^ 1u);
+            if (elect_one()) {
+              if (p.dbg & 2) {
+                mbar_arrive(&b_full[bs]);
+              } else {
+                mbar_expect_tx(&b_full[bs], (uint32_t)tps * p.b_bytes);
+                for (int j = 0; j < tps; ++j)
+                  tma_load_3d(smem_b + bs * p.b_stage + (uint32_t)j * p.b_bytes, tB, &b_full[bs], cb * 64, 0, tap + j);
+              }
+            }
+            __syncwarp();
+            if (++bs == (uint32_t)p.b_stages) {
+              bs = 0u;
+              bph ^= 1u;
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
-      uint32_t ga = 0, gb = 0;
-      int it = 0;
-      for (int st = blockIdx.x; st < supers; st += gridDim.x, ++it) {
-        const int buf = (p.nbuf == 2) ? (it & 1) : 0;
-        const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
-        mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // both epilogue groups drained this accumulator pair
-        tc_fence_after();
-        const uint32_t td0 = tmem_d + (uint32_t)(buf * 2 * N);
-        uint32_t first = 0;
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          for (int cb = 0; cb < p.cblocks[seg]; ++cb, ++ga) {
-            const uint32_t as = ga & 1u;
-            mbar_wait(&a_full[as], (ga >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t sa = smem_base + as * p.a_slot;
-            for (int tap = 0; tap < p.ntaps[seg]; ++tap, ++gb) {
-              const uint32_t bs = gb % p.b_stages;
-              mbar_wait(&b_full[bs], (gb / p.b_stages) & 1u);
+  } else if (warp <= 2) {
+    // ------------------- MMA issuers: warp 1 accumulates rows 0..127, warp 2 rows 128..255 of each super-tile -------------------
+    // Small-N MMAs (32-64 tensor-pipe cycles each) are issue-bound from a single thread, so the two independent
+    // accumulators are driven by two warps and every descriptor is a base + immediate.
+    const uint32_t hf = (uint32_t)(warp - 1);
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+    const uint64_t dhi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;  // SBO = 1024 B, version 1, SWIZZLE_128B
+    int it = 0;
+    for (int st = blockIdx.x; st < supers; st += gridDim.x, ++it) {
+      const int buf = (p.nbuf == 2) ? (it & 1) : 0;
+      const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+      mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // both epilogue groups drained this accumulator pair
+      tc_fence_after();
+      const uint32_t td = tmem_d + (uint32_t)((buf * 2 + (int)hf) * N);
+      uint32_t first = 0;
+      for (int seg = 0; seg < p.nseg; ++seg) {
+        const int ncb = p.cblocks[seg], ntp = p.ntaps[seg];
+        for (int cb = 0; cb < ncb; ++cb) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + as * p.a_slot + hf * (128u * 128u);
+          const int tps = p.tps[seg];
+          for (int tap = 0; tap < ntp; tap += tps) {
+            if (!(p.dbg & 4)) {
+              mbar_wait(&b_full[bs], bph);
               tc_fence_after();
-              // the tap is a ROW SHIFT of the shared A tile: descriptor start = tile base + shift * 128 B
-              const uint32_t a0 = sa + (uint32_t)p.tap_shift[seg][tap] * 128u;
-              const uint64_t db = make_desc(smem_b + bs * p.b_bytes, 1024u, 2u);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {  // 64 channels = 4 x K16; +32 bytes per step inside the swizzle atom
-                tc_mma_bf16(td0, make_desc(a0 + k * 32u, 1024u, 2u), db + (uint64_t)(2 * k), p.idesc, first);
-                tc_mma_bf16(td0 + (uint32_t)N, make_desc(a0 + 128u * 128u + k * 32u, 1024u, 2u), db + (uint64_t)(2 * k), p.idesc, first);
-                first = 1;
+            }
+            if (elect_one()) {
+              for (int j = 0; j < tps; ++j) {
+                // the tap is a ROW SHIFT of the shared A tile: descriptor start = tile base + shift * 128 B;
+                // +32 bytes (+2 in the >>4 address field) per K16 step inside the swizzle atom
+                const uint64_t da = dhi | (uint64_t)((sa + (uint32_t)p.tap_shift[seg][tap + j] * 128u) >> 4);
+                const uint64_t db = dhi | (uint64_t)((smem_b + bs * p.b_stage + (uint32_t)j * p.b_bytes) >> 4);
+                if (!(p.dbg & 8)) {
+                  tc_mma_bf16(td, da, db, p.idesc, first);
+                  tc_mma_bf16_acc(td, da + 2, db + 2, p.idesc);
+                  tc_mma_bf16_acc(td, da + 4, db + 4, p.idesc);
+                  tc_mma_bf16_acc(td, da + 6, db + 6, p.idesc);
+                }
+                first = 1u;
               }
               tc_commit(&b_empty[bs]);
+              if (tap + tps >= ntp) tc_commit(&a_empty[as]);
             }
-            tc_commit(&a_empty[as]);
+            __syncwarp();
+            first = 1u;
+            if (++bs == (uint32_t)p.b_stages) {
+              bs = 0u;
+              bph ^= 1u;
+            }
           }
+          as ^= 1u;
+          if (as == 0u) aph ^= 1u;
         }
-        tc_commit(&tmem_full_bar[buf]);
       }
+      if (elect_one()) tc_commit(&tmem_full_bar[buf]);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ---------------- epilogue: group eg owns rows [128*eg, 128*eg+128) of every super-tile ----------------
-    const int eg = (warp - 2) >> 2;
+    const int eg = (warp - 3) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64 - eg * 128;
+    const int et = threadIdx.x - 96 - eg * 128;
     const int r = q * 32 + lane;  // row inside the 128-row unit
     uint32_t sc = 0;              // staging-buffer use counter of this group
     int it = 0;
@@ -315,6 +372,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(&tmem_full_bar[buf], use & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + eg) * N);
+      if (p.dbg & 1) {
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[buf]);
+        continue;
+      }
       if (a.out_mode == OUT_RAW) {
         const size_t o = valid ? raw_offset(a.out_padded, n, h, w, p.out_H, p.out_W, a.Cout) : 0;
         for (int c0 = 0; c0 < N; c0 += 32) {
@@ -326,8 +388,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
           if (p.tma_store) {
             // registers -> 128B-swizzled staging tile -> one TMA store of [128 rows x 32 channels]
-            const uint32_t stg = smem_stage + (uint32_t)(eg * 2 + (sc & 1u)) * TC_STAGE_BYTES;
-            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer free again?
+            const uint32_t stg = smem_stage + (uint32_t)eg * TC_STAGE_BYTES;
+            if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has left the buffer
             if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
             else asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
@@ -448,12 +510,22 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   while (cols < (uint32_t)(2 * p.nbuf * d.CoutP)) cols <<= 1;
   p.tmem_cols = cols;
   p.tma_store = (d.out != nullptr && d.CoutP <= 128 && d.Cout == d.CoutP && d.Cout % 32 == 0) ? 1 : 0;
-  const uint32_t fixed = 2u * p.a_slot + (p.tma_store ? 4u * TC_STAGE_BYTES : 0u);
-  int stages = (int)((198u * 1024u - fixed) / p.b_bytes);
+  const uint32_t fixed = 2u * p.a_slot + (p.tma_store ? 2u * TC_STAGE_BYTES : 0u);
+  // weight-ring stage = tps taps of the 3x3 filter (tps in {9, 3, 1}): as many as keep >= 3 stages in the budget
+  const uint32_t ring_budget = 198u * 1024u - fixed;
+  int tps = 1;
+  if (d.seg[0].ks == 3) {
+    if (3u * 9u * p.b_bytes <= ring_budget) tps = 9;
+    else if (3u * 3u * p.b_bytes <= ring_budget) tps = 3;
+  }
+  p.tps[0] = tps;
+  p.tps[1] = 1;
+  p.b_stage = (uint32_t)tps * p.b_bytes;
+  int stages = (int)(ring_budget / p.b_stage);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   RGFM_CHECK(stages >= 2, "tc conv: not enough shared memory for the weight ring");
   p.b_stages = stages;
-  t->smem = (size_t)fixed + (size_t)stages * p.b_bytes + 1024;
+  t->smem = (size_t)fixed + (size_t)stages * p.b_stage + 1024;
 
   const CUtensorMapDataType dt16 = d.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   for (int sg = 0; sg < d.nseg; ++sg) {
@@ -528,6 +600,12 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
   } else {
     RGFM_CHECK(a.CoutP % 32 == 0 && a.Cout == a.CoutP && a.out_padded, "tc conv: raw outputs need Cout % 32 == 0 and the padded-linear layout");
   }
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("RGFM_TC_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  p.dbg = dbg;
   const int total_rows = a.nimg * (p.H + 1) * p.P;
   const int supers = (total_rows + TC_SUPER - 1) / TC_SUPER;
   static int num_sms = 0;

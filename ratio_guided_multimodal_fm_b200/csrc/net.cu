@@ -184,7 +184,8 @@ struct Builder {
       b.nimg = c.nimg;
       if (padded) launch_pack_padded(b, c.s);
       else launch_pack(b, c.s);
-    }, padded ? "pack_padded" : "pack", 0.0, bytes});
+    }, padded ? "pack_padded" : "pack", 0.0, bytes,
+       std::to_string(a.Hs) + "x" + std::to_string(a.Ws) + " C" + std::to_string(C) + (raw16 ? " dual" : "") + (norm == NORM_GN ? " gn" : "")});
     for (float* st : tmp_stats) pool.release(st);
     return p;
   }
@@ -266,7 +267,9 @@ struct Builder {
         launch_conv_tc(*tcp, b, c.s);
       else
         launch_conv_simt(b, c.s);
-    }, use_tc ? "conv_tc" : "conv_simt", flops, bytes});
+    }, use_tc ? "conv_tc" : "conv_simt", flops, bytes,
+       wname + " " + std::to_string(in.H) + "x" + std::to_string(in.W) + " " + std::to_string(in.C) + "->" + std::to_string(cout) +
+           " k" + std::to_string(ks) + (stride == 2 ? " s2" : "") + (skip ? " +skip" + std::to_string(skip->C) : "")});
     return o;
   }
 
@@ -593,7 +596,7 @@ void Net::forward(cudaStream_t s, int nimg, const float* x, const float* y, floa
     c.prof = prof;
     for (auto& op : ops_) {
       if (prof) {
-        ProfRec r{op.kind, nullptr, nullptr, op.flops_per_img * c.nimg, op.bytes_per_img * c.nimg};
+        ProfRec r{op.kind, op.label.c_str(), nullptr, nullptr, op.flops_per_img * c.nimg, op.bytes_per_img * c.nimg};
         RGFM_CUDA(cudaEventCreate(&r.e0));
         RGFM_CUDA(cudaEventCreate(&r.e1));
         RGFM_CUDA(cudaEventRecord(r.e0, s));

@@ -83,6 +83,7 @@ class Net {
     const char* kind;       // kernel family, e.g. "conv_simt"
     double flops_per_img;   // algorithmic FLOPs (2*MACs of the reference op)
     double bytes_per_img;   // algorithmic bytes: operands read once + result written once
+    std::string label;      // human-readable shape, for verbose profiles
   };
   std::vector<Op> ops_;
   std::vector<TcPtr> tc_;

@@ -3,6 +3,7 @@
 // reference: flow_utils.py:178-375 (28x28 pair), sample_mnist_svhn.py:39-177 (MNIST32 <-> SVHN).
 #include "net.h"
 #include <cmath>
+#include <cstdlib>
 #include <algorithm>
 
 namespace rgfm {
@@ -294,9 +295,11 @@ void sampler_run_host(Sampler* s, const float* x0, const float* y0, const float*
 int sampler_profile(Sampler* s, rgfm_prof_entry* out, int max_entries) {
   std::vector<ProfRec> recs = s->profile_step();
   std::vector<rgfm_prof_entry> agg;
+  const bool verbose = getenv("RGFM_PROFILE_VERBOSE") != nullptr;
   for (auto& r : recs) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (verbose) fprintf(stderr, "PROF %-12s %8.2f us  %7.1f TFLOP/s  %s\n", r.kind, ms * 1e3, r.flops / (ms * 1e-3 + 1e-12) / 1e12, r.label ? r.label : "");
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
     size_t k = 0;
