@@ -237,6 +237,7 @@ def run_gpu(args):
     if rank == 0:
         pk = peaks()
         prof = plan.profile_step()
+        graph_step_ms = prof.pop("graph_step", {"ms": None})["ms"]
         step_ms = sum(v["ms"] for v in prof.values())
         conv_kinds = [k for k in prof if k.startswith("conv")]
         top = max(conv_kinds, key=lambda k: prof[k]["ms"])
@@ -252,6 +253,7 @@ def run_gpu(args):
             roof["update_kernel"] = dict(bound="hbm", kernel="mcf_apply", achieved=ua, peak=pk["hbm"], unit="GB/s",
                                          frac=ua / pk["hbm"], share_of_step=upd["ms"] / step_ms)
         roof["per_kernel_ms_one_euler_step"] = {k: round(v["ms"], 4) for k, v in prof.items()}
+        roof["graph_ms_one_euler_step"] = graph_step_ms
         total_flops = EULER_STEPS * (N_MC + B_PER_GPU) * (FLOPS_UNET_X + FLOPS_UNET_Y) + N_MC * FLOPS_RATIO
         cpu_v, cpu_sample, _ = cpu_sample_throughput(budget_s=15.0)
         line = dict(metric=METRIC, value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,

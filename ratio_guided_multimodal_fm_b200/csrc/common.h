@@ -88,13 +88,54 @@ __host__ __device__ inline size_t raw_offset(int padded, int n, int h, int w, in
   return padded ? ((size_t)((size_t)n * (H + 1) + h) * (W + 2) + w) * C : (((size_t)n * H + h) * W + w) * C;
 }
 
+// GroupNorm partial statistics of a raw activation, {sum, sumsq} per channel, in one of two layouts:
+//   ST_PARTS: [image][parts][C][2]              (SIMT conv: one partial per output tile of the image)
+//   ST_UNITS: [unit][slots][C][2]               (tcgen05 conv: one partial per 128-row unit of the padded-linear GEMM
+//             row space and per image slot inside the unit; image n owns rows [n*R, (n+1)*R), the first image of
+//             unit u is (u*128)/R and slot s is image (u*128)/R + s)
+// Partials are combined by the consumer in a fixed order, so results are deterministic.
+enum StatsMode { ST_NONE = 0, ST_PARTS = 1, ST_UNITS = 2 };
+struct StatsRef {
+  const float* p = nullptr;
+  int mode = ST_NONE;
+  int C = 0;      // channel stride of a partial row
+  int parts = 0;  // ST_PARTS
+  int R = 0;      // ST_UNITS: GEMM rows per image
+  int slots = 0;  // ST_UNITS: image slots per unit
+};
+
+__host__ __device__ inline int stats_slots_for(int R) { return 127 / R + 2; }
+
+// {sum, sumsq} of channel c of image n, combined from the partials in a fixed order
+__device__ __forceinline__ void stats_channel_sums(const StatsRef& st, int n, int c, float& s, float& ss) {
+  s = 0.f;
+  ss = 0.f;
+  if (st.mode == ST_PARTS) {
+    const float* q = st.p + ((size_t)n * st.parts * st.C + c) * 2;
+    for (int p = 0; p < st.parts; ++p) {
+      s += q[(size_t)p * st.C * 2];
+      ss += q[(size_t)p * st.C * 2 + 1];
+    }
+  } else if (st.mode == ST_UNITS) {
+    const int u0 = (n * st.R) >> 7, u1 = ((n + 1) * st.R - 1) >> 7;
+    for (int u = u0; u <= u1; ++u) {
+      const int slot = n - (u << 7) / st.R;
+      const float2 v = *reinterpret_cast<const float2*>(st.p + (((size_t)u * st.slots + slot) * st.C + c) * 2);
+      s += v.x;
+      ss += v.y;
+    }
+  }
+}
+
 struct Act {
-  float* p = nullptr;
+  float* p = nullptr;      // element type per `fmt` (the pointer is reinterpreted for 16-bit storage)
   int H = 0, W = 0, C = 0;
-  bool padded = false;     // padded-linear layout (tcgen05 path)
-  float* stats = nullptr;  // [n][parts][C][2]
+  int Cs = 0;              // channel stride of a pixel row (>= C; tcgen05 raws pad it to a multiple of 64 with zeros)
+  bool padded = false;     // padded-linear layout (tcgen05 path); pad rows / columns hold exact zeros
+  int fmt = 0;             // storage: 0 = fp32, 1 = bf16, 2 = fp16 (tensor-core nets keep raw activations in 16 bits)
+  float* stats = nullptr;  // partial GroupNorm statistics (layout per `st`)
+  StatsRef st;
   int parts = 0;
-  size_t elems_per_img() const { return (size_t)H * W * C; }
 };
 
 // Normalised/activated conv operand: NHWC, fp32 (SIMT path) or bf16 (tcgen05 path)
@@ -113,9 +154,11 @@ enum ActMode { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2 };
 // ---- kernel launch descriptors (plain structs passed by value) ----
 struct PackSrc {
   const float* p;      // raw NHWC
-  const float* stats;  // may be null when norm != GN
-  int C, parts;
+  StatsRef st;         // GroupNorm partials (mode ST_NONE when norm != GN)
+  int C;               // real channels taken from this source
+  int Cs;              // channel stride of the source rows
   int padded;          // source layout (see raw_offset)
+  int fmt;             // source storage: 0 = fp32, 1 = bf16, 2 = fp16
 };
 
 struct PackArgs {
@@ -131,7 +174,6 @@ struct PackArgs {
   void* out;
   int out_bf16;         // 0 = fp32, 1 = bf16, 2 = fp16
   int nimg;
-  void* out2;           // padded-linear layout only: optional second output, the un-normalised 16-bit copy of the sources
   int Cpad;             // padded-linear layout only: channels of the operand tensor (multiple of 64, zero filled)
 };
 
@@ -154,12 +196,13 @@ struct ConvArgs {
   float* stats;       // [n][parts][Cout][2] or null
   float dt;
   int out_padded;     // OUT_RAW: write the padded-linear layout (see raw_offset)
+  int out_fmt;        // OUT_RAW storage: 0 = fp32, 1 = bf16, 2 = fp16
 };
 
 // ops_simt.cu
 void launch_pack(const PackArgs& a, cudaStream_t s);
 void launch_pack_padded(const PackArgs& a, cudaStream_t s);
-void launch_gn_stats(const float* x, int H, int W, int C, int padded, float* stats, int nimg, cudaStream_t s);
+void launch_pack_nchw_padded(const float* x, int C, int H, int W, void* out, int fmt, int nimg, cudaStream_t s);
 void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, int out_bf16, int nimg, cudaStream_t s);
 void launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 void launch_gap_fc(const float* in, int HW, int C, const float* w, const float* b, int Cout, float* out, int ld,
@@ -182,6 +225,7 @@ struct ProfRec {  // one timed op launch (CUDA events on the launching stream)
   const char* label = nullptr;  // optional per-op description (RGFM_PROFILE_VERBOSE)
   cudaEvent_t e0, e1;
   double flops, bytes;
+  int reps = 1;  // the op was launched `reps` times back to back between the events (GPU-bound timing)
 };
 struct ProfScope {  // brackets a launch with events when profiling is on
   std::vector<ProfRec>* prof;

@@ -102,15 +102,19 @@ struct TcSegment {
   int Cin;               // operand channels (multiple of 64, zero padded)
   int Cin_real;
   int ks;                // 1 or 3
-  const float* w_oihw;   // host weights, torch layout [Cout][Cin_real][ks][ks]; nullptr = identity (folded residual)
+  const float* w_oihw;   // host weights, torch layout [Cout][w_cin_total][ks][ks]; nullptr = identity (folded residual)
+  bool raw;              // the operand is a (zero-padded) raw activation tensor: rows indexed by the GEMM row itself
+  int w_cin_total;       // input channels of the weight tensor (0 = Cin_real); this segment uses [w_c0, w_c0 + Cin_real)
+  int w_c0;
 };
 struct TcConvDesc {
   int Hin, Win;          // operand image geometry (stride-1 output geometry)
   int Cout, CoutP;       // real / padded output channels
   int chunk;             // max images
-  int nseg;              // 1, or 2 when a 1x1 skip conv / identity residual is folded in as extra K
-  TcSegment seg[2];
-  float* out;            // raw padded-linear fp32 output buffer (TMA store) or nullptr
+  int nseg;              // 1, or 2-3 when a 1x1 skip conv / identity residual is folded in as extra K segments
+  TcSegment seg[3];
+  void* out;             // raw padded-linear 16-bit output buffer (TMA store) or nullptr
+  float* stats;          // GroupNorm partials of the output [unit][slots][CoutP][2] or nullptr
   bool fp16;             // operand format: fp16 (true) or bf16 (false); fp32 accumulate either way
 };
 TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool);
@@ -118,5 +122,6 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s);
 bool tc_available();
 size_t tc_operand_slots(int H, int W, int chunk);  // rows of a padded-linear operand tensor
 size_t tc_raw_rows(int H, int W, int chunk);       // rows of a padded-linear raw activation tensor
+size_t tc_stats_floats(int H, int W, int chunk, int CoutP);  // floats of a conv's GroupNorm partials buffer
 
 }  // namespace rgfm

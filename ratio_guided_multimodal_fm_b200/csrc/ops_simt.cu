@@ -22,6 +22,47 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// load `N` consecutive channel values of a raw activation stored as fp32 (fmt 0), bf16 (1) or fp16 (2)
+__device__ __forceinline__ void load_raw4(const float* base, size_t off, int fmt, float* v) {
+  if (fmt == 0) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(base + off));
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  } else {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + off));
+    if (fmt == 1) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+  }
+}
+__device__ __forceinline__ void load_raw8(const float* base, size_t off, int fmt, float* v) {
+  if (fmt == 0) {
+    load_raw4(base, off, 0, v);
+    load_raw4(base, off + 4, 0, v + 4);
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + off));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = fmt == 1 ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]))
+                                : __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      v[2 * j] = a.x;
+      v[2 * j + 1] = a.y;
+    }
+  }
+}
+__device__ __forceinline__ float load_raw1(const float* base, size_t off, int fmt) {
+  if (fmt == 0) return base[off];
+  const uint16_t u = reinterpret_cast<const uint16_t*>(base)[off];
+  if (fmt == 1) return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&u));
+  return __half2float(*reinterpret_cast<const __half*>(&u));
+}
+
 // store 4 consecutive operand values as fp32 (FMT 0), bf16 (FMT 1) or fp16 (FMT 2)
 template <int FMT>
 __device__ __forceinline__ void store4(void* out, size_t idx, float a, float b, float c, float d) {
@@ -77,118 +118,6 @@ void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, in
   post_launch("pack_nchw");
 }
 
-// ------------------------------------------------------------------------------------------------
-// PACK: raw NHWC (1 or 2 concatenated sources) -> normalised + activated (+pooled / upsampled) conv operand.
-// GroupNorm statistics come from the producers' per-tile {sum, sumsq} partials; they are combined here in
-// double, in a fixed order (deterministic).  reference: F.group_norm at unet.py:83,91,274;
-// BatchNorm(eval)/max_pool2d at ratio_flexible.py:217-226.
-// ------------------------------------------------------------------------------------------------
-constexpr int PACK_PIX = 32;
-constexpr int PACK_MAXC = 512;
-
-template <int FMT>
-__global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
-  __shared__ float s_scale[PACK_MAXC];
-  __shared__ float s_shift[PACK_MAXC];
-  __shared__ float s_mean[32];
-  __shared__ float s_rstd[32];
-  const int n = blockIdx.y;
-  const int tid = threadIdx.x;
-  const int C0 = a.src[0].C;
-
-  if (a.norm == NORM_GN) {
-    const int cpg = a.C / a.groups;
-    if (tid < a.groups) {
-      double s = 0.0, ss = 0.0;
-      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
-        const int si = (c < C0) ? 0 : 1;
-        const int cl = si ? c - C0 : c;
-        const int Cs = a.src[si].C, parts = a.src[si].parts;
-        const float* st = a.src[si].stats + (size_t)n * parts * Cs * 2;
-        for (int p = 0; p < parts; ++p) {
-          s += (double)st[((size_t)p * Cs + cl) * 2];
-          ss += (double)st[((size_t)p * Cs + cl) * 2 + 1];
-        }
-      }
-      const double cnt = (double)cpg * a.Hs * a.Ws;
-      const double mean = s / cnt;
-      double var = ss / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      s_mean[tid] = (float)mean;
-      s_rstd[tid] = (float)(1.0 / sqrt(var + 1e-5));
-    }
-    __syncthreads();
-    for (int c = tid; c < a.C; c += blockDim.x) {
-      const int g = c / cpg;
-      const float sc = s_rstd[g] * a.gamma[c];
-      s_scale[c] = sc;
-      s_shift[c] = a.beta[c] - s_mean[g] * sc;
-    }
-  } else if (a.norm == NORM_AFFINE) {
-    for (int c = tid; c < a.C; c += blockDim.x) {
-      s_scale[c] = a.gamma[c];
-      s_shift[c] = a.beta[c];
-    }
-  } else {
-    for (int c = tid; c < a.C; c += blockDim.x) {
-      s_scale[c] = 1.0f;
-      s_shift[c] = 0.0f;
-    }
-  }
-  __syncthreads();
-
-  const int C4 = a.C >> 2;
-  const int npix = a.Ho * a.Wo;
-  const int p0 = blockIdx.x * PACK_PIX;
-  const bool plain = (a.norm == NORM_NONE && a.act == ACT_NONE);
-  for (int i = tid; i < PACK_PIX * C4; i += blockDim.x) {
-    const int p = p0 + i / C4;
-    if (p >= npix) break;
-    const int c = (i % C4) << 2;
-    const int ho = p / a.Wo, wo = p - ho * a.Wo;
-    const int si = (c < C0) ? 0 : 1;
-    const int cl = si ? c - C0 : c;
-    const int Cs = a.src[si].C;
-    const float* base = a.src[si].p + cl;
-    const int spad = a.src[si].padded;
-    float4 r;
-    if (a.spatial == SP_POOL2) {
-      r = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-#pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          float4 v = __ldg(reinterpret_cast<const float4*>(base + raw_offset(spad, n, 2 * ho + dy, 2 * wo + dx, a.Hs, a.Ws, Cs)));
-          v.x = apply_act(v.x * s_scale[c] + s_shift[c], a.act);
-          v.y = apply_act(v.y * s_scale[c + 1] + s_shift[c + 1], a.act);
-          v.z = apply_act(v.z * s_scale[c + 2] + s_shift[c + 2], a.act);
-          v.w = apply_act(v.w * s_scale[c + 3] + s_shift[c + 3], a.act);
-          r.x = fmaxf(r.x, v.x); r.y = fmaxf(r.y, v.y); r.z = fmaxf(r.z, v.z); r.w = fmaxf(r.w, v.w);
-        }
-    } else {
-      const int hs = (a.spatial == SP_UP2) ? (ho >> 1) : ho;
-      const int ws = (a.spatial == SP_UP2) ? (wo >> 1) : wo;
-      r = __ldg(reinterpret_cast<const float4*>(base + raw_offset(spad, n, hs, ws, a.Hs, a.Ws, Cs)));
-      if (!plain) {
-        r.x = apply_act(r.x * s_scale[c] + s_shift[c], a.act);
-        r.y = apply_act(r.y * s_scale[c + 1] + s_shift[c + 1], a.act);
-        r.z = apply_act(r.z * s_scale[c + 2] + s_shift[c + 2], a.act);
-        r.w = apply_act(r.w * s_scale[c + 3] + s_shift[c + 3], a.act);
-      }
-    }
-    const size_t o = ((size_t)n * npix + p) * a.C + c;
-    store4<FMT>(a.out, o, r.x, r.y, r.z, r.w);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// PACK (padded-linear layout) for the tcgen05 convolution.  The operand is a 2-D tensor [slot][Cpad] of 16-bit
-// values where slot = (1 + n*(H+1) + h) * P + (w + 1), P = W + 2: every image row carries one zero pixel on each
-// side and every image is followed by one zero row (row 0 is zero too), so the nine taps of a 3x3 convolution are
-// nine ROW SHIFTS (ky*P + kx) of one shared-memory tile and the conv's zero padding is physically in memory.
-// This kernel writes the pad slots (zeros) together with the valid pixels, so arena blocks can be recycled.
-// ------------------------------------------------------------------------------------------------
-
 __device__ __forceinline__ float fast_act(float x, int act) {
   if (act == ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
   if (act == ACT_RELU) return fmaxf(x, 0.0f);
@@ -206,56 +135,69 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// One CTA per image.  GroupNorm statistics are computed HERE, on the concatenated view of the (one or two) fp32
-// sources: pass A accumulates per-channel sum / sum-of-squares (fp32 per thread, combined in double), pass B
-// normalises, activates and writes the 16-bit padded-linear operand.  The second read of the image hits L2.
+// NCHW fp32 image -> padded-linear 16-bit operand for the tensor-core input conv: 64 channels per slot holding
+// [x_hi (C), x_lo (C), 0...] with x_hi = round16(x), x_lo = round16(x - x_hi).  The weights are duplicated over the two
+// halves, so the state x_t enters the first conv with ~22 mantissa bits instead of 11 (8 for bf16) at no extra cost
+// (the K block is 64 channels wide anyway).
 template <int FMT>
-__global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
-  __shared__ float s_scale[PACK_MAXC];
-  __shared__ float s_shift[PACK_MAXC];
-  __shared__ float s_red[2][PACK_MAXC];   // per-channel sum / sumsq
-  __shared__ double s_grp[32][2];
-  const int n = blockIdx.x;
+__global__ void __launch_bounds__(256) pack_nchw_padded_kernel(const float* __restrict__ x, int C, int H, int W,
+                                                               uint4* __restrict__ out) {
+  const int n = blockIdx.y;
+  const int P = W + 2;
+  const int slots_img = (H + 1) * P;
+  const int pp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n == 0 && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < P * 8; i += blockDim.x) out[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (pp >= slots_img) return;
+  const int ho = pp / P, ww = pp - ho * P;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ho < H && ww >= 1 && ww <= W) {
+    for (int c = 0; c < C; ++c) {
+      const float xv = __ldg(x + ((size_t)(n * C + c) * H + ho) * W + (ww - 1));
+      float hi;
+      if (FMT == 1) hi = __bfloat162float(__float2bfloat16(xv));
+      else hi = __half2float(__float2half_rn(xv));
+      v[c] = hi;
+      v[C + c] = xv - hi;
+    }
+  }
+  uint4* dst = out + ((size_t)(1 + n * (H + 1)) * P + pp) * 8;
+  dst[0] = make_uint4(pack2<FMT>(v[0], v[1]), pack2<FMT>(v[2], v[3]), pack2<FMT>(v[4], v[5]), pack2<FMT>(v[6], v[7]));
+#pragma unroll
+  for (int j = 1; j < 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+void launch_pack_nchw_padded(const float* x, int C, int H, int W, void* out, int fmt, int nimg, cudaStream_t s) {
+  RGFM_CHECK(2 * C <= 8 && (fmt == 1 || fmt == 2), "pack_nchw_padded: at most 4 image channels, 16-bit output");
+  dim3 grid(((H + 1) * (W + 2) + 255) / 256, nimg);
+  if (fmt == 1)
+    pack_nchw_padded_kernel<1><<<grid, 256, 0, s>>>(x, C, H, W, reinterpret_cast<uint4*>(out));
+  else
+    pack_nchw_padded_kernel<2><<<grid, 256, 0, s>>>(x, C, H, W, reinterpret_cast<uint4*>(out));
+  post_launch("pack_nchw_padded");
+}
+
+// ------------------------------------------------------------------------------------------------
+// PACK: raw NHWC (1 or 2 concatenated sources) -> normalised + activated (+pooled / upsampled) conv operand.
+// GroupNorm statistics come from the producers' {sum, sumsq} partials (per output tile for the SIMT conv, per
+// 128-row unit for the tcgen05 conv); they are combined here in a fixed order (deterministic), group moments in
+// double.  reference: F.group_norm at unet.py:83,91,274; BatchNorm(eval)/max_pool2d at ratio_flexible.py:217-226.
+// ------------------------------------------------------------------------------------------------
+constexpr int PACK_PIX = 32;
+constexpr int PACK_MAXC = 512;
+
+// per-channel scale / shift of the normalisation of image n into shared memory (all threads of the CTA call this)
+__device__ __forceinline__ void pack_scale_shift(const PackArgs& a, int n, float* s_scale, float* s_shift, float (*s_red)[PACK_MAXC],
+                                                 double (*s_grp)[2]) {
   const int tid = threadIdx.x;
   const int C0 = a.src[0].C;
-  const int C8 = a.C >> 3;
-  const int HWs = a.Hs * a.Ws;
-
   if (a.norm == NORM_GN) {
     for (int c = tid; c < a.C; c += blockDim.x) {
-      s_red[0][c] = 0.f;
-      s_red[1][c] = 0.f;
-    }
-    __syncthreads();
-    const int PL = blockDim.x / C8;  // pixel lanes
-    const int co = tid % C8, pl = tid / C8;
-    if (pl < PL) {
-      const int c = co << 3;
       const int si = (c < C0) ? 0 : 1;
-      const int cl = si ? c - C0 : c;
-      const int Cs = a.src[si].C;
-      const float* base = a.src[si].p + cl;
-      const int spad = a.src[si].padded;
-      float s1[8], s2[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-      for (int p = pl; p < HWs; p += PL) {
-        const int ph = p / a.Ws, pw = p - ph * a.Ws;
-        const float* q = base + raw_offset(spad, n, ph, pw, a.Hs, a.Ws, Cs);
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(q));
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(q + 4));
-        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s1[j] += xv[j];
-          s2[j] = fmaf(xv[j], xv[j], s2[j]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&s_red[0][c + j], s1[j]);
-        atomicAdd(&s_red[1][c + j], s2[j]);
-      }
+      float s, ss;
+      stats_channel_sums(a.src[si].st, n, si ? c - C0 : c, s, ss);
+      s_red[0][c] = s;
+      s_red[1][c] = ss;
     }
     __syncthreads();
     const int cpg = a.C / a.groups;
@@ -265,7 +207,7 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
         s += (double)s_red[0][c];
         ss += (double)s_red[1][c];
       }
-      const double cnt = (double)cpg * HWs;
+      const double cnt = (double)cpg * a.Hs * a.Ws;
       const double mean = s / cnt;
       double var = ss / cnt - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -286,31 +228,124 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
     }
   }
   __syncthreads();
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
+  __shared__ float s_scale[PACK_MAXC];
+  __shared__ float s_shift[PACK_MAXC];
+  __shared__ float s_red[2][PACK_MAXC];
+  __shared__ double s_grp[32][2];
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int C0 = a.src[0].C;
+  pack_scale_shift(a, n, s_scale, s_shift, s_red, s_grp);
+
+  const int C4 = a.C >> 2;
+  const int npix = a.Ho * a.Wo;
+  const int p0 = blockIdx.x * PACK_PIX;
+  const bool plain = (a.norm == NORM_NONE && a.act == ACT_NONE);
+  for (int i = tid; i < PACK_PIX * C4; i += blockDim.x) {
+    const int p = p0 + i / C4;
+    if (p >= npix) break;
+    const int c = (i % C4) << 2;
+    const int ho = p / a.Wo, wo = p - ho * a.Wo;
+    const int si = (c < C0) ? 0 : 1;
+    const int cl = si ? c - C0 : c;
+    const int Cs = a.src[si].Cs;
+    const int spad = a.src[si].padded;
+    float4 r;
+    if (a.spatial == SP_POOL2) {
+      r = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float lv[4];
+          load_raw4(a.src[si].p, raw_offset(spad, n, 2 * ho + dy, 2 * wo + dx, a.Hs, a.Ws, Cs) + cl, a.src[si].fmt, lv);
+          float4 v = make_float4(lv[0], lv[1], lv[2], lv[3]);
+          v.x = apply_act(v.x * s_scale[c] + s_shift[c], a.act);
+          v.y = apply_act(v.y * s_scale[c + 1] + s_shift[c + 1], a.act);
+          v.z = apply_act(v.z * s_scale[c + 2] + s_shift[c + 2], a.act);
+          v.w = apply_act(v.w * s_scale[c + 3] + s_shift[c + 3], a.act);
+          r.x = fmaxf(r.x, v.x); r.y = fmaxf(r.y, v.y); r.z = fmaxf(r.z, v.z); r.w = fmaxf(r.w, v.w);
+        }
+    } else {
+      const int hs = (a.spatial == SP_UP2) ? (ho >> 1) : ho;
+      const int ws = (a.spatial == SP_UP2) ? (wo >> 1) : wo;
+      float lv[4];
+      load_raw4(a.src[si].p, raw_offset(spad, n, hs, ws, a.Hs, a.Ws, Cs) + cl, a.src[si].fmt, lv);
+      r = make_float4(lv[0], lv[1], lv[2], lv[3]);
+      if (!plain) {
+        r.x = apply_act(r.x * s_scale[c] + s_shift[c], a.act);
+        r.y = apply_act(r.y * s_scale[c + 1] + s_shift[c + 1], a.act);
+        r.z = apply_act(r.z * s_scale[c + 2] + s_shift[c + 2], a.act);
+        r.w = apply_act(r.w * s_scale[c + 3] + s_shift[c + 3], a.act);
+      }
+    }
+    const size_t o = ((size_t)n * npix + p) * a.C + c;
+    store4<FMT>(a.out, o, r.x, r.y, r.z, r.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PACK (padded-linear layout) for the tcgen05 convolution.  The operand is a 2-D tensor [slot][Cpad] of 16-bit
+// values where slot = (1 + n*(H+1) + h) * P + (w + 1), P = W + 2: every image row carries one zero pixel on each
+// side and every image is followed by one zero row (row 0 is zero too), so the nine taps of a 3x3 convolution are
+// nine ROW SHIFTS (ky*P + kx) of one shared-memory tile and the conv's zero padding is physically in memory.
+// This kernel writes the pad slots (zeros) together with the valid pixels, so arena blocks can be recycled.
+//
+// Streaming kernel: grid (slabs, images).  Each thread owns one 8-channel octet (its scale / shift live in
+// registers) and walks pixel slots with stride 256 / (Cpad / 8); every load and store is 16 bytes and consecutive
+// threads touch consecutive addresses.  GroupNorm statistics come from the producer's partials (no second pass
+// over the image).
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
+  __shared__ float s_scale[PACK_MAXC];
+  __shared__ float s_shift[PACK_MAXC];
+  __shared__ float s_red[2][PACK_MAXC];
+  __shared__ double s_grp[32][2];
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int C0 = a.src[0].C;
+  pack_scale_shift(a, n, s_scale, s_shift, s_red, s_grp);
 
   const int P = a.Wo + 2;
   const int CP8 = a.Cpad >> 3;
   const int slots_img = (a.Ho + 1) * P;
   uint4* out = reinterpret_cast<uint4*>(a.out);
-  uint4* out2 = reinterpret_cast<uint4*>(a.out2);
-  if (n == 0)  // the leading zero row
-    for (int i = tid; i < P * CP8; i += blockDim.x) {
-      out[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (out2) out2[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
+  if (n == 0 && blockIdx.x == 0)  // the leading zero row
+    for (int i = tid; i < P * CP8; i += blockDim.x) out[i] = make_uint4(0u, 0u, 0u, 0u);
+  const int PL = 256 / CP8;  // pixel lanes
+  const int co = tid % CP8, pl = tid / CP8;
+  if (pl >= PL) return;
+  const int c = co << 3;
+  const bool cvalid = c < a.C;
+  const int si = (c < C0) ? 0 : 1;
+  const int cl = si ? c - C0 : c;
+  const int Cs = a.src[si].Cs;
+  const int spad = a.src[si].padded, sfmt = a.src[si].fmt;
+  const float* sp = a.src[si].p;
   const bool plain = (a.norm == NORM_NONE && a.act == ACT_NONE);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = cvalid ? s_scale[c + j] : 0.f;
+    sh[j] = cvalid ? s_shift[c + j] : 0.f;
+  }
+  // this CTA's slab of pixel slots
+  const int per = (slots_img + gridDim.x - 1) / gridDim.x;
+  const int s_begin = blockIdx.x * per;
+  const int s_end = min(slots_img, s_begin + per);
   const size_t slot0 = (size_t)(1 + n * (a.Ho + 1)) * P;
-  for (int i = tid; i < slots_img * CP8; i += blockDim.x) {
-    const int pp = i / CP8;
-    const int c = (i - pp * CP8) << 3;
-    const int ho = pp / P, ww = pp - ho * P;
-    uint4 o = make_uint4(0u, 0u, 0u, 0u), o2 = o;
-    if (ho < a.Ho && ww >= 1 && ww <= a.Wo && c < a.C) {
+  int pp = s_begin + pl;
+  int ho = pp / P, ww = pp - ho * P;
+  const int dh = PL / P, dw = PL - dh * P;
+  for (; pp < s_end; pp += PL) {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (cvalid && ho < a.Ho && ww >= 1 && ww <= a.Wo) {
       const int wo = ww - 1;
-      const int si = (c < C0) ? 0 : 1;
-      const int cl = si ? c - C0 : c;
-      const int Cs = a.src[si].C;
-      const float* base = a.src[si].p + cl;
-      const int spad = a.src[si].padded;
       float v[8];
       if (a.spatial == SP_POOL2) {
 #pragma unroll
@@ -319,69 +354,50 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
           for (int dx = 0; dx < 2; ++dx) {
-            const float* q = base + raw_offset(spad, n, 2 * ho + dy, 2 * wo + dx, a.Hs, a.Ws, Cs);
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(q));
-            const float4 x1 = __ldg(reinterpret_cast<const float4*>(q + 4));
-            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            float xv[8];
+            load_raw8(sp, raw_offset(spad, n, 2 * ho + dy, 2 * wo + dx, a.Hs, a.Ws, Cs) + cl, sfmt, xv);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], fast_act(fmaf(xv[j], s_scale[c + j], s_shift[c + j]), a.act));
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], fast_act(fmaf(xv[j], sc[j], sh[j]), a.act));
           }
       } else {
         const int hs = (a.spatial == SP_UP2) ? (ho >> 1) : ho;
         const int ws = (a.spatial == SP_UP2) ? (wo >> 1) : wo;
-        const float* q = base + raw_offset(spad, n, hs, ws, a.Hs, a.Ws, Cs);
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(q));
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(q + 4));
-        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        float xv[8];
+        load_raw8(sp, raw_offset(spad, n, hs, ws, a.Hs, a.Ws, Cs) + cl, sfmt, xv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = plain ? xv[j] : fast_act(fmaf(xv[j], s_scale[c + j], s_shift[c + j]), a.act);
-        if (out2) {  // second output: the raw (un-normalised) 16-bit copy, operand of the folded skip / identity segment
-          o2.x = pack2<FMT>(xv[0], xv[1]);
-          o2.y = pack2<FMT>(xv[2], xv[3]);
-          o2.z = pack2<FMT>(xv[4], xv[5]);
-          o2.w = pack2<FMT>(xv[6], xv[7]);
-        }
+        for (int j = 0; j < 8; ++j) v[j] = plain ? xv[j] : fast_act(fmaf(xv[j], sc[j], sh[j]), a.act);
       }
       o.x = pack2<FMT>(v[0], v[1]);
       o.y = pack2<FMT>(v[2], v[3]);
       o.z = pack2<FMT>(v[4], v[5]);
       o.w = pack2<FMT>(v[6], v[7]);
     }
-    out[(slot0 + pp) * CP8 + (c >> 3)] = o;
-    if (out2) out2[(slot0 + pp) * CP8 + (c >> 3)] = o2;
+    out[(slot0 + pp) * CP8 + co] = o;
+    ho += dh;
+    ww += dw;
+    if (ww >= P) {
+      ww -= P;
+      ++ho;
+    }
   }
 }
 
 void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
-  RGFM_CHECK(a.C <= PACK_MAXC && a.C % 8 == 0 && a.Cpad % 8 == 0 && a.Cpad >= a.C, "pack_padded: channel counts");
+  RGFM_CHECK(a.C <= PACK_MAXC && a.C % 8 == 0 && a.Cpad % 8 == 0 && a.Cpad >= a.C && a.Cpad <= 2048, "pack_padded: channel counts");
   RGFM_CHECK(a.src[0].C % 8 == 0, "pack_padded: first source channels must be a multiple of 8");
   RGFM_CHECK(a.out_bf16 == 1 || a.out_bf16 == 2, "pack_padded: 16-bit output only");
+  // one CTA per image when the batch alone fills the machine, otherwise split images into slabs
+  const int slots_img = (a.Ho + 1) * (a.Wo + 2);
+  int slabs = (4 * 148 + a.nimg - 1) / a.nimg;
+  const int max_slabs = (slots_img * (a.Cpad / 8) + 2047) / 2048;  // >= 8 iterations of 256 threads per CTA
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  dim3 grid(slabs, a.nimg);
   if (a.out_bf16 == 1)
-    pack_padded_kernel<1><<<a.nimg, 256, 0, s>>>(a);
+    pack_padded_kernel<1><<<grid, 256, 0, s>>>(a);
   else
-    pack_padded_kernel<2><<<a.nimg, 256, 0, s>>>(a);
+    pack_padded_kernel<2><<<grid, 256, 0, s>>>(a);
   post_launch("pack_padded");
-}
-
-// Per-(image, channel) {sum, sumsq} of a raw NHWC fp32 tensor, one CTA per image (used where an fp32-operand pack
-// follows a producer that does not emit GroupNorm partials, i.e. the tcgen05 conv).
-__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int H, int W, int C, int padded,
-                                                       float* __restrict__ stats) {
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f, ss = 0.f;
-    for (int p = 0; p < H * W; ++p) {
-      const float v = x[raw_offset(padded, n, p / W, p % W, H, W, C) + c];
-      s += v;
-      ss = fmaf(v, v, ss);
-    }
-    stats[((size_t)n * C + c) * 2] = s;
-    stats[((size_t)n * C + c) * 2 + 1] = ss;
-  }
-}
-void launch_gn_stats(const float* x, int H, int W, int C, int padded, float* stats, int nimg, cudaStream_t s) {
-  gn_stats_kernel<<<nimg, 256, 0, s>>>(x, H, W, C, padded, stats);
-  post_launch("gn_stats");
 }
 
 void launch_pack(const PackArgs& a, cudaStream_t s) {
@@ -493,7 +509,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
         const size_t o = (((size_t)n * a.g.H + ho) * a.g.W + wo) * a.Cout + co;
         if (a.res) val += a.res[o];
         if (a.out_mode == OUT_RAW) {
-          a.out[a.out_padded ? raw_offset(1, n, ho, wo, a.g.H, a.g.W, a.Cout) + co : o] = val;
+          const size_t oo = a.out_padded ? raw_offset(1, n, ho, wo, a.g.H, a.g.W, a.Cout) + co : o;
+          if (a.out_fmt == 0) a.out[oo] = val;
+          else if (a.out_fmt == 1) reinterpret_cast<__nv_bfloat16*>(a.out)[oo] = __float2bfloat16(val);
+          else reinterpret_cast<__half*>(a.out)[oo] = __float2half_rn(fminf(fmaxf(val, -65504.f), 65504.f));
         } else {
           const size_t oc = (((size_t)n * a.Cout + co) * a.g.H + ho) * a.g.W + wo;
           if (a.out_mode == OUT_NCHW)

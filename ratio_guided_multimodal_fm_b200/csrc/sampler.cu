@@ -76,8 +76,28 @@ struct Sampler {
       fy->forward(cap, B, y, nullptr, y, OUT_EULER, dtf, step, &recs);
     }
     RGFM_CUDA(cudaStreamSynchronize(cap));
+    // the same step as ONE CUDA-graph launch (what run() executes): no per-kernel CPU launch gaps
+    {
+      const int reps = 5;
+      cudaGraphExec_t ge = (guided && st >= first_guided) ? g_guided.e : g_plain.e;
+      ProfRec r{"graph_step", nullptr, nullptr, nullptr, 0.0, 0.0};
+      RGFM_CUDA(cudaEventCreate(&r.e0));
+      RGFM_CUDA(cudaEventCreate(&r.e1));
+      RGFM_CUDA(cudaMemcpyAsync(step, &st, sizeof(int), cudaMemcpyHostToDevice, cap));
+      RGFM_CUDA(cudaGraphLaunch(ge, cap));  // warm
+      RGFM_CUDA(cudaEventRecord(r.e0, cap));
+      for (int i = 0; i < reps; ++i) {
+        RGFM_CUDA(cudaMemcpyAsync(step, &st, sizeof(int), cudaMemcpyHostToDevice, cap));  // replay the same step
+        RGFM_CUDA(cudaGraphLaunch(ge, cap));
+      }
+      RGFM_CUDA(cudaEventRecord(r.e1, cap));
+      RGFM_CUDA(cudaStreamSynchronize(cap));
+      graph_reps = reps;
+      recs.push_back(r);
+    }
     return recs;
   }
+  int graph_reps = 1;
 
   template <typename F>
   void capture(Graph& G, F&& body) {
@@ -299,6 +319,7 @@ int sampler_profile(Sampler* s, rgfm_prof_entry* out, int max_entries) {
   for (auto& r : recs) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
+    ms /= (float)r.reps;
     if (verbose) fprintf(stderr, "PROF %-12s %8.2f us  %7.1f TFLOP/s  %s\n", r.kind, ms * 1e3, r.flops / (ms * 1e-3 + 1e-12) / 1e12, r.label ? r.label : "");
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -310,6 +331,7 @@ int sampler_profile(Sampler* s, rgfm_prof_entry* out, int max_entries) {
       snprintf(e.name, sizeof(e.name), "%s", r.kind);
       agg.push_back(e);
     }
+    if (std::string(r.kind) == "graph_step") ms /= (float)s->graph_reps;
     agg[k].ms += ms;
     agg[k].flops += r.flops;
     agg[k].bytes += r.bytes;

@@ -22,8 +22,9 @@ x0 = torch.randn(args.batch, 1, 32, 32, device=dev, generator=g); y0 = torch.ran
 m0 = torch.randn(args.nmc, 1, 32, 32, device=dev, generator=g); n0 = torch.randn(args.nmc, 3, 32, 32, device=dev, generator=g)
 plan.run(x0, y0, m0, n0); torch.cuda.synchronize()
 prof = plan.profile_step()
+graph_ms = prof.pop("graph_step", {"ms": float("nan")})["ms"]
 tot = sum(v["ms"] for v in prof.values())
 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
     print(f"{k:14s} {v['ms']:8.3f} ms  {100*v['ms']/tot:5.1f}%  launches {v['launches']:4d}  "
           f"{v['flops']/max(v['ms'],1e-9)/1e9:8.1f} TFLOP/s  {v['bytes']/max(v['ms'],1e-9)/1e6:8.1f} GB/s(alg)")
-print("total", round(tot, 3), "ms")
+print("total", round(tot, 3), "ms (eager, per-kernel events);  one CUDA-graph step:", round(graph_ms, 3), "ms")
