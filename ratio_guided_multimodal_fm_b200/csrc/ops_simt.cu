@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
   const int P = a.Wo + 2;
   const int CP8 = a.Cpad >> 3;
   const int slots_img = (a.Ho + 1) * P;
-  uint4* out = reinterpret_cast<uint4*>(a.out);
+  uint4* __restrict__ out = reinterpret_cast<uint4*>(a.out);
   if (n == 0 && blockIdx.x == 0)  // the leading zero row
     for (int i = tid; i < P * CP8; i += blockDim.x) out[i] = make_uint4(0u, 0u, 0u, 0u);
   const int PL = 256 / CP8;  // pixel lanes
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
   const int cl = si ? c - C0 : c;
   const int Cs = a.src[si].Cs;
   const int spad = a.src[si].padded, sfmt = a.src[si].fmt;
-  const float* sp = a.src[si].p;
+  const float* __restrict__ sp = a.src[si].p;
   const bool plain = (a.norm == NORM_NONE && a.act == ACT_NONE);
   float sc[8], sh[8];
 #pragma unroll
@@ -382,6 +382,103 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
   }
 }
 
+// Fast path of the padded-linear pack: 16-bit sources, no pooling.  Same mapping as pack_padded_kernel (one 8-channel
+// octet per thread, scale / shift in registers), but every thread keeps FOUR independent 16-byte loads in flight per
+// iteration: the kernel is a pure stream and one dependent load per thread leaves it latency-bound at ~2 TB/s.
+template <int FMT>
+__global__ void __launch_bounds__(256) pack_padded_fast_kernel(PackArgs a) {
+  __shared__ float s_scale[PACK_MAXC];
+  __shared__ float s_shift[PACK_MAXC];
+  __shared__ float s_red[2][PACK_MAXC];
+  __shared__ double s_grp[32][2];
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int C0 = a.src[0].C;
+  pack_scale_shift(a, n, s_scale, s_shift, s_red, s_grp);
+
+  const int P = a.Wo + 2;
+  const int CP8 = a.Cpad >> 3;
+  const int slots_img = (a.Ho + 1) * P;
+  uint4* __restrict__ out = reinterpret_cast<uint4*>(a.out);
+  if (n == 0 && blockIdx.x == 0)  // the leading zero row
+    for (int i = tid; i < P * CP8; i += blockDim.x) out[i] = make_uint4(0u, 0u, 0u, 0u);
+  const int PL = 256 / CP8;  // pixel lanes
+  const int co = tid % CP8, pl = tid / CP8;
+  if (pl >= PL) return;
+  const int c = co << 3;
+  const bool cvalid = c < a.C;
+  const int si = (c < C0) ? 0 : 1;
+  const int cl = si ? c - C0 : c;
+  const int Cs = a.src[si].Cs;
+  const int sfmt = a.src[si].fmt;  // 1 = bf16, 2 = fp16
+  const uint16_t* __restrict__ sp = reinterpret_cast<const uint16_t*>(a.src[si].p);
+  const bool plain = (a.norm == NORM_NONE && a.act == ACT_NONE);
+  const bool up2 = a.spatial == SP_UP2;
+  const int act = a.act;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = cvalid ? s_scale[c + j] : 0.f;
+    sh[j] = cvalid ? s_shift[c + j] : 0.f;
+  }
+  const int per = (slots_img + gridDim.x - 1) / gridDim.x;
+  const int s_begin = blockIdx.x * per;
+  const int s_end = min(slots_img, s_begin + per);
+  const size_t slot0 = (size_t)(1 + n * (a.Ho + 1)) * P;
+  const size_t src_img = (size_t)n * (a.Hs + 1) * (a.Ws + 2);  // first padded-linear row of the source image
+  const int Ps = a.Ws + 2;
+  int pp = s_begin + pl;
+  int ho = pp / P, ww = pp - ho * P;
+  const int dh = PL / P, dw = PL - dh * P;
+  for (; pp < s_end; pp += 4 * PL) {
+    uint4 rawv[4];
+    bool ok[4];
+    int pps[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pps[u] = pp + u * PL;
+      ok[u] = cvalid && pps[u] < s_end && ho < a.Ho && ww >= 1 && ww <= a.Wo;
+      rawv[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[u]) {
+        const int wo = ww - 1;
+        const int hs = up2 ? (ho >> 1) : ho, ws = up2 ? (wo >> 1) : wo;
+        rawv[u] = __ldg(reinterpret_cast<const uint4*>(sp + (src_img + (size_t)hs * Ps + ws) * Cs + cl));
+      }
+      ho += dh;
+      ww += dw;
+      if (ww >= P) {
+        ww -= P;
+        ++ho;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (pps[u] >= s_end) break;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[u]) {
+        if (plain && sfmt == FMT) {
+          o = rawv[u];
+        } else {
+          const uint32_t w4[4] = {rawv[u].x, rawv[u].y, rawv[u].z, rawv[u].w};
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = sfmt == 1 ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]))
+                                       : __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
+            v[2 * j] = plain ? f.x : fast_act(fmaf(f.x, sc[2 * j], sh[2 * j]), act);
+            v[2 * j + 1] = plain ? f.y : fast_act(fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]), act);
+          }
+          o.x = pack2<FMT>(v[0], v[1]);
+          o.y = pack2<FMT>(v[2], v[3]);
+          o.z = pack2<FMT>(v[4], v[5]);
+          o.w = pack2<FMT>(v[6], v[7]);
+        }
+      }
+      out[(slot0 + pps[u]) * CP8 + co] = o;
+    }
+  }
+}
+
 void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
   RGFM_CHECK(a.C <= PACK_MAXC && a.C % 8 == 0 && a.Cpad % 8 == 0 && a.Cpad >= a.C && a.Cpad <= 2048, "pack_padded: channel counts");
   RGFM_CHECK(a.src[0].C % 8 == 0, "pack_padded: first source channels must be a multiple of 8");
@@ -393,10 +490,17 @@ void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
   dim3 grid(slabs, a.nimg);
-  if (a.out_bf16 == 1)
+  const bool fast = a.spatial != SP_POOL2 && a.src[0].fmt != 0 && a.src[0].padded && (a.nsrc == 1 || (a.src[1].fmt != 0 && a.src[1].padded));
+  if (fast) {
+    if (a.out_bf16 == 1)
+      pack_padded_fast_kernel<1><<<grid, 256, 0, s>>>(a);
+    else
+      pack_padded_fast_kernel<2><<<grid, 256, 0, s>>>(a);
+  } else if (a.out_bf16 == 1) {
     pack_padded_kernel<1><<<grid, 256, 0, s>>>(a);
-  else
+  } else {
     pack_padded_kernel<2><<<grid, 256, 0, s>>>(a);
+  }
   post_launch("pack_padded");
 }
 

@@ -138,7 +138,7 @@ struct Sampler {
     } else {
       throw Error("unknown pair kind");
     }
-    int chunk = d.chunk > 0 ? d.chunk : 512;
+    int chunk = d.chunk > 0 ? d.chunk : 1024;
     chunk = std::min(chunk, std::max(B, guided ? N : 1));
     fx.reset(new Net(kx, wx, chunk, d.precision, d.device));
     fy.reset(new Net(ky, wy, chunk, d.precision, d.device));
