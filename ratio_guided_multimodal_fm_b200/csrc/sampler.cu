@@ -32,8 +32,9 @@ struct Sampler {
   StepScalars* sc = nullptr;
   int first_guided = 0;  // first step with t > eps
   int ksx = 1, ksy = 1;
-  cudaStream_t cap = nullptr;
-  Graph g_pre_x, g_pre_y, g_ratio, g_plain, g_guided;
+  cudaStream_t cap = nullptr, cap2 = nullptr;   // capture streams: the x- and y-network forwards are independent branches
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  Graph g_pre, g_ratio, g_plain, g_guided;
   int64_t launches = 0;
   float *hx = nullptr, *hy = nullptr, *hmx = nullptr, *hmy = nullptr;  // pinned staging for run_host
   std::vector<float*> stage;  // device staging for run_host
@@ -41,6 +42,9 @@ struct Sampler {
   ~Sampler() {
     cudaSetDevice(d.device);
     if (cap) cudaStreamDestroy(cap);
+    if (cap2) cudaStreamDestroy(cap2);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     if (hx) cudaFreeHost(hx);
     if (hy) cudaFreeHost(hy);
     if (hmx) cudaFreeHost(hmx);
@@ -186,15 +190,29 @@ struct Sampler {
       scratch = (float*)pool.persistent(nf * sizeof(float));
     }
     RGFM_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    RGFM_CUDA(cudaStreamCreateWithFlags(&cap2, cudaStreamNonBlocking));
+    RGFM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    RGFM_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    // fork / join inside a capture: the second stream becomes a parallel branch of the graph, so the tail of one
+    // network's persistent kernels overlaps the head of the other's (and small-batch pre-pass kernels run side by side)
+    auto fork = [&](cudaStream_t s) {
+      RGFM_CUDA(cudaEventRecord(ev_fork, s));
+      RGFM_CUDA(cudaStreamWaitEvent(cap2, ev_fork, 0));
+    };
+    auto join = [&](cudaStream_t s) {
+      RGFM_CUDA(cudaEventRecord(ev_join, cap2));
+      RGFM_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
+    };
 
     // ---- graphs ----
     if (guided) {
-      capture(g_pre_x, [&](cudaStream_t s) {  // mc_x += fm_x(mc_x, t) * dt   (flow_utils.py:236-241)
+      // mc_x += fm_x(mc_x, t) * dt and mc_y += fm_y(mc_y, t) * dt (flow_utils.py:236-250): the reference runs the two
+      // chains one after the other; they are independent, so step s of both runs concurrently here
+      capture(g_pre, [&](cudaStream_t s) {
+        fork(s);
         fx->forward(s, N, mcx, nullptr, mcx, OUT_EULER, dtf, step);
-        launch_step_inc(step, s);
-      });
-      capture(g_pre_y, [&](cudaStream_t s) {
-        fy->forward(s, N, mcy, nullptr, mcy, OUT_EULER, dtf, step);
+        fy->forward(cap2, N, mcy, nullptr, mcy, OUT_EULER, dtf, step);
+        join(s);
         launch_step_inc(step, s);
       });
       capture(g_ratio, [&](cudaStream_t s) {  // mc_ratios = exp(log_ratio(mc_x, mc_y))  (flow_utils.py:255-258)
@@ -203,8 +221,10 @@ struct Sampler {
         launch_ratio_stats(ratios, N, diag + 9, s);
       });
       capture(g_guided, [&](cudaStream_t s) {
+        fork(s);
         fx->forward(s, B, x, nullptr, vx, OUT_NCHW, dtf, step);
-        fy->forward(s, B, y, nullptr, vy, OUT_NCHW, dtf, step);
+        fy->forward(cap2, B, y, nullptr, vy, OUT_NCHW, dtf, step);
+        join(s);
         McfArgs a = mcf_args();
         launch_mcf(a, s);
         DiagArgs da{B, Dx, Dy, N, vx, vy, gx, gy, a.zbuf, sc, step, (int)(0.3 * steps), diag};
@@ -213,13 +233,15 @@ struct Sampler {
       });
     }
     capture(g_plain, [&](cudaStream_t s) {  // x += fm_x(x, t) * dt ; y += fm_y(y, t) * dt
+      fork(s);
       fx->forward(s, B, x, nullptr, x, OUT_EULER, dtf, step);
-      fy->forward(s, B, y, nullptr, y, OUT_EULER, dtf, step);
+      fy->forward(cap2, B, y, nullptr, y, OUT_EULER, dtf, step);
+      join(s);
       launch_step_inc(step, s);
     });
     RGFM_CUDA(cudaStreamSynchronize(cap));
     launches = 0;
-    if (guided) launches += (int64_t)steps * (g_pre_x.kernels + g_pre_y.kernels) + g_ratio.kernels;
+    if (guided) launches += (int64_t)steps * g_pre.kernels + g_ratio.kernels;
     for (int s = 0; s < steps; ++s) launches += (guided && s >= first_guided) ? g_guided.kernels : g_plain.kernels;
   }
 
@@ -235,9 +257,7 @@ struct Sampler {
       RGFM_CUDA(cudaMemcpyAsync(mcx, mx0, (size_t)N * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
       RGFM_CUDA(cudaMemcpyAsync(mcy, my0, (size_t)N * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
       RGFM_CUDA(cudaMemsetAsync(step, 0, sizeof(int), s));
-      for (int i = 0; i < steps; ++i) RGFM_CUDA(cudaGraphLaunch(g_pre_x.e, s));
-      RGFM_CUDA(cudaMemsetAsync(step, 0, sizeof(int), s));
-      for (int i = 0; i < steps; ++i) RGFM_CUDA(cudaGraphLaunch(g_pre_y.e, s));
+      for (int i = 0; i < steps; ++i) RGFM_CUDA(cudaGraphLaunch(g_pre.e, s));
       RGFM_CUDA(cudaGraphLaunch(g_ratio.e, s));
     }
     RGFM_CUDA(cudaMemsetAsync(step, 0, sizeof(int), s));
