@@ -148,6 +148,7 @@ class Net:
 
     def __init__(self, kind: str, state_dict, max_batch: int, precision: str = "fp32", device="cuda"):
         self.kind = kind
+        self.max_batch = int(max_batch)
         self.device = torch.device("cuda", _dev_index(device))
         self.h = C.c_void_p()
         w = Weights(state_dict)
@@ -169,6 +170,15 @@ class Net:
         check(lib().rgfm_ratio_log_ratio(self.h, _ptr(x), _ptr(y), x.shape[0], LOSS[loss_type], _ptr(out), _ptr(sc),
                                          _stream_ptr(self.device)))
         return (out, sc) if return_scores else out
+
+    def classifier_logits(self, x: torch.Tensor) -> torch.Tensor:
+        """logits [B, 10] of an evaluator classifier (evaluate_mnist_svhn.py:45-47, evaluate.py:77-80); exact fp32."""
+        x = _f32c(x, self.device)
+        if x.shape[0] > self.max_batch:
+            raise RgfmError(f"batch {x.shape[0]} exceeds the net's max_batch {self.max_batch}")
+        out = torch.empty(x.shape[0], 10, device=self.device, dtype=torch.float32)
+        check(lib().rgfm_classifier_logits(self.h, _ptr(x), x.shape[0], _ptr(out), _stream_ptr(self.device)))
+        return out
 
     def close(self):
         if self.h:

@@ -128,9 +128,14 @@ int rgfm_ratio_log_ratio(rgfm_net* net, const float* x, const float* y, int32_t 
   RGFM_API_END
 }
 
-int rgfm_classifier_logits(rgfm_net*, const float*, int32_t, float*, void*) {
-  g_err = "rgfm_classifier_logits: not implemented in this build";
-  return 1;
+int rgfm_classifier_logits(rgfm_net* net, const float* x, int32_t batch, float* logits, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(net && net->net->kind() >= RGFM_NET_CLF_MNIST28 && net->net->kind() <= RGFM_NET_CLF_SVHN,
+             "rgfm_classifier_logits: not a classifier");
+  RGFM_CHECK(x && logits && batch >= 1, "rgfm_classifier_logits: null argument");
+  RGFM_CUDA(cudaSetDevice(net->device));
+  net->net->forward((cudaStream_t)stream, batch, x, nullptr, logits, 0, 0.f, nullptr);
+  RGFM_API_END
 }
 
 void rgfm_net_destroy(rgfm_net* net) { delete net; }

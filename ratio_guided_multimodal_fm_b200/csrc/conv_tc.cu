@@ -209,14 +209,15 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& d0, uint3
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(addr));
 }
-// D(16x8, fp32) += A(16x16) * B(16x8); only rows 0..7 of A are non-zero here (a1 = a3 = 0), c2/c3 are a shared dummy pair
-__device__ __forceinline__ void mma_f16_16816(float& c0, float& c1, float& z0, float& z1, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+// D(16x8, fp32) += A(16x16, row) * B(16x8, col) on the legacy tensor path (HMMA: ~16 cycles each on B200 and it shares
+// the tensor pipe with tcgen05, so the epilogue spends as few of them as it can)
+__device__ __forceinline__ void mma_f16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c0), "+f"(c1), "+f"(z0), "+f"(z1) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void mma_bf16_16816(float& c0, float& c1, float& z0, float& z1, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c0), "+f"(c1), "+f"(z0), "+f"(z1) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // packed fp16 pair -> packed bf16 pair of the squares (fp32 multiply, round to nearest: no overflow / underflow issues)
 __device__ __forceinline__ uint32_t sq2_bf16(uint32_t h2) {
@@ -572,47 +573,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           if (p.stats != nullptr && c0 < N) {
-            // GroupNorm partials of the ROUNDED values on the legacy tensor path: per warp, D[slot][channel] =
-            // Ind[slot][row] * X[row][channel] with mma.sync m16n8k16 (Ind = 0/1 image-slot indicator, rows = the
-            // warp's 32 staged rows, B fragments by ldmatrix.trans from the swizzled staging tile); the squares go
-            // through a bf16 MMA (fp32 multiply, rounded to bf16: no fp16 overflow / underflow).
-            float sm[8][2], sq[8][2];
+            // GroupNorm partials of the ROUNDED values on the legacy tensor path, channels on M and image slots on N:
+            //   S[ch][slot] = sum_row X[row][ch] * Ind[row][slot]   (Ind = 0/1: row belongs to image slot of the unit)
+            // per warp = its 32 staged rows: 4 channel blocks x 2 row blocks of mma.sync m16n8k16, A = X^T by
+            // ldmatrix.trans from the swizzled staging tile, B = the indicator built in registers.  The squares go through
+            // a bf16 MMA (fp32 multiply, rounded to bf16: no fp16 overflow / underflow).  16 + 16 HMMAs per warp and
+            // 64-channel chunk (a [slot][row] x [row][ch] formulation needs 4x as many, and HMMA is what bounds the epilogue).
+            float sm[4][4], sq[4][4];
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) sm[nb][0] = sm[nb][1] = sq[nb][0] = sq[nb][1] = 0.f;
-            float z0 = 0.f, z1 = 0.f;
-            const int mslot = lane >> 2;  // row of the indicator this thread's A fragment holds (only 0..2 are used)
+            for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) sm[cb][e] = sq[cb][e] = 0.f;
+            const int g = lane >> 2, t4 = lane & 3;
             const int mat = lane >> 3, rrow = lane & 7;
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
               const int r0 = wq * 32 + kb * 16;
-              // A fragment: a0 = Ind[mslot][k0, k0+1], a2 = Ind[mslot][k0+8, k0+9], k0 = 2 * (lane & 3)
-              const int k0 = r0 + ((lane & 3) << 1);
+              // B fragment: b0 = Ind[k0, k0+1][g], b1 = Ind[k0+8, k0+9][g], k0 = 2 * t4 (column g = image slot g)
               uint32_t ind[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int row = k0 + (e & 1) + ((e >> 1) << 3);
+                const int row = r0 + (t4 << 1) + (e & 1) + ((e >> 1) << 3);
                 const int sl = (row >= b1) + (row >= b2);
-                ind[e] = (sl == mslot) ? 1u : 0u;
+                ind[e] = (sl == g) ? 1u : 0u;
               }
-              const uint32_t a0h = ind[0] * 0x3C00u + ind[1] * 0x3C000000u, a2h = ind[2] * 0x3C00u + ind[3] * 0x3C000000u;  // fp16 1.0
-              const uint32_t a0b = ind[0] * 0x3F80u + ind[1] * 0x3F800000u, a2b = ind[2] * 0x3F80u + ind[3] * 0x3F800000u;  // bf16 1.0
-              const int lrow = r0 + ((mat & 1) << 3) + rrow;  // staged row this lane addresses for ldmatrix
+              const uint32_t b0h = ind[0] * 0x3C00u + ind[1] * 0x3C000000u, b1h = ind[2] * 0x3C00u + ind[3] * 0x3C000000u;  // fp16 1.0
+              const uint32_t b0b = ind[0] * 0x3F80u + ind[1] * 0x3F800000u, b1b = ind[2] * 0x3F80u + ind[3] * 0x3F800000u;  // bf16 1.0
+              // ldmatrix.x4.trans: matrices (rows r0.., chunk 2cb), (rows r0.., chunk 2cb+1), (rows r0+8.., 2cb), (rows r0+8.., 2cb+1)
+              // = A fragments a0 (ch 0-7, k 0-7), a1 (ch 8-15, k 0-7), a2 (ch 0-7, k 8-15), a3 (ch 8-15, k 8-15)
+              const int lrow = r0 + ((mat >> 1) << 3) + rrow;
 #pragma unroll
-              for (int jp = 0; jp < 4; ++jp) {
-                const uint32_t chunk16 = (uint32_t)(2 * jp + (mat >> 1));
-                uint32_t d0, d1, d2, d3;
-                ldsm_x4_trans(stg + (uint32_t)lrow * 128u + ((chunk16 ^ (uint32_t)(lrow & 7)) << 4), d0, d1, d2, d3);
-                mma_f16_16816(sm[2 * jp][0], sm[2 * jp][1], z0, z1, a0h, a2h, d0, d1);
-                mma_f16_16816(sm[2 * jp + 1][0], sm[2 * jp + 1][1], z0, z1, a0h, a2h, d2, d3);
-                mma_bf16_16816(sq[2 * jp][0], sq[2 * jp][1], z0, z1, a0b, a2b, sq2_bf16(d0), sq2_bf16(d1));
-                mma_bf16_16816(sq[2 * jp + 1][0], sq[2 * jp + 1][1], z0, z1, a0b, a2b, sq2_bf16(d2), sq2_bf16(d3));
+              for (int cb = 0; cb < 4; ++cb) {
+                const uint32_t chunk16 = (uint32_t)(2 * cb + (mat & 1));
+                uint32_t a[4];
+                ldsm_x4_trans(stg + (uint32_t)lrow * 128u + ((chunk16 ^ (uint32_t)(lrow & 7)) << 4), a[0], a[1], a[2], a[3]);
+                mma_f16_16816(sm[cb], a, b0h, b1h);
+                uint32_t a2[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a2[e] = sq2_bf16(a[e]);
+                mma_bf16_16816(sq[cb], a2, b0b, b1b);
               }
             }
-            if (mslot < 3) {  // lanes 0..11 hold D rows 0..2: slot mslot, channels nb*8 + 2*(lane&3) + {0,1}
+            // D fragment: c0 = (ch g, slot 2*t4), c1 = (ch g, slot 2*t4+1), c2 / c3 = the same for ch g + 8
+            if (t4 < 2) {
 #pragma unroll
-              for (int nb = 0; nb < 8; ++nb)
-                *reinterpret_cast<float4*>(&s_part[eg][wq][mslot][nb * 8 + ((lane & 3) << 1)][0]) =
-                    make_float4(sm[nb][0], sq[nb][0], sm[nb][1], sq[nb][1]);
+              for (int cb = 0; cb < 4; ++cb) {
+                float* d0 = &s_part[eg][wq][2 * t4][cb * 16 + g][0];
+                d0[0] = sm[cb][0]; d0[1] = sq[cb][0];       // slot 2*t4, channel g
+                d0[16] = sm[cb][2]; d0[17] = sq[cb][2];     // slot 2*t4, channel g + 8
+                if (t4 == 0) {
+                  float* d1 = &s_part[eg][wq][1][cb * 16 + g][0];
+                  d1[0] = sm[cb][1]; d1[1] = sq[cb][1];     // slot 1
+                  d1[16] = sm[cb][3]; d1[17] = sq[cb][3];
+                }
+              }
             }
             if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
             else asm volatile("bar.sync 2, 128;" ::: "memory");

@@ -586,6 +586,36 @@ struct Builder {
                         "mlp", mf, 512 * 4.0});
   }
 
+  // Evaluators' classifiers (classifier.py:9-52, svhn_classifier.py:11-118): conv [-> BN(eval)] -> ReLU [-> maxpool2] ... ->
+  // flatten (NCHW order) -> fc1 -> ReLU -> fc2.  Always exact fp32 (they decide an argmax; 8-44 MFLOP per sample).
+  struct ClfLayer { std::string conv, bn; int cin, cout; bool pool; };
+  void build_classifier(int in_ch, int img, const std::vector<ClfLayer>& L, int fc_hidden) {
+    net.in_ch_ = in_ch; net.img_ = img; net.out_stride_ = 10;
+    Packed cur = pack_input(in_ch, img, img, 16, false);
+    for (const ClfLayer& l : L) {
+      Act h = conv(cur, l.conv, l.cin, l.cout, 3, 1, -1, nullptr, false, false);
+      release(cur);
+      const float *g = nullptr, *b = nullptr;
+      if (!l.bn.empty()) bn_affine(l.bn, l.cout, &g, &b);
+      cur = pack({h}, l.bn.empty() ? NORM_NONE : NORM_AFFINE, g, b, ACT_RELU, l.pool ? SP_POOL2 : SP_ID, false);
+      release(h);
+    }
+    // fc1 consumes x.view(B, -1) of an NCHW tensor: permute its columns to our NHWC order once
+    const int HW = cur.H * cur.W, C = cur.C, in = HW * C;
+    const float* w1 = W.get("fc1.weight", (int64_t)fc_hidden * in);
+    std::vector<float> w1p((size_t)fc_hidden * in);
+    for (int j = 0; j < fc_hidden; ++j)
+      for (int c = 0; c < C; ++c)
+        for (int q = 0; q < HW; ++q) w1p[(size_t)j * in + (size_t)q * C + c] = w1[(size_t)j * in + (size_t)c * HW + q];
+    std::vector<MlpLayer> layers(2);
+    layers[0] = MlpLayer{pool.upload(w1p), vec("fc1.bias", fc_hidden), nullptr, nullptr, in, fc_hidden, ACT_RELU};
+    layers[1] = MlpLayer{vec("fc2.weight", 10 * fc_hidden), vec("fc2.bias", 10), nullptr, nullptr, fc_hidden, 10, ACT_NONE};
+    const float* src = (const float*)cur.p;
+    net.ops_.push_back({[=](const RunCtx& c) { launch_mlp(src, in, layers.data(), 2, c.out, 10, c.nimg, c.s); }, "mlp",
+                        2.0 * in * fc_hidden + 20.0 * fc_hidden, (double)in * 4.0});
+    // `cur` stays allocated: it is the MLP's input
+  }
+
   void build_ratio28() {  // reference: ratio_estimator.py:34-158
     net.in_ch_ = 1; net.in_ch_y_ = 1; net.img_ = 28;
     float* feat = (float*)pool.persistent((size_t)chunk * 512 * sizeof(float));
@@ -624,6 +654,19 @@ Net::Net(int kind, const rgfm_weights* w, int chunk, int precision, int device)
     case RGFM_NET_UNET_SVHN: b.build_unet(3, 32, 64, {1, 2, 2}, 2); break;
     case RGFM_NET_RATIO28: b.build_ratio28(); break;
     case RGFM_NET_RATIO_MNIST_SVHN: b.build_ratio_mnist_svhn(); break;
+    case RGFM_NET_CLF_MNIST28:
+      b.tc_mode = false;
+      b.build_classifier(1, 28, {{"conv1", "", 1, 32, true}, {"conv2", "", 32, 64, true}}, 128);
+      break;
+    case RGFM_NET_CLF_MNIST32:
+      b.tc_mode = false;
+      b.build_classifier(1, 32, {{"conv1", "", 1, 32, true}, {"conv2", "", 32, 64, true}, {"conv3", "", 64, 64, false}}, 128);
+      break;
+    case RGFM_NET_CLF_SVHN:
+      b.tc_mode = false;
+      b.build_classifier(3, 32, {{"conv1", "bn1", 3, 32, true}, {"conv2", "bn2", 32, 64, true}, {"conv3", "bn3", 64, 128, false},
+                                 {"conv4", "bn4", 128, 128, false}}, 256);
+      break;
     default: throw Error("net kind " + std::to_string(kind) + " is not implemented");
   }
   if (is_unet()) set_times({0.0f});
@@ -687,7 +730,7 @@ void Net::forward(cudaStream_t s, int nimg, const float* x, const float* y, floa
     c.nimg = std::min(chunk_, nimg - c0);
     c.x = x + c0 * dx;
     c.y = y ? y + c0 * dy : nullptr;
-    c.out = is_unet() ? out + c0 * dx : out + c0;
+    c.out = is_unet() ? out + c0 * dx : out + (size_t)c0 * out_stride_;
     c.out_mode = out_mode;
     c.dt = dt;
     c.step = step;

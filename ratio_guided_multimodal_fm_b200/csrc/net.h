@@ -69,7 +69,7 @@ class Net {
   void set_times(const std::vector<float>& ts);
 
   // Run on `nimg` images (looping over chunks).  U-Net: out_mode OUT_NCHW writes v, OUT_EULER does x += dt*v
-  // in place on `out`.  Ratio: x, y -> scores[nimg].
+  // in place on `out`.  Ratio: x, y -> scores[nimg].  Classifier: x -> logits[nimg][10].
   void forward(cudaStream_t s, int nimg, const float* x, const float* y, float* out, int out_mode, float dt,
                const int* step, std::vector<ProfRec>* prof = nullptr);
 
@@ -77,6 +77,7 @@ class Net {
   friend struct Builder;
   int kind_, chunk_, precision_, device_;
   int in_ch_ = 0, img_ = 0, in_ch_y_ = 0;
+  int out_stride_ = 1;  // floats per image of a non-U-Net output (ratio score: 1, classifier logits: 10)
   DevPool pool_;
   struct Op {
     std::function<void(const RunCtx&)> fn;

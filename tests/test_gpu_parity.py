@@ -234,3 +234,66 @@ def test_full_size_properties(synth):
     ps = mk("mc_feng", 0.5, 96, sdr)
     d = ps.run(x0[300:396], y0[300:396], m0, n0)
     assert maxabs(d[0], c[0][300:396]) <= 1e-3 and maxabs(d[1], c[1][300:396]) <= 1e-3  # D-split differs with B
+
+
+# ---- coherence evaluators (BASELINE configs[2]) -------------------------------------------
+@pytest.mark.parametrize("kind", ["clf_mnist28", "clf_mnist32", "clf_svhn"])
+def test_classifier_logits(kind, synth):
+    g = load_golden(f"{kind}_forward")
+    net = _lib.Net(kind, synth(kind, g["seed"]), max_batch=3, precision="fp32", device=DEV)  # ragged: 4 images, chunk 3
+    with pytest.raises(_lib.RgfmError):
+        net.classifier_logits(T(g["x"]).to(DEV))  # over max_batch
+    net.close()
+    net = _lib.Net(kind, synth(kind, g["seed"]), max_batch=4, precision="fp32", device=DEV)
+    logits = net.classifier_logits(T(g["x"]).to(DEV))
+    ref = T(g["logits"])
+    assert maxabs(logits, ref) <= 2e-4 * max(1.0, ref.abs().max().item())
+    assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1))
+    net.close()
+
+
+def test_coherence_evaluators_match_oracle(synth):
+    """evaluate_coherence* == the reference's argmax-agreement on the same pairs (exact: fp32 classifiers)."""
+    from ratio_guided_multimodal_fm_b200 import evaluate_coherence, evaluate_coherence_mnist_svhn
+    gen = torch.Generator().manual_seed(3)
+    n = 300
+    xm, ys = torch.randn(n, 1, 32, 32, generator=gen), torch.randn(n, 3, 32, 32, generator=gen)
+    cm = synthetic.StateDictModule("clf_mnist32", synth("clf_mnist32", 31))
+    cs = synthetic.StateDictModule("clf_svhn", synth("clf_svhn", 32))
+    ours = evaluate_coherence_mnist_svhn(xm, ys, cm, cs, DEV)
+    pm = O.classifier_logits(cm.state_dict(), "clf_mnist32", xm).argmax(1)
+    ps = O.classifier_logits(cs.state_dict(), "clf_svhn", ys).argmax(1)
+    assert ours["num_samples"] == n and abs(ours["coherence_acc"] - float((pm == ps).double().mean())) < 1e-9
+    # 28x28 pair with the rotate90 inverse transform (evaluate.py:56-90)
+    x, y = torch.randn(n, 1, 28, 28, generator=gen), torch.randn(n, 1, 28, 28, generator=gen)
+    c28 = synthetic.StateDictModule("clf_mnist28", synth("clf_mnist28", 33))
+    ours = evaluate_coherence(x, y, c28, DEV, transform_type="rotate90")
+    px = O.classifier_logits(c28.state_dict(), "clf_mnist28", x).argmax(1)
+    py = O.classifier_logits(c28.state_dict(), "clf_mnist28", torch.rot90(y, 1, dims=(-2, -1))).argmax(1)
+    assert abs(ours["coherence_acc"] - float((px == py).double().mean())) < 1e-9
+
+
+@pytest.mark.parametrize("gamma", [0.0, 0.5, 2.0, 5.0])
+def test_guidance_strength_sweep_coherence(gamma, synth):
+    """BASELINE configs[2] shape at a CPU-oracle-sized batch: gamma sweep incl. the extrapolating 2 and 5, pair coherence
+    of the CUDA sampler within 0.5 pt of the reference sampler's (fp32: identical predictions; fp16: <= 1 of 64 flips)."""
+    from ratio_guided_multimodal_fm_b200 import evaluate_coherence_mnist_svhn
+    sdx, sdy, sdr = synth("unet_mnist32", 12), synth("unet_svhn", 13), synth("ratio_mnist_svhn", 22)
+    cm = synthetic.StateDictModule("clf_mnist32", synth("clf_mnist32", 31))
+    cs = synthetic.StateDictModule("clf_svhn", synth("clf_svhn", 32))
+    B, N, steps = 64, 16, 8
+    gen = torch.Generator().manual_seed(77)
+    x0, y0 = torch.randn(B, 1, 32, 32, generator=gen), torch.randn(B, 3, 32, 32, generator=gen)
+    m0, n0 = torch.randn(N, 1, 32, 32, generator=gen), torch.randn(N, 3, 32, 32, generator=gen)
+    method = "mc_feng" if gamma > 0 else "none"
+    ox, oy = O.sample_pair(sdx, sdy, sdr if gamma > 0 else None, "mnist_svhn", method, gamma, steps, x0, y0, m0, n0, "disc")
+    ref = float((O.classifier_logits(cm.state_dict(), "clf_mnist32", ox).argmax(1) ==
+                 O.classifier_logits(cs.state_dict(), "clf_svhn", oy).argmax(1)).float().mean())
+    for prec, slack in (("fp32", 0.005), ("fp16", 1.0 / B + 1e-9)):
+        plan = _lib.SamplerPlan("mnist_svhn", sdx, sdy, sdr if gamma > 0 else None, guidance_method=method,
+                                guidance_strength=gamma, num_samples=B, num_steps=steps, mc_batch_size=N, precision=prec, device=DEV)
+        x1, y1 = plan.run(x0.to(DEV), y0.to(DEV), m0.to(DEV) if gamma > 0 else None, n0.to(DEV) if gamma > 0 else None)
+        got = evaluate_coherence_mnist_svhn(x1, y1, cm, cs, DEV)["coherence_acc"]
+        assert abs(got - ref) <= slack, (gamma, prec, got, ref)
+        assert torch.isfinite(x1).all() and torch.isfinite(y1).all()
+        plan.close()

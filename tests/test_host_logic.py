@@ -62,10 +62,12 @@ def _worker(rank, world, port, n, q):
         xl, yl = x0[lo:hi] * 2 + 1, y0[lo:hi] * 3 - 1  # stand-in for the per-rank sampler
         xg, yg = gather_pairs(xl, yl, n)
         ok = torch.equal(xg, x0 * 2 + 1) and torch.equal(yg, y0 * 3 - 1)
-        # coherence count all_reduce
-        cnt = torch.tensor([hi - lo], dtype=torch.int64)
-        dist.all_reduce(cnt)
-        ok = ok and int(cnt) == n
+        # coherence count all_reduce (evaluate._coherence: per-rank match counts summed over ranks)
+        from ratio_guided_multimodal_fm_b200.evaluate import _coherence
+        pa = torch.arange(n)[lo:hi] % 3
+        pb = torch.zeros(hi - lo, dtype=torch.int64)
+        res = _coherence(pa, pb, n, True, None)
+        ok = ok and res["num_samples"] == n and abs(res["coherence_acc"] - float(((torch.arange(n) % 3) == 0).sum()) / n) < 1e-12
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
@@ -83,3 +85,15 @@ def test_gloo_world2_gather_equals_single_device(n):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_inverse_transforms_are_the_reference_pixel_permutations():
+    """evaluate.py:30-53 uses torchvision rotate / flips; ours are torch.rot90 / flip."""
+    from ratio_guided_multimodal_fm_b200 import get_inverse_transform
+    tvf = pytest.importorskip("torchvision.transforms.functional")
+    img = torch.randn(3, 1, 28, 28)
+    ref = {"rotate90": lambda t: tvf.rotate(t, 90), "rotate180": lambda t: tvf.rotate(t, 180),
+           "rotate270": lambda t: tvf.rotate(t, -90), "flip_h": tvf.hflip, "flip_v": tvf.vflip, "invert": lambda t: -t,
+           "none": lambda t: t}
+    for name, f in ref.items():
+        assert torch.allclose(get_inverse_transform(name)(img), f(img), atol=0), name
