@@ -280,6 +280,12 @@ def sample_pair(sd_x: StateDict, sd_y: StateDict, sd_r: Optional[StateDict], pai
                     w_min=w.min().item(), w_max=w.max().item(), z_bar=Z.mean().item())
             v_x = (1 - guidance_strength) * v_x + guidance_strength * g_x
             v_y = (1 - guidance_strength) * v_y + guidance_strength * g_y
+        elif guidance_method == "grad_log_ratio" and sd_r is not None:
+            # README.md:159-164: v_guided = v_ind + gamma * grad log r(x_t, y_t) (no reference implementation: UNPINNED)
+            _, _, kr, _, _ = PAIR_KINDS[pair]
+            g_x, g_y, _ = grad_log_ratio(sd_r, kr, x_t, y_t, loss_type)
+            v_x = v_x + guidance_strength * g_x
+            v_y = v_y + guidance_strength * g_y
         x_t = x_t + v_x * dt
         y_t = y_t + v_y * dt
     if return_aux:

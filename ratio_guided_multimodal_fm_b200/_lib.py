@@ -57,7 +57,7 @@ _lib = None
 EXPORTS = [
     "rgfm_last_error", "rgfm_abi_version", "rgfm_sampler_create", "rgfm_sampler_run", "rgfm_sampler_run_host",
     "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
-    "rgfm_unet_forward", "rgfm_ratio_log_ratio", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
+    "rgfm_unet_forward", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_log_ratio", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
 ]
 
 
@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
     L.rgfm_unet_forward.argtypes = [vp, vp, C.c_float, C.c_int32, vp, vp]
     L.rgfm_ratio_log_ratio.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
     L.rgfm_classifier_logits.argtypes = [vp, vp, C.c_int32, vp, vp]
+    L.rgfm_ratio_grad_create.argtypes = [C.c_int32, C.POINTER(_Weights), C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.rgfm_ratio_grad_log_ratio.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
     L.rgfm_net_destroy.argtypes = [vp]
     L.rgfm_net_destroy.restype = None
     L.rgfm_mc_feng_step.argtypes = [C.c_int32] * 4 + [vp] * 7 + [C.c_double] * 3 + [vp] * 5 + [vp]
@@ -146,14 +148,28 @@ def _f32c(t: torch.Tensor, device) -> torch.Tensor:
 class Net:
     """One network of the path behind the C ABI (component entry points)."""
 
-    def __init__(self, kind: str, state_dict, max_batch: int, precision: str = "fp32", device="cuda"):
+    def __init__(self, kind: str, state_dict, max_batch: int, precision: str = "fp32", device="cuda", grad: bool = False):
         self.kind = kind
         self.max_batch = int(max_batch)
         self.device = torch.device("cuda", _dev_index(device))
         self.h = C.c_void_p()
         w = Weights(state_dict)
-        check(lib().rgfm_net_create(NET_KINDS[kind], w.ref(), int(max_batch), PRECISION[precision],
-                                    self.device.index, C.byref(self.h)))
+        if grad:  # forward + input-gradient program of a ratio estimator (exact fp32)
+            check(lib().rgfm_ratio_grad_create(NET_KINDS[kind], w.ref(), int(max_batch), self.device.index, C.byref(self.h)))
+        else:
+            check(lib().rgfm_net_create(NET_KINDS[kind], w.ref(), int(max_batch), PRECISION[precision],
+                                        self.device.index, C.byref(self.h)))
+
+    def grad_log_ratio(self, x: torch.Tensor, y: torch.Tensor, loss_type: str = "disc"):
+        """(d log r/dx, d log r/dy, log r) -- README.md:159-164; oracle: autograd through the restated estimator."""
+        if loss_type not in LOSS:
+            raise ValueError(f"Unknown loss_type: {loss_type}")
+        x, y = _f32c(x, self.device), _f32c(y, self.device)
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        lr = torch.empty(x.shape[0], device=self.device, dtype=torch.float32)
+        check(lib().rgfm_ratio_grad_log_ratio(self.h, _ptr(x), _ptr(y), x.shape[0], LOSS[loss_type], _ptr(gx), _ptr(gy), _ptr(lr),
+                                              _stream_ptr(self.device)))
+        return gx, gy, lr
 
     def unet_forward(self, x: torch.Tensor, t: float) -> torch.Tensor:
         x = _f32c(x, self.device)
@@ -203,8 +219,9 @@ class SamplerPlan:
         self.B, self.N, self.steps = int(num_samples), int(mc_batch_size), int(num_steps)
         # unknown guidance methods silently degrade to unguided like the reference (flow_utils.py:231,273)
         g = GUIDANCE.get(guidance_method, 0)
-        self.guided = (g == 1 and sd_ratio is not None)
-        if sd_ratio is not None and g == 1 and loss_type not in LOSS:
+        self.guided = (g == 1 and sd_ratio is not None)          # needs the MC noise
+        self.grad_guided = (g == 2 and sd_ratio is not None)
+        if sd_ratio is not None and g in (1, 2) and loss_type not in LOSS:
             raise ValueError(f"Unknown loss_type: {loss_type}")
         d = _SamplerDesc(ABI_VERSION, PAIRS[pair], g, LOSS.get(loss_type, 0), PRECISION[precision], self.B, self.N,
                          self.steps, float(guidance_strength), self.device.index, int(chunk))

@@ -128,6 +128,27 @@ int rgfm_ratio_log_ratio(rgfm_net* net, const float* x, const float* y, int32_t 
   RGFM_API_END
 }
 
+int rgfm_ratio_grad_create(int32_t net_kind, const rgfm_weights* w, int32_t max_batch, int32_t device, rgfm_net** out) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(out != nullptr, "rgfm_ratio_grad_create: null out");
+  std::unique_ptr<rgfm_net> n(new rgfm_net());
+  n->device = device;
+  n->net.reset(new rgfm::Net(net_kind, w, max_batch, RGFM_PREC_FP32, device, /*want_grad=*/true));
+  *out = n.release();
+  RGFM_API_END
+}
+
+int rgfm_ratio_grad_log_ratio(rgfm_net* net, const float* x, const float* y, int32_t batch, int32_t loss_type, float* grad_x,
+                              float* grad_y, float* log_ratio, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(net && net->net->has_grad(), "rgfm_ratio_grad_log_ratio: not a gradient-mode ratio estimator");
+  RGFM_CHECK(x && y && grad_x && grad_y && batch >= 1, "rgfm_ratio_grad_log_ratio: null argument");
+  RGFM_CHECK(loss_type == RGFM_LOSS_DISC || loss_type == RGFM_LOSS_RULSIF, "Unknown loss_type");
+  RGFM_CUDA(cudaSetDevice(net->device));
+  net->net->grad_log_ratio((cudaStream_t)stream, batch, x, y, loss_type, grad_x, grad_y, log_ratio);
+  RGFM_API_END
+}
+
 int rgfm_classifier_logits(rgfm_net* net, const float* x, int32_t batch, float* logits, void* stream) {
   RGFM_API_BEGIN
   RGFM_CHECK(net && net->net->kind() >= RGFM_NET_CLF_MNIST28 && net->net->kind() <= RGFM_NET_CLF_SVHN,

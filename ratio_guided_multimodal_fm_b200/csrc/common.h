@@ -216,6 +216,11 @@ struct MlpLayer {
 };
 void launch_mlp(const float* in, int ld_in, const MlpLayer* layers, int nlayers, float* out, int ld_out, int nimg,
                 cudaStream_t s);
+void launch_mlp_bwd(const float* in, int ld_in, const MlpLayer* layers, int nlayers, int loss_type, float* scores, float* log_ratio,
+                    float* dfeat, int ld_d, int nimg, cudaStream_t s);
+void launch_gap_fc_bwd(const float* dfeat, int ld, const float* w, int Cout, int HW, int C, float* dact, int nimg, cudaStream_t s);
+void launch_pack_bwd(const PackArgs& a, const float* dcur, float* draw, cudaStream_t s);
+void launch_euler_grad(float* x, const float* v, const float* g, float gamma, float dt, size_t n, cudaStream_t s);
 void launch_ratio_head(const float* scores, int loss_type, float* log_ratio, float* ratios, int n, cudaStream_t s);
 void launch_step_inc(int* step, cudaStream_t s);
 void launch_euler(float* x, const float* v, float dt, size_t n, cudaStream_t s);

@@ -169,7 +169,7 @@ struct Builder {
   }
 
   Packed pack(const std::vector<Act>& srcs, int norm, const float* gamma, const float* beta, int act, int spatial,
-              bool out_bf16) {
+              bool out_bf16, PackArgs* saved = nullptr) {
     PackArgs a{};
     a.nsrc = (int)srcs.size();
     RGFM_CHECK(a.nsrc >= 1 && a.nsrc <= 2, "pack: 1 or 2 sources");
@@ -195,6 +195,7 @@ struct Builder {
     a.Cpad = p.C;
     const double bytes = in_bytes + (double)a.Ho * a.Wo * C * (out_bf16 ? 2.0 : 4.0);
     const bool padded = p.padded;
+    if (saved) *saved = a;
     net.ops_.push_back({[a, padded](const RunCtx& c) {
       PackArgs b = a;
       b.nimg = c.nimg;
@@ -518,9 +519,13 @@ struct Builder {
   }
 
   // conv -> (GN | BN-eval) -> SiLU [-> maxpool2] ... -> GAP -> fc into feat[:, off:off+256]
+  // `bwd` (gradient mode): every raw activation is kept, and the dgrad chain of this encoder is appended to *bwd:
+  //   dfeat -> GAP/fc backward -> [pack backward (pool routing, SiLU', GN / BN backward) -> conv dgrad] x layers -> d input.
+  // Conv dgrad is the same fp32 implicit-GEMM kernel run with the transposed, spatially flipped filter.
   void encoder(const std::string& pre, const std::vector<EncLayer>& L, bool gn, int in_ch, int img, bool from_y,
-               float* feat, int feat_ld, int feat_off, int fc_in) {
+               float* feat, int feat_ld, int feat_off, int fc_in, std::vector<Net::Op>* bwd = nullptr, const float* dfeat = nullptr) {
     Packed cur = pack_input(in_ch, img, img, 16, from_y);
+    std::vector<PackArgs> saved(L.size());
     // spatial size seen by each conv, and whether it runs on the tensor cores: layer 0 (K = 9/27) and the tiny
     // late layers (fewer than 64 GEMM rows per image) stay on the exact fp32 path
     std::vector<int> sp(L.size());
@@ -551,8 +556,9 @@ struct Builder {
       } else {
         bn_affine(pre + l.norm, l.cout, &g, &b);
       }
-      cur = pack({h}, gn ? NORM_GN : NORM_AFFINE, g, b, ACT_SILU, l.pool ? SP_POOL2 : SP_ID, last ? false : (bool)ltc[i + 1]);
-      release(h);
+      cur = pack({h}, gn ? NORM_GN : NORM_AFFINE, g, b, ACT_SILU, l.pool ? SP_POOL2 : SP_ID, last ? false : (bool)ltc[i + 1],
+                 &saved[i]);
+      if (!bwd) release(h);
     }
     const float* fw = vec(pre + "fc.weight", 256 * fc_in);
     const float* fb = vec(pre + "fc.bias", 256);
@@ -560,10 +566,55 @@ struct Builder {
     const int HW = cur.H * cur.W, C = cur.C;
     net.ops_.push_back({[=](const RunCtx& c) { launch_gap_fc(src, HW, C, fw, fb, 256, feat + feat_off, feat_ld, c.nimg, c.s); },
                         "gap_fc", 2.0 * 256 * C, (double)HW * C * 4.0});
-    release(cur);
+    if (!bwd) {
+      release(cur);
+      return;
+    }
+    // ---- dgrad chain (appended after the score-net backward) ----
+    float* dcur = (float*)pool.alloc((size_t)chunk * HW * C * sizeof(float));
+    bwd->push_back({[=](const RunCtx& c) { launch_gap_fc_bwd(dfeat + feat_off, feat_ld, fw, 256, HW, C, dcur, c.nimg, c.s); }, "gap_fc_bwd",
+                    2.0 * 256 * C, (double)HW * C * 4.0});
+    for (int i = (int)L.size() - 1; i >= 0; --i) {
+      const EncLayer& l = L[i];
+      const int H = saved[i].Hs;
+      float* draw = (float*)pool.alloc((size_t)chunk * H * H * l.cout * sizeof(float));
+      const PackArgs pa = saved[i];
+      const float* dc = dcur;
+      bwd->push_back({[=](const RunCtx& c) {
+        PackArgs b = pa;
+        b.nimg = c.nimg;
+        launch_pack_bwd(b, dc, draw, c.s);
+      }, "pack_bwd", 0.0, (double)H * H * l.cout * 12.0});
+      // conv dgrad: dIn[h][w][ci] = sum_{tap, co} dRaw[h + ky - 1][w + kx - 1][co] * W[co][ci][2 - ky][2 - kx]
+      const int cinP = (l.cin + 31) / 32 * 32;
+      const float* wt = W.get(pre + l.conv + ".weight", (int64_t)l.cout * l.cin * 9);
+      std::vector<float> wf((size_t)9 * l.cout * cinP, 0.f);
+      for (int co = 0; co < l.cout; ++co)
+        for (int ci = 0; ci < l.cin; ++ci)
+          for (int t = 0; t < 9; ++t) wf[((size_t)t * l.cout + co) * cinP + ci] = wt[((size_t)co * l.cin + ci) * 9 + (8 - t)];
+      ConvArgs ca{};
+      ca.in = draw; ca.Hin = H; ca.Win = H; ca.Cin = l.cout;
+      ca.w = pool.upload(wf);
+      ca.bias = pool.upload(std::vector<float>(cinP, 0.f));
+      ca.CoutP = cinP; ca.Cout = l.cin; ca.ks = 3; ca.stride = 1; ca.pad = 1;
+      ca.g = make_geom(H, H);
+      const bool first = (i == 0);
+      float* dnext = first ? nullptr : (float*)pool.alloc((size_t)chunk * H * H * l.cin * sizeof(float));
+      ca.out_mode = first ? OUT_NCHW : OUT_RAW;
+      ca.out = dnext;
+      bwd->push_back({[=](const RunCtx& c) {
+        ConvArgs b = ca;
+        b.nimg = c.nimg;
+        if (first) b.out = from_y ? c.gy : c.gx;
+        launch_conv_simt(b, c.s);
+      }, "conv_dgrad", 2.0 * H * H * (double)l.cout * l.cin * 9, (double)H * H * (l.cout + l.cin) * 4.0,
+         pre + l.conv + " dgrad " + std::to_string(H) + "x" + std::to_string(H) + " " + std::to_string(l.cout) + "->" + std::to_string(l.cin)});
+      dcur = dnext;
+    }
   }
 
-  void score_net(const float* feat, const std::vector<std::pair<int, int>>& lin_ln, int last, const std::vector<int>& dims) {
+  void score_net(const float* feat, const std::vector<std::pair<int, int>>& lin_ln, int last, const std::vector<int>& dims,
+                 float* dfeat = nullptr) {
     std::vector<MlpLayer> layers;
     int in = 512;
     for (size_t i = 0; i < lin_ln.size(); ++i) {
@@ -582,6 +633,12 @@ struct Builder {
     layers.push_back(f);
     double mf = 0;
     for (auto& l : layers) mf += 2.0 * l.in * l.out;
+    if (dfeat) {  // forward + head + backward to the 512 features in one kernel
+      net.ops_.push_back({[=](const RunCtx& c) {
+        launch_mlp_bwd(feat, 512, layers.data(), (int)layers.size(), c.loss_type, nullptr, c.out, dfeat, 512, c.nimg, c.s);
+      }, "mlp_bwd", 3.0 * mf, 512 * 8.0});
+      return;
+    }
     net.ops_.push_back({[=](const RunCtx& c) { launch_mlp(feat, 512, layers.data(), (int)layers.size(), c.out, 1, c.nimg, c.s); },
                         "mlp", mf, 512 * 4.0});
   }
@@ -616,31 +673,38 @@ struct Builder {
     // `cur` stays allocated: it is the MLP's input
   }
 
-  void build_ratio28() {  // reference: ratio_estimator.py:34-158
+  void build_ratio28(bool grad) {  // reference: ratio_estimator.py:34-158
     net.in_ch_ = 1; net.in_ch_y_ = 1; net.img_ = 28;
     float* feat = (float*)pool.persistent((size_t)chunk * 512 * sizeof(float));
+    float* dfeat = grad ? (float*)pool.persistent((size_t)chunk * 512 * sizeof(float)) : nullptr;
+    std::vector<Net::Op> bwd;
     std::vector<EncLayer> L{{"conv1", "gn1", 1, 32, true}, {"conv2", "gn2", 32, 64, true}, {"conv3", "gn3", 64, 128, true}, {"conv4", "gn4", 128, 128, false}};
-    encoder("encoder_x.", L, true, 1, 28, false, feat, 512, 0, 128);
-    encoder("encoder_y.", L, true, 1, 28, true, feat, 512, 256, 128);
-    score_net(feat, {{0, 1}, {4, 5}}, 8, {512, 256});
+    encoder("encoder_x.", L, true, 1, 28, false, feat, 512, 0, 128, grad ? &bwd : nullptr, dfeat);
+    encoder("encoder_y.", L, true, 1, 28, true, feat, 512, 256, 128, grad ? &bwd : nullptr, dfeat);
+    score_net(feat, {{0, 1}, {4, 5}}, 8, {512, 256}, dfeat);
+    for (auto& op : bwd) net.ops_.push_back(op);
   }
 
-  void build_ratio_mnist_svhn() {  // reference: ratio_flexible.py:185-364
+  void build_ratio_mnist_svhn(bool grad) {  // reference: ratio_flexible.py:185-364
     net.in_ch_ = 1; net.in_ch_y_ = 3; net.img_ = 32;
     float* feat = (float*)pool.persistent((size_t)chunk * 512 * sizeof(float));
+    float* dfeat = grad ? (float*)pool.persistent((size_t)chunk * 512 * sizeof(float)) : nullptr;
+    std::vector<Net::Op> bwd;
     std::vector<EncLayer> M{{"conv1", "bn1", 1, 32, true}, {"conv2", "bn2", 32, 64, true}, {"conv3", "bn3", 64, 128, true}, {"conv4", "bn4", 128, 128, false}};
-    encoder("encoder_mnist.", M, false, 1, 32, false, feat, 512, 0, 128);
+    encoder("encoder_mnist.", M, false, 1, 32, false, feat, 512, 0, 128, grad ? &bwd : nullptr, dfeat);
     std::vector<EncLayer> S{{"conv1a", "bn1a", 3, 64, false},   {"conv1b", "bn1b", 64, 64, true},   {"conv2a", "bn2a", 64, 128, false},
                             {"conv2b", "bn2b", 128, 128, true}, {"conv3a", "bn3a", 128, 256, false}, {"conv3b", "bn3b", 256, 256, true},
                             {"conv4a", "bn4a", 256, 256, false}, {"conv4b", "bn4b", 256, 256, true}};
-    encoder("encoder_svhn.", S, false, 3, 32, true, feat, 512, 256, 256);
-    score_net(feat, {{0, 1}, {4, 5}, {8, 9}}, 11, {512, 512, 256});
+    encoder("encoder_svhn.", S, false, 3, 32, true, feat, 512, 256, 256, grad ? &bwd : nullptr, dfeat);
+    score_net(feat, {{0, 1}, {4, 5}, {8, 9}}, 11, {512, 512, 256}, dfeat);
+    for (auto& op : bwd) net.ops_.push_back(op);
   }
 };
 
 // ------------------------------------------------------------------------------------------------
-Net::Net(int kind, const rgfm_weights* w, int chunk, int precision, int device)
-    : kind_(kind), chunk_(chunk), precision_(precision), device_(device) {
+Net::Net(int kind, const rgfm_weights* w, int chunk, int precision, int device, bool want_grad)
+    : kind_(kind), chunk_(chunk), precision_(precision), device_(device), want_grad_(want_grad) {
+  RGFM_CHECK(!want_grad || kind == RGFM_NET_RATIO28 || kind == RGFM_NET_RATIO_MNIST_SVHN, "net: only ratio estimators have a gradient program");
   RGFM_CHECK(chunk >= 1, "net: chunk");
   RGFM_CHECK(precision == RGFM_PREC_FP32 || precision == RGFM_PREC_BF16 || precision == RGFM_PREC_FP16,
              "net: precision must be fp32, bf16 or fp16");
@@ -652,8 +716,14 @@ Net::Net(int kind, const rgfm_weights* w, int chunk, int precision, int device)
     case RGFM_NET_UNET_MNIST28: b.build_unet(1, 28, 32, {1, 2}, 2); break;
     case RGFM_NET_UNET_MNIST32: b.build_unet(1, 32, 32, {1, 2}, 2); break;
     case RGFM_NET_UNET_SVHN: b.build_unet(3, 32, 64, {1, 2, 2}, 2); break;
-    case RGFM_NET_RATIO28: b.build_ratio28(); break;
-    case RGFM_NET_RATIO_MNIST_SVHN: b.build_ratio_mnist_svhn(); break;
+    case RGFM_NET_RATIO28:
+      if (want_grad) b.tc_mode = false;  // the dgrad chain is exact fp32
+      b.build_ratio28(want_grad);
+      break;
+    case RGFM_NET_RATIO_MNIST_SVHN:
+      if (want_grad) b.tc_mode = false;
+      b.build_ratio_mnist_svhn(want_grad);
+      break;
     case RGFM_NET_CLF_MNIST28:
       b.tc_mode = false;
       b.build_classifier(1, 28, {{"conv1", "", 1, 32, true}, {"conv2", "", 32, 64, true}}, 128);
@@ -670,6 +740,7 @@ Net::Net(int kind, const rgfm_weights* w, int chunk, int precision, int device)
     default: throw Error("net kind " + std::to_string(kind) + " is not implemented");
   }
   if (is_unet()) set_times({0.0f});
+  if (want_grad_) d_lr_scratch_ = (float*)pool_.persistent((size_t)chunk_ * sizeof(float));  // never allocate inside a capture
 }
 
 Net::~Net() {
@@ -720,17 +791,30 @@ void Net::set_times(const std::vector<float>& ts) {
   RGFM_CUDA(cudaMemcpy(d_temb_, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice));
 }
 
+void Net::grad_log_ratio(cudaStream_t s, int nimg, const float* x, const float* y, int loss_type, float* gx, float* gy,
+                         float* log_ratio, std::vector<ProfRec>* prof) {
+  RGFM_CHECK(want_grad_, "net: built without the gradient program");
+  RGFM_CHECK(loss_type == RGFM_LOSS_DISC || loss_type == RGFM_LOSS_RULSIF, "Unknown loss_type");
+  g_gx_ = gx; g_gy_ = gy; g_loss_ = loss_type; g_lr_null_ = (log_ratio == nullptr);
+  forward(s, nimg, x, y, log_ratio ? log_ratio : d_lr_scratch_, 0, 0.f, nullptr, prof);
+  g_gx_ = g_gy_ = nullptr;
+}
+
 void Net::forward(cudaStream_t s, int nimg, const float* x, const float* y, float* out, int out_mode, float dt,
                   const int* step, std::vector<ProfRec>* prof) {
   const size_t dx = (size_t)in_ch_ * img_ * img_;
   const size_t dy = (size_t)in_ch_y_ * img_ * img_;
+  RGFM_CHECK(!want_grad_ || g_gx_ != nullptr, "net: a gradient-mode estimator runs through grad_log_ratio()");
   for (int c0 = 0; c0 < nimg; c0 += chunk_) {
     RunCtx c;
+    c.gx = g_gx_ ? g_gx_ + c0 * dx : nullptr;
+    c.gy = g_gy_ ? g_gy_ + c0 * dy : nullptr;
+    c.loss_type = g_loss_;
     c.s = s;
     c.nimg = std::min(chunk_, nimg - c0);
     c.x = x + c0 * dx;
     c.y = y ? y + c0 * dy : nullptr;
-    c.out = is_unet() ? out + c0 * dx : out + (size_t)c0 * out_stride_;
+    c.out = is_unet() ? out + c0 * dx : (g_lr_null_ ? out : out + (size_t)c0 * out_stride_);
     c.out_mode = out_mode;
     c.dt = dt;
     c.step = step;

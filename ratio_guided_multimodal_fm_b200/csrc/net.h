@@ -47,6 +47,9 @@ struct RunCtx {
   int out_mode;
   float dt;
   const int* step;     // device step index selecting the time-bias row (null = row 0)
+  float* gx = nullptr; // ratio estimator in gradient mode: d log r / dx, dy of the chunk (NCHW fp32)
+  float* gy = nullptr;
+  int loss_type = 0;
 };
 
 struct TcConv;  // conv_tc.cu
@@ -55,7 +58,12 @@ using TcPtr = std::unique_ptr<TcConv, TcDeleter>;
 
 class Net {
  public:
-  Net(int kind, const rgfm_weights* w, int chunk, int precision, int device);
+  // want_grad (ratio estimators only): build the forward + input-gradient (dgrad-only) program; exact fp32
+  Net(int kind, const rgfm_weights* w, int chunk, int precision, int device, bool want_grad = false);
+  bool has_grad() const { return want_grad_; }
+  // d log r(x, y) / d(x, y) per README.md:159-164; log_ratio [nimg] optional
+  void grad_log_ratio(cudaStream_t s, int nimg, const float* x, const float* y, int loss_type, float* gx, float* gy,
+                      float* log_ratio, std::vector<ProfRec>* prof = nullptr);
   ~Net();
   int kind() const { return kind_; }
   bool is_unet() const { return kind_ <= RGFM_NET_UNET_SVHN; }
@@ -76,6 +84,11 @@ class Net {
  private:
   friend struct Builder;
   int kind_, chunk_, precision_, device_;
+  bool want_grad_ = false;
+  float* d_lr_scratch_ = nullptr;
+  float *g_gx_ = nullptr, *g_gy_ = nullptr;  // set for the duration of grad_log_ratio()
+  int g_loss_ = 0;
+  bool g_lr_null_ = false;
   int in_ch_ = 0, img_ = 0, in_ch_y_ = 0;
   int out_stride_ = 1;  // floats per image of a non-U-Net output (ratio score: 1, classifier logits: 10)
   DevPool pool_;

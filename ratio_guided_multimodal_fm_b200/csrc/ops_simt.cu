@@ -809,6 +809,307 @@ void launch_ratio_head(const float* scores, int loss_type, float* log_ratio, flo
   post_launch("ratio_head");
 }
 
+// ================================================================================================
+// Input-gradient (dgrad-only) chain of the ratio estimators: d log r(x, y) / d(x, y), no weight gradients.
+// README.md:159-164 (v = v_ind + gamma * grad log r); oracle: autograd through the restated estimator.
+// ================================================================================================
+
+// ---- score-net backward: one CTA per sample recomputes the MLP forward keeping every intermediate in shared memory,
+// applies the head (disc: log r = T; rulsif: log(softplus(T) + 1e-8)) and back-propagates to the 512 features.
+__device__ __forceinline__ float block_sum256(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < 8; ++w) r += red[w];
+  return r;
+}
+
+struct MlpPackB {
+  MlpLayer l[4];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) mlp_bwd_kernel(const float* __restrict__ in, int ld_in, MlpPackB mp, int loss_type,
+                                                      float* __restrict__ scores, float* __restrict__ log_ratio,
+                                                      float* __restrict__ dfeat, int ld_d) {
+  extern __shared__ float sm[];
+  __shared__ float red[8];
+  __shared__ float s_mean[4], s_rstd[4];
+  const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // layout: a[0] = input (in0), then per layer: h (pre-LN), a (post-activation); finally two gradient buffers
+  float* act[5];
+  float* pre[4];
+  int off = 0;
+  act[0] = sm;
+  off += mp.l[0].in;
+  for (int li = 0; li < mp.n; ++li) {
+    pre[li] = sm + off; off += mp.l[li].out;
+    act[li + 1] = sm + off; off += mp.l[li].out;
+  }
+  float* gcur = sm + off; off += 512;
+  float* gnext = sm + off;
+  for (int i = tid; i < mp.l[0].in; i += 256) act[0][i] = in[(size_t)n * ld_in + i];
+  __syncthreads();
+  // ---- forward ----
+  for (int li = 0; li < mp.n; ++li) {
+    const MlpLayer L = mp.l[li];
+    for (int j = warp; j < L.out; j += 8) {
+      const float* wr = L.w + (size_t)j * L.in;
+      float s = 0.f;
+      for (int c = lane; c < L.in; c += 32) s = fmaf(wr[c], act[li][c], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) pre[li][j] = s + L.b[j];
+    }
+    __syncthreads();
+    if (L.ln_g) {
+      float s = 0.f;
+      for (int c = tid; c < L.out; c += 256) s += pre[li][c];
+      const float mean = block_sum256(s, red) / (float)L.out;
+      float v = 0.f;
+      for (int c = tid; c < L.out; c += 256) {
+        const float d = pre[li][c] - mean;
+        v = fmaf(d, d, v);
+      }
+      const float rstd = rsqrtf(block_sum256(v, red) / (float)L.out + 1e-5f);
+      if (tid == 0) {
+        s_mean[li] = mean;
+        s_rstd[li] = rstd;
+      }
+      for (int c = tid; c < L.out; c += 256) {
+        const float z = (pre[li][c] - mean) * rstd * L.ln_g[c] + L.ln_b[c];
+        act[li + 1][c] = apply_act(z, L.act);
+      }
+    } else {
+      for (int c = tid; c < L.out; c += 256) act[li + 1][c] = apply_act(pre[li][c], L.act);
+    }
+    __syncthreads();
+  }
+  // ---- head ----
+  const float T = act[mp.n][0];
+  float dT, lr;
+  if (loss_type == 0) {
+    const float l1p = log1pf(expf(-fabsf(T)));
+    lr = (fminf(T, 0.f) - l1p) - (fminf(-T, 0.f) - l1p);
+    dT = 1.0f;  // logsigmoid(T) - logsigmoid(-T) = T
+  } else {
+    const float sp = (T > 20.f) ? T : log1pf(expf(T));
+    lr = logf(sp + 1e-8f);
+    dT = (1.0f / (1.0f + expf(-T))) / (sp + 1e-8f);
+  }
+  if (tid == 0) {
+    if (scores) scores[n] = T;
+    if (log_ratio) log_ratio[n] = lr;
+  }
+  // ---- backward ----
+  for (int c = tid; c < mp.l[mp.n - 1].out; c += 256) gcur[c] = (c == 0) ? dT : 0.f;
+  __syncthreads();
+  for (int li = mp.n - 1; li >= 0; --li) {
+    const MlpLayer L = mp.l[li];
+    // gcur = d / d act[li+1]  ->  dh (in place)
+    if (L.ln_g) {
+      const float mean = s_mean[li], rstd = s_rstd[li];
+      float s1 = 0.f, s2 = 0.f;
+      for (int c = tid; c < L.out; c += 256) {
+        const float xh = (pre[li][c] - mean) * rstd;
+        const float z = xh * L.ln_g[c] + L.ln_b[c];
+        float dz = gcur[c];
+        if (L.act == ACT_SILU) {
+          const float sg = 1.0f / (1.0f + expf(-z));
+          dz *= sg * (1.0f + z * (1.0f - sg));
+        } else if (L.act == ACT_RELU) {
+          dz = z > 0.f ? dz : 0.f;
+        }
+        const float dg = dz * L.ln_g[c];
+        gcur[c] = dg;  // gamma * dz
+        s1 += dg;
+        s2 = fmaf(dg, xh, s2);
+      }
+      const float m1 = block_sum256(s1, red) / (float)L.out;
+      const float m2 = block_sum256(s2, red) / (float)L.out;
+      for (int c = tid; c < L.out; c += 256) {
+        const float xh = (pre[li][c] - mean) * rstd;
+        gcur[c] = rstd * (gcur[c] - m1 - xh * m2);
+      }
+    } else if (L.act != ACT_NONE) {
+      for (int c = tid; c < L.out; c += 256) {
+        const float z = pre[li][c];
+        float dz = gcur[c];
+        if (L.act == ACT_SILU) {
+          const float sg = 1.0f / (1.0f + expf(-z));
+          dz *= sg * (1.0f + z * (1.0f - sg));
+        } else {
+          dz = z > 0.f ? dz : 0.f;
+        }
+        gcur[c] = dz;
+      }
+    }
+    __syncthreads();
+    // d / d act[li] = W^T dh   (thread i walks column i of W: consecutive threads read consecutive addresses)
+    for (int i = tid; i < L.in; i += 256) {
+      float s = 0.f;
+      for (int j = 0; j < L.out; ++j) s = fmaf(L.w[(size_t)j * L.in + i], gcur[j], s);
+      gnext[i] = s;
+    }
+    __syncthreads();
+    float* t = gcur;
+    gcur = gnext;
+    gnext = t;
+  }
+  for (int i = tid; i < mp.l[0].in; i += 256) dfeat[(size_t)n * ld_d + i] = gcur[i];
+}
+
+void launch_mlp_bwd(const float* in, int ld_in, const MlpLayer* layers, int nlayers, int loss_type, float* scores, float* log_ratio,
+                    float* dfeat, int ld_d, int nimg, cudaStream_t s) {
+  RGFM_CHECK(nlayers >= 1 && nlayers <= 4, "mlp_bwd: layer count");
+  MlpPackB mp;
+  mp.n = nlayers;
+  size_t floats = layers[0].in + 2 * 512;
+  for (int i = 0; i < nlayers; ++i) {
+    mp.l[i] = layers[i];
+    RGFM_CHECK(layers[i].in <= 512 && layers[i].out <= 512, "mlp_bwd: width");
+    floats += 2 * (size_t)layers[i].out;
+  }
+  const size_t smem = floats * sizeof(float);
+  RGFM_CHECK(smem <= 48 * 1024, "mlp_bwd: shared memory");
+  mlp_bwd_kernel<<<nimg, 256, smem, s>>>(in, ld_in, mp, loss_type, scores, log_ratio, dfeat, ld_d);
+  post_launch("mlp_bwd");
+}
+
+// ---- GAP + fc backward: feat = fc(mean_p act[p][c])  ->  dAct[p][c] = (W^T dfeat)[c] / HW for every pixel p
+__global__ void __launch_bounds__(256) gap_fc_bwd_kernel(const float* __restrict__ dfeat, int ld, const float* __restrict__ w, int Cout,
+                                                         int HW, int C, float* __restrict__ dact) {
+  __shared__ float dm[PACK_MAXC];
+  __shared__ float df[512];
+  const int n = blockIdx.x;
+  for (int j = threadIdx.x; j < Cout; j += blockDim.x) df[j] = dfeat[(size_t)n * ld + j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < Cout; ++j) s = fmaf(w[(size_t)j * C + c], df[j], s);
+    dm[c] = s / (float)HW;
+  }
+  __syncthreads();
+  float* dst = dact + (size_t)n * HW * C;
+  for (int i = threadIdx.x; i < HW * C; i += blockDim.x) dst[i] = dm[i % C];
+}
+void launch_gap_fc_bwd(const float* dfeat, int ld, const float* w, int Cout, int HW, int C, float* dact, int nimg, cudaStream_t s) {
+  RGFM_CHECK(C <= PACK_MAXC && Cout <= 512, "gap_fc_bwd: sizes");
+  gap_fc_bwd_kernel<<<nimg, 256, 0, s>>>(dfeat, ld, w, Cout, HW, C, dact);
+  post_launch("gap_fc_bwd");
+}
+
+// ---- pack backward (fp32 dense NHWC): cur = pool?(act(norm(raw)))  ->  dRaw from dCur.
+// Max-pool routes the gradient to the first maximum of the 2x2 window of act(norm(raw)) (recomputed); GroupNorm needs the
+// two per-(image, group) moments of gamma * dz, so one CTA per image makes two passes (the image stays in L2).
+__global__ void __launch_bounds__(256) pack_bwd_kernel(PackArgs a, const float* __restrict__ dcur, float* __restrict__ draw) {
+  __shared__ float s_scale[PACK_MAXC];
+  __shared__ float s_shift[PACK_MAXC];
+  __shared__ float s_red[2][PACK_MAXC];
+  __shared__ double s_grp[32][2];
+  __shared__ float s_m1[32], s_m2[32];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  pack_scale_shift(a, n, s_scale, s_shift, s_red, s_grp);  // scale = rstd * gamma (GN) | BN scale ; shift likewise
+  const int C = a.C, H = a.Hs, Wd = a.Ws;
+  const bool pool = a.spatial == SP_POOL2;
+  const float* raw = a.src[0].p + (size_t)n * H * Wd * C;
+  const float* dc = dcur + (size_t)n * a.Ho * a.Wo * C;
+  float* dr = draw + (size_t)n * H * Wd * C;
+  const int cpg = C / a.groups;
+  // gradient arriving at act(norm(raw))[h][w][c]
+  auto grad_out = [&](int h, int w, int c, float av) -> float {
+    if (!pool) return dc[((size_t)h * a.Wo + w) * C + c];
+    const int ho = h >> 1, wo = w >> 1;
+    if (ho >= a.Ho || wo >= a.Wo) return 0.f;  // odd sizes: the last row / column is not pooled
+    // first maximum of the window in scan order
+    float best = -INFINITY;
+    int bi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int hh = 2 * ho + (k >> 1), ww = 2 * wo + (k & 1);
+      const float z = fmaf(raw[((size_t)hh * Wd + ww) * C + c], s_scale[c], s_shift[c]);
+      const float v = apply_act(z, a.act);
+      if (v > best) {
+        best = v;
+        bi = k;
+      }
+    }
+    (void)av;
+    return (bi == ((h & 1) * 2 + (w & 1))) ? dc[((size_t)ho * a.Wo + wo) * C + c] : 0.f;
+  };
+  auto dact = [&](float z) -> float {
+    if (a.act == ACT_SILU) {
+      const float sg = 1.0f / (1.0f + expf(-z));
+      return sg * (1.0f + z * (1.0f - sg));
+    }
+    if (a.act == ACT_RELU) return z > 0.f ? 1.0f : 0.f;
+    return 1.0f;
+  };
+  const int total = H * Wd * C;
+  if (a.norm == NORM_GN) {
+    // pass A: per-group means of gamma*dz and gamma*dz*xhat
+    for (int g = tid; g < a.groups; g += blockDim.x) s_m1[g] = s_m2[g] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < total; i += blockDim.x) {
+      const int c = i % C, pix = i / C, h = pix / Wd, w = pix - h * Wd;
+      const float z = fmaf(raw[i], s_scale[c], s_shift[c]);
+      const float dz = grad_out(h, w, c, 0.f) * dact(z);
+      const float dg = dz * a.gamma[c];
+      const float xh = (a.gamma[c] != 0.f) ? (z - a.beta[c]) / a.gamma[c] : 0.f;
+      atomicAdd(&s_m1[c / cpg], dg);
+      atomicAdd(&s_m2[c / cpg], dg * xh);
+    }
+    __syncthreads();
+    const float cnt = (float)cpg * H * Wd;
+    for (int i = tid; i < total; i += blockDim.x) {
+      const int c = i % C, pix = i / C, h = pix / Wd, w = pix - h * Wd;
+      const int g = c / cpg;
+      const float z = fmaf(raw[i], s_scale[c], s_shift[c]);
+      const float dz = grad_out(h, w, c, 0.f) * dact(z);
+      const float xh = (a.gamma[c] != 0.f) ? (z - a.beta[c]) / a.gamma[c] : 0.f;
+      const float rstd = (float)s_grp[g][1];
+      dr[i] = rstd * (dz * a.gamma[c] - s_m1[g] / cnt - xh * s_m2[g] / cnt);
+    }
+  } else {
+    for (int i = tid; i < total; i += blockDim.x) {
+      const int c = i % C, pix = i / C, h = pix / Wd, w = pix - h * Wd;
+      const float z = fmaf(raw[i], s_scale[c], s_shift[c]);
+      dr[i] = grad_out(h, w, c, 0.f) * dact(z) * s_scale[c];
+    }
+  }
+}
+void launch_pack_bwd(const PackArgs& a, const float* dcur, float* draw, cudaStream_t s) {
+  RGFM_CHECK(a.nsrc == 1 && a.src[0].fmt == 0 && !a.src[0].padded && a.C <= PACK_MAXC && a.spatial != SP_UP2,
+             "pack_bwd: one dense fp32 source, no upsampling");
+  pack_bwd_kernel<<<a.nimg, 256, 0, s>>>(a, dcur, draw);
+  post_launch("pack_bwd");
+}
+
+// x <- x + dt * (v + gamma * g)   (README.md:163: v_guided = v_ind + gamma * grad log r)
+__global__ void euler_grad_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ g, float gamma, float dt,
+                                  size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<float4*>(x)[i];
+  const float4 b = __ldg(reinterpret_cast<const float4*>(v) + i);
+  const float4 c = __ldg(reinterpret_cast<const float4*>(g) + i);
+  a.x = __fadd_rn(a.x, __fmul_rn(__fadd_rn(b.x, __fmul_rn(gamma, c.x)), dt));
+  a.y = __fadd_rn(a.y, __fmul_rn(__fadd_rn(b.y, __fmul_rn(gamma, c.y)), dt));
+  a.z = __fadd_rn(a.z, __fmul_rn(__fadd_rn(b.z, __fmul_rn(gamma, c.z)), dt));
+  a.w = __fadd_rn(a.w, __fmul_rn(__fadd_rn(b.w, __fmul_rn(gamma, c.w)), dt));
+  reinterpret_cast<float4*>(x)[i] = a;
+}
+void launch_euler_grad(float* x, const float* v, const float* g, float gamma, float dt, size_t n, cudaStream_t s) {
+  RGFM_CHECK(n % 4 == 0, "euler_grad: n % 4");
+  const size_t n4 = n / 4;
+  euler_grad_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(x, v, g, gamma, dt, n4);
+  post_launch("euler_grad");
+}
+
 __global__ void step_inc_kernel(int* step) { *step += 1; }
 void launch_step_inc(int* step, cudaStream_t s) {
   step_inc_kernel<<<1, 1, 0, s>>>(step);

@@ -22,7 +22,8 @@ struct Sampler {
   rgfm_sampler_desc d;
   std::unique_ptr<Net> fx, fy, fr;
   int Dx = 0, Dy = 0, B = 0, N = 0, steps = 0;
-  bool guided = false;
+  bool guided = false;      // mc_feng with a ratio estimator
+  bool grad_guided = false; // grad_log_ratio with a ratio estimator
   float dtf = 0.f;
   DevPool pool;
   float *x = nullptr, *y = nullptr, *vx = nullptr, *vy = nullptr, *gx = nullptr, *gy = nullptr;
@@ -34,7 +35,7 @@ struct Sampler {
   int ksx = 1, ksy = 1;
   cudaStream_t cap = nullptr, cap2 = nullptr;   // capture streams: the x- and y-network forwards are independent branches
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  Graph g_pre, g_ratio, g_plain, g_guided;
+  Graph g_pre, g_ratio, g_plain, g_guided, g_grad;
   int64_t launches = 0;
   float *hx = nullptr, *hy = nullptr, *hmx = nullptr, *hmy = nullptr;  // pinned staging for run_host
   std::vector<float*> stage;  // device staging for run_host
@@ -130,7 +131,7 @@ struct Sampler {
     // Unknown methods, or mc_feng without a ratio estimator, silently degrade to unguided exactly like the
     // reference (flow_utils.py:231,273).
     guided = (d.guidance == RGFM_GUIDE_MC_FENG) && wr != nullptr && N >= 1;
-    RGFM_CHECK(d.guidance != RGFM_GUIDE_GRAD_LOG_RATIO, "grad_log_ratio guidance is not implemented in this build");
+    grad_guided = (d.guidance == RGFM_GUIDE_GRAD_LOG_RATIO) && wr != nullptr;
     int kx, ky, kr;
     if (d.pair == RGFM_PAIR_28) {
       kx = ky = RGFM_NET_UNET_MNIST28;
@@ -147,6 +148,8 @@ struct Sampler {
     fx.reset(new Net(kx, wx, chunk, d.precision, d.device));
     fy.reset(new Net(ky, wy, chunk, d.precision, d.device));
     if (guided) fr.reset(new Net(kr, wr, std::min(chunk, N), d.precision, d.device));
+    // gradient guidance: forward + dgrad of the estimator at the sampler's batch, every step, exact fp32, 256-image chunks
+    if (grad_guided) fr.reset(new Net(kr, wr, std::min(256, B), RGFM_PREC_FP32, d.device, /*want_grad=*/true));
     Dx = (int)fx->dim();
     Dy = (int)fy->dim();
 
@@ -177,6 +180,12 @@ struct Sampler {
     diag = (float*)pool.persistent(RGFM_DIAG_FLOATS * sizeof(float));
     x = (float*)pool.persistent((size_t)B * Dx * sizeof(float));
     y = (float*)pool.persistent((size_t)B * Dy * sizeof(float));
+    if (grad_guided) {
+      vx = (float*)pool.persistent((size_t)B * Dx * sizeof(float));
+      vy = (float*)pool.persistent((size_t)B * Dy * sizeof(float));
+      gx = (float*)pool.persistent((size_t)B * Dx * sizeof(float));
+      gy = (float*)pool.persistent((size_t)B * Dy * sizeof(float));
+    }
     if (guided) {
       vx = (float*)pool.persistent((size_t)B * Dx * sizeof(float));
       vy = (float*)pool.persistent((size_t)B * Dy * sizeof(float));
@@ -232,6 +241,21 @@ struct Sampler {
         launch_step_inc(step, s);
       });
     }
+    if (grad_guided) {
+      // v = v_ind + gamma * grad log r(x_t, y_t) (README.md:163), then x += v * dt; every step, no MC bank
+      const float gam = (float)d.guidance_strength;
+      const int lt = d.loss_type;
+      capture(g_grad, [&](cudaStream_t s) {
+        fork(s);
+        fx->forward(s, B, x, nullptr, vx, OUT_NCHW, dtf, step);
+        fy->forward(cap2, B, y, nullptr, vy, OUT_NCHW, dtf, step);
+        join(s);
+        fr->grad_log_ratio(s, B, x, y, lt, gx, gy, nullptr);
+        launch_euler_grad(x, vx, gx, gam, dtf, (size_t)B * Dx, s);
+        launch_euler_grad(y, vy, gy, gam, dtf, (size_t)B * Dy, s);
+        launch_step_inc(step, s);
+      });
+    }
     capture(g_plain, [&](cudaStream_t s) {  // x += fm_x(x, t) * dt ; y += fm_y(y, t) * dt
       fork(s);
       fx->forward(s, B, x, nullptr, x, OUT_EULER, dtf, step);
@@ -242,7 +266,8 @@ struct Sampler {
     RGFM_CUDA(cudaStreamSynchronize(cap));
     launches = 0;
     if (guided) launches += (int64_t)steps * g_pre.kernels + g_ratio.kernels;
-    for (int s = 0; s < steps; ++s) launches += (guided && s >= first_guided) ? g_guided.kernels : g_plain.kernels;
+    for (int s = 0; s < steps; ++s)
+      launches += grad_guided ? g_grad.kernels : ((guided && s >= first_guided) ? g_guided.kernels : g_plain.kernels);
   }
 
   void run(const float* x0, const float* y0, const float* mx0, const float* my0, float* x1, float* y1,
@@ -262,7 +287,7 @@ struct Sampler {
     }
     RGFM_CUDA(cudaMemsetAsync(step, 0, sizeof(int), s));
     for (int i = 0; i < steps; ++i)
-      RGFM_CUDA(cudaGraphLaunch((guided && i >= first_guided) ? g_guided.e : g_plain.e, s));
+      RGFM_CUDA(cudaGraphLaunch(grad_guided ? g_grad.e : ((guided && i >= first_guided) ? g_guided.e : g_plain.e), s));
     RGFM_CUDA(cudaMemcpyAsync(x1, x, (size_t)B * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
     RGFM_CUDA(cudaMemcpyAsync(y1, y, (size_t)B * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (diag_out) RGFM_CUDA(cudaMemcpyAsync(diag_out, diag, RGFM_DIAG_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -86,8 +86,10 @@ def _sample(pair, shape_x, shape_y, fm_x, fm_y, ratio_estimator, guidance_method
         raise _lib.RgfmError("rgfm samplers run on CUDA devices only; there is no CPU fallback")
     precision = precision or default_precision()
     guided = guidance_method == "mc_feng" and ratio_estimator is not None
+    # README.md:159-164 extension (the reference's argparse only offers none / mc_feng): no MC bank, no extra RNG draws
+    grad_guided = guidance_method == "grad_log_ratio" and ratio_estimator is not None
     loss_type = getattr(ratio_estimator, "loss_type", "disc") if ratio_estimator is not None else "disc"
-    if guided and loss_type not in _lib.LOSS:
+    if (guided or grad_guided) and loss_type not in _lib.LOSS:
         raise ValueError(f"Unknown loss_type: {loss_type}")
 
     # The reference consumes the device's global RNG with exactly these draws, in this order
@@ -111,7 +113,8 @@ def _sample(pair, shape_x, shape_y, fm_x, fm_y, ratio_estimator, guidance_method
         lo, hi = shard_bounds(num_samples, dist.get_world_size(group), dist.get_rank(group))
     n_local = hi - lo
     if n_local > 0:
-        plan = _get_plan(pair, fm_x, fm_y, ratio_estimator if guided else None, guidance_method if guided else "none",
+        use_ratio = guided or grad_guided
+        plan = _get_plan(pair, fm_x, fm_y, ratio_estimator if use_ratio else None, guidance_method if use_ratio else "none",
                          guidance_strength, n_local, num_steps, mc_batch_size, loss_type, precision, device, chunk)
         x1, y1, diag = plan.run(x0[lo:hi], y0[lo:hi], mc_x0, mc_y0, want_diag=True)
     else:

@@ -297,3 +297,58 @@ def test_guidance_strength_sweep_coherence(gamma, synth):
         assert abs(got - ref) <= slack, (gamma, prec, got, ref)
         assert torch.isfinite(x1).all() and torch.isfinite(y1).all()
         plan.close()
+
+
+# ---- grad_log_ratio guidance: ratio-estimator forward + dgrad chain (README.md:159-164; SURVEY.md D1: unpinned extension) ----
+@pytest.mark.parametrize("loss_type", ["disc", "rulsif"])
+@pytest.mark.parametrize("kind", ["ratio28", "ratio_mnist_svhn"])
+def test_ratio_grad_log_ratio(kind, loss_type, synth):
+    """d log r / d(x, y) from the CUDA dgrad chain vs autograd through the restated estimator; ragged chunk (5 images, chunk 2)."""
+    sd = synth(kind, 21 if kind == "ratio28" else 22)
+    hw, cy = (28, 1) if kind == "ratio28" else (32, 3)
+    gen = torch.Generator().manual_seed(17)
+    x, y = torch.randn(5, 1, hw, hw, generator=gen), torch.randn(5, cy, hw, hw, generator=gen)
+    ogx, ogy, olr = O.grad_log_ratio(sd, kind, x, y, loss_type)
+    net = _lib.Net(kind, sd, max_batch=2, device=DEV, grad=True)
+    gx, gy, lr = net.grad_log_ratio(x.to(DEV), y.to(DEV), loss_type)
+    torch.cuda.synchronize()
+    assert maxabs(lr, olr) <= 2e-4 * max(1.0, olr.abs().max().item())
+    for ours, ref in ((gx, ogx), (gy, ogy)):
+        # fp32 on both sides, different summation orders through ~10 layers of cancellation: relative L2 2e-3, max-abs 2 %
+        scale = ref.abs().max().item()
+        rel_l2 = ((ours.cpu() - ref).norm() / ref.norm()).item()
+        assert scale > 0 and rel_l2 <= 2e-3 and maxabs(ours, ref) <= 2e-2 * scale, (rel_l2, maxabs(ours, ref), scale)
+    with pytest.raises(ValueError):
+        net.grad_log_ratio(x.to(DEV), y.to(DEV), "nope")
+    net.close()
+
+
+@pytest.mark.parametrize("pair,kinds", [("pair28", ("unet_mnist28", "unet_mnist28", "ratio28")),
+                                        ("mnist_svhn", ("unet_mnist32", "unet_svhn", "ratio_mnist_svhn"))])
+def test_sampler_grad_log_ratio(pair, kinds, synth):
+    """guidance_method='grad_log_ratio' end to end vs the oracle loop (v = v_ind + gamma * grad log r, every step)."""
+    sdx, sdy, sdr = synth(kinds[0], 12), synth(kinds[1], 13), synth(kinds[2], 22)
+    shape_x, shape_y = O.PAIR_KINDS[pair][3], O.PAIR_KINDS[pair][4]
+    B, steps, gamma = 5, 4, 0.3
+    gen = torch.Generator().manual_seed(5)
+    x0, y0 = torch.randn(B, *shape_x, generator=gen), torch.randn(B, *shape_y, generator=gen)
+    ox, oy = O.sample_pair(sdx, sdy, sdr, pair, "grad_log_ratio", gamma, steps, x0, y0, None, None, "rulsif")
+    ux, uy = O.sample_pair(sdx, sdy, None, pair, "none", 0.0, steps, x0, y0)
+    assert maxabs(ox, ux) > 1e-4  # the guidance term does something
+    plan = _lib.SamplerPlan(pair, sdx, sdy, sdr, guidance_method="grad_log_ratio", guidance_strength=gamma, num_samples=B,
+                            num_steps=steps, mc_batch_size=4, loss_type="rulsif", precision="fp32", device=DEV)
+    x1, y1 = plan.run(x0.to(DEV), y0.to(DEV))
+    torch.cuda.synchronize()
+    assert maxabs(x1, ox) <= 1e-3 and maxabs(y1, oy) <= 1e-3, (maxabs(x1, ox), maxabs(y1, oy))
+    plan.close()
+    # through the drop-in function: only the two state draws are consumed from the device RNG
+    fx = synthetic.StateDictModule(kinds[0], sdx); fy = synthetic.StateDictModule(kinds[1], sdy)
+    fr = synthetic.StateDictModule(kinds[2], sdr, loss_type="rulsif")
+    fn = sample_bimodal_guided if pair == "pair28" else sample_bimodal_guided_mnist_svhn
+    torch.manual_seed(3); torch.cuda.manual_seed_all(3)
+    a = fn(fx, fy, fr, guidance_method="grad_log_ratio", guidance_strength=gamma, num_samples=B, num_steps=steps, device=DEV,
+           precision="fp32", verbose=False)
+    torch.manual_seed(3); torch.cuda.manual_seed_all(3)
+    x0d = torch.randn(B, *shape_x, device=DEV); y0d = torch.randn(B, *shape_y, device=DEV)
+    ox, oy = O.sample_pair(sdx, sdy, sdr, pair, "grad_log_ratio", gamma, steps, x0d.cpu(), y0d.cpu(), None, None, "rulsif")
+    assert maxabs(a[0], ox) <= 1e-3 and maxabs(a[1], oy) <= 1e-3
