@@ -34,7 +34,7 @@ constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_THREADS = 96 + 2 * 128;  // producer warp, two MMA warps (one per accumulator half), two epilogue groups of 4 warps
 constexpr int TC_SUPER = 256;             // output rows per super-tile (two M=128 accumulators sharing every B tile)
 constexpr uint32_t TC_STAGE_BYTES = 128 * 128;
-constexpr uint32_t TC_SMEM_BUDGET = 196u * 1024u;  // dynamic shared memory for A slots + staging + weights (static: ~14 KB)  // epilogue staging buffer: 128 rows x 32 fp32, 128B-swizzled
+constexpr uint32_t TC_SMEM_BUDGET = 212u * 1024u;  // dynamic shared memory for A slots + staging + weights (static: ~14 KB)  // epilogue staging buffer: 128 rows x 32 fp32, 128B-swizzled
 
 struct TcArgs {
   ConvArgs c;           // epilogue description (bias, time bias, output, nimg, out_mode, dt)
@@ -764,7 +764,11 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   uint32_t b_total = 0;
   for (int sg = 0; sg < d.nseg; ++sg) b_total += (uint32_t)((d.seg[sg].Cin_real + 63) / 64) * (uint32_t)(d.seg[sg].ks * d.seg[sg].ks) * p.b_bytes;
   p.b_total = b_total;
-  p.resident = (2u * p.a_slot + 2u * TC_STAGE_BYTES + b_total <= budget) ? 1 : 0;
+  // Measured (profiles/notes_r01.md): keeping the weights resident is worth far more than a deeper A pipeline -- streaming
+  // the weight tiles from L2 for every super-tile is what bounds the ring mode (L2 -> SM bandwidth), not load latency.
+  static const int force_slots = getenv("RGFM_TC_A_SLOTS") ? atoi(getenv("RGFM_TC_A_SLOTS")) : 0;
+  const uint32_t min_slots = force_slots ? (uint32_t)force_slots : 2u;
+  p.resident = (min_slots * p.a_slot + 2u * TC_STAGE_BYTES + b_total <= budget) ? 1 : 0;
   p.tps[0] = p.tps[1] = p.tps[2] = 1;
   if (p.resident) {
     int slots = (int)((budget - 2u * TC_STAGE_BYTES - b_total) / p.a_slot);
@@ -773,13 +777,20 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     p.b_stage = p.b_bytes;
     t->smem = (size_t)p.a_slots * p.a_slot + 2u * TC_STAGE_BYTES + b_total + 1024;
   } else {
-    p.a_slots = 2;
-    const uint32_t fixed = 2u * p.a_slot + 2u * TC_STAGE_BYTES;
+    // weight ring: at least two stages of >= 1 tap must fit next to the A slots, else fall back to two slots
+    uint32_t slots = min_slots;
+    while (slots > 2u && slots * p.a_slot + 2u * TC_STAGE_BYTES + 2u * p.b_bytes > budget) --slots;
+    p.a_slots = (int)slots;
+    const uint32_t fixed = slots * p.a_slot + 2u * TC_STAGE_BYTES;
     const uint32_t ring_budget = budget - fixed;
+    // Every ring stage costs the single producer / MMA threads ~500 cycles of hand-off (wait, fence, commit at one
+    // dependent instruction per ~5 cycles), so stages are made as large as two of them fit: measured 6.37 -> 5.99 ms of
+    // conv time per Euler step against three-plus smaller stages (profiles/notes_r01.md).
     int tps = 1;
+    static const int min_stages = getenv("RGFM_TC_MIN_STAGES") ? atoi(getenv("RGFM_TC_MIN_STAGES")) : 2;
     if (d.seg[0].ks == 3) {
-      if (3u * 9u * p.b_bytes <= ring_budget) tps = 9;
-      else if (3u * 3u * p.b_bytes <= ring_budget) tps = 3;
+      if ((uint32_t)min_stages * 9u * p.b_bytes <= ring_budget) tps = 9;
+      else if ((uint32_t)min_stages * 3u * p.b_bytes <= ring_budget) tps = 3;
     }
     for (int sg = 0; sg < d.nseg; ++sg)
       if (d.seg[sg].ks == 3) p.tps[sg] = tps;
@@ -880,6 +891,8 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CHECK(a.CoutP % 64 == 0 && a.CoutP >= p.nmma && a.out_padded && a.out_fmt == p.out_fmt && a.out != nullptr,
                "tc conv: raw outputs are 16-bit, padded-linear, channel stride % 64 == 0");
   }
+  static const bool no_stats = getenv("RGFM_TC_NO_STATS") != nullptr;  // timing experiment only (results are wrong)
+  if (no_stats) p.stats = nullptr;
   const int total_rows = a.nimg * (p.H + 1) * p.P;
   const int supers = (total_rows + TC_SUPER - 1) / TC_SUPER;
   static int num_sms = 0;
