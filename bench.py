@@ -135,6 +135,7 @@ def run_reference(args):
     if rank != 0:
         return
     torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     cores = torch.get_num_threads()
     vals = []
     for i in range(args.warmup + args.steps):
@@ -255,7 +256,12 @@ def run_gpu(args):
         roof["per_kernel_ms_one_euler_step"] = {k: round(v["ms"], 4) for k, v in prof.items()}
         roof["graph_ms_one_euler_step"] = graph_step_ms
         total_flops = EULER_STEPS * (N_MC + B_PER_GPU) * (FLOPS_UNET_X + FLOPS_UNET_Y) + N_MC * FLOPS_RATIO
-        cpu_v, cpu_sample, _ = cpu_sample_throughput(budget_s=15.0)
+        # the CPU baseline is an N=1 number (rank 0, all host threads); multi-GPU lines carry null
+        cpu_base = None
+        if world == 1:
+            torch.set_num_threads(os.cpu_count() or 1)
+            cpu_v, cpu_sample, _ = cpu_sample_throughput(budget_s=15.0)
+            cpu_base = dict(value=cpu_v, unit="pairs/s", cores=torch.get_num_threads(), kind="port", sample=cpu_sample)
         line = dict(metric=METRIC, value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[prec], data="synthetic",
@@ -264,7 +270,7 @@ def run_gpu(args):
                                 precision=prec, l2="256 MiB flush between timed iterations", sharding=f"batch x{world}, all_gather of pairs"),
                     e2e=dict(value=B_total / e2e_s, unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=int(plan.launch_count) * args.steps, clocks=clk, roofline=roof,
-                    cpu_baseline=dict(value=cpu_v, unit="pairs/s", cores=torch.get_num_threads(), kind="port", sample=cpu_sample),
+                    cpu_baseline=cpu_base,
                     model_flops_utilisation=dict(algorithmic_tflop_per_call=total_flops / 1e12,
                                                  achieved_tflops=total_flops / (ms_per_step * 1e-3) / 1e12 ,
                                                  frac_of_peak=total_flops / (ms_per_step * 1e-3) / 1e12 / pk["tc_sustained"]),
