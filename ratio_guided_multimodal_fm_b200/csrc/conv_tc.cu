@@ -63,6 +63,7 @@ struct TcArgs {
   int sub;              // stride-2: store rows with even (h, w) only, into the half-resolution raw tensor
   int tma_store;        // raw output leaves through swizzled smem staging + TMA store (fully coalesced)
   int out_H, out_W;     // output spatial size (H, W or halved when sub)
+  int rows_alloc;       // rows of the raw output tensor (chunk * R): bound for direct row stores
   int out_fmt;          // raw output storage: 1 = bf16, 2 = fp16
   float* stats;         // GroupNorm partials [unit][nslots][CoutP][2] of the rounded output (null = none)
   int nslots;
@@ -487,7 +488,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int et = threadIdx.x - eg * 128;
     const int wq = et >> 5;  // warp inside the group (row quarter for the column sums)
     const int r = q * 32 + lane;  // row inside the 128-row unit
-    const int CP = a.CoutP;  // channel stride of the raw output (multiple of 64; channels >= nmma are written as zeros)
+    const int CP = a.CoutP;  // channel stride of the raw output (32, or a multiple of 64; channels >= nmma are written as zeros)
+    const int total_rows_alloc = p.rows_alloc;  // rows of the output tensor (direct-store bound)
     const uint32_t stg = smem_stage + (uint32_t)eg * TC_STAGE_BYTES;
     int it = 0;
     for (int st = blockIdx.x; st < supers; st += gridDim.x, ++it) {
@@ -502,6 +504,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // w == W + 1 writes the second pad column, so the half-resolution raw tensor is zero padded like every other one
       bool wr = false;
       size_t o = 0;
+      if (!p.sub && !p.tma_store && a.out_mode == OUT_RAW) {  // 32-channel raw output: every row of the unit inside the tensor
+        wr = m < total_rows_alloc;
+        o = (size_t)m * CP;
+      }
       if (p.sub) {
         const bool inimg = (n < a.nimg) && (h <= p.H);
         valid = valid && !(h & 1) && !(w & 1);
@@ -554,7 +560,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
                            "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
             }
-            if (!p.tma_store && wr) {
+            if (!p.tma_store && wr && c0 + hh * 32 < CP) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<uint4*>(out16 + o + c0 + hh * 32 + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -634,7 +640,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const int slot = i >> 7, rem = i & 127;
               const float* pp = &s_part[eg][0][slot][0][0] + rem;
               const float tot = ((pp[0] + pp[3 * 128]) + pp[2 * 3 * 128]) + pp[3 * 3 * 128];
-              p.stats[((size_t)(unit * p.nslots + slot) * CP + c0) * 2 + rem] = tot;
+              if (c0 + (rem >> 1) < CP) p.stats[((size_t)(unit * p.nslots + slot) * CP + c0) * 2 + rem] = tot;
             }
           }
         }
@@ -722,7 +728,8 @@ size_t tc_stats_floats(int H, int W, int chunk, int CoutP) {
 TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   const int nmma = (d.Cout + 15) / 16 * 16;
   RGFM_CHECK(nmma >= 16 && nmma <= 256, "tc conv: Cout must be 1..256");
-  RGFM_CHECK(d.out == nullptr || (d.CoutP % 64 == 0 && d.CoutP >= nmma && nmma % 32 == 0), "tc conv: raw outputs need Cout % 32 == 0 and a channel stride % 64 == 0");
+  RGFM_CHECK(d.out == nullptr || ((d.CoutP % 64 == 0 || d.CoutP == 32) && d.CoutP >= nmma && nmma % 32 == 0),
+             "tc conv: raw outputs need Cout % 32 == 0 and a channel stride of 32 or a multiple of 64");
   RGFM_CHECK(d.Win + 2 <= 39, "tc conv: image width must be <= 37");
   RGFM_CHECK(d.nseg >= 1 && d.nseg <= 3, "tc conv: one to three K segments");
   TcPtr t(new TcConv());
@@ -752,9 +759,10 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.nbuf * nmma)) cols <<= 1;
   p.tmem_cols = cols;
-  p.tma_store = (d.out != nullptr) ? 1 : 0;
+  p.tma_store = (d.out != nullptr) ? 1 : 0;  // 32-channel raws: the same 64-wide store box, its upper half clipped by TMA
   p.out_fmt = 2;  // raw activations are stored in fp16 in both 16-bit modes (11-bit mantissa; the epilogue saturates)
   p.stats = d.stats;
+  p.rows_alloc = d.chunk * p.R;
   p.nslots = stats_slots_for(p.R);
   RGFM_CHECK(d.stats == nullptr || p.nslots <= 3, "tc conv: GroupNorm partials need images of at least 64 GEMM rows");
   // shared-memory plan: [A slots][2 staging tiles][weights].  If every weight tile of the conv fits next to two A slots
@@ -808,7 +816,9 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     const CUtensorMapDataType dt16 = seg_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const uint32_t fmt = seg_fp16 ? 0u : 1u;  // UMMA F16F32Format: 0 = F16, 1 = BF16
     p.idesc[sg] = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    RGFM_CHECK(S.Cin % 64 == 0 && S.Cin <= 256, "tc conv: operand channels must be a multiple of 64, at most 256");
+    // a 32-channel tensor (64-byte rows) is read through the same 64-channel TMA box: the upper half is out of bounds and
+    // zero-filled, so the shared-memory tile and the MMA loop are unchanged while the global traffic halves
+    RGFM_CHECK((S.Cin % 64 == 0 || S.Cin == 32) && S.Cin <= 256, "tc conv: operand channels must be 32 or a multiple of 64, at most 256");
     RGFM_CHECK(S.ks == 1 || S.ks == 3, "tc conv: 1x1 or 3x3");
     RGFM_CHECK(S.Cin_real >= 1 && S.Cin_real <= S.Cin, "tc conv: real channel count");
     p.cblocks[sg] = (S.Cin_real + 63) / 64;  // blocks that hold no real channel are skipped altogether
@@ -888,8 +898,8 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CHECK(p.nmma == 16, "tc conv: the output conv uses a 16-column accumulator");
     p.tma_store = 0;
   } else {
-    RGFM_CHECK(a.CoutP % 64 == 0 && a.CoutP >= p.nmma && a.out_padded && a.out_fmt == p.out_fmt && a.out != nullptr,
-               "tc conv: raw outputs are 16-bit, padded-linear, channel stride % 64 == 0");
+    RGFM_CHECK((a.CoutP % 64 == 0 || a.CoutP == 32) && a.CoutP >= p.nmma && a.out_padded && a.out_fmt == p.out_fmt && a.out != nullptr,
+               "tc conv: raw outputs are 16-bit, padded-linear, channel stride 32 or a multiple of 64");
   }
   static const bool no_stats = getenv("RGFM_TC_NO_STATS") != nullptr;  // timing experiment only (results are wrong)
   if (no_stats) p.stats = nullptr;

@@ -82,6 +82,10 @@ struct Builder {
         tc_mode(n.precision_ == RGFM_PREC_BF16 || n.precision_ == RGFM_PREC_FP16), fp16(n.precision_ == RGFM_PREC_FP16),
         fmt16(n.precision_ == RGFM_PREC_FP16 ? 2 : 1) {}
 
+  // channel stride of a tensor-core tensor: 32-channel tensors keep 64-byte rows (the conv reads them through a 64-wide
+  // TMA box whose upper half is out of bounds = zero), everything else is padded to a multiple of 64 (128-byte rows)
+  static int tc_stride(int C) { return C == 32 ? 32 : (C + 63) / 64 * 64; }
+
   // ---- buffers ----
   // fp32 dense raw activation (SIMT path) with optional per-tile GroupNorm partials
   Act new_act(int H, int Wd, int C, int parts) {
@@ -99,7 +103,7 @@ struct Builder {
   // GEMM row space (differs from (H, W) for stride-2 convs), which is what the GroupNorm partials are indexed by
   Act new_act_tc(int H, int Wd, int C, bool stats, int Hc, int Wc) {
     Act a;
-    a.H = H; a.W = Wd; a.C = C; a.Cs = (C + 63) / 64 * 64;
+    a.H = H; a.W = Wd; a.C = C; a.Cs = tc_stride(C);
     a.padded = true; a.fmt = 2;  // raw activations are fp16 in both 16-bit modes
     a.p = (float*)pool.alloc(tc_raw_rows(H, Wd, chunk) * a.Cs * 2);
     if (stats) {
@@ -118,7 +122,7 @@ struct Builder {
     p.H = H; p.W = Wd; p.bf16 = bf16;
     if (bf16) {  // tcgen05 operand: padded-linear layout, channels padded to a multiple of 64
       p.padded = true;
-      p.C = (C + 63) / 64 * 64;
+      p.C = tc_stride(C);
       p.p = pool.alloc(tc_operand_slots(H, Wd, chunk) * p.C * 2);
     } else {
       p.C = C;
@@ -351,7 +355,7 @@ struct Builder {
       // tensor-core path: 2 packs + 2 convs.  conv2 accumulates the block input as extra K segments read straight from
       // the raw 16-bit activations (the 1x1 skip conv, or identity weights for the plain residual): no separate skip
       // kernel, no residual read in the epilogue.
-      const int coutP = (cout + 63) / 64 * 64;
+      const int coutP = (cout + 63) / 64 * 64;  // bias array length (>= nmma)
       Packed a1 = pack(x, NORM_GN, vec(p + "norm1.weight", cin), vec(p + "norm1.bias", cin), ACT_SILU, SP_ID, true);
       Act h1 = conv_tc(H, Wd, {seg_of(a1, cin, 3, W.get(p + "conv1.weight", (int64_t)cout * cin * 9))},
                        vec(p + "conv1.bias", cout, coutP), cout, 1, toff, true, false, shape_label(p + "conv1", H, Wd, cin, cout));
