@@ -818,7 +818,7 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     p.idesc[sg] = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // a 32-channel tensor (64-byte rows) is read through the same 64-channel TMA box: the upper half is out of bounds and
     // zero-filled, so the shared-memory tile and the MMA loop are unchanged while the global traffic halves
-    RGFM_CHECK((S.Cin % 64 == 0 || S.Cin == 32) && S.Cin <= 256, "tc conv: operand channels must be 32 or a multiple of 64, at most 256");
+    RGFM_CHECK((S.Cin % 64 == 0 || S.Cin == 32 || S.Cin == 16) && S.Cin <= 256, "tc conv: operand channels must be 16, 32 or a multiple of 64, at most 256");
     RGFM_CHECK(S.ks == 1 || S.ks == 3, "tc conv: 1x1 or 3x3");
     RGFM_CHECK(S.Cin_real >= 1 && S.Cin_real <= S.Cin, "tc conv: real channel count");
     p.cblocks[sg] = (S.Cin_real + 63) / 64;  // blocks that hold no real channel are skipped altogether

@@ -163,11 +163,13 @@ struct Builder {
   }
   // tensor-core input operand: NCHW fp32 image -> padded-linear 16-bit [x_hi | x_lo | 0...] (64 channels per slot)
   Packed pack_input_tc(int C, int H, int Wd) {
-    Packed p = new_packed(H, Wd, 64, true);
+    Packed p;  // 16-channel (32-byte) rows
+    p.H = H; p.W = Wd; p.bf16 = true; p.padded = true; p.C = 16;
+    p.p = pool.alloc(tc_operand_slots(H, Wd, chunk) * 16 * 2);
     void* out = p.p;
     const int f = fmt16;
     net.ops_.push_back({[=](const RunCtx& c) { launch_pack_nchw_padded(c.x, C, H, Wd, out, f, c.nimg, c.s); },
-                        "pack_nchw", 0.0, (double)H * Wd * C * 4.0 + (double)(H + 1) * (Wd + 2) * 128.0,
+                        "pack_nchw", 0.0, (double)H * Wd * C * 4.0 + (double)(H + 1) * (Wd + 2) * 32.0,
                         std::to_string(H) + "x" + std::to_string(Wd) + " C" + std::to_string(C) + " hi/lo"});
     return p;
   }

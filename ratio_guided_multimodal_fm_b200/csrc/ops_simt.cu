@@ -136,8 +136,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// NCHW fp32 image -> padded-linear 16-bit operand for the tensor-core input conv: 64 channels per slot holding
-// [x_hi (C), x_lo (C), 0...] with x_hi = round16(x), x_lo = round16(x - x_hi).  The weights are duplicated over the two
+// NCHW fp32 image -> padded-linear 16-bit operand for the tensor-core input conv: 16 channels (32 bytes) per slot holding
+// [x_hi (C), x_lo (C), 0...] with x_hi = round16(x), x_lo = round16(x - x_hi); the conv reads it through a 64-channel TMA box
+// whose upper 48 channels are out of bounds (zero).  The weights are duplicated over the two
 // halves, so the state x_t enters the first conv with ~22 mantissa bits instead of 11 (8 for bf16) at no extra cost
 // (the K block is 64 channels wide anyway).
 template <int FMT>
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) pack_nchw_padded_kernel(const float* __re
   const int slots_img = (H + 1) * P;
   const int pp = blockIdx.x * blockDim.x + threadIdx.x;
   if (n == 0 && blockIdx.x == 0)
-    for (int i = threadIdx.x; i < P * 8; i += blockDim.x) out[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < P * 2; i += blockDim.x) out[i] = make_uint4(0u, 0u, 0u, 0u);
   if (pp >= slots_img) return;
   const int ho = pp / P, ww = pp - ho * P;
   float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -162,10 +163,9 @@ __global__ void __launch_bounds__(256) pack_nchw_padded_kernel(const float* __re
       v[C + c] = xv - hi;
     }
   }
-  uint4* dst = out + ((size_t)(1 + n * (H + 1)) * P + pp) * 8;
+  uint4* dst = out + ((size_t)(1 + n * (H + 1)) * P + pp) * 2;
   dst[0] = make_uint4(pack2<FMT>(v[0], v[1]), pack2<FMT>(v[2], v[3]), pack2<FMT>(v[4], v[5]), pack2<FMT>(v[6], v[7]));
-#pragma unroll
-  for (int j = 1; j < 8; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+  dst[1] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 void launch_pack_nchw_padded(const float* x, int C, int H, int W, void* out, int fmt, int nimg, cudaStream_t s) {
