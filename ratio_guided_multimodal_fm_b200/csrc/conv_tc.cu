@@ -263,6 +263,13 @@ __device__ __forceinline__ bool slot_pixel(int m, int H, int P, uint32_t magic_P
 }
 
 
+// -DRGFM_TC_TRACE: block 0 records clock64 stamps of the first 24 super-tiles per role and prints them (debug builds only)
+#ifdef RGFM_TC_TRACE
+#define TRC(role, idx) do { if (blockIdx.x == 0 && (idx) < 12) s_trace[role][idx] = clock64() - t_start; } while (0)
+#else
+#define TRC(role, idx) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -278,6 +285,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #define b_full(i) (bar_base + 8u * (12u + (uint32_t)(i)))
 #define b_empty(i) (bar_base + 8u * (12u + TC_MAX_STAGES + (uint32_t)(i)))
   __shared__ uint32_t tmem_slot;
+#ifdef RGFM_TC_TRACE
+  __shared__ long long s_trace[6][12];
+  const long long t_start = clock64();
+#endif
   __shared__ __align__(16) float s_bias[256];
   __shared__ __align__(16) float s_part[2][4][3][64][2];
   // per epilogue group / warp / image slot: {sum, sumsq} of a 64-channel chunk
@@ -376,6 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t sa = smem_base + as * p.a_slot;
             tma_load_2d(sa, tA, a_full(as), cb * 64, ra);
             tma_load_2d(sa + (p.a_slot >> 1), tA, a_full(as), cb * 64, ra + p.a_box_rows);
+            if (seg == 0 && cb == 0) TRC(0, (st - (int)blockIdx.x) / (int)gridDim.x);
             if (++as == a_slots) {
               as = 0u;
               aph ^= 1u;
@@ -434,6 +446,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int cb = 0; cb < ncb; ++cb) {
             mbar_wait(a_full(as), aph);
             tc_fence_after();
+            if (hf == 0 && seg == 0 && cb == 0) TRC(1, it);
             const int ks = p.ksteps[seg][cb];
             // descriptor low word of the current tap; a 1x1 segment reads the centre tap (shift P + 1 rows)
             uint32_t a_lo = ((smem_base + as * p.a_slot + hf * (128u * 128u)) >> 4) + (ntp == 1 ? rowstep + 8u : 0u);
@@ -479,6 +492,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
         tc_commit(tmem_full_bar(buf));
+        if (hf == 0) TRC(2, it);
       }
     }
   } else {
@@ -522,6 +536,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (lane == 0) mbar_wait_sleep(tmem_full_bar(buf), use & 1u);
       __syncwarp();
       tc_fence_after();
+      if (threadIdx.x == 0) TRC(3, it);
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + eg) * N);
       if (a.out_mode == OUT_RAW) {
         // raw activation, 16-bit, channel stride CP; rows that are not real pixels are stored as exact zeros, so the
@@ -537,6 +552,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           else asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
+            if (c0 + hh * 32 >= CP) break;  // 32-channel outputs: the upper half of the staging tile is never read
             uint32_t pk[16];
             if (c0 + hh * 32 < N) {
               uint32_t v[32];
@@ -560,7 +576,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
                            "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
             }
-            if (!p.tma_store && wr && c0 + hh * 32 < CP) {
+            if (!p.tma_store && wr) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<uint4*>(out16 + o + c0 + hh * 32 + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -578,6 +594,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tma_store_2d(&tmO, stg, c0, unit * 128);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (threadIdx.x == 0 && c0 == 0) TRC(4, it);
           if (p.stats != nullptr && c0 < N) {
             // GroupNorm partials of the ROUNDED values on the legacy tensor path, channels on M and image slots on N:
             //   S[ch][slot] = sum_row X[row][ch] * Ind[row][slot]   (Ind = 0/1: row belongs to image slot of the unit)
@@ -610,6 +627,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const int lrow = r0 + ((mat >> 1) << 3) + rrow;
 #pragma unroll
               for (int cb = 0; cb < 4; ++cb) {
+                if (c0 + cb * 16 >= N) break;  // channel blocks past the real output channels hold zeros
                 const uint32_t chunk16 = (uint32_t)(2 * cb + (mat & 1));
                 uint32_t a[4];
                 ldsm_x4_trans(stg + (uint32_t)lrow * 128u + ((chunk16 ^ (uint32_t)(lrow & 7)) << 4), a[0], a[1], a[2], a[3]);
@@ -624,6 +642,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (t4 < 2) {
 #pragma unroll
               for (int cb = 0; cb < 4; ++cb) {
+                if (c0 + cb * 16 >= N) break;
                 float* d0 = &s_part[eg][wq][2 * t4][cb * 16 + g][0];
                 d0[0] = sm[cb][0]; d0[1] = sq[cb][0];       // slot 2*t4, channel g
                 d0[16] = sm[cb][2]; d0[17] = sq[cb][2];     // slot 2*t4, channel g + 8
@@ -640,10 +659,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const int slot = i >> 7, rem = i & 127;
               const float* pp = &s_part[eg][0][slot][0][0] + rem;
               const float tot = ((pp[0] + pp[3 * 128]) + pp[2 * 3 * 128]) + pp[3 * 3 * 128];
-              if (c0 + (rem >> 1) < CP) p.stats[((size_t)(unit * p.nslots + slot) * CP + c0) * 2 + rem] = tot;
+              if (c0 + (rem >> 1) < N) p.stats[((size_t)(unit * p.nslots + slot) * CP + c0) * 2 + rem] = tot;
             }
           }
         }
+        if (threadIdx.x == 0) TRC(5, it);
       } else {
         // output conv: Cout <= 16 real channels -> NCHW velocity, or fused Euler update x += dt * v
         uint32_t v[16];
@@ -666,6 +686,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the stores
   }
+#ifdef RGFM_TC_TRACE
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    printf("TRACE nmma=%d cblocks=%d taps=%d resident=%d a_slots=%d supers=%d end=%lld\n", p.nmma, p.cblocks[0], p.ntaps[0], p.resident, p.a_slots,
+           supers, clock64() - t_start);
+    for (int i = 0; i < 12 && blockIdx.x + i * gridDim.x < supers; ++i)
+      printf("  st%2d prodA %7lld | mma a_full %7lld committed %7lld | epi tmem_full %7lld stored %7lld unit_done %7lld\n", i, s_trace[0][i],
+             s_trace[1][i], s_trace[2][i], s_trace[3][i], s_trace[4][i], s_trace[5][i]);
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
