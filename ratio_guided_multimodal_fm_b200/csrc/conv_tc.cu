@@ -1,21 +1,24 @@
-// tcgen05 implicit-GEMM convolution for sm_100a: bf16 operands staged in shared memory by TMA, fp32 accumulators
-// in TMEM, one elected thread issuing tcgen05.mma, epilogue reading TMEM with tcgen05.ld.
+// tcgen05 implicit-GEMM convolution for sm_100a: 16-bit operands staged in shared memory by TMA, fp32 accumulators in
+// TMEM, tcgen05.mma issued by one thread per accumulator half, epilogue reading TMEM with tcgen05.ld.
 //
-// GEMM view of a 3x3 (or 1x1) stride-1 convolution over an NHWC bf16 operand:
-//   M = 128 output pixels (TileGeom: whole rows of one image, or several whole small images)
-//   N = CoutP (16..256, all output channels in one tile -> the accumulator is 128 lanes x N TMEM columns)
-//   K = taps x Cin, walked in K-blocks of BK = 64 (or 32) channels of one tap.
-// The A tile of K-block (tap=(ky,kx), c0) is the SAME pixel tile shifted by (ky-1, kx-1): one 4-D TMA box
-// {BK, W, th, imgs} at coordinates (c0, kx-1, h0+ky-1, n0).  TMA zero-fills out-of-bounds coordinates, which
-// implements the conv's zero padding for free and lands the rows in exactly the K-major 128B-swizzled layout the
-// UMMA shared-memory descriptor expects.  The B tile is a {BK, CoutP, 1} box of the repacked weights
-// [tap][CoutP][Cin].  Stride-2 convolutions are computed at stride 1 and stored subsampled.
+// GEMM view of a 3x3 (or 1x1) convolution over padded-linear NHWC tensors:
+//   M = 256 GEMM rows per super-tile = two M=128 accumulators that share every weight tile
+//   N = Cout rounded up to 16 (<= 256): the accumulator is 128 lanes x N TMEM columns per half
+//   K = (segment, 64-channel block, tap, K16 step); K16 steps that hold only zero padding are never issued.
+// In the padded-linear layout every tap of the filter is a ROW SHIFT (ky * P + kx, P = W + 2) of ONE shared-memory tile,
+// so one 2-box TMA load of 256 + 2P + 2 rows per (super-tile, channel block) serves all nine taps and the conv's zero
+// padding is physically in memory (plus TMA's out-of-bounds zero fill before the first / after the last row).  Raw
+// activation tensors are themselves valid operands (row offset -(P + 1)): 1x1 skip convs, identity residuals and
+// stride-2 convs read them directly.  Stride-2 convolutions are computed at stride 1 and stored subsampled.
 //
-// Persistent kernel, one CTA per SM, static round-robin over tiles.  Warp roles (352 threads): warps 0..7 = two
-// epilogue groups, warp 8 = TMA producer + TMEM allocator, warps 9..10 = MMA issuers, each epilogue group owning one of
-// two TMEM accumulators, so the MMAs of tile i+1 overlap the epilogue of tile i (TMEM -> registers -> + bias +
-// time bias + residual -> fp32 NHWC store, per-tile GroupNorm partial sums by a butterfly transpose-reduce, or
-// NCHW velocity / fused Euler update for the output conv).  The smem ring runs across tile boundaries.
+// Persistent kernel, one CTA per SM, static round-robin over super-tiles, 352 threads: warps 0..7 = two epilogue groups
+// (one per 128-row unit; TMEM lane quarter = warp & 3), warp 8 = TMA producer (one thread) + TMEM allocator, warps
+// 9..10 = MMA issuers (one thread each).  Weights are RESIDENT in shared memory when they fit (loaded once per CTA),
+// otherwise they stream through a two-stage ring; A tiles use 2..4 slots; TMEM accumulators are double buffered when
+// 4 * N <= 512 columns so the epilogue of tile i overlaps the MMAs of tile i + 1.
+// Epilogue: TMEM -> + bias (+ this step's time bias) -> saturating fp16 -> 128B-swizzled staging tile -> TMA store of
+// the raw activation (invalid rows as zeros), GroupNorm partials of the staged tile by ldmatrix.trans + mma.sync; the
+// output conv writes the NCHW velocity or applies the fused Euler update.
 #include "net.h"
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -45,7 +48,6 @@ struct TcArgs {
   int cblocks[3];       // operand channels / 64 per segment
   int ksteps[3][4];     // K16 steps that hold real channels in each 64-channel block (all-zero steps are never issued)
   int ntaps[3];         // 9 (3x3) or 1 (1x1)
-  int tap_shift[3][9];  // row shift of each tap inside the A tile: ky*P + kx (3x3), P + 1 (1x1)
   int row_off[3];       // TMA row coordinate of GEMM row 0: 0 for packed operands, -(P + 1) for raw activation tensors
   int a_box_rows;       // rows per TMA box; an A tile is two boxes
   uint32_t a_slot;      // bytes of one A slot (2 * a_box_rows * 128)
@@ -64,6 +66,9 @@ struct TcArgs {
   int tma_store;        // raw output leaves through swizzled smem staging + TMA store (fully coalesced)
   int out_H, out_W;     // output spatial size (H, W or halved when sub)
   int rows_alloc;       // rows of the raw output tensor (chunk * R): bound for direct row stores
+  int descend;          // walk the super-tiles from the last to the first: every tensor is a little larger than L2, the
+                        // packs stream in ascending order, so a conv that starts at the END of its operand finds the rows
+                        // the pack wrote last still in L2 (and leaves its own first rows there for the next pack)
   int out_fmt;          // raw output storage: 1 = bf16, 2 = fp16
   float* stats;         // GroupNorm partials [unit][nslots][CoutP][2] of the rounded output (null = none)
   int nslots;
@@ -371,7 +376,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
 #pragma unroll 1
-      for (int st = blockIdx.x; st < supers; st += gridDim.x) {
+      for (int sti = blockIdx.x; sti < supers; sti += gridDim.x) {
+        const int st = p.descend ? supers - 1 - sti : sti;  // see TcArgs::descend
         const int row0 = st * TC_SUPER;
 #pragma unroll 1
         for (int seg = 0; seg < p.nseg; ++seg) {
@@ -387,7 +393,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t sa = smem_base + as * p.a_slot;
             tma_load_2d(sa, tA, a_full(as), cb * 64, ra);
             tma_load_2d(sa + (p.a_slot >> 1), tA, a_full(as), cb * 64, ra + p.a_box_rows);
-            if (seg == 0 && cb == 0) TRC(0, (st - (int)blockIdx.x) / (int)gridDim.x);
+            if (seg == 0 && cb == 0) TRC(0, (sti - (int)blockIdx.x) / (int)gridDim.x);
             if (++as == a_slots) {
               as = 0u;
               aph ^= 1u;
@@ -506,7 +512,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int total_rows_alloc = p.rows_alloc;  // rows of the output tensor (direct-store bound)
     const uint32_t stg = smem_stage + (uint32_t)eg * TC_STAGE_BYTES;
     int it = 0;
-    for (int st = blockIdx.x; st < supers; st += gridDim.x, ++it) {
+    for (int sti = blockIdx.x; sti < supers; sti += gridDim.x, ++it) {
+      const int st = p.descend ? supers - 1 - sti : sti;
       const int buf = (p.nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
       const int unit = st * 2 + eg;  // 128-row unit index
@@ -859,12 +866,6 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     p.ntaps[sg] = S.ks * S.ks;
     // a raw activation tensor is indexed by the GEMM row itself: operand slot = raw row + P + 1
     p.row_off[sg] = S.raw ? -(P + 1) : 0;
-    if (S.ks == 3) {
-      for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx) p.tap_shift[sg][ky * 3 + kx] = ky * P + kx;
-    } else {
-      p.tap_shift[sg][0] = P + 1;
-    }
     // weights: torch [Cout][Cin_real][ks][ks] fp32 (or identity when w_oihw == nullptr) -> [tap][nmma][Cin] 16-bit
     const int taps = p.ntaps[sg];
     std::vector<uint16_t> hw((size_t)taps * nmma * S.Cin, 0);
@@ -931,6 +932,8 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CHECK((a.CoutP % 64 == 0 || a.CoutP == 32) && a.CoutP >= p.nmma && a.out_padded && a.out_fmt == p.out_fmt && a.out != nullptr,
                "tc conv: raw outputs are 16-bit, padded-linear, channel stride 32 or a multiple of 64");
   }
+  static const int descend = getenv("RGFM_TC_DESCEND") ? atoi(getenv("RGFM_TC_DESCEND")) : 1;
+  p.descend = descend;
   static const bool no_stats = getenv("RGFM_TC_NO_STATS") != nullptr;  // timing experiment only (results are wrong)
   if (no_stats) p.stats = nullptr;
   const int total_rows = a.nimg * (p.H + 1) * p.P;
