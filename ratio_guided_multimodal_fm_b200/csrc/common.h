@@ -9,6 +9,8 @@
 #include <map>
 #include <memory>
 #include <cstdio>
+#include <utility>
+#include <cstdlib>
 
 namespace rgfm {
 
@@ -278,6 +280,29 @@ struct DiagArgs {
 };
 void launch_diag(const DiagArgs& a, cudaStream_t s);
 void launch_ratio_stats(const float* ratios, int n, float* diag3, cudaStream_t s);
+
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains; it must execute
+// pdl_wait() before touching anything the predecessor wrote (and calls pdl_trigger() early so ITS successor can follow).
+// Inside stream capture these launches become programmatic edges of the CUDA graph.  Off by default (no measured gain:
+// the persistent kernels leave nothing for the dependent's prologue to overlap with); RGFM_PDL=1 enables it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (e != cudaSuccess) throw Error(std::string("cudaLaunchKernelEx failed: ") + cudaGetErrorString(e));
+}
 
 extern thread_local int64_t g_launch_counter;  // incremented by every launch_* (graph build-time kernel count)
 

@@ -298,6 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __shared__ __align__(16) float s_part[2][4][3][64][2];
   // per epilogue group / warp / image slot: {sum, sumsq} of a 64-channel chunk
 
+  pdl_trigger();  // the next kernel of the stream may be scheduled as this grid's CTAs retire
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_stage = smem_base + (uint32_t)p.a_slots * p.a_slot;  // epilogue staging tiles (one per epilogue group)
@@ -340,6 +341,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlaps the previous kernel's tail; nothing
+  // below may run before its writes are visible
+  pdl_wait();
   if (warp < 8) {
     // bias + this step's time bias: identical for every tile of the launch (t is uniform over the batch)
     const float* tb = a.temb ? a.temb + (size_t)(a.step ? *a.step : 0) * a.temb_stride + a.temb_off : nullptr;
@@ -945,7 +949,7 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = supers < num_sms ? supers : num_sms;  // persistent: one CTA per SM, static round-robin
-  conv_tc_kernel<<<grid, TC_THREADS, tc.smem, s>>>(tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, p);
+  launch_pdl(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, p);
   post_launch("conv_tc");
 }
 

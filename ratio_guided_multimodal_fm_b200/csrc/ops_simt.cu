@@ -9,6 +9,12 @@ namespace rgfm {
 
 thread_local int64_t g_launch_counter = 0;
 
+bool pdl_enabled() {
+  // measured on B200 (round 1): 890 pairs/s with programmatic edges vs 896 without -- off unless RGFM_PDL=1
+  static const bool on = getenv("RGFM_PDL") && atoi(getenv("RGFM_PDL")) != 0;
+  return on;
+}
+
 static inline void post_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw Error(std::string(what) + " launch failed: " + cudaGetErrorString(e));
@@ -388,6 +394,8 @@ __global__ void __launch_bounds__(256) pack_padded_kernel(PackArgs a) {
 // iteration: the kernel is a pure stream and one dependent load per thread leaves it latency-bound at ~2 TB/s.
 template <int FMT>
 __global__ void __launch_bounds__(256) pack_padded_fast_kernel(PackArgs a) {
+  pdl_trigger();
+  pdl_wait();  // the statistics and the raw tensor come from the previous kernel
   __shared__ float s_scale[PACK_MAXC];
   __shared__ float s_shift[PACK_MAXC];
   __shared__ float s_red[2][PACK_MAXC];
@@ -488,6 +496,8 @@ __global__ void __launch_bounds__(256) pack_padded_fast_kernel(PackArgs a) {
 // GroupNorm output cannot leave the fp16 range).
 template <int FMT, int U>
 __global__ void __launch_bounds__(256) pack_gn_silu_kernel(PackArgs a) {
+  pdl_trigger();
+  pdl_wait();  // the statistics and the raw tensor come from the previous kernel
   __shared__ float s_scale[PACK_MAXC];
   __shared__ float s_shift[PACK_MAXC];
   __shared__ float s_red[2][PACK_MAXC];
@@ -593,16 +603,16 @@ void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
   if (gn_silu) {
     static const int u8 = getenv("RGFM_PACK_U8") ? 1 : 0;
     if (a.out_bf16 == 1)
-      pack_gn_silu_kernel<1, 4><<<grid, 256, 0, s>>>(a);
+      launch_pdl(pack_gn_silu_kernel<1, 4>, grid, dim3(256), 0, s, a);
     else if (u8)
-      pack_gn_silu_kernel<2, 8><<<grid, 256, 0, s>>>(a);
+      launch_pdl(pack_gn_silu_kernel<2, 8>, grid, dim3(256), 0, s, a);
     else
-      pack_gn_silu_kernel<2, 4><<<grid, 256, 0, s>>>(a);
+      launch_pdl(pack_gn_silu_kernel<2, 4>, grid, dim3(256), 0, s, a);
   } else if (fast) {
     if (a.out_bf16 == 1)
-      pack_padded_fast_kernel<1><<<grid, 256, 0, s>>>(a);
+      launch_pdl(pack_padded_fast_kernel<1>, grid, dim3(256), 0, s, a);
     else
-      pack_padded_fast_kernel<2><<<grid, 256, 0, s>>>(a);
+      launch_pdl(pack_padded_fast_kernel<2>, grid, dim3(256), 0, s, a);
   } else if (a.out_bf16 == 1) {
     pack_padded_kernel<1><<<grid, 256, 0, s>>>(a);
   } else {
