@@ -352,3 +352,13 @@ def test_sampler_grad_log_ratio(pair, kinds, synth):
     x0d = torch.randn(B, *shape_x, device=DEV); y0d = torch.randn(B, *shape_y, device=DEV)
     ox, oy = O.sample_pair(sdx, sdy, sdr, pair, "grad_log_ratio", gamma, steps, x0d.cpu(), y0d.cpu(), None, None, "rulsif")
     assert maxabs(a[0], ox) <= 1e-3 and maxabs(a[1], oy) <= 1e-3
+
+
+def test_empty_batch_returns_empty_tensors(synth):
+    """num_samples=0: the reference's randn(0, ...) / empty loops return empty tensors; no plan is built."""
+    fx = synthetic.StateDictModule("unet_mnist28", synth("unet_mnist28", 11))
+    fy = synthetic.StateDictModule("unet_mnist28", synth("unet_mnist28", 14))
+    fr = synthetic.StateDictModule("ratio28", synth("ratio28", 21))
+    x1, y1 = sample_bimodal_guided(fx, fy, fr, guidance_method="mc_feng", guidance_strength=0.5, num_samples=0, num_steps=3,
+                                   device=DEV, mc_batch_size=4, verbose=False)
+    assert x1.shape == (0, 1, 28, 28) and y1.shape == (0, 1, 28, 28) and x1.device.type == "cuda"
