@@ -176,6 +176,7 @@ int rgfm_mc_feng_step(int32_t batch, int32_t n_mc, int32_t dx, int32_t dy, const
   a.B = batch; a.N = n_mc; a.Dx = dx; a.Dy = dy;
   a.x = x; a.y = y; a.vx = v_x; a.vy = v_y; a.mcx = mc_x; a.mcy = mc_y; a.ratios = mc_ratios;
   a.x_out = x_out; a.y_out = y_out; a.gx = g_x; a.gy = g_y; a.w = weights;
+  a.g_step = -1;  // always write the optional g outputs
   const size_t nf = mcf_scratch_floats(batch, n_mc, dx, dy, &a.ksplit_x, &a.ksplit_y);
   float* scratch = nullptr;
   StepScalars* dsc = nullptr;

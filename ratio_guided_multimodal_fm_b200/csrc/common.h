@@ -265,8 +265,9 @@ struct McfArgs {
   float *gx, *gy, *w;     // optional
   float* logits;          // scratch [ksplit][B][N]
   float* wbuf;            // scratch [B][N]
-  float* zbuf;            // scratch [B][4]: Z_bar, w_min, w_max
+  float* zbuf;            // scratch [B][4]: Z_bar, w_min, w_max; followed by the sparse-weight lists (see guidance.cu)
   int ksplit_x, ksplit_y;
+  int g_step;             // write gx / gy only at this step (diagnostics); < 0 = always
 };
 size_t mcf_scratch_floats(int B, int N, int Dx, int Dy, int* ksx, int* ksy);
 void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof = nullptr);

@@ -910,11 +910,8 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     encode_2d(&t->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out, (uint64_t)d.CoutP, tc_raw_rows(d.Hin, d.Win, d.chunk), 64, 128, "out");
   else
     t->tmO = t->tmA[0];
-  static bool attr = false;
-  if (!attr) {
-    RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
-    attr = true;
-  }
+  // per device (function attributes belong to the current context): cheap enough to set for every plan
+  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
   return t;
 }
 
@@ -942,7 +939,7 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
   if (no_stats) p.stats = nullptr;
   const int total_rows = a.nimg * (p.H + 1) * p.P;
   const int supers = (total_rows + TC_SUPER - 1) / TC_SUPER;
-  static int num_sms = 0;
+  static int num_sms = 0;  // B200 only: every device of the box has the same count
   if (!num_sms) {
     int dev = 0;
     RGFM_CUDA(cudaGetDevice(&dev));

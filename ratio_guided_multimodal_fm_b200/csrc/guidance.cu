@@ -7,6 +7,7 @@
 // The direct (x - t m)^2 form is kept (no ||x||^2 - 2 x.m expansion) so late-time logits, which are divided by
 // sigma_t^2 ~ 1e-4, do not lose the bits the reference has.
 #include "common.h"
+#include <algorithm>
 
 namespace rgfm {
 
@@ -18,6 +19,13 @@ static inline void post_launch(const char* what) {
 
 constexpr int DT = 64;   // tile edge (b and i / d)
 constexpr int DK = 16;   // reduction chunk
+constexpr int MCF_KMAX = 8;  // longest non-zero weight list the sparse apply path handles
+
+// sparse-weight scratch, laid out after zbuf[B][4]: max_cnt (4 ints), cnt[B], idx[B][KMAX], w[B][KMAX]
+__host__ __device__ inline int* sparse_max(const McfArgs& a) { return reinterpret_cast<int*>(a.zbuf + (size_t)a.B * 4); }
+__host__ __device__ inline int* sparse_cnt(const McfArgs& a) { return sparse_max(a) + 4; }
+__host__ __device__ inline int* sparse_idx(const McfArgs& a) { return sparse_cnt(a) + a.B; }
+__host__ __device__ inline float* sparse_w(const McfArgs& a) { return reinterpret_cast<float*>(sparse_idx(a) + (size_t)a.B * MCF_KMAX); }
 
 // grid: (ceil(B/64), ceil(N/64), ksx + ksy).  z < ksx handles a D-range of x, else of y.
 __global__ void __launch_bounds__(256) mcf_dist_kernel(McfArgs a) {
@@ -36,6 +44,7 @@ __global__ void __launch_bounds__(256) mcf_dist_kernel(McfArgs a) {
   const float* X = isx ? a.x : a.y;
   const float* M = isx ? a.mcx : a.mcy;
   const float t = a.sc[a.step ? *a.step : 0].t;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) *sparse_max(a) = 0;  // re-armed for mcf_weights
 
   const int lb = tid >> 2, l4 = tid & 3;  // load assignment: row, float4 within the 16-wide chunk
   const int tb = tid >> 4, ti = tid & 15; // compute assignment: 4 b x 4 i
@@ -150,6 +159,31 @@ __global__ void __launch_bounds__(128) mcf_weights_kernel(McfArgs a) {
     a.zbuf[b * 4 + 1] = wmin;
     a.zbuf[b * 4 + 2] = wmax;
   }
+  // Once the softmax saturates almost every weight is EXACTLY zero (exp underflow), so the guidance sum has a handful of
+  // terms per sample: warp 0 compacts the non-zero (index, weight) pairs in increasing index order (deterministic), and
+  // the apply kernel walks the list instead of the dense [B, N_mc] x [N_mc, D] product.
+  __syncthreads();
+  if (tid < 32) {
+    int* nzc = sparse_cnt(a);
+    int* nzi = sparse_idx(a) + (size_t)b * MCF_KMAX;
+    float* nzw = sparse_w(a) + (size_t)b * MCF_KMAX;
+    int cnt = 0;
+    for (int base = 0; base < a.N; base += 32) {
+      const int i = base + tid;
+      const float wv = (i < a.N) ? sw[i] / den : 0.f;  // the value written to wbuf above (same __fdiv_rn)
+      const unsigned m = __ballot_sync(0xffffffffu, wv != 0.f);
+      const int pos = cnt + __popc(m & ((1u << tid) - 1u));
+      if (wv != 0.f && pos < MCF_KMAX) {
+        nzi[pos] = i;
+        nzw[pos] = wv;
+      }
+      cnt += __popc(m);
+    }
+    if (tid == 0) {
+      nzc[b] = cnt;
+      if (cnt > MCF_KMAX) atomicMax(sparse_max(a), cnt);  // any long row -> the dense kernel handles this launch
+    }
+  }
 }
 
 // grid: (ceil(B/64), ceil(D/64)); one launch per modality
@@ -159,9 +193,56 @@ struct ApplyArgs {
   const StepScalars* sc;
   const int* step;
   float *x_out, *g;
+  const int* max_cnt;   // > MCF_KMAX: some sample has a long weight list -> dense path; else sparse path
+  const int* nz_cnt;
+  const int* nz_idx;
+  const float* nz_w;
+  int g_step;           // write g only at this step (< 0: always)
 };
 
+// Sparse path of the fused guidance sum + blend + Euler update: a pure stream over [B, D] (read x, v; write x) with the
+// few non-zero bank rows gathered from L2.  Terms are accumulated in increasing index order with the dense kernel's exact
+// arithmetic (an fma with a zero weight leaves the accumulator unchanged), so both paths give the same bits.
+__global__ void __launch_bounds__(256) mcf_apply_sparse_kernel(ApplyArgs ax, ApplyArgs ay) {
+  if (*ax.max_cnt > MCF_KMAX) return;  // the dense kernel owns this launch
+  const StepScalars sc = ax.sc[ax.step ? *ax.step : 0];
+  const int Dx4 = ax.D >> 2, D4t = (ax.D + ay.D) >> 2;  // both modalities in one element space: [b][x quads | y quads]
+  const size_t total = (size_t)ax.B * D4t;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / D4t);
+    const int q4 = (int)(e - (size_t)b * D4t);
+    const bool isx = q4 < Dx4;
+    const ApplyArgs& a = isx ? ax : ay;
+    const int d = (isx ? q4 : q4 - Dx4) << 2;
+    const bool write_g = a.g != nullptr && (a.g_step < 0 || (a.step ? *a.step : 0) == a.g_step);
+    const float4 xv = *reinterpret_cast<const float4*>(a.x + (size_t)b * a.D + d);
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + (size_t)b * a.D + d));
+    const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float va[4] = {vv.x, vv.y, vv.z, vv.w};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int cnt = a.nz_cnt[b];
+    for (int k = 0; k < cnt; ++k) {
+      const int i = a.nz_idx[(size_t)b * MCF_KMAX + k];
+      const float w = a.nz_w[(size_t)b * MCF_KMAX + k];
+      const float4 mv = __ldg(reinterpret_cast<const float4*>(a.m + (size_t)i * a.D + d));
+      const float ma[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(w, __fsub_rn(ma[q], xr[q]), acc[q]);
+    }
+    float go[4], xo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      go[q] = __fmul_rn(acc[q], sc.inv_sigma);
+      const float vg = __fadd_rn(__fmul_rn(sc.one_minus_gamma, va[q]), __fmul_rn(sc.gamma, go[q]));
+      xo[q] = __fadd_rn(xr[q], __fmul_rn(vg, sc.dt));
+    }
+    *reinterpret_cast<float4*>(a.x_out + (size_t)b * a.D + d) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+    if (write_g) *reinterpret_cast<float4*>(a.g + (size_t)b * a.D + d) = make_float4(go[0], go[1], go[2], go[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256) mcf_apply_kernel(ApplyArgs a) {
+  if (*a.max_cnt <= MCF_KMAX) return;  // every sample has a short weight list: the sparse kernel owns this launch
   __shared__ __align__(16) float Ws[DK][DT + 4];  // [i][b]
   __shared__ __align__(16) float Ms[DK][DT];      // [i][d]
   const int tid = threadIdx.x;
@@ -233,7 +314,8 @@ __global__ void __launch_bounds__(256) mcf_apply_kernel(ApplyArgs a) {
       xo[q] = __fadd_rn(xr[p][q], __fmul_rn(vg, sc.dt));
     }
     *reinterpret_cast<float4*>(a.x_out + (size_t)b * a.D + dcol) = make_float4(xo[0], xo[1], xo[2], xo[3]);
-    if (a.g) *reinterpret_cast<float4*>(a.g + (size_t)b * a.D + dcol) = make_float4(go[0], go[1], go[2], go[3]);
+    if (a.g != nullptr && (a.g_step < 0 || (a.step ? *a.step : 0) == a.g_step))
+      *reinterpret_cast<float4*>(a.g + (size_t)b * a.D + dcol) = make_float4(go[0], go[1], go[2], go[3]);
   }
 }
 
@@ -253,7 +335,8 @@ size_t mcf_scratch_floats(int B, int N, int Dx, int Dy, int* ksx, int* ksy) {
   (void)unit;
   *ksx = kx;
   *ksy = ky;
-  return (size_t)(kx + ky) * B * N + (size_t)B * N + (size_t)B * 4;
+  // logits partials, weights, zbuf, then the sparse lists: 4 + B + 2 * B * KMAX words
+  return (size_t)(kx + ky) * B * N + (size_t)B * N + (size_t)B * 4 + 4 + (size_t)B * (1 + 2 * MCF_KMAX);
 }
 
 void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof) {
@@ -274,15 +357,27 @@ void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof) {
   }
   {
     // fused guidance-sum + blend + Euler update: algorithmic bytes = read x, v, write x (+ bank and weights once)
-    ProfScope ps(prof, s, "mcf_apply", 2.0 * BN * D, 4.0 * (3.0 * a.B * D + a.N * D + BN));
-    ApplyArgs ax{a.B, a.N, a.Dx, a.x, a.vx, a.mcx, a.wbuf, a.sc, a.step, a.x_out, a.gx};
-    dim3 g3x((a.B + DT - 1) / DT, (a.Dx + DT - 1) / DT);
-    mcf_apply_kernel<<<g3x, 256, 0, s>>>(ax);
-    post_launch("mcf_apply_x");
-    ApplyArgs ay{a.B, a.N, a.Dy, a.y, a.vy, a.mcy, a.wbuf, a.sc, a.step, a.y_out, a.gy};
-    dim3 g3y((a.B + DT - 1) / DT, (a.Dy + DT - 1) / DT);
-    mcf_apply_kernel<<<g3y, 256, 0, s>>>(ay);
-    post_launch("mcf_apply_y");
+    // one of the two paths runs per launch (device-side switch on the longest weight list, no host round trip); the
+    // profile times them separately and credits the algorithmic work to whichever did it (bench.py: the longer one)
+    ApplyArgs ax{a.B, a.N, a.Dx, a.x, a.vx, a.mcx, a.wbuf, a.sc, a.step, a.x_out, a.gx,
+                 sparse_max(a), sparse_cnt(a), sparse_idx(a), sparse_w(a), a.g_step};
+    ApplyArgs ay{a.B, a.N, a.Dy, a.y, a.vy, a.mcy, a.wbuf, a.sc, a.step, a.y_out, a.gy,
+                 sparse_max(a), sparse_cnt(a), sparse_idx(a), sparse_w(a), a.g_step};
+    {
+      ProfScope ps(prof, s, "mcf_apply_dense", 2.0 * BN * D, 4.0 * (3.0 * a.B * D + a.N * D + BN));
+      dim3 g3x((a.B + DT - 1) / DT, (a.Dx + DT - 1) / DT);
+      mcf_apply_kernel<<<g3x, 256, 0, s>>>(ax);
+      post_launch("mcf_apply_x");
+      dim3 g3y((a.B + DT - 1) / DT, (a.Dy + DT - 1) / DT);
+      mcf_apply_kernel<<<g3y, 256, 0, s>>>(ay);
+      post_launch("mcf_apply_y");
+    }
+    // sparse path: read x, v once, write x once (+ the few gathered bank rows from L2)
+    ProfScope ps(prof, s, "mcf_apply", 2.0 * a.B * D * MCF_KMAX, 4.0 * 3.0 * a.B * D);
+    const size_t e4 = (size_t)a.B * (a.Dx + a.Dy) / 4;
+    const unsigned sb = (unsigned)std::min<size_t>((e4 + 255) / 256, 148 * 8);
+    mcf_apply_sparse_kernel<<<sb, 256, 0, s>>>(ax, ay);
+    post_launch("mcf_apply_sparse");
   }
 }
 

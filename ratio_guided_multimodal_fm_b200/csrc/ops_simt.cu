@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(256) pack_padded_fast_kernel(PackArgs a) {
 //   z = fma(x, sc, sh);  e = ex2(fma(x, -sc*log2e, -sh*log2e));  silu = z * rcp(1 + e)
 // with both coefficient pairs per channel in registers, four 16-byte loads in flight per thread and no saturation (a
 // GroupNorm output cannot leave the fp16 range).
-template <int FMT, int U>
+template <int FMT, int U, int STREAM>
 __global__ void __launch_bounds__(256) pack_gn_silu_kernel(PackArgs a) {
   pdl_trigger();
   pdl_wait();  // the statistics and the raw tensor come from the previous kernel
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(256) pack_gn_silu_kernel(PackArgs a) {
       const int q = pp + u * PL;
       ok[u] = cvalid && q < s_end && ho < a.Ho && ww >= 1 && ww <= a.Wo;
       rawv[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok[u]) rawv[u] = __ldg(reinterpret_cast<const uint4*>(src_img + (size_t)(q - 1) * Cs));
+      if (ok[u]) rawv[u] = STREAM ? __ldcs(reinterpret_cast<const uint4*>(src_img + (size_t)(q - 1) * Cs)) : __ldg(reinterpret_cast<const uint4*>(src_img + (size_t)(q - 1) * Cs));
       ho += dh;
       ww += dw;
       if (ww >= P) {
@@ -580,7 +580,8 @@ __global__ void __launch_bounds__(256) pack_gn_silu_kernel(PackArgs a) {
         }
         o = make_uint4(r4[0], r4[1], r4[2], r4[3]);
       }
-      out[(slot0 + q) * CP8 + co] = o;
+      if (STREAM) __stcs(&out[(slot0 + q) * CP8 + co], o);
+      else out[(slot0 + q) * CP8 + co] = o;
     }
   }
 }
@@ -602,12 +603,15 @@ void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
                        (a.nsrc == 1 || a.src[1].fmt == 2);
   if (gn_silu) {
     static const int u8 = getenv("RGFM_PACK_U8") ? 1 : 0;
+    static const int stream_hint = getenv("RGFM_PACK_STREAM") ? atoi(getenv("RGFM_PACK_STREAM")) : 0;
     if (a.out_bf16 == 1)
-      launch_pdl(pack_gn_silu_kernel<1, 4>, grid, dim3(256), 0, s, a);
+      launch_pdl(pack_gn_silu_kernel<1, 4, 0>, grid, dim3(256), 0, s, a);
     else if (u8)
-      launch_pdl(pack_gn_silu_kernel<2, 8>, grid, dim3(256), 0, s, a);
+      launch_pdl(pack_gn_silu_kernel<2, 8, 0>, grid, dim3(256), 0, s, a);
+    else if (stream_hint)
+      launch_pdl(pack_gn_silu_kernel<2, 4, 1>, grid, dim3(256), 0, s, a);
     else
-      launch_pdl(pack_gn_silu_kernel<2, 4>, grid, dim3(256), 0, s, a);
+      launch_pdl(pack_gn_silu_kernel<2, 4, 0>, grid, dim3(256), 0, s, a);
   } else if (fast) {
     if (a.out_bf16 == 1)
       launch_pdl(pack_padded_fast_kernel<1>, grid, dim3(256), 0, s, a);
@@ -890,11 +894,13 @@ void launch_mlp(const float* in, int ld_in, const MlpLayer* layers, int nlayers,
     mp.l[i] = layers[i];
     RGFM_CHECK(layers[i].in <= MLP_MAXW && layers[i].out <= MLP_MAXW, "mlp: width");
   }
-  static bool attr_set = false;
   const size_t smem = 2 * MLP_MAXW * sizeof(float);
-  if (!attr_set) {
+  static thread_local int attr_dev = -1;  // function attributes are per device
+  int dev = 0;
+  RGFM_CUDA(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
     RGFM_CUDA(cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_dev = dev;
   }
   mlp_kernel<<<nimg, 256, smem, s>>>(in, ld_in, mp, out, ld_out);
   post_launch("mlp");

@@ -61,6 +61,7 @@ struct Sampler {
     a.wbuf = scratch + (size_t)(ksx + ksy) * B * N;
     a.zbuf = a.wbuf + (size_t)B * N;
     a.ksplit_x = ksx; a.ksplit_y = ksy;
+    a.g_step = (int)(0.3 * steps);  // g_x / g_y are only read by the diagnostics of that step (flow_utils.py:349-363)
     return a;
   }
 
