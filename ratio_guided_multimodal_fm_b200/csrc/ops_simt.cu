@@ -602,14 +602,9 @@ void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
   const bool gn_silu = fast && a.norm == NORM_GN && a.act == ACT_SILU && a.spatial == SP_ID && a.src[0].fmt == 2 &&
                        (a.nsrc == 1 || a.src[1].fmt == 2);
   if (gn_silu) {
-    static const int u8 = getenv("RGFM_PACK_U8") ? 1 : 0;
-    static const int stream_hint = getenv("RGFM_PACK_STREAM") ? atoi(getenv("RGFM_PACK_STREAM")) : 0;
+    // measured slower on B200 and removed: 8 loads in flight, evict-first hints, software-pipelined batches, more slabs
     if (a.out_bf16 == 1)
       launch_pdl(pack_gn_silu_kernel<1, 4, 0>, grid, dim3(256), 0, s, a);
-    else if (u8)
-      launch_pdl(pack_gn_silu_kernel<2, 8, 0>, grid, dim3(256), 0, s, a);
-    else if (stream_hint)
-      launch_pdl(pack_gn_silu_kernel<2, 4, 1>, grid, dim3(256), 0, s, a);
     else
       launch_pdl(pack_gn_silu_kernel<2, 4, 0>, grid, dim3(256), 0, s, a);
   } else if (fast) {
