@@ -120,11 +120,23 @@ __device__ __forceinline__ void stats_channel_sums(const StatsRef& st, int n, in
     }
   } else if (st.mode == ST_UNITS) {
     const int u0 = (n * st.R) >> 7, u1 = ((n + 1) * st.R - 1) >> 7;
-    for (int u = u0; u <= u1; ++u) {
-      const int slot = n - (u << 7) / st.R;
-      const float2 v = *reinterpret_cast<const float2*>(st.p + (((size_t)u * st.slots + slot) * st.C + c) * 2);
-      s += v.x;
-      ss += v.y;
+    // four partials in flight at a time (a rolled loop waits out one global-load latency per unit); summed in unit order
+    for (int ub = u0; ub <= u1; ub += 4) {
+      float2 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int u = ub + j;
+        v[j] = make_float2(0.f, 0.f);
+        if (u <= u1) {
+          const int slot = n - (u << 7) / st.R;
+          v[j] = __ldg(reinterpret_cast<const float2*>(st.p + (((size_t)u * st.slots + slot) * st.C + c) * 2));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s += v[j].x;
+        ss += v[j].y;
+      }
     }
   }
 }
@@ -204,6 +216,7 @@ struct ConvArgs {
 // ops_simt.cu
 void launch_pack(const PackArgs& a, cudaStream_t s);
 void launch_pack_padded(const PackArgs& a, cudaStream_t s);
+void launch_gn_coef(const PackArgs& a, float* coef, cudaStream_t s);  // coef[nimg][C][2] = {scale, shift}
 void launch_pack_nchw_padded(const float* x, int C, int H, int W, void* out, int fmt, int nimg, cudaStream_t s);
 void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, int out_bf16, int nimg, cudaStream_t s);
 void launch_conv_simt(const ConvArgs& a, cudaStream_t s);

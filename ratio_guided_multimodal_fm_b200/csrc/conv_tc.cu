@@ -34,10 +34,17 @@ static inline void post_launch(const char* what) {
 }
 
 constexpr int TC_MAX_STAGES = 12;
-constexpr int TC_THREADS = 96 + 2 * 128;  // producer warp, two MMA warps (one per accumulator half), two epilogue groups of 4 warps
+constexpr int TC_XF_THREADS = 256;        // transform group: fused GroupNorm + SiLU on the A tiles in shared memory (12 warps: no faster)
+// two epilogue groups of 4 warps, producer warp, two MMA warps (one per accumulator half), transform group
+constexpr int TC_THREADS = 2 * 128 + 96 + TC_XF_THREADS;
 constexpr int TC_SUPER = 256;             // output rows per super-tile (two M=128 accumulators sharing every B tile)
 constexpr uint32_t TC_STAGE_BYTES = 128 * 128;
-constexpr uint32_t TC_SMEM_BUDGET = 212u * 1024u;  // dynamic shared memory for A slots + staging + weights (static: ~14 KB)  // epilogue staging buffer: 128 rows x 32 fp32, 128B-swizzled
+// dynamic shared memory for A slots + epilogue staging + weights (static: ~14 KB; trace builds add their stamp table)
+#ifdef RGFM_TC_TRACE
+constexpr uint32_t TC_SMEM_BUDGET = 211u * 1024u;
+#else
+constexpr uint32_t TC_SMEM_BUDGET = 212u * 1024u;
+#endif
 
 struct TcArgs {
   ConvArgs c;           // epilogue description (bias, time bias, output, nimg, out_mode, dt)
@@ -66,6 +73,12 @@ struct TcArgs {
   int tma_store;        // raw output leaves through swizzled smem staging + TMA store (fully coalesced)
   int out_H, out_W;     // output spatial size (H, W or halved when sub)
   int rows_alloc;       // rows of the raw output tensor (chunk * R): bound for direct row stores
+  int any_xform;        // some segment applies GroupNorm + SiLU to its raw A tiles in shared memory (transform warps active)
+  int xform[3];         // per segment
+  const float2* coef[3];  // per segment: {scale, shift}[image][coef_C]
+  int coef_C[3], coef_c0[3];
+  int cin_real[3];      // real channels of the segment (transform touches only those)
+  int xf_bf16;          // format the transform writes: 1 = bf16, 0 = fp16 (the net's operand format)
   int descend;          // walk the super-tiles from the last to the first: every tensor is a little larger than L2, the
                         // packs stream in ascending order, so a conv that starts at the END of its operand finds the rows
                         // the pack wrote last still in L2 (and leaves its own first rows there for the next pack)
@@ -281,19 +294,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmO, const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bars[12 + 2 * TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t s_bars[16 + 2 * TC_MAX_STAGES];
   const uint32_t bar_base = smem_u32(s_bars);
 #define a_full(i) (bar_base + 8u * (uint32_t)(i))
 #define a_empty(i) (bar_base + 8u * (4u + (uint32_t)(i)))
 #define tmem_full_bar(i) (bar_base + 8u * (8u + (uint32_t)(i)))
 #define tmem_empty_bar(i) (bar_base + 8u * (10u + (uint32_t)(i)))
-#define b_full(i) (bar_base + 8u * (12u + (uint32_t)(i)))
-#define b_empty(i) (bar_base + 8u * (12u + TC_MAX_STAGES + (uint32_t)(i)))
+// a_ready(slot): transform group -> MMA warps (convs with a fused GroupNorm + SiLU segment)
+#define a_ready(i) (bar_base + 8u * (12u + (uint32_t)(i)))
+#define b_full(i) (bar_base + 8u * (16u + (uint32_t)(i)))
+#define b_empty(i) (bar_base + 8u * (16u + TC_MAX_STAGES + (uint32_t)(i)))
   __shared__ uint32_t tmem_slot;
 #ifdef RGFM_TC_TRACE
   __shared__ long long s_trace[6][12];
   const long long t_start = clock64();
 #endif
+  __shared__ uint8_t s_rown[400];  // transform group: image (relative to the tile's first) of each A-tile row, 0xff = not a pixel
   __shared__ __align__(16) float s_bias[256];
   __shared__ __align__(16) float s_part[2][4][3][64][2];
   // per epilogue group / warp / image slot: {sum, sumsq} of a 64-channel chunk
@@ -322,7 +338,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
     for (int s = 0; s < 4; ++s) {
       mbar_init(a_full(s), 1);
-      mbar_init(a_empty(s), 2);         // both MMA warps
+      mbar_init(a_empty(s), 2);                    // both MMA warps
+      mbar_init(a_ready(s), 1);  // transform group -> MMA warps
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar(s), 2);   // both MMA warps
@@ -419,7 +436,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
-  } else if (warp >= 9) {
+  } else if (warp == 9 || warp == 10) {
     // ------------------- MMA issuers: warp 9 accumulates rows 0..127, warp 10 rows 128..255 of each super-tile -------------------
     // One thread per warp runs the role.  A tap is a ROW SHIFT of the shared A tile: descriptor start + (ky * P + kx)
     // rows * 8 sixteen-byte units; K16 step k adds 2 units to both descriptors; tap j of a ring stage sits j * b_tap16
@@ -454,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint32_t idesc = p.idesc[seg];
 #pragma unroll 1
           for (int cb = 0; cb < ncb; ++cb) {
-            mbar_wait(a_full(as), aph);
+            mbar_wait(p.any_xform ? a_ready(as) : a_full(as), aph);
             tc_fence_after();
             if (hf == 0 && seg == 0 && cb == 0) TRC(1, it);
             const int ks = p.ksteps[seg][cb];
@@ -503,6 +520,118 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         tc_commit(tmem_full_bar(buf));
         if (hf == 0) TRC(2, it);
+      }
+    }
+  } else if (warp >= 11) {
+    // ---------------- transform group: fused GroupNorm + SiLU on the raw A tiles ----------------
+    // The tile was loaded by TMA from a RAW activation tensor; these 256 threads rewrite its real pixels in place as
+    // silu(x * scale + shift) (per image and channel, coefficients from gn_coef_kernel) in the swizzled layout the MMA
+    // reads, then hand the slot to the MMA threads.  Pad rows / columns are zeros in the raw tensor (and out-of-range
+    // rows are zero-filled by TMA), so they are simply left alone.  Segments without a transform are passed through.
+    // Measured alternatives (profiles/notes_r01.md): reading the raw rows with plain global loads instead of TMA, and
+    // splitting the tile into three boxes with their own barriers so that the first accumulator half starts early,
+    // were both slower; a single warp of this kernel runs at ~0.2 IPC, hence eight of them.
+    if (p.any_xform) {
+      const int tt = threadIdx.x - 11 * 32;
+      const int rows_used = TC_SUPER + 2 * p.P + 2;
+      uint32_t as = 0, aph = 0;
+      const uint32_t a_slots = (uint32_t)p.a_slots;
+#pragma unroll 1
+      for (int sti = blockIdx.x; sti < supers; sti += gridDim.x) {
+        const int st = p.descend ? supers - 1 - sti : sti;
+        const int rbase = st * TC_SUPER - (p.P + 1);  // raw row of tile row 0 (every raw segment has this row offset)
+        const int nbase = fast_div(rbase < 0 ? 0 : rbase, p.magic_R);
+        // row table of the super-tile, shared by all its (segment, channel block) tiles: one division chain per row here
+        // instead of one per row and tile in the hot loop
+        // (the previous super-tile's readers are behind the closing barrier of its last tile; the opening barrier of the
+        // first tile below publishes the new table)
+        for (int r = tt; r < 400; r += TC_XF_THREADS) {
+          int n = -1, h, w;
+          const int R = rbase + r;
+          const bool ok = r < rows_used && R >= 0 && slot_pixel(R, p.H, p.P, p.magic_P, p.magic_H1, a.nimg, n, h, w);
+          s_rown[r] = ok ? (uint8_t)(n - nbase) : (uint8_t)0xff;
+        }
+#pragma unroll 1
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const int ncb = p.cblocks[seg];
+#pragma unroll 1
+          for (int cb = 0; cb < ncb; ++cb) {
+            // a 32-channel block uses 4 octets x 64 row lanes so that every thread works
+            const int left = p.cin_real[seg] - cb * 64;
+            const int ol = left == 32 ? 2 : 3;
+            const int oct = tt & ((1 << ol) - 1), rl = tt >> ol, rstride = TC_XF_THREADS >> ol;
+            const bool work = p.xform[seg] && oct * 8 < left;
+            const float2* cf = p.coef[seg] + (size_t)nbase * p.coef_C[seg] + p.coef_c0[seg] + cb * 64 + oct * 8;
+            const int cC = p.coef_C[seg];
+            const uint32_t sa = smem_base + as * p.a_slot;
+            const bool to_bf16 = p.xf_bf16 != 0;
+            uint32_t cur = 0xffu;
+            float hs[8], hb[8];  // half scale / half shift: silu(z) = hz + hz * tanh(hz), hz = z / 2
+            if (work) {  // coefficients of the tile's first image: in flight while the tile itself is still loading
+              cur = 0u;
+              const float4* c4 = reinterpret_cast<const float4*>(cf);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 v = __ldg(c4 + q);  // {scale, shift} of two channels
+                hs[2 * q] = 0.5f * v.x; hb[2 * q] = 0.5f * v.y; hs[2 * q + 1] = 0.5f * v.z; hb[2 * q + 1] = 0.5f * v.w;
+              }
+            }
+            // ONE polling thread + a group barrier: one polling lane per warp (and per-warp arrivals below) was measured
+            // 15 % slower -- concurrent pollers slow the mbarrier unit the single-thread roles depend on
+            if (tt == 0) mbar_wait(a_full(as), aph);
+            asm volatile("bar.sync 3, %0;" ::"n"(TC_XF_THREADS) : "memory");
+            if (tt == 0 && seg == 0 && cb == 0) TRC(4, (sti - (int)blockIdx.x) / (int)gridDim.x);
+            if (work) {
+#pragma unroll 1
+              for (int r0 = rl; r0 < rows_used; r0 += 2 * rstride) {
+                uint32_t w4[2][4], addr[2], nr[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {  // both loads in flight before the math
+                  const int r = r0 + j * rstride;
+                  nr[j] = s_rown[r];
+                  addr[j] = sa + (uint32_t)r * 128u + (uint32_t)((oct ^ (r & 7)) << 4);
+                  if (r < rows_used)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(w4[j][0]), "=r"(w4[j][1]), "=r"(w4[j][2]), "=r"(w4[j][3]) : "r"(addr[j]));
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  if (nr[j] == 0xffu) continue;  // not a pixel: the raw row is zero already (conv padding)
+                  if (nr[j] != cur) {
+                    cur = nr[j];
+                    const float4* c4 = reinterpret_cast<const float4*>(cf + (size_t)cur * cC);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const float4 v = __ldg(c4 + q);
+                      hs[2 * q] = 0.5f * v.x; hb[2 * q] = 0.5f * v.y; hs[2 * q + 1] = 0.5f * v.z; hb[2 * q + 1] = 0.5f * v.w;
+                    }
+                  }
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[j][q]));
+                    const float z0 = fmaf(f.x, hs[2 * q], hb[2 * q]), z1 = fmaf(f.y, hs[2 * q + 1], hb[2 * q + 1]);
+                    float t0, t1;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
+                    const float v0 = fmaf(z0, t0, z0), v1 = fmaf(z1, t1, z1);
+                    const __half2 hv = __floats2half2_rn(v0, v1);
+                    const __nv_bfloat162 bv = __floats2bfloat162_rn(v0, v1);
+                    w4[j][q] = to_bf16 ? *reinterpret_cast<const uint32_t*>(&bv) : *reinterpret_cast<const uint32_t*>(&hv);
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[j]), "r"(w4[j][0]), "r"(w4[j][1]), "r"(w4[j][2]), "r"(w4[j][3]) : "memory");
+                }
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
+            asm volatile("bar.sync 3, %0;" ::"n"(TC_XF_THREADS) : "memory");
+            if (tt == 0) mbar_arrive(a_ready(as));
+            if (tt == 0 && seg == 0 && cb == 0) TRC(5, (sti - (int)blockIdx.x) / (int)gridDim.x);
+            if (++as == a_slots) {
+              as = 0u;
+              aph ^= 1u;
+            }
+          }
+        }
       }
     }
   } else {
@@ -605,7 +734,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tma_store_2d(&tmO, stg, c0, unit * 128);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (threadIdx.x == 0 && c0 == 0) TRC(4, it);
+          if (threadIdx.x == 0 && c0 == 0 && !p.any_xform) TRC(4, it);
           if (p.stats != nullptr && c0 < N) {
             // GroupNorm partials of the ROUNDED values on the legacy tensor path, channels on M and image slots on N:
             //   S[ch][slot] = sum_row X[row][ch] * Ind[row][slot]   (Ind = 0/1: row belongs to image slot of the unit)
@@ -674,7 +803,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           }
         }
-        if (threadIdx.x == 0) TRC(5, it);
+        if (threadIdx.x == 0 && !p.any_xform) TRC(5, it);
       } else {
         // output conv: Cout <= 16 real channels -> NCHW velocity, or fused Euler update x += dt * v
         uint32_t v[16];
@@ -700,8 +829,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #ifdef RGFM_TC_TRACE
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    printf("TRACE nmma=%d cblocks=%d taps=%d resident=%d a_slots=%d supers=%d end=%lld\n", p.nmma, p.cblocks[0], p.ntaps[0], p.resident, p.a_slots,
-           supers, clock64() - t_start);
+    printf("TRACE nmma=%d nseg=%d cblocks=%d taps=%d resident=%d a_slots=%d supers=%d xform=%d (then columns 5, 6 = transform a_full / done) end=%lld\n",
+           p.nmma, p.nseg, p.cblocks[0], p.ntaps[0], p.resident, p.a_slots, supers, p.any_xform, clock64() - t_start);
     for (int i = 0; i < 12 && blockIdx.x + i * gridDim.x < supers; ++i)
       printf("  st%2d prodA %7lld | mma a_full %7lld committed %7lld | epi tmem_full %7lld stored %7lld unit_done %7lld\n", i, s_trace[0][i],
              s_trace[1][i], s_trace[2][i], s_trace[3][i], s_trace[4][i], s_trace[5][i]);
@@ -853,8 +982,21 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
 
   for (int sg = 0; sg < d.nseg; ++sg) {
     const TcSegment& S = d.seg[sg];
-    const bool seg_fp16 = d.fp16 || S.raw;
+    const bool xf = S.coef != nullptr;
+    RGFM_CHECK(!xf || (S.raw && S.Cin_real % 16 == 0), "tc conv: a fused GroupNorm + SiLU segment must be a raw tensor with channels % 16 == 0");
+    // raw tensors are fp16 in memory; a transformed tile is rewritten in the net's operand format before the MMA reads it
+    const bool seg_fp16 = d.fp16 || (S.raw && !xf);
     const CUtensorMapDataType dt16 = seg_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    p.xform[sg] = xf ? 1 : 0;
+    p.coef[sg] = reinterpret_cast<const float2*>(S.coef);
+    p.coef_C[sg] = S.coef_C;
+    p.coef_c0[sg] = S.coef_c0;
+    p.cin_real[sg] = S.Cin_real;
+    if (xf) {
+      p.any_xform = 1;
+      p.xf_bf16 = d.fp16 ? 0 : 1;
+      RGFM_CHECK(S.coef_c0 % 2 == 0 && S.coef_C % 2 == 0, "tc conv: GroupNorm coefficient offsets must be even");
+    }
     const uint32_t fmt = seg_fp16 ? 0u : 1u;  // UMMA F16F32Format: 0 = F16, 1 = BF16
     p.idesc[sg] = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // a 32-channel tensor (64-byte rows) is read through the same 64-channel TMA box: the upper half is out of bounds and
@@ -890,7 +1032,7 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
         }
     uint16_t* dw = pool.upload(hw);
     // operand: 2-D [rows][Cin]; rows before the first / after the last are zero-filled by TMA
-    encode_2d(&t->tmA[sg], dt16, 2, S.in, (uint64_t)S.Cin,
+    encode_2d(&t->tmA[sg], S.raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : dt16, 2, S.in, (uint64_t)S.Cin,
               S.raw ? tc_raw_rows(d.Hin, d.Win, d.chunk) : tc_operand_slots(d.Hin, d.Win, d.chunk), 64, (uint32_t)p.a_box_rows, "A");
     {
       cuuint64_t dims[3] = {(cuuint64_t)S.Cin, (cuuint64_t)nmma, (cuuint64_t)taps};

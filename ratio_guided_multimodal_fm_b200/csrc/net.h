@@ -120,6 +120,10 @@ struct TcSegment {
   bool raw;              // the operand is a (zero-padded) raw activation tensor: rows indexed by the GEMM row itself
   int w_cin_total;       // input channels of the weight tensor (0 = Cin_real); this segment uses [w_c0, w_c0 + Cin_real)
   int w_c0;
+  // fused GroupNorm + SiLU (raw segments only): the kernel's transform warps rewrite the raw tile in shared memory as
+  // silu(x * scale + shift) with coef[image][coef_C][2], channels [coef_c0, coef_c0 + Cin_real) -- no packed operand tensor
+  const float* coef;
+  int coef_C, coef_c0;
 };
 struct TcConvDesc {
   int Hin, Win;          // operand image geometry (stride-1 output geometry)

@@ -620,6 +620,25 @@ void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
   post_launch("pack_padded");
 }
 
+// GroupNorm coefficients for the conv kernel's fused operand path: per (image, channel) {scale, shift} with
+// operand = silu(raw * scale + shift), from the producers' partial statistics (same reduction as the pack kernels).
+// Per-image GroupNorm {scale, shift} for the conv kernel's fused GroupNorm + SiLU segments: the prologue of the pack
+// kernels on its own (one block per image), written once per layer instead of being re-derived by every consumer CTA.
+__global__ void __launch_bounds__(256) gn_coef_kernel(PackArgs a, float2* __restrict__ coef) {
+  __shared__ float s_scale[PACK_MAXC];
+  __shared__ float s_shift[PACK_MAXC];
+  __shared__ float s_red[2][PACK_MAXC];
+  __shared__ double s_grp[32][2];
+  const int n = blockIdx.x;
+  pack_scale_shift(a, n, s_scale, s_shift, s_red, s_grp);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) coef[(size_t)n * a.C + c] = make_float2(s_scale[c], s_shift[c]);
+}
+void launch_gn_coef(const PackArgs& a, float* coef, cudaStream_t s) {
+  RGFM_CHECK(a.C <= PACK_MAXC && a.norm == NORM_GN, "gn_coef: GroupNorm over at most 512 channels");
+  gn_coef_kernel<<<a.nimg, 256, 0, s>>>(a, reinterpret_cast<float2*>(coef));
+  post_launch("gn_coef");
+}
+
 void launch_pack(const PackArgs& a, cudaStream_t s) {
   RGFM_CHECK(a.C <= PACK_MAXC && a.C % 4 == 0, "pack: channel count");
   RGFM_CHECK(a.groups <= 32, "pack: groups");
