@@ -55,7 +55,8 @@ struct TcArgs {
   int cblocks[3];       // operand channels / 64 per segment
   int ksteps[3][4];     // K16 steps that hold real channels in each 64-channel block (all-zero steps are never issued)
   int ntaps[3];         // 9 (3x3) or 1 (1x1)
-  int row_off[3];       // TMA row coordinate of GEMM row 0: 0 for packed operands, -(P + 1) for raw activation tensors
+  int row_off[3];       // TMA row coordinate of tile row 0 relative to the super-tile's first GEMM row (see make_tc_conv)
+  int box_rows[3];      // rows per TMA box of the segment: a_box_rows for 3x3 segments, 128 for 1x1 (no halo, aligned)
   int a_box_rows;       // rows per TMA box; an A tile is two boxes
   uint32_t a_slot;      // bytes of one A slot (2 * a_box_rows * 128)
   uint32_t b_bytes;     // bytes of one weight tap tile (nmma * 128)
@@ -410,10 +411,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
           for (int cb = 0; cb < ncb; ++cb) {
             mbar_wait(a_empty(as), aph ^ 1u);
-            mbar_expect_tx(a_full(as), p.a_slot);
+            const uint32_t half_bytes = (uint32_t)p.box_rows[seg] * 128u;
+            mbar_expect_tx(a_full(as), 2u * half_bytes);
             const uint32_t sa = smem_base + as * p.a_slot;
             tma_load_2d(sa, tA, a_full(as), cb * 64, ra);
-            tma_load_2d(sa + (p.a_slot >> 1), tA, a_full(as), cb * 64, ra + p.a_box_rows);
+            tma_load_2d(sa + half_bytes, tA, a_full(as), cb * 64, ra + p.box_rows[seg]);
             if (seg == 0 && cb == 0) TRC(0, (sti - (int)blockIdx.x) / (int)gridDim.x);
             if (++as == a_slots) {
               as = 0u;
@@ -475,8 +477,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tc_fence_after();
             if (hf == 0 && seg == 0 && cb == 0) TRC(1, it);
             const int ks = p.ksteps[seg][cb];
-            // descriptor low word of the current tap; a 1x1 segment reads the centre tap (shift P + 1 rows)
-            uint32_t a_lo = ((smem_base + as * p.a_slot + hf * (128u * 128u)) >> 4) + (ntp == 1 ? rowstep + 8u : 0u);
+            // descriptor low word of the current tap (a 1x1 segment's tile starts at the super-tile's own first row)
+            uint32_t a_lo = (smem_base + as * p.a_slot + hf * (128u * 128u)) >> 4;
             uint32_t kx = 0;
 #pragma unroll 1
             for (int tap = 0; tap < ntp; tap += tps) {
@@ -556,11 +558,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int ncb = p.cblocks[seg];
 #pragma unroll 1
           for (int cb = 0; cb < ncb; ++cb) {
+            if (!p.xform[seg]) {  // a TMA tile used as it is (1x1 skip / identity segment): one thread passes it on
+              if (tt == 0) {
+                mbar_wait(a_full(as), aph);
+                mbar_arrive(a_ready(as));
+              }
+              if (++as == a_slots) {
+                as = 0u;
+                aph ^= 1u;
+              }
+              continue;
+            }
             // a 32-channel block uses 4 octets x 64 row lanes so that every thread works
             const int left = p.cin_real[seg] - cb * 64;
             const int ol = left == 32 ? 2 : 3;
             const int oct = tt & ((1 << ol) - 1), rl = tt >> ol, rstride = TC_XF_THREADS >> ol;
-            const bool work = p.xform[seg] && oct * 8 < left;
+            const bool work = oct * 8 < left;
             const float2* cf = p.coef[seg] + (size_t)nbase * p.coef_C[seg] + p.coef_c0[seg] + cb * 64 + oct * 8;
             const int cC = p.coef_C[seg];
             const uint32_t sa = smem_base + as * p.a_slot;
@@ -1011,7 +1024,11 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     }
     p.ntaps[sg] = S.ks * S.ks;
     // a raw activation tensor is indexed by the GEMM row itself: operand slot = raw row + P + 1
-    p.row_off[sg] = S.raw ? -(P + 1) : 0;
+    // 3x3: the tile starts P + 1 rows before the super-tile's first pixel (halo); 1x1: exactly at it -- 256 rows instead
+    // of 256 + 2P + 2, and MMA operand rows aligned to the 8-row swizzle atom
+    p.row_off[sg] = (S.raw ? -(P + 1) : 0) + (S.ks == 1 ? P + 1 : 0);
+    p.box_rows[sg] = S.ks == 1 ? 128 : p.a_box_rows;
+    RGFM_CHECK(!xf || S.ks == 3, "tc conv: fused GroupNorm + SiLU segments are 3x3");
     // weights: torch [Cout][Cin_real][ks][ks] fp32 (or identity when w_oihw == nullptr) -> [tap][nmma][Cin] 16-bit
     const int taps = p.ntaps[sg];
     std::vector<uint16_t> hw((size_t)taps * nmma * S.Cin, 0);
@@ -1033,7 +1050,7 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     uint16_t* dw = pool.upload(hw);
     // operand: 2-D [rows][Cin]; rows before the first / after the last are zero-filled by TMA
     encode_2d(&t->tmA[sg], S.raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : dt16, 2, S.in, (uint64_t)S.Cin,
-              S.raw ? tc_raw_rows(d.Hin, d.Win, d.chunk) : tc_operand_slots(d.Hin, d.Win, d.chunk), 64, (uint32_t)p.a_box_rows, "A");
+              S.raw ? tc_raw_rows(d.Hin, d.Win, d.chunk) : tc_operand_slots(d.Hin, d.Win, d.chunk), 64, (uint32_t)p.box_rows[sg], "A");
     {
       cuuint64_t dims[3] = {(cuuint64_t)S.Cin, (cuuint64_t)nmma, (cuuint64_t)taps};
       cuuint64_t strides[2] = {(cuuint64_t)S.Cin * 2, (cuuint64_t)nmma * S.Cin * 2};
