@@ -108,7 +108,9 @@ struct StatsRef {
 
 __host__ __device__ inline int stats_slots_for(int R) { return 127 / R + 2; }
 
-// {sum, sumsq} of channel c of image n, combined from the partials in a fixed order
+// {sum, sumsq} of channel c of image n, combined from the partials in a fixed order.  BATCH partials are in flight at a
+// time (a rolled loop would wait out one global-load latency per unit); the sum runs in unit order whatever BATCH is.
+template <int BATCH = 4>
 __device__ __forceinline__ void stats_channel_sums(const StatsRef& st, int n, int c, float& s, float& ss) {
   s = 0.f;
   ss = 0.f;
@@ -120,11 +122,10 @@ __device__ __forceinline__ void stats_channel_sums(const StatsRef& st, int n, in
     }
   } else if (st.mode == ST_UNITS) {
     const int u0 = (n * st.R) >> 7, u1 = ((n + 1) * st.R - 1) >> 7;
-    // four partials in flight at a time (a rolled loop waits out one global-load latency per unit); summed in unit order
-    for (int ub = u0; ub <= u1; ub += 4) {
-      float2 v[4];
+    for (int ub = u0; ub <= u1; ub += BATCH) {
+      float2 v[BATCH];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < BATCH; ++j) {
         const int u = ub + j;
         v[j] = make_float2(0.f, 0.f);
         if (u <= u1) {
@@ -133,7 +134,7 @@ __device__ __forceinline__ void stats_channel_sums(const StatsRef& st, int n, in
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < BATCH; ++j) {
         s += v[j].x;
         ss += v[j].y;
       }

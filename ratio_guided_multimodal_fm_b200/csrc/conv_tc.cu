@@ -80,6 +80,7 @@ struct TcArgs {
   int coef_C[3], coef_c0[3];
   int cin_real[3];      // real channels of the segment (transform touches only those)
   int xf_bf16;          // format the transform writes: 1 = bf16, 0 = fp16 (the net's operand format)
+  int l2_prefetch;      // prefetch the next super-tile's A boxes into L2 (RGFM_TC_L2_PREFETCH, default on)
   int descend;          // walk the super-tiles from the last to the first: every tensor is a little larger than L2, the
                         // packs stream in ascending order, so a conv that starts at the END of its operand finds the rows
                         // the pack wrote last still in L2 (and leaves its own first rows there for the next pack)
@@ -146,6 +147,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// pull a box into L2 only (no shared-memory slot needed): the later tma_load_2d of the same box pays L2 instead of HBM latency
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -416,6 +421,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t sa = smem_base + as * p.a_slot;
             tma_load_2d(sa, tA, a_full(as), cb * 64, ra);
             tma_load_2d(sa + half_bytes, tA, a_full(as), cb * 64, ra + p.box_rows[seg]);
+            if (p.l2_prefetch && sti + (int)gridDim.x < supers) {
+              // The same tile of this CTA's NEXT super-tile, into L2 now: with two A slots the load -> (transform) -> MMA
+              // chain of a slot is serial, and the ~1.9 us HBM latency of the load was the largest term in it.
+              const int st2 = p.descend ? supers - 1 - (sti + (int)gridDim.x) : sti + (int)gridDim.x;
+              const int ra2 = st2 * TC_SUPER + p.row_off[seg];
+              tma_prefetch_2d(tA, cb * 64, ra2);
+              tma_prefetch_2d(tA, cb * 64, ra2 + p.box_rows[seg]);
+            }
             if (seg == 0 && cb == 0) TRC(0, (sti - (int)blockIdx.x) / (int)gridDim.x);
             if (++as == a_slots) {
               as = 0u;
@@ -1094,6 +1107,8 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
   }
   static const int descend = getenv("RGFM_TC_DESCEND") ? atoi(getenv("RGFM_TC_DESCEND")) : 1;
   p.descend = descend;
+  static const int l2pf = getenv("RGFM_TC_L2_PREFETCH") ? atoi(getenv("RGFM_TC_L2_PREFETCH")) : 1;
+  p.l2_prefetch = l2pf;
   static const bool no_stats = getenv("RGFM_TC_NO_STATS") != nullptr;  // timing experiment only (results are wrong)
   if (no_stats) p.stats = nullptr;
   const int total_rows = a.nimg * (p.H + 1) * p.P;

@@ -194,6 +194,7 @@ constexpr int PACK_PIX = 32;
 constexpr int PACK_MAXC = 512;
 
 // per-channel scale / shift of the normalisation of image n into shared memory (all threads of the CTA call this)
+template <int BATCH = 4>
 __device__ __forceinline__ void pack_scale_shift(const PackArgs& a, int n, float* s_scale, float* s_shift, float (*s_red)[PACK_MAXC],
                                                  double (*s_grp)[2]) {
   const int tid = threadIdx.x;
@@ -202,24 +203,32 @@ __device__ __forceinline__ void pack_scale_shift(const PackArgs& a, int n, float
     for (int c = tid; c < a.C; c += blockDim.x) {
       const int si = (c < C0) ? 0 : 1;
       float s, ss;
-      stats_channel_sums(a.src[si].st, n, si ? c - C0 : c, s, ss);
+      stats_channel_sums<BATCH>(a.src[si].st, n, si ? c - C0 : c, s, ss);
       s_red[0][c] = s;
       s_red[1][c] = ss;
     }
     __syncthreads();
     const int cpg = a.C / a.groups;
-    if (tid < a.groups) {
+    // one warp per group: lane-strided partial sums in double, butterfly reduction (a fixed order, so deterministic)
+    for (int g = tid >> 5; g < a.groups; g += blockDim.x >> 5) {
       double s = 0.0, ss = 0.0;
-      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+      for (int c = g * cpg + (tid & 31); c < (g + 1) * cpg; c += 32) {
         s += (double)s_red[0][c];
         ss += (double)s_red[1][c];
       }
-      const double cnt = (double)cpg * a.Hs * a.Ws;
-      const double mean = s / cnt;
-      double var = ss / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      s_grp[tid][0] = mean;
-      s_grp[tid][1] = 1.0 / sqrt(var + 1e-5);
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      }
+      if ((tid & 31) == 0) {
+        const double cnt = (double)cpg * a.Hs * a.Ws;
+        const double mean = s / cnt;
+        double var = ss / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_grp[g][0] = mean;
+        s_grp[g][1] = 1.0 / sqrt(var + 1e-5);
+      }
     }
     __syncthreads();
     for (int c = tid; c < a.C; c += blockDim.x) {
@@ -630,12 +639,55 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(PackArgs a, float2* __rest
   __shared__ float s_red[2][PACK_MAXC];
   __shared__ double s_grp[32][2];
   const int n = blockIdx.x;
-  pack_scale_shift(a, n, s_scale, s_shift, s_red, s_grp);
+  pack_scale_shift<12>(a, n, s_scale, s_shift, s_red, s_grp);
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) coef[(size_t)n * a.C + c] = make_float2(s_scale[c], s_shift[c]);
 }
+// C <= 256: one thread per channel, one barrier.  gamma / beta and every statistics partial are requested before anything
+// is consumed (one global round trip), each thread sums its own group from shared memory in double, and the count enters
+// as a host-computed reciprocal (no fp64 division or square root on the critical path of a ~3 us kernel that sits between
+// two convolutions 60 times per Euler step).
+__global__ void __launch_bounds__(256) gn_coef256_kernel(PackArgs a, float2* __restrict__ coef, double inv_cnt, int ipb) {
+  __shared__ float s_red[2][256];
+  // ipb = 256 / C images per block, thread -> (image, channel): every thread of the block has work
+  const int il = threadIdx.x / a.C, c = threadIdx.x - il * a.C;
+  const int n = blockIdx.x * ipb + il;
+  const bool on = il < ipb && n < a.nimg;
+  const int C0 = a.src[0].C;
+  const int cpg = a.C / a.groups;
+  float gam = 0.f, bet = 0.f, s = 0.f, ss = 0.f;
+  if (on) {
+    gam = __ldg(a.gamma + c);
+    bet = __ldg(a.beta + c);
+    const int si = (c < C0) ? 0 : 1;
+    stats_channel_sums<12>(a.src[si].st, n, si ? c - C0 : c, s, ss);
+  }
+  s_red[0][threadIdx.x] = s;
+  s_red[1][threadIdx.x] = ss;
+  __syncthreads();
+  if (!on) return;
+  const int g0 = (int)threadIdx.x - c + (c / cpg) * cpg;
+  double gs = 0.0, gss = 0.0;
+  for (int k = 0; k < cpg; ++k) {  // ascending channel order, like pack_scale_shift
+    gs += (double)s_red[0][g0 + k];
+    gss += (double)s_red[1][g0 + k];
+  }
+  const double mean = gs * inv_cnt;
+  double var = gss * inv_cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float sc = rsqrtf((float)var + 1e-5f) * gam;
+  coef[(size_t)n * a.C + c] = make_float2(sc, bet - (float)mean * sc);
+}
 void launch_gn_coef(const PackArgs& a, float* coef, cudaStream_t s) {
-  RGFM_CHECK(a.C <= PACK_MAXC && a.norm == NORM_GN, "gn_coef: GroupNorm over at most 512 channels");
-  gn_coef_kernel<<<a.nimg, 256, 0, s>>>(a, reinterpret_cast<float2*>(coef));
+  RGFM_CHECK(a.C <= PACK_MAXC && a.norm == NORM_GN && a.C % a.groups == 0, "gn_coef: GroupNorm over at most 512 channels");
+  static const bool skip = getenv("RGFM_EXPERIMENT_SKIP_GN_COEF") != nullptr;  // timing experiments only: results are garbage
+  if (skip) return;
+  if (a.C <= 256) {
+    const int ipb = 256 / a.C;
+    gn_coef256_kernel<<<(a.nimg + ipb - 1) / ipb, 256, 0, s>>>(a, reinterpret_cast<float2*>(coef),
+                                                                  1.0 / ((double)(a.C / a.groups) * a.Hs * a.Ws), ipb);
+  }
+  else
+    gn_coef_kernel<<<a.nimg, 256, 0, s>>>(a, reinterpret_cast<float2*>(coef));
   post_launch("gn_coef");
 }
 
