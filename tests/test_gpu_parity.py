@@ -52,6 +52,27 @@ def test_unet_forward(kind, prec, synth):
     net.close()
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("kind", ["unet_mnist28", "unet_mnist32", "unet_svhn"])
+def test_fused_groupnorm_conv_matches_pack_path_and_oracle(kind, prec, synth, monkeypatch):
+    """The conv kernel's in-shared-memory GroupNorm + SiLU (default) against the separate pack kernels (RGFM_FUSE_GN=0)
+    and the oracle, on a batch whose operand tiles straddle several images and a ragged last chunk (37 images, chunk 16)."""
+    sd = synth(kind, 31)
+    c, hw = (3, 32) if kind == "unet_svhn" else (1, 28 if kind == "unet_mnist28" else 32)
+    x = torch.randn(37, c, hw, hw, generator=torch.Generator().manual_seed(5))
+    ref = O.unet_forward(sd, kind, x, torch.full((37,), 0.37))
+    outs = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("RGFM_FUSE_GN", fuse)  # read when the plan is built
+        net = _lib.Net(kind, sd, max_batch=16, precision=prec, device=DEV)
+        outs[fuse] = net.unet_forward(x.to(DEV), 0.37).cpu()
+        net.close()
+    scale = max(1.0, ref.abs().max().item())
+    for fuse, v in outs.items():
+        assert maxabs(v, ref) <= TOL_FWD[prec] * scale, (kind, prec, fuse, maxabs(v, ref))
+    assert maxabs(outs["1"], outs["0"]) <= TOL_FWD[prec] * scale
+
+
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("kind", ["ratio28", "ratio_mnist_svhn"])
 def test_ratio_log_ratio(kind, prec, synth):
