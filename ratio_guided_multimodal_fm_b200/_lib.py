@@ -56,7 +56,7 @@ _lib = None
 # every symbol include/rgfm.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     "rgfm_last_error", "rgfm_abi_version", "rgfm_sampler_create", "rgfm_sampler_run", "rgfm_sampler_run_host",
-    "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
+    "rgfm_sampler_set_strength", "rgfm_sampler_run_reuse_bank", "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
     "rgfm_unet_forward", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_log_ratio", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
 ]
 
@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
                                       C.POINTER(_Weights), C.POINTER(vp)]
     L.rgfm_sampler_run.argtypes = [vp] + [vp] * 7 + [vp]
     L.rgfm_sampler_run_host.argtypes = [vp] + [vp] * 7
+    L.rgfm_sampler_set_strength.argtypes = [vp, C.c_double, vp]
+    L.rgfm_sampler_run_reuse_bank.argtypes = [vp] + [vp] * 5 + [vp]
     L.rgfm_sampler_get_bank.argtypes = [vp, vp, vp, vp, vp]
     L.rgfm_sampler_profile_step.argtypes = [vp, C.POINTER(_ProfEntry), C.c_int32, C.POINTER(C.c_int32)]
     L.rgfm_sampler_launch_count.argtypes = [vp]
@@ -236,11 +238,22 @@ class SamplerPlan:
     def launch_count(self) -> int:
         return int(lib().rgfm_sampler_launch_count(self.h))
 
-    def run(self, x0, y0, mc_x0=None, mc_y0=None, want_diag: bool = False):
-        """Device-resident run on the current stream; returns fresh tensors (inputs are not mutated)."""
+    def set_strength(self, guidance_strength: float):
+        """Change gamma in place (mc_feng / unguided plans): the graphs read it from a device table."""
+        check(lib().rgfm_sampler_set_strength(self.h, float(guidance_strength), _stream_ptr(self.device)))
+
+    def run(self, x0, y0, mc_x0=None, mc_y0=None, want_diag: bool = False, reuse_bank: bool = False):
+        """Device-resident run on the current stream; returns fresh tensors (inputs are not mutated).
+        reuse_bank: main loop only, guided by the MC bank of the previous full run on this plan."""
         dev = self.device
         x0, y0 = _f32c(x0, dev), _f32c(y0, dev)
         assert tuple(x0.shape) == (self.B,) + self.shape_x and tuple(y0.shape) == (self.B,) + self.shape_y
+        if reuse_bank:
+            x1, y1 = torch.empty_like(x0), torch.empty_like(y0)
+            diag = torch.zeros(DIAG_FLOATS, device=dev, dtype=torch.float32)
+            check(lib().rgfm_sampler_run_reuse_bank(self.h, _ptr(x0), _ptr(y0), _ptr(x1), _ptr(y1), _ptr(diag),
+                                                    _stream_ptr(dev)))
+            return (x1, y1, diag) if want_diag else (x1, y1)
         if self.guided:
             mc_x0, mc_y0 = _f32c(mc_x0, dev), _f32c(mc_y0, dev)
             assert mc_x0.shape[0] == self.N and mc_y0.shape[0] == self.N

@@ -11,6 +11,8 @@ void sampler_run(Sampler*, const float*, const float*, const float*, const float
 void sampler_run_host(Sampler*, const float*, const float*, const float*, const float*, float*, float*, float*);
 void sampler_get_bank(Sampler*, float*, float*, float*, cudaStream_t);
 int64_t sampler_launches(const Sampler*);
+void sampler_run_reuse_bank(Sampler*, const float*, const float*, float*, float*, float*, cudaStream_t);
+void sampler_set_strength(Sampler*, double, cudaStream_t);
 int sampler_profile(Sampler*, rgfm_prof_entry*, int);
 }  // namespace rgfm
 
@@ -61,6 +63,21 @@ int rgfm_sampler_run_host(rgfm_sampler* s, const float* x0, const float* y0, con
   RGFM_API_BEGIN
   RGFM_CHECK(s != nullptr, "rgfm_sampler_run_host: null plan");
   rgfm::sampler_run_host(reinterpret_cast<rgfm::Sampler*>(s), x0, y0, mc_x0, mc_y0, x1, y1, diag);
+  RGFM_API_END
+}
+
+int rgfm_sampler_set_strength(rgfm_sampler* s, double guidance_strength, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(s != nullptr, "rgfm_sampler_set_strength: null plan");
+  rgfm::sampler_set_strength(reinterpret_cast<rgfm::Sampler*>(s), guidance_strength, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_sampler_run_reuse_bank(rgfm_sampler* s, const float* x0, const float* y0, float* x1, float* y1, float* diag,
+                                void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(s != nullptr, "rgfm_sampler_run_reuse_bank: null plan");
+  rgfm::sampler_run_reuse_bank(reinterpret_cast<rgfm::Sampler*>(s), x0, y0, x1, y1, diag, (cudaStream_t)stream);
   RGFM_API_END
 }
 

@@ -31,6 +31,8 @@ struct Sampler {
   float* diag = nullptr;
   int* step = nullptr;
   StepScalars* sc = nullptr;
+  std::vector<StepScalars> hsc;  // host copy of the per-step scalars (set_strength rewrites gamma)
+  bool bank_valid = false;       // a guided run has left its MC bank (mc_x, mc_y, mc_ratios) in the plan
   int first_guided = 0;  // first step with t > eps
   int ksx = 1, ksy = 1;
   cudaStream_t cap = nullptr, cap2 = nullptr;   // capture streams: the x- and y-network forwards are independent branches
@@ -177,6 +179,7 @@ struct Sampler {
     fx->set_times(ts);
     fy->set_times(ts);
     sc = pool.upload(hs);
+    hsc = hs;
     step = (int*)pool.persistent(sizeof(int));
     diag = (float*)pool.persistent(RGFM_DIAG_FLOATS * sizeof(float));
     x = (float*)pool.persistent((size_t)B * Dx * sizeof(float));
@@ -271,20 +274,39 @@ struct Sampler {
       launches += grad_guided ? g_grad.kernels : ((guided && s >= first_guided) ? g_guided.kernels : g_plain.kernels);
   }
 
+  // gamma lives in the per-step scalar table the kernels read through a pointer: a sweep over guidance strengths needs
+  // no new plan and no graph re-capture.  (grad_log_ratio bakes gamma into its update kernel's arguments.)
+  void set_strength(double gamma, cudaStream_t s) {
+    RGFM_CHECK(!grad_guided, "rgfm_sampler_set_strength: not supported for grad_log_ratio plans (build a new plan)");
+    RGFM_CUDA(cudaSetDevice(d.device));
+    d.guidance_strength = gamma;
+    for (auto& h : hsc) {
+      h.one_minus_gamma = (float)(1.0 - gamma);
+      h.gamma = (float)gamma;
+    }
+    RGFM_CUDA(cudaMemcpyAsync(sc, hsc.data(), hsc.size() * sizeof(StepScalars), cudaMemcpyHostToDevice, s));
+    RGFM_CUDA(cudaStreamSynchronize(s));  // hsc may change again before an asynchronous copy has read it
+  }
+
+  // reuse_bank: skip the MC pre-pass and the ratio pass and guide with the bank of the previous run on this plan
+  // (the evaluators' gamma sweep recomputes an identical-in-distribution bank per gamma)
   void run(const float* x0, const float* y0, const float* mx0, const float* my0, float* x1, float* y1,
-           float* diag_out, cudaStream_t s) {
+           float* diag_out, cudaStream_t s, bool reuse_bank = false) {
     RGFM_CHECK(x0 && y0 && x1 && y1, "rgfm_sampler_run: null state pointer");
+    RGFM_CHECK(!reuse_bank || (guided && bank_valid), "rgfm_sampler_run_reuse_bank: needs an mc_feng plan that has completed a full run");
     RGFM_CUDA(cudaSetDevice(d.device));
     RGFM_CUDA(cudaMemcpyAsync(x, x0, (size_t)B * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
     RGFM_CUDA(cudaMemcpyAsync(y, y0, (size_t)B * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    RGFM_CUDA(cudaMemsetAsync(diag, 0, RGFM_DIAG_FLOATS * sizeof(float), s));
-    if (guided) {
+    // diag[9..] are the bank's ratio statistics (written by the ratio pass): kept when the bank is reused
+    RGFM_CUDA(cudaMemsetAsync(diag, 0, (reuse_bank ? 9 : RGFM_DIAG_FLOATS) * sizeof(float), s));
+    if (guided && !reuse_bank) {
       RGFM_CHECK(mx0 && my0, "rgfm_sampler_run: mc_feng needs mc_x0 and mc_y0");
       RGFM_CUDA(cudaMemcpyAsync(mcx, mx0, (size_t)N * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
       RGFM_CUDA(cudaMemcpyAsync(mcy, my0, (size_t)N * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
       RGFM_CUDA(cudaMemsetAsync(step, 0, sizeof(int), s));
       for (int i = 0; i < steps; ++i) RGFM_CUDA(cudaGraphLaunch(g_pre.e, s));
       RGFM_CUDA(cudaGraphLaunch(g_ratio.e, s));
+      bank_valid = true;
     }
     RGFM_CUDA(cudaMemsetAsync(step, 0, sizeof(int), s));
     for (int i = 0; i < steps; ++i)
@@ -308,6 +330,10 @@ void sampler_run(Sampler* s, const float* x0, const float* y0, const float* mx0,
                  float* diag, cudaStream_t st) {
   s->run(x0, y0, mx0, my0, x1, y1, diag, st);
 }
+void sampler_run_reuse_bank(Sampler* s, const float* x0, const float* y0, float* x1, float* y1, float* diag, cudaStream_t st) {
+  s->run(x0, y0, nullptr, nullptr, x1, y1, diag, st, /*reuse_bank=*/true);
+}
+void sampler_set_strength(Sampler* s, double gamma, cudaStream_t st) { s->set_strength(gamma, st); }
 int64_t sampler_launches(const Sampler* s) { return s->launches; }
 
 void sampler_run_host(Sampler* s, const float* x0, const float* y0, const float* mx0, const float* my0, float* x1,

@@ -157,3 +157,56 @@ def sample_bimodal_guided_mnist_svhn(fm_mnist, fm_svhn, ratio_estimator=None, gu
     return _sample("mnist_svhn", (1, 32, 32), (3, 32, 32), fm_mnist, fm_svhn, ratio_estimator, guidance_method,
                    guidance_strength, num_samples, num_steps, device, mc_batch_size, precision, shard, group, chunk,
                    verbose, _noise)
+
+
+def sample_guidance_sweep(pair, fm_x, fm_y, ratio_estimator, guidance_strengths, num_samples=16, num_steps=100,
+                          device='cuda', mc_batch_size=64, *, precision: Optional[str] = None, same_prior: bool = False,
+                          chunk: int = 0):
+    """mc_feng pairs for SEVERAL guidance strengths from ONE plan and ONE MC bank.
+
+    The reference's evaluators call the sampler once per gamma (src/evaluate.py:189-199,
+    src/evaluate_mnist_svhn.py:155-165) and every call rebuilds the bank: N_mc samples through 100 steps of both flows
+    plus the ratio pass, a quarter of a call at B=1024 / N_mc=256.  Here the MC noise is drawn once, the first gamma
+    runs the full call, and every further gamma only rewrites the per-step scalar table and runs the main loop.
+    pair: "pair28" (1x28x28, 1x28x28) or "mnist_svhn" (1x32x32, 3x32x32).  A fresh prior (x0, y0) is drawn per gamma,
+    in call order like the reference would, unless same_prior=True (paired comparison across gammas).
+    Returns {gamma: (samples_x, samples_y)}."""
+    shapes = {"pair28": ((1, 28, 28), (1, 28, 28)), "mnist_svhn": ((1, 32, 32), (3, 32, 32))}
+    if pair not in shapes:
+        raise ValueError(f"Unknown pair: {pair}")
+    if ratio_estimator is None:
+        raise ValueError("sample_guidance_sweep needs a ratio estimator (mc_feng guidance)")
+    shape_x, shape_y = shapes[pair]
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.RgfmError("rgfm samplers run on CUDA devices only; there is no CPU fallback")
+    for m in (fm_x, fm_y, ratio_estimator):
+        m.eval()
+    loss_type = getattr(ratio_estimator, "loss_type", "disc")
+    if loss_type not in _lib.LOSS:
+        raise ValueError(f"Unknown loss_type: {loss_type}")
+    gammas = [float(g) for g in guidance_strengths]
+    out: Dict[float, Tuple[torch.Tensor, torch.Tensor]] = {}
+    if not gammas:
+        return out
+    plan = _lib.SamplerPlan(pair, fm_x.state_dict(), fm_y.state_dict(), ratio_estimator.state_dict(),
+                            guidance_method="mc_feng", guidance_strength=gammas[0], num_samples=num_samples,
+                            num_steps=num_steps, mc_batch_size=mc_batch_size, loss_type=loss_type,
+                            precision=precision or default_precision(), device=device, chunk=chunk)
+    try:
+        x0 = y0 = None
+        for i, g in enumerate(gammas):
+            if x0 is None or not same_prior:
+                x0 = torch.randn(num_samples, *shape_x, device=device)
+                y0 = torch.randn(num_samples, *shape_y, device=device)
+            if i == 0:
+                mc_x0 = torch.randn(mc_batch_size, *shape_x, device=device)
+                mc_y0 = torch.randn(mc_batch_size, *shape_y, device=device)
+                out[g] = plan.run(x0, y0, mc_x0, mc_y0)
+            else:
+                plan.set_strength(g)
+                out[g] = plan.run(x0, y0, reuse_bank=True)
+        torch.cuda.current_stream(device).synchronize()
+    finally:
+        plan.close()
+    return out

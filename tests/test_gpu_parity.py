@@ -383,3 +383,33 @@ def test_empty_batch_returns_empty_tensors(synth):
     x1, y1 = sample_bimodal_guided(fx, fy, fr, guidance_method="mc_feng", guidance_strength=0.5, num_samples=0, num_steps=3,
                                    device=DEV, mc_batch_size=4, verbose=False)
     assert x1.shape == (0, 1, 28, 28) and y1.shape == (0, 1, 28, 28) and x1.device.type == "cuda"
+
+
+def test_guidance_sweep_shares_one_bank(synth):
+    """Several guidance strengths from one plan and one MC bank (rgfm_sampler_set_strength + _run_reuse_bank): every
+    gamma equals the oracle's full call with the same noise, because the bank does not depend on gamma."""
+    from ratio_guided_multimodal_fm_b200 import sample_guidance_sweep, StateDictModule
+    sdx, sdy, sdr = synth("unet_mnist28", 11), synth("unet_mnist28", 14), synth("ratio28", 21)
+    B, N, steps, gammas = 6, 7, 5, [0.5, 1.0, 0.0, 0.25]
+    torch.manual_seed(77)
+    out = sample_guidance_sweep("pair28", StateDictModule("unet_mnist28", sdx), StateDictModule("unet_mnist28", sdy),
+                                StateDictModule("ratio28", sdr, "disc"), gammas, num_samples=B, num_steps=steps, device=DEV, mc_batch_size=N, precision="fp32",
+                                same_prior=True)
+    torch.manual_seed(77)  # the sweep's draws, in its order: prior, then the MC noise once
+    x0, y0 = torch.randn(B, 1, 28, 28, device=DEV), torch.randn(B, 1, 28, 28, device=DEV)
+    m0, n0 = torch.randn(N, 1, 28, 28, device=DEV), torch.randn(N, 1, 28, 28, device=DEV)
+    assert sorted(out) == sorted(gammas)
+    for g in gammas:
+        ox, oy = O.sample_pair(sdx, sdy, sdr, "pair28", "mc_feng", g, steps, x0.cpu(), y0.cpu(), m0.cpu(), n0.cpu(), "disc")
+        assert maxabs(out[g][0], ox) <= 1e-3 and maxabs(out[g][1], oy) <= 1e-3, g
+    # error behaviour: no bank yet / gradient plans bake gamma
+    plan = _lib.SamplerPlan("pair28", sdx, sdy, sdr, guidance_method="mc_feng", guidance_strength=0.5, num_samples=B,
+                            num_steps=steps, mc_batch_size=N, precision="fp32", device=DEV)
+    with pytest.raises(_lib.RgfmError):
+        plan.run(x0, y0, reuse_bank=True)
+    plan.close()
+    plan = _lib.SamplerPlan("pair28", sdx, sdy, sdr, guidance_method="grad_log_ratio", guidance_strength=0.5,
+                            num_samples=B, num_steps=steps, mc_batch_size=N, precision="fp32", device=DEV)
+    with pytest.raises(_lib.RgfmError):
+        plan.set_strength(1.0)
+    plan.close()
