@@ -44,7 +44,7 @@ from src.models.ratio_flexible import RatioEstimatorMNISTSVHN  # noqa: E402
 from src.models.classifier import MNISTClassifier  # noqa: E402
 from src.models.svhn_classifier import SVHNClassifier, MNISTClassifier32  # noqa: E402
 from src.utils import set_seed  # noqa: E402
-from src.utils.flow_utils import sample_bimodal_guided  # noqa: E402
+from src.utils.flow_utils import sample_bimodal_guided, CFMSchedule  # noqa: E402
 from src.sample_mnist_svhn import sample_bimodal_guided_mnist_svhn  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -176,6 +176,17 @@ def case_sampler(name, pair, seeds, B, N_mc, steps, method, gamma, loss_type, no
          digests=np.array([sd_digest(sdx), sd_digest(sdy), sd_digest(sdr)]), **extra)
 
 
+def case_cfm_sample(seed, B, steps, noise_seed=42):
+    """CFMSchedule.sample (flow_utils.py:69-100): the unguided single-modality sampler, 28x28 by construction."""
+    fm, sd = ref_module("unet_mnist28", seed)
+    set_seed(noise_seed)
+    x1 = CFMSchedule().sample(fm, B, num_steps=steps, device="cpu")
+    set_seed(noise_seed)
+    x0 = torch.randn(B, 1, 28, 28)
+    exact(x1, O.flow_sample(sd, "unet_mnist28", x0, steps), "cfm_sample")
+    save("cfm_sample_mnist28", seed=seed, B=B, steps=steps, x0=x0, x1=x1, digest=sd_digest(sd))
+
+
 def case_mc_feng_block():
     """One guidance block on random state, several t (incl. the saturated regime)."""
     g = torch.Generator().manual_seed(77)
@@ -208,6 +219,7 @@ def main():
         ("clf_mnist32", lambda: case_classifier("clf_mnist32", 32, 4)),
         ("clf_svhn", lambda: case_classifier("clf_svhn", 33, 4)),
         ("mc_feng_block", case_mc_feng_block),
+        ("cfm_sample_mnist28", lambda: case_cfm_sample(11, 4, 7)),
         ("sampler_pair28_small", lambda: case_sampler("sampler_pair28_small", "pair28", (11, 14, 21), 5, 8, 6, "mc_feng", 0.5, "disc")),
         ("sampler_pair28_rulsif", lambda: case_sampler("sampler_pair28_rulsif", "pair28", (11, 14, 21), 4, 8, 5, "mc_feng", 1.0, "rulsif")),
         ("sampler_pair28_none", lambda: case_sampler("sampler_pair28_none", "pair28", (11, 14, 21), 4, 8, 5, "none", 0.0, "disc")),

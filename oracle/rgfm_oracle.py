@@ -245,6 +245,19 @@ def mc_prepass(sd_x: StateDict, sd_y: StateDict, sd_r: StateDict, pair: str, los
 
 
 @torch.no_grad()
+def flow_sample(sd: StateDict, kind: str, x0: Tensor, num_steps: int) -> Tensor:
+    """Unguided single-modality Euler sampler on explicit prior noise.
+    reference: CFMSchedule.sample, flow_utils.py:69-100 (which draws x0 = randn(num_samples, 1, 28, 28) itself)."""
+    dt = 1.0 / num_steps
+    x_t = x0
+    n = x0.shape[0]
+    for step in range(num_steps):
+        v_t = unet_forward(sd, kind, x_t, torch.full((n,), step * dt))
+        x_t = x_t + v_t * dt
+    return x_t
+
+
+@torch.no_grad()
 def sample_pair(sd_x: StateDict, sd_y: StateDict, sd_r: Optional[StateDict], pair: str,
                 guidance_method: str, guidance_strength: float, num_steps: int,
                 x0: Tensor, y0: Tensor, mc_x0: Optional[Tensor] = None, mc_y0: Optional[Tensor] = None,

@@ -57,7 +57,7 @@ _lib = None
 EXPORTS = [
     "rgfm_last_error", "rgfm_abi_version", "rgfm_sampler_create", "rgfm_sampler_run", "rgfm_sampler_run_host",
     "rgfm_sampler_set_strength", "rgfm_sampler_run_reuse_bank", "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
-    "rgfm_unet_forward", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_log_ratio", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
+    "rgfm_unet_forward", "rgfm_unet_sample", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_log_ratio", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
 ]
 
 
@@ -178,6 +178,12 @@ class Net:
         v = torch.empty_like(x)
         check(lib().rgfm_unet_forward(self.h, _ptr(x), float(t), x.shape[0], _ptr(v), _stream_ptr(self.device)))
         return v
+
+    def unet_sample(self, x0: torch.Tensor, num_steps: int = 100) -> torch.Tensor:
+        """CFMSchedule.sample's loop (flow_utils.py:69-100) from the prior noise x0; returns a fresh tensor."""
+        x = _f32c(x0, self.device).clone()
+        check(lib().rgfm_unet_sample(self.h, _ptr(x), x.shape[0], int(num_steps), _stream_ptr(self.device)))
+        return x
 
     def log_ratio(self, x: torch.Tensor, y: torch.Tensor, loss_type: str = "disc", return_scores: bool = False):
         if loss_type not in LOSS:

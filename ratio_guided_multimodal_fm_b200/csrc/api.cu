@@ -34,6 +34,7 @@ static thread_local std::string g_err;
 struct rgfm_net {
   std::unique_ptr<rgfm::Net> net;
   float* scores = nullptr;  // ratio scratch
+  int* step = nullptr;      // device step counter of rgfm_unet_sample
   int device = 0;
 };
 
@@ -124,6 +125,27 @@ int rgfm_unet_forward(rgfm_net* net, const float* x, float t, int32_t batch, flo
   RGFM_API_END
 }
 
+int rgfm_unet_sample(rgfm_net* net, float* x, int32_t batch, int32_t num_steps, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(net && net->net->is_unet(), "rgfm_unet_sample: not a U-Net");
+  RGFM_CHECK(x != nullptr && batch >= 0 && num_steps >= 1, "rgfm_unet_sample: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  RGFM_CUDA(cudaSetDevice(net->device));
+  RGFM_CUDA(cudaStreamSynchronize(s));  // the time-bias table is rewritten synchronously
+  // dt and t = step * dt as Python doubles, rounded once to fp32 like torch.full((n,), t) (flow_utils.py:85-90)
+  const double dt = 1.0 / num_steps;
+  std::vector<float> ts(num_steps);
+  for (int i = 0; i < num_steps; ++i) ts[i] = (float)(i * dt);
+  net->net->set_times(ts);
+  if (!net->step) RGFM_CUDA(cudaMalloc(&net->step, sizeof(int)));
+  RGFM_CUDA(cudaMemsetAsync(net->step, 0, sizeof(int), s));
+  for (int i = 0; i < num_steps && batch > 0; ++i) {  // x_t = x_t + v_t * dt, fused into the output conv (flow_utils.py:93-96)
+    net->net->forward(s, batch, x, nullptr, x, rgfm::OUT_EULER, (float)dt, net->step);
+    rgfm::launch_step_inc(net->step, s);
+  }
+  RGFM_API_END
+}
+
 int rgfm_ratio_log_ratio(rgfm_net* net, const float* x, const float* y, int32_t batch, int32_t loss_type,
                          float* log_ratio, float* scores, void* stream) {
   RGFM_API_BEGIN
@@ -176,7 +198,10 @@ int rgfm_classifier_logits(rgfm_net* net, const float* x, int32_t batch, float* 
   RGFM_API_END
 }
 
-void rgfm_net_destroy(rgfm_net* net) { delete net; }
+void rgfm_net_destroy(rgfm_net* net) {
+  if (net && net->step) cudaFree(net->step);
+  delete net;
+}
 
 int rgfm_mc_feng_step(int32_t batch, int32_t n_mc, int32_t dx, int32_t dy, const float* x, const float* y,
                       const float* v_x, const float* v_y, const float* mc_x, const float* mc_y,

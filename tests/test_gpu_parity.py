@@ -413,3 +413,24 @@ def test_guidance_sweep_shares_one_bank(synth):
     with pytest.raises(_lib.RgfmError):
         plan.set_strength(1.0)
     plan.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_cfm_schedule_sample_matches_reference(prec, synth):
+    """CFMSchedule.sample (flow_utils.py:69-100), unguided single-modality sampler: the golden is the live reference's
+    output; the drop-in must consume the device RNG with the reference's one draw and land within the sampler tolerance."""
+    from ratio_guided_multimodal_fm_b200 import CFMSchedule, StateDictModule
+    g = load_golden("cfm_sample_mnist28")
+    sd = synth("unet_mnist28", int(g["seed"]))
+    B, steps = int(g["B"]), int(g["steps"])
+    net = _lib.Net("unet_mnist28", sd, max_batch=3, precision=prec, device=DEV)  # chunk 3 < batch 4
+    x1 = net.unet_sample(T(g["x0"]).to(DEV), steps)
+    net.close()
+    assert maxabs(x1, T(g["x1"])) <= TOL_FINAL[prec], maxabs(x1, T(g["x1"]))
+    torch.manual_seed(5)
+    out = CFMSchedule().sample(StateDictModule("unet_mnist28", sd), B, num_steps=steps, device=DEV, precision=prec)
+    torch.manual_seed(5)
+    x0 = torch.randn(B, 1, 28, 28, device=DEV)
+    assert out.shape == (B, 1, 28, 28) and out.device.type == "cuda"
+    assert maxabs(out, O.flow_sample(sd, "unet_mnist28", x0.cpu(), steps)) <= TOL_FINAL[prec]
+    assert CFMSchedule().sample(StateDictModule("unet_mnist28", sd), 0, num_steps=steps, device=DEV).shape == (0, 1, 28, 28)

@@ -65,6 +65,13 @@ def test_mc_feng_block_golden():
         assert torch.allclose(w.sum(dim=1), torch.ones(w.shape[0]), atol=1e-5)
 
 
+def test_cfm_sample_golden(synth):
+    """CFMSchedule.sample (flow_utils.py:69-100): oracle against the live reference's output on the replayed prior draw."""
+    g = load_golden("cfm_sample_mnist28")
+    sd = synth("unet_mnist28", int(g["seed"]))
+    close(O.flow_sample(sd, "unet_mnist28", T(g["x0"]), int(g["steps"])), g["x1"], 1e-5)
+
+
 @pytest.mark.parametrize("name", ["sampler_pair28_small", "sampler_pair28_rulsif", "sampler_pair28_none",
                                   "sampler_mnist_svhn_small", "sampler_mnist_svhn_g2"])
 def test_sampler_golden(name, synth):
