@@ -648,6 +648,8 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(PackArgs a, float2* __rest
 // two convolutions 60 times per Euler step).
 __global__ void __launch_bounds__(256) gn_coef256_kernel(PackArgs a, float2* __restrict__ coef, double inv_cnt, int ipb) {
   __shared__ float s_red[2][256];
+  pdl_trigger();  // the consuming conv may set up (barriers, TMEM, tensor maps) while this grid runs
+  pdl_wait();     // the statistics come from the previous kernel
   // ipb = 256 / C images per block, thread -> (image, channel): every thread of the block has work
   const int il = threadIdx.x / a.C, c = threadIdx.x - il * a.C;
   const int n = blockIdx.x * ipb + il;
@@ -683,8 +685,8 @@ void launch_gn_coef(const PackArgs& a, float* coef, cudaStream_t s) {
   if (skip) return;
   if (a.C <= 256) {
     const int ipb = 256 / a.C;
-    gn_coef256_kernel<<<(a.nimg + ipb - 1) / ipb, 256, 0, s>>>(a, reinterpret_cast<float2*>(coef),
-                                                                  1.0 / ((double)(a.C / a.groups) * a.Hs * a.Ws), ipb);
+    launch_pdl(gn_coef256_kernel, dim3((a.nimg + ipb - 1) / ipb), dim3(256), 0, s, a, reinterpret_cast<float2*>(coef),
+               1.0 / ((double)(a.C / a.groups) * a.Hs * a.Ws), ipb);
   }
   else
     gn_coef_kernel<<<a.nimg, 256, 0, s>>>(a, reinterpret_cast<float2*>(coef));
