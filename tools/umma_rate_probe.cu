@@ -26,7 +26,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   __trap();
 }
 
-__global__ void __launch_bounds__(128, 1) probe(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(256, 1) probe(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                 int shift, int N, int reps, int mode, long long* out) {
   // mode 0: one issuing thread; 1: + 3 warps streaming ld/st.shared.v4 over 32 KB; 2: two issuing threads, two accumulators
   extern __shared__ uint8_t smem_raw[];
@@ -51,7 +51,31 @@ __global__ void __launch_bounds__(128, 1) probe(const __grid_constant__ CUtensor
   __shared__ volatile int s_go, s_stop;
   if (threadIdx.x == 0) { s_go = 0; s_stop = 0; }
   __syncthreads();
-  if (mode == 1 && warp >= 1) {  // background shared-memory traffic on a region the MMAs do not touch
+  if ((mode == 3 || mode == 4) && warp >= 1) {
+    // How much do warps that SHARE the issuing thread's scheduler (warp 4: same sub-partition as warp 0) progress while
+    // the MMA queue is kept full?  mode 3: ld/st.shared loop, mode 4: dependent FMA chain.  Iterations per warp -> out[2 + warp]
+    const uint32_t scratch = sB + NMAX * K * 2 + (threadIdx.x - 32) * 16;
+    while (!s_go) {}
+    long long iters = 0;
+    uint32_t a0 = 1, a1 = 2, a2 = 3, a3 = 4;
+    float f = 1.0f;
+    while (!s_stop) {
+      if (mode == 3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t ad = scratch + i * 4096;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(ad));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f = fmaf(f, 1.0001f, 0.5f);
+      }
+      ++iters;
+    }
+    if (lane == 0) out[2 + warp] = iters + (a0 == 0x12345u) + (f == 3.f);
+  }
+  if (mode == 1 && warp >= 1 && warp < 4) {  // background shared-memory traffic on a region the MMAs do not touch
     const uint32_t scratch = sB + NMAX * K * 2 + (threadIdx.x - 32) * 16;
     while (!s_go) {}
     uint32_t a0 = 1, a1 = 2, a2 = 3, a3 = 4;
@@ -98,6 +122,7 @@ __global__ void __launch_bounds__(128, 1) probe(const __grid_constant__ CUtensor
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
       }
+    if (reps == 0) while (clock64() - t0 < 400000) {}  // baseline: the background warps alone for the same kind of interval
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma)) : "memory");
     mbar_wait(&bar_mma, 0);
     out[0] = clock64() - t0;
@@ -125,7 +150,7 @@ int main() {
   for (auto& v : hA) v = __float2bfloat16((float)((rand() % 15) - 7) * 0.01f);
   for (auto& v : hB) v = __float2bfloat16((float)((rand() % 7) - 3) * 0.01f);
   __nv_bfloat16 *dA, *dB; long long* dOut;
-  CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dOut, 16));
+  CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dOut, 128));
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
   CUtensorMap tmA, tmB;
@@ -141,7 +166,7 @@ int main() {
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("encode B failed %d\n", (int)r); return 1; }
   }
-  const size_t smem = (ROWS + NMAX) * K * 2 + 2048 + 40 * 1024;
+  const size_t smem = (ROWS + NMAX) * K * 2 + 2048 + 48 * 1024;
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int reps = 64;
   for (int mode = 0; mode < 3; ++mode)
@@ -150,7 +175,7 @@ int main() {
     for (int shift : {0, 1, 35, 70}) {
       long long best = 1ll << 60;
       for (int it = 0; it < 3; ++it) {
-        probe<<<1, 128, smem>>>(tmA, tmB, shift, N, reps, mode, dOut);
+        probe<<<1, 256, smem>>>(tmA, tmB, shift, N, reps, mode, dOut);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("kernel error %s\n", cudaGetErrorString(e)); return 1; }
         long long c; CK(cudaMemcpy(&c, dOut, 8, cudaMemcpyDeviceToHost));
@@ -160,5 +185,18 @@ int main() {
     }
     printf("   cycles/MMA\n");
   }
+  // scheduler sharing: N = 64, full-rate MMA issue from warp 0 (sub-partition 0) for reps2 x 4 MMAs; iterations of warps 1..7
+  for (int mode = 3; mode <= 4; ++mode)
+    for (int reps2 : {0, 2048}) {
+      CK(cudaMemset(dOut, 0, 128));
+      probe<<<1, 256, smem>>>(tmA, tmB, 0, 64, reps2, mode, dOut);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("kernel error %s\n", cudaGetErrorString(e)); return 1; }
+      long long h[16]; CK(cudaMemcpy(h, dOut, 128, cudaMemcpyDeviceToHost));
+      printf("mode %d (%s) %5d MMAs in %lld cycles; background iterations per 1000 cycles, warps 1..7 (warp 4 shares the issuer's scheduler):",
+             mode, mode == 3 ? "ld/st.shared" : "fma chain", reps2 * 4, h[0]);
+      for (int w = 1; w < 8; ++w) printf(" %.1f", 1000.0 * h[2 + w] / (double)h[0]);
+      printf("\n");
+    }
   return 0;
 }
