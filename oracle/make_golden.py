@@ -38,6 +38,7 @@ from oracle import rgfm_oracle as O  # noqa: E402
 from ratio_guided_multimodal_fm_b200 import synthetic as S  # noqa: E402
 
 from src.models.unet import FlowMatchingUNet  # noqa: E402
+from src.models.flow_matching import FlowMatchingModel  # noqa: E402
 from src.models.unet_flexible import FlowMatchingUNetMNIST, FlowMatchingUNetSVHN  # noqa: E402
 from src.models.ratio_estimator import RatioEstimator  # noqa: E402
 from src.models.ratio_flexible import RatioEstimatorMNISTSVHN  # noqa: E402
@@ -51,6 +52,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 REF_CLASSES = {
     "unet_mnist28": lambda lt: FlowMatchingUNet(),
+    "flow28": lambda lt: FlowMatchingModel(),
     "unet_mnist32": lambda lt: FlowMatchingUNetMNIST(img_size=32),
     "unet_svhn": lambda lt: FlowMatchingUNetSVHN(),
     "ratio28": lambda lt: RatioEstimator(loss_type=lt),
@@ -141,8 +143,10 @@ def case_classifier(kind, seed, B):
     save(f"{kind}_forward", seed=seed, x=x, logits=l_ref, digest=sd_digest(sd))
 
 
-def case_sampler(name, pair, seeds, B, N_mc, steps, method, gamma, loss_type, noise_seed=42):
+def case_sampler(name, pair, seeds, B, N_mc, steps, method, gamma, loss_type, noise_seed=42, kinds=None):
     kx, ky, kr, sx, sy = O.PAIR_KINDS[pair]
+    if kinds:
+        kx, ky = kinds
     fx, sdx = ref_module(kx, seeds[0])
     fy, sdy = ref_module(ky, seeds[1])
     fr, sdr = ref_module(kr, seeds[2], loss_type)
@@ -213,6 +217,7 @@ def main():
         ("unet_mnist28", lambda: case_unet("unet_mnist28", 11, 3)),
         ("unet_mnist32", lambda: case_unet("unet_mnist32", 12, 3)),
         ("unet_svhn", lambda: case_unet("unet_svhn", 13, 3)),
+        ("flow28", lambda: case_unet("flow28", 15, 3)),
         ("ratio28", lambda: case_ratio("ratio28", 21, 4)),
         ("ratio_mnist_svhn", lambda: case_ratio("ratio_mnist_svhn", 22, 4)),
         ("clf_mnist28", lambda: case_classifier("clf_mnist28", 31, 4)),
@@ -223,6 +228,9 @@ def main():
         ("sampler_pair28_small", lambda: case_sampler("sampler_pair28_small", "pair28", (11, 14, 21), 5, 8, 6, "mc_feng", 0.5, "disc")),
         ("sampler_pair28_rulsif", lambda: case_sampler("sampler_pair28_rulsif", "pair28", (11, 14, 21), 4, 8, 5, "mc_feng", 1.0, "rulsif")),
         ("sampler_pair28_none", lambda: case_sampler("sampler_pair28_none", "pair28", (11, 14, 21), 4, 8, 5, "none", 0.0, "disc")),
+        # `--model original` (src/sample.py --model original): both flows are FlowMatchingModel
+        ("sampler_pair28_original", lambda: case_sampler("sampler_pair28_original", "pair28", (15, 16, 21), 4, 8, 5, "mc_feng", 0.5, "disc",
+                                                         kinds=("flow28", "flow28"))),
         ("sampler_mnist_svhn_small", lambda: case_sampler("sampler_mnist_svhn_small", "mnist_svhn", (12, 13, 22), 3, 6, 5, "mc_feng", 0.5, "disc")),
         ("sampler_mnist_svhn_g2", lambda: case_sampler("sampler_mnist_svhn_g2", "mnist_svhn", (12, 13, 22), 3, 6, 5, "mc_feng", 2.0, "rulsif")),
     ]

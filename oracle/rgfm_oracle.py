@@ -74,8 +74,33 @@ def _resblock(sd: StateDict, p: str, x: Tensor, t_emb: Tensor) -> Tensor:
     return h + sk
 
 
+def flow28_forward(sd: StateDict, x: Tensor, t: Tensor) -> Tensor:
+    """`--model original` velocity field.  reference: flow_matching.py:10-31 (sinusoidal embedding: sin then cos,
+    log(1e4)/(half-1) spacing, t unscaled), :34-73 (encoder), :76-126 (decoder), :129-173 (model)."""
+    half = 64  # time_emb_dim 128
+    f = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+    e = t[:, None] * f[None, :]
+    t_emb = torch.cat((e.sin(), e.cos()), dim=-1)
+    h = x
+    for i, stride in ((1, 1), (2, 2), (3, 2), (4, 1)):
+        h = F.conv2d(h, sd[f"encoder.conv{i}.weight"], sd[f"encoder.conv{i}.bias"], stride=stride, padding=1)
+        h = F.silu(F.group_norm(h, GN_GROUPS, sd[f"encoder.gn{i}.weight"], sd[f"encoder.gn{i}.bias"]))
+    feat = F.linear(h.reshape(h.shape[0], -1), sd["encoder.fc.weight"], sd["encoder.fc.bias"])
+    h = F.linear(torch.cat([feat, t_emb], dim=1), sd["decoder.fc1.weight"], sd["decoder.fc1.bias"])
+    h = h.view(h.shape[0], 256, 7, 7)
+    for i in (1, 2):
+        h = F.conv_transpose2d(h, sd[f"decoder.deconv{i}.weight"], sd[f"decoder.deconv{i}.bias"], stride=2, padding=1)
+        h = F.silu(F.group_norm(h, GN_GROUPS, sd[f"decoder.gn{i}.weight"], sd[f"decoder.gn{i}.bias"]))
+    h = F.conv2d(h, sd["decoder.conv3.weight"], sd["decoder.conv3.bias"], padding=1)
+    h = F.silu(F.group_norm(h, GN_GROUPS, sd["decoder.gn3.weight"], sd["decoder.gn3.bias"]))
+    return F.conv2d(h, sd["decoder.conv_out.weight"], sd["decoder.conv_out.bias"], padding=1)
+
+
 def unet_forward(sd: StateDict, kind: str, x: Tensor, t: Tensor) -> Tensor:
-    """Velocity field v = fm(x, t).  reference: unet.py:216-278, unet_flexible.py:203-261."""
+    """Velocity field v = fm(x, t).  reference: unet.py:216-278, unet_flexible.py:203-261.
+    A state_dict of the `--model original` network (flow_matching.py) is recognised by its keys, like the CUDA plan does."""
+    if kind == "flow28" or "encoder.conv1.weight" in sd:
+        return flow28_forward(sd, x, t)
     cfg = UNET_CONFIGS[kind]
     mc, mult, nres = cfg["model_channels"], cfg["channel_mult"], cfg["num_res_blocks"]
     t_emb = timestep_embedding(t, mc)

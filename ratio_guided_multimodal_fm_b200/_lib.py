@@ -20,7 +20,7 @@ ABI_VERSION = 1
 DIAG_FLOATS = 16
 
 NET_KINDS = {"unet_mnist28": 0, "unet_mnist32": 1, "unet_svhn": 2, "ratio28": 3, "ratio_mnist_svhn": 4,
-             "clf_mnist28": 5, "clf_mnist32": 6, "clf_svhn": 7}
+             "clf_mnist28": 5, "clf_mnist32": 6, "clf_svhn": 7, "flow28": 8}
 PAIRS = {"pair28": 0, "mnist_svhn": 1}
 GUIDANCE = {"none": 0, "mc_feng": 1, "grad_log_ratio": 2}
 LOSS = {"disc": 0, "rulsif": 1}

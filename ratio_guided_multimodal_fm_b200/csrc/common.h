@@ -162,7 +162,9 @@ struct Packed {
 };
 
 enum NormMode { NORM_NONE = 0, NORM_GN = 1, NORM_AFFINE = 2 };
-enum SpatialMode { SP_ID = 0, SP_UP2 = 1, SP_POOL2 = 2 };
+// SP_D2S: depth-to-space x2 of a [H][W][4*C] source whose channel (a*2+b)*C + c is output pixel (2h+a, 2w+b), channel c --
+// a ConvTranspose2d(4, stride 2, padding 1) computed as a 3x3 convolution with 4*C_out outputs (fp32 pack kernel only)
+enum SpatialMode { SP_ID = 0, SP_UP2 = 1, SP_POOL2 = 2, SP_D2S = 3 };
 enum OutMode { OUT_RAW = 0, OUT_NCHW = 1, OUT_EULER = 2 };
 enum ActMode { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2 };
 

@@ -195,8 +195,13 @@ struct Builder {
     }
     if (a.nsrc == 1) a.src[1] = a.src[0];
     a.Hs = srcs[0].H; a.Ws = srcs[0].W;
-    a.Ho = spatial == SP_UP2 ? a.Hs * 2 : (spatial == SP_POOL2 ? a.Hs / 2 : a.Hs);
-    a.Wo = spatial == SP_UP2 ? a.Ws * 2 : (spatial == SP_POOL2 ? a.Ws / 2 : a.Ws);
+    if (spatial == SP_D2S) {
+      RGFM_CHECK(a.nsrc == 1 && C % 4 == 0 && !out_bf16 && srcs[0].fmt == 0 && !srcs[0].padded, "pack: depth-to-space is an fp32, single-source mode");
+      C /= 4;
+    }
+    const bool x2 = spatial == SP_UP2 || spatial == SP_D2S;
+    a.Ho = x2 ? a.Hs * 2 : (spatial == SP_POOL2 ? a.Hs / 2 : a.Hs);
+    a.Wo = x2 ? a.Ws * 2 : (spatial == SP_POOL2 ? a.Ws / 2 : a.Ws);
     a.C = C; a.norm = norm; a.act = act; a.spatial = spatial;
     a.gamma = gamma; a.beta = beta; a.groups = 8;
     Packed p = new_packed(a.Ho, a.Wo, C, out_bf16);
@@ -212,7 +217,7 @@ struct Builder {
       else launch_pack(b, c.s);
     }, padded ? "pack_padded" : "pack", 0.0, bytes,
        std::to_string(a.Hs) + "x" + std::to_string(a.Ws) + " C" + std::to_string(C) + (norm == NORM_GN ? " gn" : "") +
-           (spatial == SP_UP2 ? " up2" : (spatial == SP_POOL2 ? " pool2" : ""))});
+           (spatial == SP_UP2 ? " up2" : (spatial == SP_POOL2 ? " pool2" : (spatial == SP_D2S ? " d2s" : "")))});
     return p;
   }
 
@@ -322,6 +327,15 @@ struct Builder {
   // ---- fp32 SIMT convolution; returns the dense fp32 raw activation (or none when `final`) ----
   Act conv(const Packed& in, const std::string& wname, int cin_real, int cout, int ks, int stride, int temb_off,
            const float* res, bool stats, bool final) {
+    const int coutP = (cout + 31) / 32 * 32;
+    return conv_dev(in, conv_w_simt(wname + ".weight", cout, cin_real, ks, in.C, coutP), vec(wname + ".bias", cout, coutP), cout, ks,
+                    stride, temb_off, res, stats, final, 2.0 * cout * cin_real * ks * ks,
+                    wname + " " + std::to_string(in.H) + "x" + std::to_string(in.W) + " " + std::to_string(in.C) + "->" +
+                        std::to_string(cout) + " k" + std::to_string(ks) + (stride == 2 ? " s2" : ""));
+  }
+  // the same with device weights already in the kernel's [tap][in.C][coutP] layout and a bias of coutP entries
+  Act conv_dev(const Packed& in, const float* w, const float* bias, int cout, int ks, int stride, int temb_off, const float* res,
+               bool stats, bool final, double flops_per_out_pixel, const std::string& label) {
     RGFM_CHECK(!in.bf16, "SIMT conv needs an fp32 operand");
     const int pad = ks / 2;
     const int Ho = (in.H + 2 * pad - ks) / stride + 1, Wo = (in.W + 2 * pad - ks) / stride + 1;
@@ -329,7 +343,7 @@ struct Builder {
     const int coutP = (cout + 31) / 32 * 32;
     ConvArgs a{};
     a.in = in.p; a.Hin = in.H; a.Win = in.W; a.Cin = in.C;
-    a.bias = vec(wname + ".bias", cout, coutP);
+    a.bias = bias;
     a.temb_off = temb_off < 0 ? 0 : temb_off;
     a.res = res;
     a.CoutP = coutP; a.Cout = cout; a.ks = ks; a.stride = stride; a.pad = pad;
@@ -341,10 +355,10 @@ struct Builder {
       a.out = o.p;
       a.stats = o.stats;
     }
-    a.w = conv_w_simt(wname + ".weight", cout, cin_real, ks, in.C, coutP);
+    a.w = w;
     const bool has_temb = temb_off >= 0;
     Net* np = &net;
-    const double flops = 2.0 * Ho * Wo * (double)cout * cin_real * ks * ks;
+    const double flops = flops_per_out_pixel * Ho * Wo;
     const double bytes = (double)in.H * in.W * in.C * 4.0 + (double)Ho * Wo * cout * 4.0 * (res ? 2.0 : 1.0);
     net.ops_.push_back({[a, final, has_temb, np](const RunCtx& c) {
       ConvArgs b = a;
@@ -360,9 +374,7 @@ struct Builder {
         b.dt = c.dt;
       }
       launch_conv_simt(b, c.s);
-    }, "conv_simt", flops, bytes,
-       wname + " " + std::to_string(in.H) + "x" + std::to_string(in.W) + " " + std::to_string(in.C) + "->" + std::to_string(cout) +
-           " k" + std::to_string(ks) + (stride == 2 ? " s2" : "")});
+    }, "conv_simt", flops, bytes, label});
     return o;
   }
 
@@ -486,6 +498,108 @@ struct Builder {
     }
     release(a2);
     return out;
+  }
+
+  // ---- `--model original`: FlowMatchingModel (flow_matching.py:34-173), fp32 kernels ------------------------------
+  // encoder: 4 x [conv3x3 (stride 1,2,2,1) -> GroupNorm(8) -> SiLU] -> flatten -> fc 12544->256
+  // decoder: fc [features | time] -> 12544 -> view [256,7,7] -> 2 x [ConvTranspose2d(4,2,1) -> GN -> SiLU] -> conv3x3 -> GN
+  //          -> SiLU -> conv3x3 -> v.  The Linear layers run as 1x1 convolutions over a 1x1 "image" (the NHWC activation
+  //          [7][7][256] IS the 12544-vector once the weight rows are permuted); a transposed conv is a 3x3 convolution
+  //          with 4*C_out outputs -- one block per output-pixel parity -- followed by the pack's depth-to-space.
+  void build_flow28() {
+    net.in_ch_ = 1; net.img_ = 28; net.model_ch_ = 0; net.temb_dim_ = 128;
+    const int F = 256, S = 49, FS = F * S;  // feature channels, 7x7 pixels
+    auto gn = [&](const Act& h, const std::string& p, int c, int spatial) {
+      Act hh = h;
+      Packed o = pack({hh}, NORM_GN, vec(p + ".weight", c), vec(p + ".bias", c), ACT_SILU, spatial, false);
+      return o;
+    };
+    // encoder
+    Packed cur = pack_input(1, 28, 28, 16, false);
+    const int chans[5] = {1, 32, 64, 128, 256};
+    const int strides[4] = {1, 2, 2, 1};
+    for (int i = 0; i < 4; ++i) {
+      const std::string n = std::to_string(i + 1);
+      Act h = conv(cur, "encoder.conv" + n, chans[i], chans[i + 1], 3, strides[i], -1, nullptr, true, false);
+      release(cur);
+      cur = gn(h, "encoder.gn" + n, chans[i + 1], SP_ID);
+      release(h);
+    }
+    // encoder.fc: y[o] = b[o] + sum_{c,hw} W[o][c*49 + hw] x[c][hw]  ->  operand index k = hw*256 + c
+    Act feat;
+    {
+      const float* w = W.get("encoder.fc.weight", (int64_t)F * FS);
+      std::vector<float> v((size_t)FS * F);
+      for (int o = 0; o < F; ++o)
+        for (int c = 0; c < F; ++c)
+          for (int hw = 0; hw < S; ++hw) v[((size_t)hw * F + c) * F + o] = w[(size_t)o * FS + c * S + hw];
+      Packed flat = cur;
+      flat.H = 1; flat.W = 1; flat.C = FS;
+      feat = conv_dev(flat, pool.upload(v), vec("encoder.fc.bias", F), F, 1, 1, -1, nullptr, false, false, 2.0 * F * FS,
+                      "encoder.fc 12544->256");
+      release(cur);
+    }
+    // decoder.fc1 over [features | time]: feature columns as a 1x1 conv, time columns as the per-step bias row; output
+    // row o = c*49 + hw of the reference lands at hw*256 + c, i.e. directly as the NHWC [7][7][256] operand of deconv1
+    Packed dec_in;
+    {
+      const int Kin = F + 128;
+      const float* w = W.get("decoder.fc1.weight", (int64_t)FS * Kin);
+      const float* b = W.get("decoder.fc1.bias", FS);
+      std::vector<float> v((size_t)F * FS), bias(FS);
+      net.flow_tw_.assign((size_t)FS * 128, 0.f);
+      for (int c = 0; c < F; ++c)
+        for (int hw = 0; hw < S; ++hw) {
+          const int o = c * S + hw, op = hw * F + c;
+          bias[op] = b[o];
+          for (int k = 0; k < F; ++k) v[(size_t)k * FS + op] = w[(size_t)o * Kin + k];
+          for (int j = 0; j < 128; ++j) net.flow_tw_[(size_t)op * 128 + j] = w[(size_t)o * Kin + F + j];
+        }
+      net.temb_C_ = FS;
+      Packed fin;
+      fin.p = feat.p; fin.H = 1; fin.W = 1; fin.C = F; fin.bf16 = false;
+      Act h = conv_dev(fin, pool.upload(v), pool.upload(bias), FS, 1, 1, /*temb_off=*/0, nullptr, false, false, 2.0 * FS * Kin,
+                       "decoder.fc1 384->12544");
+      release(feat);
+      dec_in.p = h.p; dec_in.H = 7; dec_in.W = 7; dec_in.C = F; dec_in.bf16 = false;
+    }
+    // ConvTranspose2d(cin, cout, 4, stride 2, padding 1): out[2i+a] takes in[i+dy] * W[ky] with (a, dy) -> ky:
+    // (0,0)->1, (0,-1)->3, (1,+1)->0, (1,0)->2 (same along x); torch weight layout [cin][cout][4][4]
+    auto deconv = [&](Packed& in, const std::string& name, int cin, int cout, const std::string& gname) {
+      const float* w = W.get(name + ".weight", (int64_t)cin * cout * 16);
+      const float* b = W.get(name + ".bias", cout);
+      const int co4 = 4 * cout;
+      std::vector<float> v((size_t)9 * cin * co4, 0.f), bias(co4);
+      auto kof = [](int par, int d) { return par == 0 ? (d == 0 ? 1 : (d == -1 ? 3 : -1)) : (d == 1 ? 0 : (d == 0 ? 2 : -1)); };
+      for (int a = 0; a < 2; ++a)
+        for (int bb = 0; bb < 2; ++bb)
+          for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int ky = kof(a, dy), kx = kof(bb, dx);
+              if (ky < 0 || kx < 0) continue;
+              const int tap = (dy + 1) * 3 + (dx + 1);
+              for (int ci = 0; ci < cin; ++ci)
+                for (int co = 0; co < cout; ++co)
+                  v[((size_t)tap * cin + ci) * co4 + (a * 2 + bb) * cout + co] = w[(((size_t)ci * cout + co) * 4 + ky) * 4 + kx];
+            }
+      for (int q = 0; q < 4; ++q)
+        for (int co = 0; co < cout; ++co) bias[q * cout + co] = b[co];
+      Act h = conv_dev(in, pool.upload(v), pool.upload(bias), co4, 3, 1, -1, nullptr, true, false, 2.0 * 16 * cin * cout,
+                       name + " " + std::to_string(in.H) + "x" + std::to_string(in.W) + " " + std::to_string(cin) + "->" +
+                           std::to_string(cout) + " k4 s2 transposed (3x3 conv, 4 parities)");
+      release(in);
+      Packed o = gn(h, gname, cout, SP_D2S);
+      release(h);
+      return o;
+    };
+    Packed d1 = deconv(dec_in, "decoder.deconv1", 256, 128, "decoder.gn1");
+    Packed d2 = deconv(d1, "decoder.deconv2", 128, 64, "decoder.gn2");
+    Act h3 = conv(d2, "decoder.conv3", 64, 32, 3, 1, -1, nullptr, true, false);
+    release(d2);
+    Packed p3 = gn(h3, "decoder.gn3", 32, SP_ID);
+    release(h3);
+    conv(p3, "decoder.conv_out", 32, 1, 3, 1, -1, nullptr, false, true);
+    release(p3);
   }
 
   void build_unet(int in_ch, int img, int mc, const std::vector<int>& mult, int nres) {
@@ -805,6 +919,10 @@ Net::Net(int kind, const rgfm_weights* w, int chunk, int precision, int device, 
     case RGFM_NET_UNET_MNIST28: b.build_unet(1, 28, 32, {1, 2}, 2); break;
     case RGFM_NET_UNET_MNIST32: b.build_unet(1, 32, 32, {1, 2}, 2); break;
     case RGFM_NET_UNET_SVHN: b.build_unet(3, 32, 64, {1, 2, 2}, 2); break;
+    case RGFM_NET_FLOW28:
+      b.tc_mode = false;  // fp32 kernels in every precision mode (compatibility path, not the headline)
+      b.build_flow28();
+      break;
     case RGFM_NET_RATIO28:
       if (want_grad) b.tc_mode = false;  // the dgrad chain is exact fp32
       b.build_ratio28(want_grad);
@@ -844,8 +962,27 @@ void Net::set_times(const std::vector<float>& ts) {
   RGFM_CHECK(is_unet(), "set_times: not a U-Net");
   const int half = model_ch_ / 2;
   std::vector<float> table((size_t)ts.size() * temb_C_);
+  if (kind_ == RGFM_NET_FLOW28) {
+    // SinusoidalPositionEmbeddings(128) (flow_matching.py:18-31): f_k = exp(k * -(ln 1e4 / 63)), emb = [sin(t f), cos(t f)],
+    // t unscaled; its contribution to decoder.fc1 (the last 128 input columns, flow_matching.py:115-118) is a per-step bias
+    const int hd = 64;
+    const float step_f = -(float)(std::log(10000.0) / (hd - 1));
+    std::vector<float> e(2 * hd);
+    for (size_t r = 0; r < ts.size(); ++r) {
+      for (int k = 0; k < hd; ++k) {
+        const float arg = ts[r] * std::exp((float)k * step_f);
+        e[k] = std::sin(arg);
+        e[hd + k] = std::cos(arg);
+      }
+      for (int o = 0; o < temb_C_; ++o) {
+        double s = 0.0;
+        for (int j = 0; j < 2 * hd; ++j) s += (double)flow_tw_[(size_t)o * 2 * hd + j] * e[j];
+        table[r * temb_C_ + o] = (float)s;
+      }
+    }
+  }
   std::vector<float> e(model_ch_), h1(temb_dim_), h2(temb_dim_);
-  for (size_t r = 0; r < ts.size(); ++r) {
+  for (size_t r = 0; r < ts.size() && kind_ != RGFM_NET_FLOW28; ++r) {
     const float t = ts[r];
     for (int k = 0; k < half; ++k) {
       // freqs = exp(-ln(1e4) * k / half) in fp32; emb = [cos(t f), sin(t f)]  (unet.py:25-30)

@@ -66,7 +66,7 @@ class Net {
                       float* log_ratio, std::vector<ProfRec>* prof = nullptr);
   ~Net();
   int kind() const { return kind_; }
-  bool is_unet() const { return kind_ <= RGFM_NET_UNET_SVHN; }
+  bool is_unet() const { return kind_ <= RGFM_NET_UNET_SVHN || kind_ == RGFM_NET_FLOW28; }  // velocity fields v(x, t)
   int in_ch() const { return in_ch_; }
   int img() const { return img_; }
   int chunk() const { return chunk_; }
@@ -106,6 +106,7 @@ class Net {
   std::vector<float> te0_w_, te0_b_, te2_w_, te2_b_;
   struct TimeMlp { std::vector<float> w, b; int cout, off; };
   std::vector<TimeMlp> tmlps_;
+  std::vector<float> flow_tw_;  // RGFM_NET_FLOW28: time columns of decoder.fc1, rows in the kernel's (pixel, channel) order
   float* d_temb_ = nullptr;
   int temb_rows_ = 0;
 };

@@ -204,6 +204,14 @@ __device__ __forceinline__ void pack_scale_shift(const PackArgs& a, int n, float
       const int si = (c < C0) ? 0 : 1;
       float s, ss;
       stats_channel_sums<BATCH>(a.src[si].st, n, si ? c - C0 : c, s, ss);
+      if (a.spatial == SP_D2S) {  // an output channel is four source channels (one per output-pixel parity)
+        for (int q = 1; q < 4; ++q) {
+          float s2, ss2;
+          stats_channel_sums<BATCH>(a.src[0].st, n, c + q * a.C, s2, ss2);
+          s += s2;
+          ss += ss2;
+        }
+      }
       s_red[0][c] = s;
       s_red[1][c] = ss;
     }
@@ -222,7 +230,7 @@ __device__ __forceinline__ void pack_scale_shift(const PackArgs& a, int n, float
         ss += __shfl_xor_sync(0xffffffffu, ss, off);
       }
       if ((tid & 31) == 0) {
-        const double cnt = (double)cpg * a.Hs * a.Ws;
+        const double cnt = (double)cpg * (a.spatial == SP_D2S ? a.Ho * a.Wo : a.Hs * a.Ws);
         const double mean = s / cnt;
         double var = ss / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
@@ -287,10 +295,12 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
           r.x = fmaxf(r.x, v.x); r.y = fmaxf(r.y, v.y); r.z = fmaxf(r.z, v.z); r.w = fmaxf(r.w, v.w);
         }
     } else {
-      const int hs = (a.spatial == SP_UP2) ? (ho >> 1) : ho;
-      const int ws = (a.spatial == SP_UP2) ? (wo >> 1) : wo;
+      const bool half_res = a.spatial == SP_UP2 || a.spatial == SP_D2S;
+      const int hs = half_res ? (ho >> 1) : ho;
+      const int ws = half_res ? (wo >> 1) : wo;
+      const int csub = a.spatial == SP_D2S ? ((ho & 1) * 2 + (wo & 1)) * a.C : 0;  // parity sub-channel block
       float lv[4];
-      load_raw4(a.src[si].p, raw_offset(spad, n, hs, ws, a.Hs, a.Ws, Cs) + cl, a.src[si].fmt, lv);
+      load_raw4(a.src[si].p, raw_offset(spad, n, hs, ws, a.Hs, a.Ws, Cs) + csub + cl, a.src[si].fmt, lv);
       r = make_float4(lv[0], lv[1], lv[2], lv[3]);
       if (!plain) {
         r.x = apply_act(r.x * s_scale[c] + s_shift[c], a.act);

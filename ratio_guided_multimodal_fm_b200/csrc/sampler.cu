@@ -137,7 +137,12 @@ struct Sampler {
     grad_guided = (d.guidance == RGFM_GUIDE_GRAD_LOG_RATIO) && wr != nullptr;
     int kx, ky, kr;
     if (d.pair == RGFM_PAIR_28) {
-      kx = ky = RGFM_NET_UNET_MNIST28;
+      // src/sample.py --model {unet, original}: the same sampler takes either flow; the state_dict says which one it is
+      auto kind28 = [](const rgfm_weights* w) {
+        return WeightMap(w).has("encoder.conv1.weight") ? (int)RGFM_NET_FLOW28 : (int)RGFM_NET_UNET_MNIST28;
+      };
+      kx = kind28(wx);
+      ky = kind28(wy);
       kr = RGFM_NET_RATIO28;
     } else if (d.pair == RGFM_PAIR_MNIST_SVHN) {
       kx = RGFM_NET_UNET_MNIST32;

@@ -35,7 +35,7 @@ class CFMSchedule:
         """Euler integration of dx/dt = model(x, t) from the prior, t = step / num_steps (flow_utils.py:69-100).
         Like the reference: puts the model in eval(), draws `torch.randn(num_samples, 1, 28, 28, device=device)` from
         the device's global generator, returns `[num_samples, 1, 28, 28]` on `device`.  `model` is the reference's
-        28x28 `FlowMatchingUNet` (anything with .eval() and .state_dict() in its key layout)."""
+        28x28 `FlowMatchingUNet` or `FlowMatchingModel` (anything with .eval() and .state_dict() in their key layouts)."""
         model.eval()
         device = torch.device(device)
         if device.type != "cuda":
@@ -43,7 +43,10 @@ class CFMSchedule:
         x_t = torch.randn(num_samples, 1, 28, 28, device=device)
         if num_samples == 0:
             return x_t
-        net = _lib.Net(getattr(model, "rgfm_kind", "unet_mnist28"), model.state_dict(),
+        sd = model.state_dict()
+        # `--model original` (FlowMatchingModel, flow_matching.py) or the 28x28 U-Net: the keys say which
+        kind = "flow28" if "encoder.conv1.weight" in sd else "unet_mnist28"
+        net = _lib.Net(kind, sd,
                        max_batch=chunk or min(int(num_samples), 1024), precision=precision or default_precision(),
                        device=device)
         try:

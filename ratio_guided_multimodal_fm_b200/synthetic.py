@@ -24,6 +24,8 @@ UNET_ARCH = {
     "unet_mnist28": dict(in_channels=1, img_size=28, model_channels=32, channel_mult=(1, 2), num_res_blocks=2),
     "unet_mnist32": dict(in_channels=1, img_size=32, model_channels=32, channel_mult=(1, 2), num_res_blocks=2),
     "unet_svhn": dict(in_channels=3, img_size=32, model_channels=64, channel_mult=(1, 2, 2), num_res_blocks=2),
+    # `--model original` (flow_matching.py:129-173): not a U-Net; listed for its input geometry
+    "flow28": dict(in_channels=1, img_size=28),
 }
 
 
@@ -168,7 +170,29 @@ def classifier_state_dict(kind: str, seed: int) -> Dict[str, torch.Tensor]:
     return g.sd
 
 
+def flow28_state_dict(seed: int) -> Dict[str, torch.Tensor]:
+    """`--model original`: FlowMatchingModel (src/models/flow_matching.py:34-173): conv encoder -> fc -> [features | time]
+    -> fc -> two ConvTranspose2d -> conv -> conv.  ConvTranspose2d weights are [Cin, Cout, 4, 4]."""
+    g = _Gen(seed)
+    g.conv("encoder.conv1", 32, 1, 3); g.affine("encoder.gn1", 32)
+    g.conv("encoder.conv2", 64, 32, 3); g.affine("encoder.gn2", 64)
+    g.conv("encoder.conv3", 128, 64, 3); g.affine("encoder.gn3", 128)
+    g.conv("encoder.conv4", 256, 128, 3); g.affine("encoder.gn4", 256)
+    g.linear("encoder.fc", 256, 256 * 7 * 7)
+    g.linear("decoder.fc1", 256 * 7 * 7, 256 + 128)
+    for name, cin, cout in (("decoder.deconv1", 256, 128), ("decoder.deconv2", 128, 64)):
+        b = 1.0 / math.sqrt(cout * 16)  # torch: fan_in of a transposed conv is weight.size(1) * k * k
+        g.uniform(name + ".weight", (cin, cout, 4, 4), b)
+        g.uniform(name + ".bias", (cout,), b)
+    g.affine("decoder.gn1", 128); g.affine("decoder.gn2", 64)
+    g.conv("decoder.conv3", 32, 64, 3); g.affine("decoder.gn3", 32)
+    g.conv("decoder.conv_out", 1, 32, 3)
+    return g.sd
+
+
 def state_dict(kind: str, seed: int) -> Dict[str, torch.Tensor]:
+    if kind == "flow28":
+        return flow28_state_dict(seed)
     if kind.startswith("unet"):
         return unet_state_dict(kind, seed)
     if kind.startswith("ratio"):

@@ -35,7 +35,7 @@ def _need_cuda():
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("kind", ["unet_mnist28", "unet_mnist32", "unet_svhn"])
+@pytest.mark.parametrize("kind", ["unet_mnist28", "unet_mnist32", "unet_svhn", "flow28"])
 def test_unet_forward(kind, prec, synth):
     g = load_golden(f"{kind}_forward")
     sd = synth(kind, g["seed"])
@@ -434,3 +434,19 @@ def test_cfm_schedule_sample_matches_reference(prec, synth):
     assert out.shape == (B, 1, 28, 28) and out.device.type == "cuda"
     assert maxabs(out, O.flow_sample(sd, "unet_mnist28", x0.cpu(), steps)) <= TOL_FINAL[prec]
     assert CFMSchedule().sample(StateDictModule("unet_mnist28", sd), 0, num_steps=steps, device=DEV).shape == (0, 1, 28, 28)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_sampler_with_original_flow_model(prec, synth):
+    """src/sample.py --model original: sample_bimodal_guided with two FlowMatchingModel flows (flow_matching.py:129-173).
+    The golden is the live reference's output; the plan recognises the model by its state_dict and runs it on the fp32
+    kernels in every precision mode (the ratio estimator still follows `precision`)."""
+    g = load_golden("sampler_pair28_original")
+    seeds = [int(v) for v in g["seeds"]]
+    sdx, sdy, sdr = synth("flow28", seeds[0]), synth("flow28", seeds[1]), synth("ratio28", seeds[2])
+    plan = _lib.SamplerPlan("pair28", sdx, sdy, sdr, guidance_method=str(g["method"]), guidance_strength=float(g["gamma"]),
+                            num_samples=int(g["B"]), num_steps=int(g["steps"]), mc_batch_size=int(g["N_mc"]),
+                            loss_type=str(g["loss_type"]), precision=prec, device=DEV)
+    x1, y1 = plan.run(T(g["x0"]).to(DEV), T(g["y0"]).to(DEV), T(g["mc_x0"]).to(DEV), T(g["mc_y0"]).to(DEV))
+    plan.close()
+    assert maxabs(x1, T(g["x1"])) <= TOL_FINAL[prec] and maxabs(y1, T(g["y1"])) <= TOL_FINAL[prec], (maxabs(x1, T(g["x1"])), maxabs(y1, T(g["y1"])))

@@ -17,7 +17,7 @@ def close(a, b, tol=TOL):
     assert d <= tol, f"max-abs {d} > {tol}"
 
 
-@pytest.mark.parametrize("kind", ["unet_mnist28", "unet_mnist32", "unet_svhn"])
+@pytest.mark.parametrize("kind", ["unet_mnist28", "unet_mnist32", "unet_svhn", "flow28"])
 def test_unet_forward_golden(kind, synth):
     g = load_golden(f"{kind}_forward")
     sd = synth(kind, g["seed"])
@@ -73,11 +73,13 @@ def test_cfm_sample_golden(synth):
 
 
 @pytest.mark.parametrize("name", ["sampler_pair28_small", "sampler_pair28_rulsif", "sampler_pair28_none",
-                                  "sampler_mnist_svhn_small", "sampler_mnist_svhn_g2"])
+                                  "sampler_mnist_svhn_small", "sampler_mnist_svhn_g2", "sampler_pair28_original"])
 def test_sampler_golden(name, synth):
     g = load_golden(name)
     pair = str(g["pair"])
     kx, ky, kr, _, _ = O.PAIR_KINDS[pair]
+    if name.endswith("_original"):  # src/sample.py --model original: both flows are FlowMatchingModel
+        kx = ky = "flow28"
     sx, sy, sr = (int(s) for s in g["seeds"])
     sdx, sdy, sdr = synth(kx, sx), synth(ky, sy), synth(kr, sr)
     assert [sd_digest(sdx), sd_digest(sdy), sd_digest(sdr)] == [str(d) for d in g["digests"]]
