@@ -434,6 +434,13 @@ def test_cfm_schedule_sample_matches_reference(prec, synth):
     assert out.shape == (B, 1, 28, 28) and out.device.type == "cuda"
     assert maxabs(out, O.flow_sample(sd, "unet_mnist28", x0.cpu(), steps)) <= TOL_FINAL[prec]
     assert CFMSchedule().sample(StateDictModule("unet_mnist28", sd), 0, num_steps=steps, device=DEV).shape == (0, 1, 28, 28)
+    # the same schedule drives `--model original` (FlowMatchingModel), recognised by its state_dict
+    sdo = synth("flow28", 15)
+    torch.manual_seed(6)
+    out = CFMSchedule().sample(StateDictModule("flow28", sdo), B, num_steps=steps, device=DEV, precision=prec)
+    torch.manual_seed(6)
+    x0 = torch.randn(B, 1, 28, 28, device=DEV)
+    assert maxabs(out, O.flow_sample(sdo, "flow28", x0.cpu(), steps)) <= TOL_FINAL[prec]
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
