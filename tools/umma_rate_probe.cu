@@ -51,6 +51,30 @@ __global__ void __launch_bounds__(256, 1) probe(const __grid_constant__ CUtensor
   __shared__ volatile int s_go, s_stop;
   if (threadIdx.x == 0) { s_go = 0; s_stop = 0; }
   __syncthreads();
+  if ((mode == 5 || mode == 6) && warp >= 1) {
+    // heavy, INDEPENDENT shared-memory traffic from seven warps (mode 5: 16 ld.shared.v4 in flight per thread, mode 6:
+    // st.shared.v4): does the MMA stream slow down when the LSU side wants the whole shared-memory bandwidth?
+    const uint32_t scratch = sB + NMAX * K * 2 + (threadIdx.x - 32) * 16;
+    while (!s_go) {}
+    long long iters = 0;
+    uint32_t acc0 = 0, acc1 = 0;
+    while (!s_stop) {
+      if (mode == 5) {
+        uint32_t v[16][4];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i][0]), "=r"(v[i][1]), "=r"(v[i][2]), "=r"(v[i][3]) : "r"(scratch + (i & 11) * 3584));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { acc0 ^= v[i][0] ^ v[i][2]; acc1 ^= v[i][1] ^ v[i][3]; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(scratch + (i & 11) * 3584), "r"(acc0), "r"(acc1), "r"((uint32_t)i), "r"((uint32_t)iters) : "memory");
+      }
+      ++iters;
+    }
+    if (lane == 0) out[2 + warp] = iters + (acc0 == 0x12345u) + (acc1 == 7u);
+  }
   if ((mode == 3 || mode == 4) && warp >= 1) {
     // How much do warps that SHARE the issuing thread's scheduler (warp 4: same sub-partition as warp 0) progress while
     // the MMA queue is kept full?  mode 3: ld/st.shared loop, mode 4: dependent FMA chain.  Iterations per warp -> out[2 + warp]
@@ -197,6 +221,19 @@ int main() {
              mode, mode == 3 ? "ld/st.shared" : "fma chain", reps2 * 4, h[0]);
       for (int w = 1; w < 8; ++w) printf(" %.1f", 1000.0 * h[2 + w] / (double)h[0]);
       printf("\n");
+    }
+  for (int mode = 5; mode <= 6; ++mode)
+    for (int reps2 : {0, 2048}) {
+      CK(cudaMemset(dOut, 0, 128));
+      probe<<<1, 256, smem>>>(tmA, tmB, 0, 64, reps2, mode, dOut);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("kernel error %s\n", cudaGetErrorString(e)); return 1; }
+      long long h[16]; CK(cudaMemcpy(h, dOut, 128, cudaMemcpyDeviceToHost));
+      double tot = 0;
+      for (int w = 1; w < 8; ++w) tot += (double)h[2 + w];
+      printf("mode %d (7 warps of independent %s) %5d MMAs in %lld cycles = %.1f cycles/MMA; LSU side: %.1f bytes/clk\n", mode,
+             mode == 5 ? "ld.shared.v4" : "st.shared.v4", reps2 * 4, h[0], reps2 ? (double)h[0] / (reps2 * 4) : 0.0,
+             tot * 16 * 32 * 16 / (double)h[0]);
     }
   return 0;
 }
