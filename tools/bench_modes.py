@@ -36,3 +36,6 @@ run(*MS, "none", "disc", 1024, 256, 100, "fp16")
 run(*MS, "grad_log_ratio", "disc", 1024, 256, 10, "fp16", reps=1)
 run(*MS, "mc_feng", "disc", 1024, 256, 100, "bf16")
 run(*MS, "mc_feng", "disc", 256, 256, 20, "fp32", reps=1)
+# `--model original` (FlowMatchingModel, fp32 kernels) in the 28x28 sampler
+P28O = ("pair28", ("flow28", "flow28", "ratio28"), ((1, 28, 28), (1, 28, 28)))
+run(*P28O, "mc_feng", "disc", 256, 128, 100, "fp16", reps=1)
