@@ -80,6 +80,7 @@ struct TcArgs {
   int coef_C[3], coef_c0[3];
   int cin_real[3];      // real channels of the segment (transform touches only those)
   int xf_bf16;          // format the transform writes: 1 = bf16, 0 = fp16 (the net's operand format)
+  int exp_no_xform;     // timing experiments only (RGFM_EXPERIMENT_NO_XFORM): transform warps keep the protocol but do no work
   int l2_prefetch;      // prefetch the next super-tile's A boxes into L2 (RGFM_TC_L2_PREFETCH, default on)
   int descend;          // walk the super-tiles from the last to the first: every tensor is a little larger than L2, the
                         // packs stream in ascending order, so a conv that starts at the END of its operand finds the rows
@@ -586,7 +587,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int left = p.cin_real[seg] - cb * 64;
             const int ol = left == 32 ? 2 : 3;
             const int oct = tt & ((1 << ol) - 1), rl = tt >> ol, rstride = TC_XF_THREADS >> ol;
-            const bool work = oct * 8 < left;
+            const bool work = oct * 8 < left && !p.exp_no_xform;
             const float2* cf = p.coef[seg] + (size_t)nbase * p.coef_C[seg] + p.coef_c0[seg] + cb * 64 + oct * 8;
             const int cC = p.coef_C[seg];
             const uint32_t sa = smem_base + as * p.a_slot;
@@ -1109,6 +1110,8 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
   p.descend = descend;
   static const int l2pf = getenv("RGFM_TC_L2_PREFETCH") ? atoi(getenv("RGFM_TC_L2_PREFETCH")) : 1;
   p.l2_prefetch = l2pf;
+  static const int noxf = getenv("RGFM_EXPERIMENT_NO_XFORM") ? 1 : 0;
+  p.exp_no_xform = noxf;
   static const bool no_stats = getenv("RGFM_TC_NO_STATS") != nullptr;  // timing experiment only (results are wrong)
   if (no_stats) p.stats = nullptr;
   const int total_rows = a.nimg * (p.H + 1) * p.P;
