@@ -122,6 +122,7 @@ __device__ __forceinline__ void stats_channel_sums(const StatsRef& st, int n, in
     }
   } else if (st.mode == ST_UNITS) {
     const int u0 = (n * st.R) >> 7, u1 = ((n + 1) * st.R - 1) >> 7;
+    const float inv_R = 1.0f / (float)st.R;
     for (int ub = u0; ub <= u1; ub += BATCH) {
       float2 v[BATCH];
 #pragma unroll
@@ -129,7 +130,13 @@ __device__ __forceinline__ void stats_channel_sums(const StatsRef& st, int n, in
         const int u = ub + j;
         v[j] = make_float2(0.f, 0.f);
         if (u <= u1) {
-          const int slot = n - (u << 7) / st.R;
+          // image of the unit's first row: floor(128 u / R) by a float reciprocal + exact correction (an integer
+          // division by a run-time divisor was half of gn_coef's instructions; 128 u < 2^24 is exact in fp32)
+          const int x = u << 7;
+          int q = (int)((float)x * inv_R);
+          q += ((q + 1) * st.R <= x) ? 1 : 0;
+          q -= (q * st.R > x) ? 1 : 0;
+          const int slot = n - q;
           v[j] = __ldg(reinterpret_cast<const float2*>(st.p + (((size_t)u * st.slots + slot) * st.C + c) * 2));
         }
       }
