@@ -11,11 +11,14 @@
 // activation tensors are themselves valid operands (row offset -(P + 1)): 1x1 skip convs, identity residuals and
 // stride-2 convs read them directly.  Stride-2 convolutions are computed at stride 1 and stored subsampled.
 //
-// Persistent kernel, one CTA per SM, static round-robin over super-tiles, 352 threads: warps 0..7 = two epilogue groups
+// Persistent kernel, one CTA per SM, static round-robin over super-tiles, 608 threads: warps 0..7 = two epilogue groups
 // (one per 128-row unit; TMEM lane quarter = warp & 3), warp 8 = TMA producer (one thread) + TMEM allocator, warps
-// 9..10 = MMA issuers (one thread each).  Weights are RESIDENT in shared memory when they fit (loaded once per CTA),
-// otherwise they stream through a two-stage ring; A tiles use 2..4 slots; TMEM accumulators are double buffered when
-// 4 * N <= 512 columns so the epilogue of tile i overlaps the MMAs of tile i + 1.
+// 9..10 = MMA issuers (one thread each), warps 11..18 = transform group.  Weights are RESIDENT in shared memory when
+// they fit (loaded once per CTA), otherwise they stream through a two-stage ring; A tiles use 2..4 slots; TMEM
+// accumulators are double buffered when 4 * N <= 512 columns so the epilogue of tile i overlaps the MMAs of tile i + 1.
+// Fused GroupNorm + SiLU: a K segment may be a RAW activation with per-image {scale, shift} coefficients; the transform
+// group rewrites the TMA-loaded tile in place (silu(x * scale + shift), one MUFU.TANH per element, swizzled layout) and
+// releases it to the MMA threads, so the normalised operand never exists in HBM.
 // Epilogue: TMEM -> + bias (+ this step's time bias) -> saturating fp16 -> 128B-swizzled staging tile -> TMA store of
 // the raw activation (invalid rows as zeros), GroupNorm partials of the staged tile by ldmatrix.trans + mma.sync; the
 // output conv writes the NCHW velocity or applies the fused Euler update.
