@@ -590,13 +590,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int left = p.cin_real[seg] - cb * 64;
             const int ol = left == 32 ? 2 : 3;
             const int oct = tt & ((1 << ol) - 1), rl = tt >> ol, rstride = TC_XF_THREADS >> ol;
-            const bool work = oct * 8 < left && !p.exp_no_xform;
+            const bool work = oct * 8 < left && p.exp_no_xform != 1;
             const float2* cf = p.coef[seg] + (size_t)nbase * p.coef_C[seg] + p.coef_c0[seg] + cb * 64 + oct * 8;
             const int cC = p.coef_C[seg];
             const uint32_t sa = smem_base + as * p.a_slot;
             const bool to_bf16 = p.xf_bf16 != 0;
-            uint32_t cur = 0xffu;
+            uint32_t cur = 0xffu, nxt = 0xffu;
             float hs[8], hb[8];  // half scale / half shift: silu(z) = hz + hz * tanh(hz), hz = z / 2
+            float4 nv[4];        // raw {scale, shift} of the NEXT image of the tile, requested one image ahead: a tile of
+                                 // 16x16 / 8x8 images spans 2..5 of them and a load at every switch cost ~4 % of the step
             if (work) {  // coefficients of the tile's first image: in flight while the tile itself is still loading
               cur = 0u;
               const float4* c4 = reinterpret_cast<const float4*>(cf);
@@ -604,6 +606,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int q = 0; q < 4; ++q) {
                 const float4 v = __ldg(c4 + q);  // {scale, shift} of two channels
                 hs[2 * q] = 0.5f * v.x; hb[2 * q] = 0.5f * v.y; hs[2 * q + 1] = 0.5f * v.z; hb[2 * q + 1] = 0.5f * v.w;
+              }
+              if (nbase + 1 < a.nimg) {
+                nxt = 1u;
+                const float4* n4 = reinterpret_cast<const float4*>(cf + (size_t)cC);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) nv[q] = __ldg(n4 + q);
               }
             }
             // ONE polling thread + a group barrier: one polling lane per warp (and per-warp arrivals below) was measured
@@ -629,11 +637,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   if (nr[j] == 0xffu) continue;  // not a pixel: the raw row is zero already (conv padding)
                   if (nr[j] != cur) {
                     cur = nr[j];
-                    const float4* c4 = reinterpret_cast<const float4*>(cf + (size_t)cur * cC);
+                    if (cur != nxt) {  // not the prefetched image (a thread whose rows skip one): load it now
+                      const float4* c4 = reinterpret_cast<const float4*>(cf + (size_t)cur * cC);
+#pragma unroll
+                      for (int q = 0; q < 4; ++q) nv[q] = __ldg(c4 + q);
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                      const float4 v = __ldg(c4 + q);
-                      hs[2 * q] = 0.5f * v.x; hb[2 * q] = 0.5f * v.y; hs[2 * q + 1] = 0.5f * v.z; hb[2 * q + 1] = 0.5f * v.w;
+                      hs[2 * q] = 0.5f * nv[q].x; hb[2 * q] = 0.5f * nv[q].y; hs[2 * q + 1] = 0.5f * nv[q].z; hb[2 * q + 1] = 0.5f * nv[q].w;
+                    }
+                    nxt = 0xffu;
+                    if (nbase + (int)cur + 1 < a.nimg) {  // and request the one after it
+                      nxt = cur + 1u;
+                      const float4* n4 = reinterpret_cast<const float4*>(cf + (size_t)nxt * cC);
+#pragma unroll
+                      for (int q = 0; q < 4; ++q) nv[q] = __ldg(n4 + q);
                     }
                   }
 #pragma unroll
@@ -1113,7 +1131,7 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
   p.descend = descend;
   static const int l2pf = getenv("RGFM_TC_L2_PREFETCH") ? atoi(getenv("RGFM_TC_L2_PREFETCH")) : 1;
   p.l2_prefetch = l2pf;
-  static const int noxf = getenv("RGFM_EXPERIMENT_NO_XFORM") ? 1 : 0;
+  static const int noxf = getenv("RGFM_EXPERIMENT_NO_XFORM") ? atoi(getenv("RGFM_EXPERIMENT_NO_XFORM")) : 0;  // 1: no work, 2: no coefficient switches
   p.exp_no_xform = noxf;
   static const bool no_stats = getenv("RGFM_TC_NO_STATS") != nullptr;  // timing experiment only (results are wrong)
   if (no_stats) p.stats = nullptr;
