@@ -286,8 +286,10 @@ def flow_sample(sd: StateDict, kind: str, x0: Tensor, num_steps: int) -> Tensor:
 def sample_pair(sd_x: StateDict, sd_y: StateDict, sd_r: Optional[StateDict], pair: str,
                 guidance_method: str, guidance_strength: float, num_steps: int,
                 x0: Tensor, y0: Tensor, mc_x0: Optional[Tensor] = None, mc_y0: Optional[Tensor] = None,
-                loss_type: str = "disc", return_aux: bool = False):
+                loss_type: str = "disc", return_aux: bool = False, bank=None):
     """Coupled guided Euler sampler on explicit noise.
+    bank: optional precomputed (mc_x, mc_y, mc_ratios) -- the full-size parity tests check a row subset of a large
+    batch against the bank the CUDA path computed, instead of paying the 256-sample CPU pre-pass.
     reference: flow_utils.py:178-375 and sample_mnist_svhn.py:39-177 (same algorithm, different shapes).
     The reference draws x0, y0, mc_x0, mc_y0 from the global RNG in this order; here they are arguments so the
     CUDA path can be fed bit-identical noise."""
@@ -296,8 +298,9 @@ def sample_pair(sd_x: StateDict, sd_y: StateDict, sd_r: Optional[StateDict], pai
     eps = 1e-3
     x_t, y_t = x0, y0
     B = x0.shape[0]
-    bank = None
-    if guidance_method == "mc_feng" and sd_r is not None:
+    if not (guidance_method == "mc_feng" and sd_r is not None):
+        bank = None
+    elif bank is None:
         bank = mc_prepass(sd_x, sd_y, sd_r, pair, loss_type, mc_x0, mc_y0, num_steps)
     aux = {}
     for step in range(num_steps):

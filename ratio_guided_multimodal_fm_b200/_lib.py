@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librgfm.so")
+# RGFM_LIB_PATH: developer override for the trace / experiment build (csrc/Makefile target `trace`)
+LIB_PATH = os.environ.get("RGFM_LIB_PATH") or os.path.join(_HERE, "csrc", "librgfm.so")
 
 ABI_VERSION = 1
 DIAG_FLOATS = 16
@@ -86,6 +87,7 @@ def lib() -> C.CDLL:
     L.rgfm_sampler_destroy.restype = None
     L.rgfm_net_create.argtypes = [C.c_int32, C.POINTER(_Weights), C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.rgfm_unet_forward.argtypes = [vp, vp, C.c_float, C.c_int32, vp, vp]
+    L.rgfm_unet_sample.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
     L.rgfm_ratio_log_ratio.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
     L.rgfm_classifier_logits.argtypes = [vp, vp, C.c_int32, vp, vp]
     L.rgfm_ratio_grad_create.argtypes = [C.c_int32, C.POINTER(_Weights), C.c_int32, C.c_int32, C.POINTER(vp)]
@@ -128,6 +130,23 @@ class Weights:
         return C.byref(self.w)
 
 
+def content_fingerprint(state_dict) -> tuple:
+    """Cache key of a state_dict by CONTENT: (name, shape) of every floating tensor plus its L1 and L2 norms, computed
+    with two fused foreach kernels and ONE device-to-host copy.  Plans hold a repacked COPY of the weights, so a key made
+    of addresses / version counters is not enough: a re-used module (`load_state_dict` of the next checkpoint into
+    recycled storage, `param.data.copy_()` EMA swaps) keeps both while the values change."""
+    if state_dict is None:
+        return ()
+    items = [(k, v) for k, v in state_dict.items() if torch.is_tensor(v) and v.dtype.is_floating_point and v.numel() > 0]
+    if not items:
+        return ()
+    with torch.no_grad():
+        ts = [v.detach() for _, v in items]
+        sig = torch.stack([n.double() for n in torch._foreach_norm(ts, 1)] + [n.double() for n in torch._foreach_norm(ts, 2)])
+        sig = tuple(sig.cpu().tolist())
+    return tuple((k, tuple(v.shape)) for k, v in items) + sig
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -166,6 +185,7 @@ class Net:
         """(d log r/dx, d log r/dy, log r) -- README.md:159-164; oracle: autograd through the restated estimator."""
         if loss_type not in LOSS:
             raise ValueError(f"Unknown loss_type: {loss_type}")
+        self._check_pair(x, y, "grad_log_ratio")
         x, y = _f32c(x, self.device), _f32c(y, self.device)
         gx, gy = torch.empty_like(x), torch.empty_like(y)
         lr = torch.empty(x.shape[0], device=self.device, dtype=torch.float32)
@@ -173,7 +193,17 @@ class Net:
                                               _stream_ptr(self.device)))
         return gx, gy, lr
 
+    _SHAPES = {"unet_mnist28": (1, 28, 28), "unet_mnist32": (1, 32, 32), "unet_svhn": (3, 32, 32), "flow28": (1, 28, 28),
+               "clf_mnist28": (1, 28, 28), "clf_mnist32": (1, 32, 32), "clf_svhn": (3, 32, 32)}
+    _RATIO_SHAPES = {"ratio28": ((1, 28, 28), (1, 28, 28)), "ratio_mnist_svhn": ((1, 32, 32), (3, 32, 32))}
+
+    def _check_images(self, x: torch.Tensor, want, what: str):
+        """The kernels take raw pointers: a wrong shape would read out of bounds instead of raising."""
+        if x.dim() != 4 or tuple(x.shape[1:]) != tuple(want):
+            raise RgfmError(f"{what}: expected [B, {want[0]}, {want[1]}, {want[2]}] for {self.kind}, got {tuple(x.shape)}")
+
     def unet_forward(self, x: torch.Tensor, t: float) -> torch.Tensor:
+        self._check_images(x, self._SHAPES[self.kind], "unet_forward")
         x = _f32c(x, self.device)
         v = torch.empty_like(x)
         check(lib().rgfm_unet_forward(self.h, _ptr(x), float(t), x.shape[0], _ptr(v), _stream_ptr(self.device)))
@@ -181,6 +211,7 @@ class Net:
 
     def unet_sample(self, x0: torch.Tensor, num_steps: int = 100) -> torch.Tensor:
         """CFMSchedule.sample's loop (flow_utils.py:69-100) from the prior noise x0; returns a fresh tensor."""
+        self._check_images(x0, self._SHAPES[self.kind], "unet_sample")
         x = _f32c(x0, self.device).clone()
         check(lib().rgfm_unet_sample(self.h, _ptr(x), x.shape[0], int(num_steps), _stream_ptr(self.device)))
         return x
@@ -188,6 +219,7 @@ class Net:
     def log_ratio(self, x: torch.Tensor, y: torch.Tensor, loss_type: str = "disc", return_scores: bool = False):
         if loss_type not in LOSS:
             raise ValueError(f"Unknown loss_type: {loss_type}")  # ratio_estimator.py:190-191
+        self._check_pair(x, y, "log_ratio")
         x, y = _f32c(x, self.device), _f32c(y, self.device)
         out = torch.empty(x.shape[0], device=self.device, dtype=torch.float32)
         sc = torch.empty_like(out)
@@ -195,8 +227,16 @@ class Net:
                                          _stream_ptr(self.device)))
         return (out, sc) if return_scores else out
 
+    def _check_pair(self, x, y, what):
+        sx, sy = self._RATIO_SHAPES[self.kind]
+        self._check_images(x, sx, what)
+        self._check_images(y, sy, what)
+        if x.shape[0] != y.shape[0]:
+            raise RgfmError(f"{what}: x and y batch sizes differ ({x.shape[0]} vs {y.shape[0]})")
+
     def classifier_logits(self, x: torch.Tensor) -> torch.Tensor:
         """logits [B, 10] of an evaluator classifier (evaluate_mnist_svhn.py:45-47, evaluate.py:77-80); exact fp32."""
+        self._check_images(x, self._SHAPES[self.kind], "classifier_logits")
         x = _f32c(x, self.device)
         if x.shape[0] > self.max_batch:
             raise RgfmError(f"batch {x.shape[0]} exceeds the net's max_batch {self.max_batch}")
@@ -237,6 +277,7 @@ class SamplerPlan:
         wr = Weights(sd_ratio) if sd_ratio is not None else None
         self.h = C.c_void_p()
         check(lib().rgfm_sampler_create(C.byref(d), wx.ref(), wy.ref(), wr.ref() if wr else None, C.byref(self.h)))
+        self.guidance_strength = float(guidance_strength)
         self.shape_x, self.shape_y = {"pair28": ((1, 28, 28), (1, 28, 28)),
                                       "mnist_svhn": ((1, 32, 32), (3, 32, 32))}[pair]
 
@@ -247,6 +288,7 @@ class SamplerPlan:
     def set_strength(self, guidance_strength: float):
         """Change gamma in place (mc_feng / unguided plans): the graphs read it from a device table."""
         check(lib().rgfm_sampler_set_strength(self.h, float(guidance_strength), _stream_ptr(self.device)))
+        self.guidance_strength = float(guidance_strength)
 
     def run(self, x0, y0, mc_x0=None, mc_y0=None, want_diag: bool = False, reuse_bank: bool = False):
         """Device-resident run on the current stream; returns fresh tensors (inputs are not mutated).

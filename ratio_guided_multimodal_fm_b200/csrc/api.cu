@@ -18,7 +18,28 @@ int sampler_profile(Sampler*, rgfm_prof_entry*, int);
 
 static thread_local std::string g_err;
 
-#define RGFM_API_BEGIN try {
+// Every entry point works on the plan's / net's device (cudaSetDevice inside) and puts the caller's current device back
+// on the way out: PyTorch reads the current device from the runtime, so a library call that left it switched would send
+// the caller's later `device="cuda"` allocations and streams to the wrong GPU.
+struct DeviceRestore {
+  int prev = -1;
+  DeviceRestore() {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  }
+  ~DeviceRestore() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+// device that owns a device pointer (cudaSetDevice to it); pointers the runtime does not know are left alone
+static void set_device_of(const void* p) {
+  cudaPointerAttributes at{};
+  if (p && cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) RGFM_CUDA(cudaSetDevice(at.device));
+  else cudaGetLastError();
+}
+
+#define RGFM_API_BEGIN   \
+  DeviceRestore _restore; \
+  try {
 #define RGFM_API_END                          \
   }                                           \
   catch (const std::exception& e) {           \
@@ -101,6 +122,7 @@ int64_t rgfm_sampler_launch_count(const rgfm_sampler* s) {
 }
 
 void rgfm_sampler_destroy(rgfm_sampler* s) {
+  DeviceRestore _restore;
   if (s) rgfm::sampler_destroy(reinterpret_cast<rgfm::Sampler*>(s));
 }
 
@@ -199,6 +221,8 @@ int rgfm_classifier_logits(rgfm_net* net, const float* x, int32_t batch, float* 
 }
 
 void rgfm_net_destroy(rgfm_net* net) {
+  DeviceRestore _restore;
+  if (net) cudaSetDevice(net->device);
   if (net && net->step) cudaFree(net->step);
   delete net;
 }
@@ -210,6 +234,8 @@ int rgfm_mc_feng_step(int32_t batch, int32_t n_mc, int32_t dx, int32_t dy, const
   RGFM_API_BEGIN
   using namespace rgfm;
   RGFM_CHECK(batch >= 1 && n_mc >= 1, "rgfm_mc_feng_step: sizes");
+  RGFM_CHECK(x && y && v_x && v_y && mc_x && mc_y && mc_ratios && x_out && y_out, "rgfm_mc_feng_step: null argument");
+  set_device_of(x);  // the scratch below must live on the GPU that holds the state
   const double eps = 1e-3, sigma = 1.0 - t + eps;
   StepScalars h{};
   h.t = (float)t; h.sig2 = (float)(sigma * sigma); h.sigma = (float)sigma; h.inv_sigma = (float)(1.0 / sigma);

@@ -92,9 +92,9 @@ __host__ __device__ inline size_t raw_offset(int padded, int n, int h, int w, in
 
 // GroupNorm partial statistics of a raw activation, {sum, sumsq} per channel, in one of two layouts:
 //   ST_PARTS: [image][parts][C][2]              (SIMT conv: one partial per output tile of the image)
-//   ST_UNITS: [unit][slots][C][2]               (tcgen05 conv: one partial per 128-row unit of the padded-linear GEMM
-//             row space and per image slot inside the unit; image n owns rows [n*R, (n+1)*R), the first image of
-//             unit u is (u*128)/R and slot s is image (u*128)/R + s)
+//   ST_UNITS: [unit][slots][C][2]               (tcgen05 conv: one partial per unit of unit_rows rows of the padded-linear
+//             GEMM row space and per image slot inside the unit; image n owns rows [n*R, (n+1)*R), the first image of
+//             unit u is (u*unit_rows)/R and slot s is image (u*unit_rows)/R + s)
 // Partials are combined by the consumer in a fixed order, so results are deterministic.
 enum StatsMode { ST_NONE = 0, ST_PARTS = 1, ST_UNITS = 2 };
 struct StatsRef {
@@ -104,6 +104,8 @@ struct StatsRef {
   int parts = 0;  // ST_PARTS
   int R = 0;      // ST_UNITS: GEMM rows per image
   int slots = 0;  // ST_UNITS: image slots per unit
+  int unit_rows = 128;            // ST_UNITS: GEMM rows per unit (128, or 127 / 126 when the producing conv stacks taps)
+  unsigned int magic_unit = 0;    // ceil(2^32 / unit_rows): x / unit_rows = umulhi(x, magic) for x * (unit_rows - 1) < 2^32
 };
 
 __host__ __device__ inline int stats_slots_for(int R) { return 127 / R + 2; }
@@ -121,7 +123,7 @@ __device__ __forceinline__ void stats_channel_sums(const StatsRef& st, int n, in
       ss += q[(size_t)p * st.C * 2 + 1];
     }
   } else if (st.mode == ST_UNITS) {
-    const int u0 = (n * st.R) >> 7, u1 = ((n + 1) * st.R - 1) >> 7;
+    const int u0 = (int)__umulhi((unsigned)(n * st.R), st.magic_unit), u1 = (int)__umulhi((unsigned)((n + 1) * st.R - 1), st.magic_unit);
     const float inv_R = 1.0f / (float)st.R;
     for (int ub = u0; ub <= u1; ub += BATCH) {
       float2 v[BATCH];
@@ -132,7 +134,7 @@ __device__ __forceinline__ void stats_channel_sums(const StatsRef& st, int n, in
         if (u <= u1) {
           // image of the unit's first row: floor(128 u / R) by a float reciprocal + exact correction (an integer
           // division by a run-time divisor was half of gn_coef's instructions; 128 u < 2^24 is exact in fp32)
-          const int x = u << 7;
+          const int x = u * st.unit_rows;
           int q = (int)((float)x * inv_R);
           q += ((q + 1) * st.R <= x) ? 1 : 0;
           q -= (q * st.R > x) ? 1 : 0;
@@ -303,6 +305,7 @@ struct DiagArgs {
   float* diag;
 };
 void launch_diag(const DiagArgs& a, cudaStream_t s);
+void launch_sat_report(const unsigned int* a, const unsigned int* b, const unsigned int* c, float* out, cudaStream_t s);
 void launch_ratio_stats(const float* ratios, int n, float* diag3, cudaStream_t s);
 
 // Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains; it must execute

@@ -40,13 +40,12 @@ constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_XF_THREADS = 256;        // transform group: fused GroupNorm + SiLU on the A tiles in shared memory (12 warps: no faster)
 // two epilogue groups of 4 warps, producer warp, two MMA warps (one per accumulator half), transform group
 constexpr int TC_THREADS = 2 * 128 + 96 + TC_XF_THREADS;
-constexpr int TC_SUPER = 256;             // output rows per super-tile (two M=128 accumulators sharing every B tile)
 constexpr uint32_t TC_STAGE_BYTES = 128 * 128;
-// dynamic shared memory for A slots + epilogue staging + weights (static: ~14 KB; trace builds add their stamp table)
+// dynamic shared memory for A slots + epilogue staging + weights (static: ~17 KB; trace builds add their stamp table)
 #ifdef RGFM_TC_TRACE
-constexpr uint32_t TC_SMEM_BUDGET = 211u * 1024u;
+constexpr uint32_t TC_SMEM_BUDGET = 208u * 1024u;
 #else
-constexpr uint32_t TC_SMEM_BUDGET = 212u * 1024u;
+constexpr uint32_t TC_SMEM_BUDGET = 209u * 1024u;
 #endif
 
 struct TcArgs {
@@ -69,9 +68,25 @@ struct TcArgs {
   int a_slots;          // A-tile pipeline depth (2..4)
   int resident;         // all weights of the conv fit next to the A slots: loaded ONCE per CTA, no weight ring traffic
   uint32_t b_total;     // bytes of all weight tiles (resident mode)
-  int nmma;             // N of the MMA / TMEM columns per accumulator (Cout rounded up to 16)
-  int nbuf;             // TMEM double buffering (2) when 4 * nmma <= 512 columns, else 1
-  uint32_t idesc[3];    // per segment: packed operands use the net's 16-bit format, raw activations are always fp16
+  int nmma;             // output channels of the conv rounded up to 16
+  // Tap stacking: the three kx taps of a filter row read the SAME A rows shifted by 0 / 1 / 2, so
+  // they can share one MMA whose B tile stacks their weights on N ([kx * nmma + co][K], which is simply three consecutive
+  // tap tiles) and whose accumulator holds nstk column groups D_j; the epilogue forms out[m] = sum_j D_j[m + j] with
+  // lane shuffles.  An M=128 MMA costs max(N / 2, ~50) cycles and 4 KB + N * 32 B of shared-memory reads whatever N is,
+  // so stacking cuts both for N <= 64 (measured: N=96 57 cycles, N=192 97 cycles against 3 x 49.7).
+  //   nstk = 3 (nmma <= 32): one MMA per filter row, N = 3 * nmma
+  //   nstk = 2 (nmma <= 64): kx = 0, 1 stacked (N = 2 * nmma) + kx = 2 on its own (N = nmma, A shifted by 2 rows) -- a
+  //                          third column group would not leave room for double-buffered accumulators in TMEM
+  //   nstk = 1: the classic nine taps
+  // A unit yields unit_rows = 128 - (nstk - 1) output rows (the last rows of the M=128 tile lack their D_j[m + j]).
+  int nstk;
+  int unit_rows;        // output rows per accumulator half
+  int super_rows;       // 2 * unit_rows: output rows per super-tile
+  int ncols;            // TMEM columns per accumulator: nstk * nmma rounded up to 32
+  uint32_t idesc3[3][3];  // [segment][kx]: descriptor (N = taps in the group * nmma) of the MMA group that starts at tap kx
+                          // of a filter row, 0 = the tap is covered by the group before it
+  int nbuf;             // TMEM double buffering (2) when 4 * ncols <= 512 columns, else 1
+  uint32_t idesc[3];    // per segment, N = nmma (1x1 segments): packed operands use the net's 16-bit format, raw activations are always fp16
   uint32_t tmem_cols;
   int sub;              // stride-2: store rows with even (h, w) only, into the half-resolution raw tensor
   int tma_store;        // raw output leaves through swizzled smem staging + TMA store (fully coalesced)
@@ -89,6 +104,7 @@ struct TcArgs {
                         // packs stream in ascending order, so a conv that starts at the END of its operand finds the rows
                         // the pack wrote last still in L2 (and leaves its own first rows there for the next pack)
   int out_fmt;          // raw output storage: 1 = bf16, 2 = fp16
+  unsigned int* sat;    // counter of output rows that hit the fp16 saturation bound (null = not counted)
   float* stats;         // GroupNorm partials [unit][nslots][CoutP][2] of the rounded output (null = none)
   int nslots;
 };
@@ -228,8 +244,12 @@ __device__ __forceinline__ uint32_t cvt2(float a, float b, int fmt) {
 __device__ __forceinline__ int fast_div(int n, uint32_t magic) { return (int)__umulhi((uint32_t)n, magic); }
 
 // two fp32 -> packed fp16, saturated to +-65504 (2 instructions after the convert instead of 4 fp32 min/max)
-__device__ __forceinline__ uint32_t cvt2_f16_sat(float a, float b) {
+// `seen` keeps the running max |value| BEFORE the clamp (inf once anything saturated): the epilogue counts saturated tiles
+// (of rows that are stored: vm = all ones, or zero for rows that are written as zeros)
+__device__ __forceinline__ uint32_t cvt2_f16_sat(float a, float b, uint32_t vm, __half2& seen) {
   __half2 v = __floats2half2_rn(a, b);
+  *reinterpret_cast<uint32_t*>(&v) &= vm;
+  seen = __hmax2(seen, __habs2(v));
   const __half2 L = __half2half2(__ushort_as_half((unsigned short)0x7BFF));
   v = __hmin2(__hmax2(v, __hneg2(L)), L);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -291,6 +311,52 @@ __device__ __forceinline__ bool slot_pixel(int m, int H, int P, uint32_t magic_P
 }
 
 
+// Sixteen output channels [c, c + 16) of this thread's row from the accumulator's column groups (TcArgs::nstk):
+//   out[m] = D_0[m] + D_1[m + 1] + D_2[m + 2]
+// Row m + j lives j lanes further along the warp; for the last lanes it is a row of the NEXT warp's TMEM lane quarter,
+// which that warp published in xn (nmma floats each: its lane 0 of D_1, then its lanes 0 and 1 of D_2).  Lanes 0 / 1 do
+// not need their own D_1 / D_2 values (those belong to the previous warp's rows), so they load the published rows in
+// their place and a ROTATING shuffle delivers them to lanes 31 / 30, 31 -- no select, no extra registers.
+__device__ __forceinline__ void acc_load16(uint32_t taddr, int c, int nstk, int nmma, int lane, const float* xn, float* o) {
+  uint32_t v0[16];
+  tmem_ld16(taddr + c, v0);
+  if (nstk == 1) {
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v0[j]);
+    return;
+  }
+  uint32_t v1[16];
+  tmem_ld16(taddr + nmma + c, v1);
+  if (nstk == 2) {
+    tmem_ld_wait();
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(&v1[4 * k]) = *reinterpret_cast<const uint4*>(xn + c + 4 * k);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      o[j] = __uint_as_float(v0[j]) + __uint_as_float(__shfl_sync(0xffffffffu, v1[j], (lane + 1) & 31));
+    return;
+  }
+  uint32_t v2[16];
+  tmem_ld16(taddr + 2 * nmma + c, v2);
+  tmem_ld_wait();
+  if (lane < 2) {
+    const float* x2 = xn + nmma * (1 + lane) + c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(&v2[4 * k]) = *reinterpret_cast<const uint4*>(x2 + 4 * k);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(&v1[4 * k]) = *reinterpret_cast<const uint4*>(xn + c + 4 * k);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    o[j] = (__uint_as_float(v0[j]) + __uint_as_float(__shfl_sync(0xffffffffu, v1[j], (lane + 1) & 31))) +
+           __uint_as_float(__shfl_sync(0xffffffffu, v2[j], (lane + 2) & 31));
+}
+
 // -DRGFM_TC_TRACE: block 0 records clock64 stamps of the first 24 super-tiles per role and prints them (debug builds only)
 #ifdef RGFM_TC_TRACE
 #define TRC(role, idx) do { if (blockIdx.x == 0 && (idx) < 12) s_trace[role][idx] = clock64() - t_start; } while (0)
@@ -316,11 +382,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #define b_empty(i) (bar_base + 8u * (16u + TC_MAX_STAGES + (uint32_t)(i)))
   __shared__ uint32_t tmem_slot;
 #ifdef RGFM_TC_TRACE
-  __shared__ long long s_trace[6][12];
+  __shared__ long long s_trace[8][12];
   const long long t_start = clock64();
 #endif
   __shared__ uint8_t s_rown[400];  // transform group: image (relative to the tile's first) of each A-tile row, 0xff = not a pixel
   __shared__ __align__(16) float s_bias[256];
+  __shared__ __align__(16) float s_xchg[2][4][96];  // tap stacking: rows a warp needs from the next warp's lane quarter (acc_load16)
   __shared__ __align__(16) float s_part[2][4][3][64][2];
   // per epilogue group / warp / image slot: {sum, sumsq} of a 64-channel chunk
 
@@ -332,7 +399,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const ConvArgs& a = p.c;
   const int N = p.nmma;
   const int total_rows = a.nimg * (p.H + 1) * p.P;
-  const int supers = (total_rows + TC_SUPER - 1) / TC_SUPER;
+  const int SR = p.super_rows, UR = p.unit_rows;
+  const int supers = (total_rows + SR - 1) / SR;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0)) : "memory");
@@ -409,7 +477,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
       for (int sti = blockIdx.x; sti < supers; sti += gridDim.x) {
         const int st = p.descend ? supers - 1 - sti : sti;  // see TcArgs::descend
-        const int row0 = st * TC_SUPER;
+        const int row0 = st * SR;
 #pragma unroll 1
         for (int seg = 0; seg < p.nseg; ++seg) {
           const CUtensorMap* tA = seg == 0 ? &tmA0 : (seg == 1 ? &tmA1 : &tmA2);
@@ -429,7 +497,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               // The same tile of this CTA's NEXT super-tile, into L2 now: with two A slots the load -> (transform) -> MMA
               // chain of a slot is serial, and the ~1.9 us HBM latency of the load was the largest term in it.
               const int st2 = p.descend ? supers - 1 - (sti + (int)gridDim.x) : sti + (int)gridDim.x;
-              const int ra2 = st2 * TC_SUPER + p.row_off[seg];
+              const int ra2 = st2 * SR + p.row_off[seg];
               tma_prefetch_2d(tA, cb * 64, ra2);
               tma_prefetch_2d(tA, cb * 64, ra2 + p.box_rows[seg]);
             }
@@ -480,7 +548,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
         mbar_wait(tmem_empty_bar(buf), (use & 1u) ^ 1u);  // both epilogue groups drained this accumulator pair
         tc_fence_after();
-        const uint32_t td = tmem_d + (uint32_t)((buf * 2 + (int)hf) * N);
+        const uint32_t td = tmem_d + (uint32_t)((buf * 2 + (int)hf) * p.ncols);
         uint32_t acc = 0;  // the first MMA of the super-tile overwrites the accumulator
         uint32_t b_res = smem_b >> 4;  // resident mode: running position in the (segment, channel block, tap) order
 #pragma unroll 1
@@ -488,14 +556,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int ncb = p.cblocks[seg], ntp = p.ntaps[seg];
           const int tps = resident ? ntp : p.tps[seg];
           const uint32_t idesc = p.idesc[seg];
+          // descriptors of the MMA groups that start at tap kx = 0, 1, 2 of a filter row (0 = covered by the group before);
+          // a 1x1 segment is one group of one tap
+          const uint32_t id0 = ntp == 1 ? idesc : p.idesc3[seg][0], id1 = p.idesc3[seg][1], id2 = p.idesc3[seg][2];
 #pragma unroll 1
           for (int cb = 0; cb < ncb; ++cb) {
             mbar_wait(p.any_xform ? a_ready(as) : a_full(as), aph);
             tc_fence_after();
             if (hf == 0 && seg == 0 && cb == 0) TRC(1, it);
             const int ks = p.ksteps[seg][cb];
-            // descriptor low word of the current tap (a 1x1 segment's tile starts at the super-tile's own first row)
-            uint32_t a_lo = (smem_base + as * p.a_slot + hf * (128u * 128u)) >> 4;
+            // descriptor low word of the current filter row (a 1x1 segment's tile starts at the super-tile's own first row)
+            uint32_t a_lo = (smem_base + as * p.a_slot + hf * ((uint32_t)UR * 128u)) >> 4;
             uint32_t kx = 0;
 #pragma unroll 1
             for (int tap = 0; tap < ntp; tap += tps) {
@@ -507,10 +578,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
 #pragma unroll 1
               for (int j = 0; j < tps; ++j) {
+                // the MMA group that STARTS at this tap (N = taps in the group * nmma: their weight tiles are consecutive in
+                // shared memory); nothing to issue when the tap belongs to the previous group
+                const uint32_t idg = kx == 0u ? id0 : (kx == 1u ? id1 : id2);
+                if (idg != 0u) {
 #pragma unroll 1
-                for (int k = 0; k < ks; ++k) {
-                  tc_mma_bf16(td, dhi | (uint64_t)(a_lo + 2u * k), dhi | (uint64_t)(b_lo + 2u * k), idesc, acc);
-                  acc = 1u;
+                  for (int k = 0; k < ks; ++k) {
+                    tc_mma_bf16(td, dhi | (uint64_t)(a_lo + 2u * k), dhi | (uint64_t)(b_lo + 2u * k), idg, acc);
+                    acc = 1u;
+                  }
                 }
                 b_lo += b_tap16;
                 if (++kx == 3u) {  // next filter row
@@ -552,13 +628,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // were both slower; a single warp of this kernel runs at ~0.2 IPC, hence eight of them.
     if (p.any_xform) {
       const int tt = threadIdx.x - 11 * 32;
-      const int rows_used = TC_SUPER + 2 * p.P + 2;
+      const int rows_used = SR + 2 * p.P + 2;
       uint32_t as = 0, aph = 0;
       const uint32_t a_slots = (uint32_t)p.a_slots;
 #pragma unroll 1
       for (int sti = blockIdx.x; sti < supers; sti += gridDim.x) {
         const int st = p.descend ? supers - 1 - sti : sti;
-        const int rbase = st * TC_SUPER - (p.P + 1);  // raw row of tile row 0 (every raw segment has this row offset)
+        const int rbase = st * SR - (p.P + 1);  // raw row of tile row 0 (every raw segment has this row offset)
         const int nbase = fast_div(rbase < 0 ? 0 : rbase, p.magic_R);
         // row table of the super-tile, shared by all its (segment, channel block) tiles: one division chain per row here
         // instead of one per row and tile in the hot loop
@@ -697,21 +773,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int st = p.descend ? supers - 1 - sti : sti;
       const int buf = (p.nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
-      const int unit = st * 2 + eg;  // 128-row unit index
-      const int m = unit * 128 + r;
+      const int unit = st * 2 + eg;  // unit index: UR output rows each
+      const int m = unit * UR + r;
       int n, h, w;
-      bool valid = slot_pixel(m, p.H, p.P, p.magic_P, p.magic_H1, a.nimg, n, h, w);  // a real pixel of an image < nimg
+      // a real pixel of an image < nimg, and one of the UR rows this unit produces (TcArgs::unit_rows)
+      bool valid = slot_pixel(m, p.H, p.P, p.magic_P, p.magic_H1, a.nimg, n, h, w) && r < UR;
       // where this thread's row goes in a stride-2 (subsampled) output: even (h, w) rows map to (h/2, w/2) -- including
       // the pad row h == H and pad column w == W, which are written as zeros -- and the otherwise idle column
       // w == W + 1 writes the second pad column, so the half-resolution raw tensor is zero padded like every other one
       bool wr = false;
       size_t o = 0;
       if (!p.sub && !p.tma_store && a.out_mode == OUT_RAW) {  // 32-channel raw output: every row of the unit inside the tensor
-        wr = m < total_rows_alloc;
+        wr = m < total_rows_alloc && r < UR;
         o = (size_t)m * CP;
       }
       if (p.sub) {
-        const bool inimg = (n < a.nimg) && (h <= p.H);
+        const bool inimg = (n < a.nimg) && (h <= p.H) && r < UR;
         valid = valid && !(h & 1) && !(w & 1);
         if (inimg && !(h & 1) && (!(w & 1) || w == p.W + 1)) {
           wr = true;
@@ -725,15 +802,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       __syncwarp();
       tc_fence_after();
       if (threadIdx.x == 0) TRC(3, it);
-      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + eg) * N);
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + eg) * p.ncols);
+      const int nstk = p.nstk;
+      const float* xn = &s_xchg[eg][(q + 1) & 3][0];  // published by the next warp of the group (unused rows for q == 3)
+      if (nstk > 1) {
+        // publish what the previous warp needs of this lane quarter: D_1 of lane 0, D_2 of lanes 0 and 1 (every channel).
+        // (the previous tile's readers are behind a group barrier of its epilogue)
+        for (int c = 0; c < N; c += 16) {
+          uint32_t t1[16], t2[16];
+          tmem_ld16(taddr + N + c, t1);
+          if (nstk == 3) tmem_ld16(taddr + 2 * N + c, t2);
+          tmem_ld_wait();
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(&s_xchg[eg][q][c + 4 * k]) = make_uint4(t1[4 * k], t1[4 * k + 1], t1[4 * k + 2], t1[4 * k + 3]);
+          }
+          if (nstk == 3 && lane < 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(&s_xchg[eg][q][N * (1 + lane) + c + 4 * k]) = make_uint4(t2[4 * k], t2[4 * k + 1], t2[4 * k + 2], t2[4 * k + 3]);
+          }
+        }
+        if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
       if (a.out_mode == OUT_RAW) {
         // raw activation, 16-bit, channel stride CP; rows that are not real pixels are stored as exact zeros, so the
         // tensor doubles as a zero-padded conv operand and the per-channel sums below need no masking
         uint16_t* out16 = reinterpret_cast<uint16_t*>(a.out);
         // image boundaries inside this unit (for the GroupNorm partials): rows >= b1 belong to slot 1, >= b2 to slot 2
-        const int nf = fast_div(unit * 128, p.magic_R);
-        const int b1 = (nf + 1) * p.R - unit * 128;
+        const int nf = fast_div(unit * UR, p.magic_R);
+        const int b1 = (nf + 1) * p.R - unit * UR;
         const int b2 = b1 + p.R;
+        __half2 sat2 = __float2half2_rn(0.f);  // running max |value| before the clamp: saturation is counted, not silent
         for (int c0 = 0; c0 < CP; c0 += 64) {
           if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has left the buffer
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -743,15 +845,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (c0 + hh * 32 >= CP) break;  // 32-channel outputs: the upper half of the staging tile is never read
             uint32_t pk[16];
             if (c0 + hh * 32 < N) {
-              uint32_t v[32];
-              tmem_ld32(taddr + c0 + hh * 32, v);
-              tmem_ld_wait();
               const uint32_t vm = valid ? 0xffffffffu : 0u;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + hh * 32 + 4 * j]);
-                pk[2 * j] = cvt2_f16_sat(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y) & vm;
-                pk[2 * j + 1] = cvt2_f16_sat(__uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w) & vm;
+              for (int sc = 0; sc < 2; ++sc) {
+                float v[16];
+                acc_load16(taddr, c0 + hh * 32 + sc * 16, nstk, N, lane, xn, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + hh * 32 + sc * 16 + 4 * j]);
+                  pk[8 * sc + 2 * j] = cvt2_f16_sat(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, vm, sat2);
+                  pk[8 * sc + 2 * j + 1] = cvt2_f16_sat(v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w, vm, sat2);
+                }
               }
             } else {
 #pragma unroll
@@ -779,10 +883,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
           else asm volatile("bar.sync 2, 128;" ::: "memory");
           if (p.tma_store && et == 0) {
-            tma_store_2d(&tmO, stg, c0, unit * 128);
+            tma_store_2d(&tmO, stg, c0, unit * UR);  // the box has UR rows
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (threadIdx.x == 0 && c0 == 0 && !p.any_xform) TRC(4, it);
+          if (threadIdx.x == 0 && c0 == 0) TRC(6, it);
           if (p.stats != nullptr && c0 < N) {
             // GroupNorm partials of the ROUNDED values on the legacy tensor path, channels on M and image slots on N:
             //   S[ch][slot] = sum_row X[row][ch] * Ind[row][slot]   (Ind = 0/1: row belongs to image slot of the unit)
@@ -851,18 +955,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           }
         }
-        if (threadIdx.x == 0 && !p.any_xform) TRC(5, it);
+        if (threadIdx.x == 0) TRC(7, it);
+        if (p.sat != nullptr) {  // rows of this tile that hit the fp16 bound (reported in diag[12]; must stay 0)
+          const uint32_t sb = *reinterpret_cast<const uint32_t*>(&sat2);
+          const unsigned hit = __ballot_sync(0xffffffffu, (sb & 0x7fffu) >= 0x7c00u || (sb & 0x7fff0000u) >= 0x7c000000u);
+          if (hit != 0u && lane == 0) atomicAdd(p.sat, (unsigned int)__popc(hit));
+        }
       } else {
         // output conv: Cout <= 16 real channels -> NCHW velocity, or fused Euler update x += dt * v
-        uint32_t v[16];
-        tmem_ld16(taddr, v);
-        tmem_ld_wait();
+        float v[16];
+        acc_load16(taddr, 0, nstk, N, lane, xn, v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+        if (nstk > 1) {  // the next tile's exchange rows may only be written once every warp has read this tile's
+          if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
         if (valid) {
           for (int c = 0; c < a.Cout; ++c) {
-            const float val = __uint_as_float(v[c]) + s_bias[c];
+            const float val = v[c] + s_bias[c];
             const size_t oc = (((size_t)n * a.Cout + c) * p.out_H + h) * p.out_W + w;
             if (a.out_mode == OUT_NCHW)
               a.out[oc] = val;
@@ -877,11 +989,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #ifdef RGFM_TC_TRACE
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    printf("TRACE nmma=%d nseg=%d cblocks=%d taps=%d resident=%d a_slots=%d supers=%d xform=%d (then columns 5, 6 = transform a_full / done) end=%lld\n",
-           p.nmma, p.nseg, p.cblocks[0], p.ntaps[0], p.resident, p.a_slots, supers, p.any_xform, clock64() - t_start);
+    printf("TRACE nmma=%d nstk=%d nseg=%d cblocks=%d taps=%d resident=%d a_slots=%d supers=%d xform=%d end=%lld\n",
+           p.nmma, p.nstk, p.nseg, p.cblocks[0], p.ntaps[0], p.resident, p.a_slots, supers, p.any_xform, clock64() - t_start);
     for (int i = 0; i < 12 && blockIdx.x + i * gridDim.x < supers; ++i)
-      printf("  st%2d prodA %7lld | mma a_full %7lld committed %7lld | epi tmem_full %7lld stored %7lld unit_done %7lld\n", i, s_trace[0][i],
-             s_trace[1][i], s_trace[2][i], s_trace[3][i], s_trace[4][i], s_trace[5][i]);
+      printf("  st%2d prodA %7lld | xform wake %7lld done %7lld | mma a_ready %7lld committed %7lld | epi tmem_full %7lld stored %7lld done %7lld\n", i,
+             s_trace[0][i], s_trace[4][i], s_trace[5][i], s_trace[1][i], s_trace[2][i], s_trace[3][i], s_trace[6][i], s_trace[7][i]);
   }
 #endif
   tc_fence_before();
@@ -937,9 +1049,20 @@ static void encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const 
   RGFM_CHECK(r == CUDA_SUCCESS, std::string("cuTensorMapEncodeTiled(") + what + ") failed with code " + std::to_string((int)r));
 }
 
-size_t tc_stats_floats(int H, int W, int chunk, int CoutP) {
+// Column groups per accumulator (TcArgs::nstk) for a conv with `cout` output channels.  RGFM_TC_STACK=0 selects the
+// classic nine-tap issue everywhere (same results up to fp32 summation order; for A/B timing).
+int tc_stack_groups(int cout) {
+  static const int enable = getenv("RGFM_TC_STACK") ? atoi(getenv("RGFM_TC_STACK")) : 1;
+  const int nmma = (cout + 15) / 16 * 16;
+  if (!enable) return 1;
+  return nmma <= 32 ? 3 : (nmma <= 64 ? 2 : 1);
+}
+int tc_unit_rows(int cout) { return 128 - (tc_stack_groups(cout) - 1); }
+
+size_t tc_stats_floats(int H, int W, int chunk, int Cout, int CoutP) {
   const int R = (H + 1) * (W + 2);
-  const size_t supers = ((size_t)chunk * R + TC_SUPER - 1) / TC_SUPER;
+  const int SR = 2 * tc_unit_rows(Cout);
+  const size_t supers = ((size_t)chunk * R + SR - 1) / SR;
   return supers * 2 * (size_t)stats_slots_for(R) * CoutP * 2;
 }
 
@@ -958,7 +1081,7 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   p.R = (d.Hin + 1) * P;
   {
     auto magic = [&](int dv) {
-      const uint64_t nmax = (uint64_t)d.chunk * p.R + 2 * TC_SUPER;
+      const uint64_t nmax = (uint64_t)d.chunk * p.R + 2 * 256;
       RGFM_CHECK(nmax * (uint64_t)(dv > 1 ? dv - 1 : 1) < (1ull << 32), "tc conv: row space too large for the fast division");
       return (uint32_t)(((1ull << 32) + dv - 1) / dv);
     };
@@ -968,14 +1091,19 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   }
   p.nseg = d.nseg;
   p.nmma = nmma;
-  const int rows_needed = TC_SUPER + 2 * P + 2;
+  p.nstk = tc_stack_groups(d.Cout);
+  p.unit_rows = 128 - (p.nstk - 1);
+  p.super_rows = 2 * p.unit_rows;
+  p.ncols = (p.nstk * nmma + 31) / 32 * 32;
+  p.sat = d.sat;
+  const int rows_needed = p.super_rows + 2 * P + 2;
   p.a_box_rows = ((rows_needed + 1) / 2 + 7) / 8 * 8;
   RGFM_CHECK(p.a_box_rows <= 256, "tc conv: A box too tall");
   p.a_slot = 2u * p.a_box_rows * 128u;
   p.b_bytes = (uint32_t)nmma * 128u;
-  p.nbuf = (4 * nmma <= 512) ? 2 : 1;
+  p.nbuf = (4 * p.ncols <= 512) ? 2 : 1;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * p.nbuf * nmma)) cols <<= 1;
+  while (cols < (uint32_t)(2 * p.nbuf * p.ncols)) cols <<= 1;
   p.tmem_cols = cols;
   p.tma_store = (d.out != nullptr) ? 1 : 0;  // 32-channel raws: the same 64-wide store box, its upper half clipped by TMA
   p.out_fmt = 2;  // raw activations are stored in fp16 in both 16-bit modes (11-bit mantissa; the epilogue saturates)
@@ -1018,6 +1146,8 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
       if ((uint32_t)min_stages * 9u * p.b_bytes <= ring_budget) tps = 9;
       else if ((uint32_t)min_stages * 3u * p.b_bytes <= ring_budget) tps = 3;
     }
+    // a stacked MMA group reads the tap tiles of one filter row as ONE B operand: they must sit in the same ring stage
+    RGFM_CHECK(p.nstk == 1 || tps % 3 == 0, "tc conv: stacked taps need whole filter rows per weight-ring stage");
     for (int sg = 0; sg < d.nseg; ++sg)
       if (d.seg[sg].ks == 3) p.tps[sg] = tps;
     p.b_stage = (uint32_t)tps * p.b_bytes;
@@ -1046,7 +1176,11 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
       RGFM_CHECK(S.coef_c0 % 2 == 0 && S.coef_C % 2 == 0, "tc conv: GroupNorm coefficient offsets must be even");
     }
     const uint32_t fmt = seg_fp16 ? 0u : 1u;  // UMMA F16F32Format: 0 = F16, 1 = BF16
-    p.idesc[sg] = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto idesc_n = [&](int n) { return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); };
+    p.idesc[sg] = idesc_n(nmma);
+    // MMA groups of a filter row (TcArgs::nstk): which tap starts a group and how many taps it stacks on N
+    const int grp[3][3] = {{1, 1, 1}, {2, 0, 1}, {3, 0, 0}};
+    for (int kx = 0; kx < 3; ++kx) p.idesc3[sg][kx] = grp[p.nstk - 1][kx] ? idesc_n(grp[p.nstk - 1][kx] * nmma) : 0u;
     // a 32-channel tensor (64-byte rows) is read through the same 64-channel TMA box: the upper half is out of bounds and
     // zero-filled, so the shared-memory tile and the MMA loop are unchanged while the global traffic halves
     RGFM_CHECK((S.Cin % 64 == 0 || S.Cin == 32 || S.Cin == 16) && S.Cin <= 256, "tc conv: operand channels must be 16, 32 or a multiple of 64, at most 256");
@@ -1101,7 +1235,8 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     t->tmB[sg] = t->tmB[0];
   }
   if (p.tma_store)
-    encode_2d(&t->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out, (uint64_t)d.CoutP, tc_raw_rows(d.Hin, d.Win, d.chunk), 64, 128, "out");
+    encode_2d(&t->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out, (uint64_t)d.CoutP, tc_raw_rows(d.Hin, d.Win, d.chunk), 64,
+              (uint32_t)p.unit_rows, "out");
   else
     t->tmO = t->tmA[0];
   // per device (function attributes belong to the current context): cheap enough to set for every plan
@@ -1131,12 +1266,14 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
   p.descend = descend;
   static const int l2pf = getenv("RGFM_TC_L2_PREFETCH") ? atoi(getenv("RGFM_TC_L2_PREFETCH")) : 1;
   p.l2_prefetch = l2pf;
+#ifdef RGFM_EXPERIMENTS  // timing-only switches that knowingly corrupt results: compiled out of the shipped library
   static const int noxf = getenv("RGFM_EXPERIMENT_NO_XFORM") ? atoi(getenv("RGFM_EXPERIMENT_NO_XFORM")) : 0;  // 1: no work, 2: no coefficient switches
   p.exp_no_xform = noxf;
-  static const bool no_stats = getenv("RGFM_TC_NO_STATS") != nullptr;  // timing experiment only (results are wrong)
+  static const bool no_stats = getenv("RGFM_TC_NO_STATS") != nullptr;
   if (no_stats) p.stats = nullptr;
+#endif
   const int total_rows = a.nimg * (p.H + 1) * p.P;
-  const int supers = (total_rows + TC_SUPER - 1) / TC_SUPER;
+  const int supers = (total_rows + p.super_rows - 1) / p.super_rows;
   static int num_sms = 0;  // B200 only: every device of the box has the same count
   if (!num_sms) {
     int dev = 0;

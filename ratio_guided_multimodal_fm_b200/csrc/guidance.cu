@@ -384,6 +384,11 @@ void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof) {
 // Diagnostics of the 28x28 reference sampler (flow_utils.py:349-363), written to a device buffer at
 // step == int(0.3*num_steps) so the loop stays free of host synchronisation.
 __global__ void __launch_bounds__(1024) diag_kernel(DiagArgs a) {
+  // which apply kernel did this step's work (the other one returned at once): diag[13] dense steps, diag[14] sparse steps
+  if (threadIdx.x == 0) {
+    const int longest = *reinterpret_cast<const int*>(a.zbuf + (size_t)a.B * 4);  // sparse_max(), armed by mcf_weights
+    a.diag[longest > MCF_KMAX ? 13 : 14] += 1.0f;
+  }
   if ((a.step ? *a.step : 0) != a.diag_step) return;
   __shared__ float sh[32][4];
   __shared__ float sz[32][3];
@@ -436,6 +441,15 @@ __global__ void __launch_bounds__(1024) diag_kernel(DiagArgs a) {
     a.diag[7] = mxv;
     a.diag[8] = zz / (float)a.B;
   }
+}
+
+// diag[12] = output rows of the tensor-core convs whose fp16 store saturated during this run (0 for valid samples)
+__global__ void sat_report_kernel(const unsigned int* a, const unsigned int* b, const unsigned int* c, float* out) {
+  *out = (float)((a ? *a : 0u) + (b ? *b : 0u) + (c ? *c : 0u));
+}
+void launch_sat_report(const unsigned int* a, const unsigned int* b, const unsigned int* c, float* out, cudaStream_t s) {
+  sat_report_kernel<<<1, 1, 0, s>>>(a, b, c, out);
+  post_launch("sat_report");
 }
 
 void launch_diag(const DiagArgs& a, cudaStream_t s) {

@@ -110,8 +110,10 @@ struct Builder {
     a.padded = true; a.fmt = 2;  // raw activations are fp16 in both 16-bit modes
     a.p = (float*)pool.alloc(tc_raw_rows(H, Wd, chunk) * a.Cs * 2);
     if (stats) {
-      a.stats = (float*)pool.alloc(tc_stats_floats(Hc, Wc, chunk, a.Cs) * sizeof(float));
+      a.stats = (float*)pool.alloc(tc_stats_floats(Hc, Wc, chunk, C, a.Cs) * sizeof(float));
       a.st.p = a.stats; a.st.mode = ST_UNITS; a.st.C = a.Cs; a.st.R = (Hc + 1) * (Wc + 2); a.st.slots = stats_slots_for(a.st.R);
+      a.st.unit_rows = tc_unit_rows(C);  // the producing conv's unit (conv_tc.cu: tap stacking shortens it)
+      a.st.magic_unit = (unsigned int)(((1ull << 32) + a.st.unit_rows - 1) / a.st.unit_rows);
     }
     return a;
   }
@@ -300,6 +302,7 @@ struct Builder {
     }
     d.out = (final || stride != 1) ? nullptr : (void*)o.p;
     d.stats = final ? nullptr : o.stats;
+    d.sat = net.d_sat_;
     net.tc_.push_back(make_tc_conv(d, pool));
     TcConv* tcp = net.tc_.back().get();
     const bool has_temb = temb_off >= 0;
@@ -914,6 +917,7 @@ Net::Net(int kind, const rgfm_weights* w, int chunk, int precision, int device, 
   RGFM_CUDA(cudaSetDevice(device));
   if (precision != RGFM_PREC_FP32) RGFM_CHECK(tc_available(), "16-bit tensor-core precision needs an sm_100 device");
   WeightMap W(w);
+  d_sat_ = (unsigned int*)pool_.persistent(sizeof(unsigned int));
   Builder b(*this, W);
   switch (kind) {
     case RGFM_NET_UNET_MNIST28: b.build_unet(1, 28, 32, {1, 2}, 2); break;

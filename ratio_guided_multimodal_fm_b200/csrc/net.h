@@ -71,6 +71,8 @@ class Net {
   int img() const { return img_; }
   int chunk() const { return chunk_; }
   size_t dim() const { return (size_t)in_ch_ * img_ * img_; }
+  // device counter: output rows of the tensor-core convs whose fp16 store hit +-65504 since the caller last cleared it
+  unsigned int* sat_counter() const { return d_sat_; }
 
   // U-Net: precompute the per-step time-bias rows for times ts (fp32 values of step*dt).
   // reference: timestep_embedding + time_embed + every ResBlock.time_mlp (unet.py:228-229,88)
@@ -86,6 +88,7 @@ class Net {
   int kind_, chunk_, precision_, device_;
   bool want_grad_ = false;
   float* d_lr_scratch_ = nullptr;
+  unsigned int* d_sat_ = nullptr;
   float *g_gx_ = nullptr, *g_gy_ = nullptr;  // set for the duration of grad_log_ratio()
   int g_loss_ = 0;
   bool g_lr_null_ = false;
@@ -134,6 +137,7 @@ struct TcConvDesc {
   TcSegment seg[3];
   void* out;             // raw padded-linear 16-bit output buffer (TMA store) or nullptr
   float* stats;          // GroupNorm partials of the output [unit][slots][CoutP][2] or nullptr
+  unsigned int* sat;     // device counter of output rows that hit the fp16 saturation bound (nullptr = not counted)
   bool fp16;             // operand format: fp16 (true) or bf16 (false); fp32 accumulate either way
 };
 TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool);
@@ -141,6 +145,7 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s);
 bool tc_available();
 size_t tc_operand_slots(int H, int W, int chunk);  // rows of a padded-linear operand tensor
 size_t tc_raw_rows(int H, int W, int chunk);       // rows of a padded-linear raw activation tensor
-size_t tc_stats_floats(int H, int W, int chunk, int CoutP);  // floats of a conv's GroupNorm partials buffer
+size_t tc_stats_floats(int H, int W, int chunk, int Cout, int CoutP);  // floats of a conv's GroupNorm partials buffer
+int tc_unit_rows(int cout);  // output rows per GroupNorm-partials unit of a conv with `cout` output channels (128, 127 or 126)
 
 }  // namespace rgfm

@@ -691,8 +691,10 @@ __global__ void __launch_bounds__(256) gn_coef256_kernel(PackArgs a, float2* __r
 }
 void launch_gn_coef(const PackArgs& a, float* coef, cudaStream_t s) {
   RGFM_CHECK(a.C <= PACK_MAXC && a.norm == NORM_GN && a.C % a.groups == 0, "gn_coef: GroupNorm over at most 512 channels");
-  static const bool skip = getenv("RGFM_EXPERIMENT_SKIP_GN_COEF") != nullptr;  // timing experiments only: results are garbage
+#ifdef RGFM_EXPERIMENTS  // timing-only switch that knowingly corrupts results: compiled out of the shipped library
+  static const bool skip = getenv("RGFM_EXPERIMENT_SKIP_GN_COEF") != nullptr;
   if (skip) return;
+#endif
   if (a.C <= 256) {
     const int ipb = 256 / a.C;
     launch_pdl(gn_coef256_kernel, dim3((a.nimg + ipb - 1) / ipb), dim3(256), 0, s, a, reinterpret_cast<float2*>(coef),

@@ -304,6 +304,9 @@ struct Sampler {
     RGFM_CUDA(cudaMemcpyAsync(y, y0, (size_t)B * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
     // diag[9..] are the bank's ratio statistics (written by the ratio pass): kept when the bank is reused
     RGFM_CUDA(cudaMemsetAsync(diag, 0, (reuse_bank ? 9 : RGFM_DIAG_FLOATS) * sizeof(float), s));
+    if (reuse_bank) RGFM_CUDA(cudaMemsetAsync(diag + 12, 0, 4 * sizeof(float), s));  // per-run counters
+    for (Net* n : {fx.get(), fy.get(), fr.get()})
+      if (n) RGFM_CUDA(cudaMemsetAsync(n->sat_counter(), 0, sizeof(unsigned int), s));
     if (guided && !reuse_bank) {
       RGFM_CHECK(mx0 && my0, "rgfm_sampler_run: mc_feng needs mc_x0 and mc_y0");
       RGFM_CUDA(cudaMemcpyAsync(mcx, mx0, (size_t)N * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -318,6 +321,7 @@ struct Sampler {
       RGFM_CUDA(cudaGraphLaunch(grad_guided ? g_grad.e : ((guided && i >= first_guided) ? g_guided.e : g_plain.e), s));
     RGFM_CUDA(cudaMemcpyAsync(x1, x, (size_t)B * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
     RGFM_CUDA(cudaMemcpyAsync(y1, y, (size_t)B * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    launch_sat_report(fx->sat_counter(), fy->sat_counter(), fr ? fr->sat_counter() : nullptr, diag + 12, s);
     if (diag_out) RGFM_CUDA(cudaMemcpyAsync(diag_out, diag, RGFM_DIAG_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
 };

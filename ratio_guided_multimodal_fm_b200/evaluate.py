@@ -32,8 +32,7 @@ def _kind_of(classifier, shape) -> str:
 
 def _net(classifier, shape, device) -> "_lib.Net":
     sd = classifier.state_dict()
-    key = (_kind_of(classifier, shape), str(device),
-           tuple((k, v.data_ptr(), getattr(v, "_version", 0)) for k, v in sd.items() if torch.is_tensor(v)))
+    key = (_kind_of(classifier, shape), str(device), _lib.content_fingerprint(sd))  # by content: see _lib.content_fingerprint
     net = _CLF_CACHE.get(key)
     if net is None:
         if len(_CLF_CACHE) >= 4:

@@ -24,14 +24,15 @@ def default_precision() -> str:
 
 
 def _fingerprint(module) -> tuple:
-    if module is None:
-        return ()
-    sd = module.state_dict()
-    return tuple((k, v.data_ptr(), getattr(v, "_version", 0)) for k, v in sd.items() if torch.is_tensor(v))
+    return () if module is None else _lib.content_fingerprint(module.state_dict())
 
 
 def _get_plan(pair, fm_x, fm_y, ratio, method, gamma, B, steps, N, loss_type, precision, device, chunk):
-    key = (pair, _fingerprint(fm_x), _fingerprint(fm_y), _fingerprint(ratio), method, float(gamma), B, steps, N,
+    """Plans are cached by weight CONTENT (see _lib.content_fingerprint) and shape.  gamma is not part of the key for
+    mc_feng / unguided plans: the kernels read it from a device table, so a hit only rewrites that table
+    (rgfm_sampler_set_strength); grad_log_ratio plans bake gamma into their update kernel and keep it in the key."""
+    baked = float(gamma) if method == "grad_log_ratio" else None
+    key = (pair, _fingerprint(fm_x), _fingerprint(fm_y), _fingerprint(ratio), method, baked, B, steps, N,
            loss_type, precision, str(device), chunk)
     plan = _PLAN_CACHE.get(key)
     if plan is None:
@@ -42,7 +43,23 @@ def _get_plan(pair, fm_x, fm_y, ratio, method, gamma, B, steps, N, loss_type, pr
                                 guidance_method=method, guidance_strength=gamma, num_samples=B, num_steps=steps,
                                 mc_batch_size=N, loss_type=loss_type, precision=precision, device=device, chunk=chunk)
         _PLAN_CACHE[key] = plan
+    elif baked is None and plan.guidance_strength != float(gamma):
+        plan.set_strength(gamma)
     return plan
+
+
+def _check_saturation(diag, precision):
+    """diag[12] counts output rows of the tensor-core convs whose fp16 store hit +-65504 (include/rgfm.h).  Activations
+    are GroupNorm-bounded, so this stays 0; with weights that do drive a layer past the fp16 range the clamp would
+    corrupt samples silently -- raise instead (RGFM_ALLOW_SATURATION=1 downgrades to a warning)."""
+    if diag[12] > 0:
+        msg = (f"{int(diag[12])} activation rows saturated at the fp16 bound in precision={precision!r}; "
+               "samples are not trustworthy -- use precision='fp32'")
+        if os.environ.get("RGFM_ALLOW_SATURATION") == "1":
+            import warnings
+            warnings.warn(msg)
+        else:
+            raise _lib.RgfmError(msg)
 
 
 def clear_plan_cache():
@@ -122,8 +139,9 @@ def _sample(pair, shape_x, shape_y, fm_x, fm_y, ratio_estimator, guidance_method
         y1 = torch.empty((0,) + shape_y, device=device)
         diag = torch.zeros(_lib.DIAG_FLOATS, device=device)
 
+    d = diag.tolist()  # one D2H after the whole loop (the reference syncs mid-loop)
+    _check_saturation(d, precision)
     if verbose and guided:
-        d = diag.tolist()  # one D2H after the whole loop (the reference syncs mid-loop)
         print(f"  Generated MC samples: x shape={torch.Size((mc_batch_size,) + shape_x)}, "
               f"y shape={torch.Size((mc_batch_size,) + shape_y)}")
         print(f"  MC ratios: min={d[9]:.4f}, max={d[10]:.4f}, mean={d[11]:.4f}")

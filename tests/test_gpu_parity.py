@@ -14,12 +14,18 @@ pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
 PRECS = ["fp32", "fp16", "bf16"]
-# fp32 mode: north_star's 1e-3 (measured ~2e-6).  fp16 mode (11-bit operand mantissa, the default 16-bit mode): held to
-# north_star's bf16-tier bound 1e-2 (measured 1.0e-3 .. 2.3e-3).  bf16 mode (8-bit mantissa): 2e-2 -- the reference
-# algorithm itself under torch.autocast(bfloat16) is 0.9e-2 .. 1.7e-2 away from its fp32 run on these fixtures
-# (profiles/autocast_reference_error_r01.txt, tools/autocast_reference_error.py), so 1e-2 is not attainable with bf16
-# operands; our bf16 mode measures 0.8e-2 .. 1.6e-2 (profiles/parity_r01.md).
-TOL_FINAL = {"fp32": 1e-3, "fp16": 1e-2, "bf16": 2e-2}
+# CONTRACT (BASELINE.json north_star): final x1, y1 within max-abs 1e-3 in the fp32 mode and 1e-2 in the 16-bit mode.
+#   fp32 mode: exact fp32 on CUDA cores, measured ~2e-6.
+#   fp16 mode: THE 16-bit contract mode (11-bit operand mantissa = TF32-class, same tensor rate as bf16), measured
+#              1.0e-3 .. 2.3e-3 against the 1e-2 bound.
+#   bf16 mode: NOT a contract mode.  8-bit mantissas cannot meet 1e-2 on this network: the reference algorithm itself under
+#              torch.autocast(bfloat16) is 0.9e-2 .. 1.7e-2 away from its own fp32 run on these fixtures
+#              (profiles/autocast_reference_error_r01.txt).  The contract bound is kept at 1e-2 and checked by
+#              test_bf16_contract_bound (xfail, not strict); TOL_GUARD is a regression guard at the measured level
+#              (0.8e-2 .. 1.6e-2, profiles/parity_r01.md), not a parity claim.
+TOL_CONTRACT = {"fp32": 1e-3, "fp16": 1e-2, "bf16": 1e-2}
+TOL_GUARD = {"fp32": 1e-3, "fp16": 1e-2, "bf16": 2e-2}
+TOL_FINAL = TOL_GUARD
 # single forward passes: velocities are O(1) per element
 TOL_FWD = {"fp32": 2e-4, "fp16": 1e-2, "bf16": 6e-2}
 
@@ -187,6 +193,15 @@ def test_sampler_mnist_svhn_100_steps(prec, synth):
     assert r["ex"] <= TOL_FINAL[prec] and r["ey"] <= TOL_FINAL[prec]
 
 
+@pytest.mark.xfail(strict=False, reason="bf16 operands (8-bit mantissa) cannot meet north_star's 1e-2: the reference itself under "
+                   "torch.autocast(bfloat16) is 0.9e-2..1.7e-2 from its fp32 run; fp16 is the 16-bit contract mode")
+@pytest.mark.parametrize("name", ["sampler_pair28_small", "sampler_mnist_svhn_small", "sampler_pair28_cfg0", "sampler_mnist_svhn_100"])
+def test_bf16_contract_bound(name, synth):
+    r = _run_golden_sampler(name, "bf16", synth)
+    print(f"{name}[bf16] vs the 1e-2 contract bound: max|dx|={r['ex']:.3e} max|dy|={r['ey']:.3e}")
+    assert r["ex"] <= TOL_CONTRACT["bf16"] and r["ey"] <= TOL_CONTRACT["bf16"], (r["ex"], r["ey"])
+
+
 def test_host_buffer_call_matches_device_call(synth):
     a = _run_golden_sampler("sampler_mnist_svhn_small", "fp32", synth)
     b = _run_golden_sampler("sampler_mnist_svhn_small", "fp32", synth, host=True)
@@ -255,6 +270,109 @@ def test_full_size_properties(synth):
     ps = mk("mc_feng", 0.5, 96, sdr)
     d = ps.run(x0[300:396], y0[300:396], m0, n0)
     assert maxabs(d[0], c[0][300:396]) <= 1e-3 and maxabs(d[1], c[1][300:396]) <= 1e-3  # D-split differs with B
+
+
+# ---- parity at the BENCHMARKED size and precision ---------------------------------------------
+def _bench_rows(B):
+    """Rows of a B=1024 batch that land on the persistent kernel's seams: first / last images, the images that straddle
+    the CTA-round boundaries of the 32x32 layers (148 CTAs x 256 rows = 33.8 images per round, walked from the end) and
+    scattered ones.  Samples are independent, so the CPU oracle only runs these."""
+    rows = {0, 1, 2, B - 3, B - 2, B - 1}
+    for k in range(1, 5):
+        for base in (k * 148 * 256 // 1122, B - 1 - k * 148 * 256 // 1122):
+            rows.update({base, base + 1})
+    g = torch.Generator().manual_seed(4)
+    while len(rows) < 32:
+        rows.add(int(torch.randint(0, B, (1,), generator=g)))
+    return sorted(r for r in rows if 0 <= r < B)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("kind", ["unet_mnist32", "unet_svhn"])
+def test_unet_forward_bench_size(kind, prec, synth):
+    """rgfm_unet_forward at B=1024 / chunk 1024 (every CTA of the persistent tcgen05 kernel walks ~30 super-tiles of the
+    32x32 layers, ~8 of the 16x16 ones): 32 scattered rows against the oracle on exactly those rows."""
+    B = 1024
+    sd = synth(kind, 12 if kind == "unet_mnist32" else 13)
+    c = 3 if kind == "unet_svhn" else 1
+    x = torch.randn(B, c, 32, 32, generator=torch.Generator().manual_seed(8))
+    net = _lib.Net(kind, sd, max_batch=B, precision=prec, device=DEV)
+    rows = _bench_rows(B)
+    for t in (0.0, 0.63):
+        v = net.unet_forward(x.to(DEV), t).cpu()
+        ref = O.unet_forward(sd, kind, x[rows], torch.full((len(rows),), t))
+        scale = max(1.0, ref.abs().max().item())
+        err = maxabs(v[rows], ref)
+        print(f"{kind}[{prec}] B=1024 t={t}: max-abs {err:.3e} (scale {scale:.2f})")
+        assert torch.isfinite(v).all()
+        assert err <= TOL_FWD[prec] * scale, (kind, prec, t, err)
+    net.close()
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_sampler_bench_size_rows_vs_oracle(prec, synth):
+    """BASELINE configs[1] exactly as bench.py runs it (B=1024, N_mc=256, chunk 1024, mc_feng gamma=0.5) for 5 steps:
+    (a) 32 scattered rows against the oracle's main loop fed the bank the CUDA path computed, (b) every row against the
+    exact-fp32 mode on the GPU, (c) the dense and the sparse mc_feng apply kernels both ran, (d) no fp16 saturation."""
+    sdx, sdy, sdr = synth("unet_mnist32", 12), synth("unet_svhn", 13), synth("ratio_mnist_svhn", 22)
+    B, N, steps, gamma = 1024, 256, 5, 0.5
+    gen = torch.Generator().manual_seed(21)
+    x0, y0 = torch.randn(B, 1, 32, 32, generator=gen), torch.randn(B, 3, 32, 32, generator=gen)
+    m0, n0 = torch.randn(N, 1, 32, 32, generator=gen), torch.randn(N, 3, 32, 32, generator=gen)
+    out = {}
+    for p in (prec, "fp32"):
+        plan = _lib.SamplerPlan("mnist_svhn", sdx, sdy, sdr, guidance_method="mc_feng", guidance_strength=gamma,
+                                num_samples=B, num_steps=steps, mc_batch_size=N, precision=p, device=DEV)
+        x1, y1, diag = plan.run(x0.to(DEV), y0.to(DEV), m0.to(DEV), n0.to(DEV), want_diag=True)
+        torch.cuda.synchronize()
+        out[p] = (x1.cpu(), y1.cpu(), [t.cpu() for t in plan.bank()], diag.cpu().tolist())
+        plan.close()
+    x1, y1, bank, diag = out[prec]
+    assert torch.isfinite(x1).all() and torch.isfinite(y1).all()
+    rows = _bench_rows(B)
+    ox, oy = O.sample_pair(sdx, sdy, sdr, "mnist_svhn", "mc_feng", gamma, steps, x0[rows], y0[rows], bank=tuple(bank))
+    ex, ey = maxabs(x1[rows], ox), maxabs(y1[rows], oy)
+    orow = torch.maximum((x1[rows] - ox).abs().flatten(1).max(1)[0], (y1[rows] - oy).abs().flatten(1).max(1)[0])
+    # every row against the exact-fp32 CUDA mode.  Its bank differs by the 16-bit error and the importance weights are
+    # nearly one-hot (SURVEY.md section 7.2), so a few samples pick another bank entry and move by O(1): bound the
+    # typical row tightly and the number of such arg-max flips loosely.
+    rowerr = torch.maximum((x1 - out["fp32"][0]).abs().flatten(1).max(1)[0], (y1 - out["fp32"][1]).abs().flatten(1).max(1)[0])
+    flips = int((rowerr > 2 * TOL_FINAL[prec]).sum())
+    print(f"bench-size[{prec}]: rows vs oracle {ex:.3e}/{ey:.3e}; all rows vs fp32 mode: median {rowerr.median():.3e}, "
+          f"{flips} of {B} rows beyond {2 * TOL_FINAL[prec]:.0e}; diag[12:15]={diag[12:15]}")
+    if prec == "fp16":  # the contract mode: every checked row, same bank, within the bound
+        assert ex <= TOL_FINAL[prec] and ey <= TOL_FINAL[prec], (ex, ey)
+    else:               # bf16: its own error flips the near-one-hot arg-max of some samples even with the same bank
+        assert orow.median().item() <= TOL_FINAL[prec] and int((orow > TOL_FINAL[prec]).sum()) <= len(rows) // 4, orow
+    assert rowerr.median().item() <= 1.5 * TOL_FINAL[prec] and flips <= B // 20, (rowerr.median().item(), flips)
+    # the fp32 mode's own rows against the oracle with ITS bank: north_star's fp32 tier at the full size
+    b32 = out["fp32"][2]
+    o32x, o32y = O.sample_pair(sdx, sdy, sdr, "mnist_svhn", "mc_feng", gamma, steps, x0[rows[:8]], y0[rows[:8]], bank=tuple(b32))
+    assert maxabs(out["fp32"][0][rows[:8]], o32x) <= 1e-3 and maxabs(out["fp32"][1][rows[:8]], o32y) <= 1e-3
+    assert diag[12] == 0, f"{diag[12]} output rows saturated at +-65504"
+    # guided steps = dense + sparse apply launches that did the work; this configuration exercises both kernels
+    assert diag[13] + diag[14] == steps - 1 and diag[13] >= 1 and diag[14] >= 1, diag[12:15]
+
+
+def test_unguided_bench_size_all_rows_fp16_vs_fp32(synth):
+    """No softmax in the loop: every one of the 1024 rows of the fp16 tensor-core path stays within the 16-bit tolerance of
+    the exact-fp32 mode (which is within 1e-3 of the oracle) -- the whole persistent grid, every tile, every row."""
+    sdx, sdy = synth("unet_mnist32", 12), synth("unet_svhn", 13)
+    B, steps = 1024, 6
+    gen = torch.Generator().manual_seed(22)
+    x0, y0 = torch.randn(B, 1, 32, 32, generator=gen), torch.randn(B, 3, 32, 32, generator=gen)
+    res = {}
+    for p in ("fp16", "fp32"):
+        plan = _lib.SamplerPlan("mnist_svhn", sdx, sdy, None, guidance_method="none", guidance_strength=0.0, num_samples=B,
+                                num_steps=steps, mc_batch_size=4, precision=p, device=DEV)
+        res[p] = [t.cpu() for t in plan.run(x0.to(DEV), y0.to(DEV))]
+        plan.close()
+    ex, ey = maxabs(res["fp16"][0], res["fp32"][0]), maxabs(res["fp16"][1], res["fp32"][1])
+    print(f"unguided B=1024 fp16 vs fp32 mode, all rows: {ex:.3e}/{ey:.3e}")
+    assert ex <= TOL_FINAL["fp16"] and ey <= TOL_FINAL["fp16"], (ex, ey)
+    rows = _bench_rows(B)[:8]
+    ox, oy = O.sample_pair(sdx, sdy, None, "mnist_svhn", "none", 0.0, steps, x0[rows], y0[rows])
+    assert maxabs(res["fp32"][0][rows], ox) <= 1e-3 and maxabs(res["fp32"][1][rows], oy) <= 1e-3
 
 
 # ---- coherence evaluators (SURVEY.md section 8f item 1; BASELINE configs[2]) -------------------------------------------
