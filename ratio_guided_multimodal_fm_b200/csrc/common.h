@@ -228,7 +228,8 @@ struct ConvArgs {
 // ops_simt.cu
 void launch_pack(const PackArgs& a, cudaStream_t s);
 void launch_pack_padded(const PackArgs& a, cudaStream_t s);
-void launch_gn_coef(const PackArgs& a, float* coef, cudaStream_t s);  // coef[nimg][C][2] = {scale, shift}
+// coef[nimg][C][2] = {scale, shift}; coef_h (optional) = fp16 {scale / 2, shift / 2} per 8-channel octet (see ops_simt.cu)
+void launch_gn_coef(const PackArgs& a, float* coef, void* coef_h, cudaStream_t s);
 void launch_pack_nchw_padded(const float* x, int C, int H, int W, void* out, int fmt, int nimg, cudaStream_t s);
 void launch_pack_nchw(const float* x, int C, int H, int W, int Cp, void* out, int out_bf16, int nimg, cudaStream_t s);
 void launch_conv_simt(const ConvArgs& a, cudaStream_t s);

@@ -41,11 +41,11 @@ constexpr int TC_XF_THREADS = 256;        // transform group: fused GroupNorm + 
 // two epilogue groups of 4 warps, producer warp, two MMA warps (one per accumulator half), transform group
 constexpr int TC_THREADS = 2 * 128 + 96 + TC_XF_THREADS;
 constexpr uint32_t TC_STAGE_BYTES = 128 * 128;
-// dynamic shared memory for A slots + epilogue staging + weights (static: ~17 KB; trace builds add their stamp table)
+// dynamic shared memory for A slots + epilogue staging + weights (static: ~20 KB; trace builds add their stamp table)
 #ifdef RGFM_TC_TRACE
-constexpr uint32_t TC_SMEM_BUDGET = 208u * 1024u;
+constexpr uint32_t TC_SMEM_BUDGET = 205u * 1024u;
 #else
-constexpr uint32_t TC_SMEM_BUDGET = 209u * 1024u;
+constexpr uint32_t TC_SMEM_BUDGET = 206u * 1024u;
 #endif
 
 struct TcArgs {
@@ -95,6 +95,7 @@ struct TcArgs {
   int any_xform;        // some segment applies GroupNorm + SiLU to its raw A tiles in shared memory (transform warps active)
   int xform[3];         // per segment
   const float2* coef[3];  // per segment: {scale, shift}[image][coef_C]
+  const uint4* coef_h[3]; // per segment: fp16 {scale / 2 x 8, shift / 2 x 8} per (image, octet) = two uint4 (fp16 mode's half2 transform)
   int coef_C[3], coef_c0[3];
   int cin_real[3];      // real channels of the segment (transform touches only those)
   int xf_bf16;          // format the transform writes: 1 = bf16, 0 = fp16 (the net's operand format)
@@ -124,44 +125,30 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-  // bounded spin: a protocol bug becomes a trap ("unspecified launch failure"), never a hung GPU.
-  // unroll 1: left alone, the compiler unrolls this loop 64x at every call site, and the resulting code size makes
-  // the single-warp producer / MMA roles miss in the instruction cache on every step.
+  // try_wait with a SUSPEND-TIME HINT: the hardware parks the thread until the phase completes (or ~20 us pass) instead
+  // of returning after a few cycles, so a waiting role costs no issue slots.  Without the hint the polling loops of
+  // the single-thread roles were 17 % of all executed instructions (ncu, profiles/notes_r02.md).
+  // Bounded: a protocol bug becomes a trap ("unspecified launch failure") after ~1 s, never a hung GPU.
+  // unroll 1: left alone, the compiler unrolls this loop at every call site, and the resulting code size makes the
+  // single-warp producer / MMA roles miss in the instruction cache on every step.
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  for (uint32_t it = 0; it < (1u << 16); ++it) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P1;\n\t"
         "}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
     if (ok) return;
   }
   __trap();
 }
-// Epilogue flavour: back off between polls so the spinning warps do not take issue slots from the producer / MMA warps
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t addr, uint32_t parity) {
-#pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-    __nanosleep(64);
-  }
-  __trap();
-}
+// (the epilogue's pollers used to back off with nanosleep; the suspend hint does that in hardware with no wake-up delay)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t addr, uint32_t parity) { mbar_wait(addr, parity); }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -243,16 +230,15 @@ __device__ __forceinline__ uint32_t cvt2(float a, float b, int fmt) {
 // n / d for n * (d - 1) < 2^32 with magic = ceil(2^32 / d) (checked on the host)
 __device__ __forceinline__ int fast_div(int n, uint32_t magic) { return (int)__umulhi((uint32_t)n, magic); }
 
-// two fp32 -> packed fp16, saturated to +-65504 (2 instructions after the convert instead of 4 fp32 min/max)
-// `seen` keeps the running max |value| BEFORE the clamp (inf once anything saturated): the epilogue counts saturated tiles
-// (of rows that are stored: vm = all ones, or zero for rows that are written as zeros)
+// two fp32 -> packed fp16, saturated to +-65504 by the conversion itself (F2FP.SATFINITE: one instruction).  `seen` keeps
+// the running max |value| of rows that are stored (vm = all ones, or zero for rows written as zeros): a tile whose max
+// reaches 0x7BFF saturated something, and the epilogue counts it (diag[12]) -- saturation is never silent.
 __device__ __forceinline__ uint32_t cvt2_f16_sat(float a, float b, uint32_t vm, __half2& seen) {
-  __half2 v = __floats2half2_rn(a, b);
-  *reinterpret_cast<uint32_t*>(&v) &= vm;
-  seen = __hmax2(seen, __habs2(v));
-  const __half2 L = __half2half2(__ushort_as_half((unsigned short)0x7BFF));
-  v = __hmin2(__hmax2(v, __hneg2(L)), L);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  r &= vm;
+  seen = __hmax2(seen, __habs2(*reinterpret_cast<const __half2*>(&r)));
+  return r;
 }
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& d0, uint32_t& d1, uint32_t& d2, uint32_t& d3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -268,11 +254,15 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// packed fp16 pair -> packed bf16 pair of the squares (fp32 multiply, round to nearest: no overflow / underflow issues)
-__device__ __forceinline__ uint32_t sq2_bf16(uint32_t h2) {
-  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
-  __nv_bfloat162 q = __floats2bfloat162_rn(f.x * f.x, f.y * f.y);
-  return *reinterpret_cast<uint32_t*>(&q);
+// packed fp16 pair -> packed fp16 pair of (x / 16)^2: two HMUL2 (the bf16 route through fp32 cost five instructions per
+// pair and the epilogue is issue-bound).  The prescale keeps x^2 inside fp16 for |x| < 4096 (beyond that the variance
+// becomes inf -- loud, not silent) and the sums are scaled back by 256 when the partials are written; each square
+// carries 11 mantissa bits (bf16 had 8) and the HMMA accumulates in fp32.
+__device__ __forceinline__ uint32_t sq2_f16_scaled(uint32_t h2) {
+  const __half2 k = __half2half2(__ushort_as_half((unsigned short)0x2C00));  // 2^-4
+  const __half2 t = __hmul2(*reinterpret_cast<const __half2*>(&h2), k);
+  const __half2 q = __hmul2(t, t);
+  return *reinterpret_cast<const uint32_t*>(&q);
 }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout) {
@@ -311,13 +301,20 @@ __device__ __forceinline__ bool slot_pixel(int m, int H, int P, uint32_t magic_P
 }
 
 
+__device__ __forceinline__ void st_shared_f4x4(float* dst, const uint32_t* v) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dst + 4 * k) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
 // Sixteen output channels [c, c + 16) of this thread's row from the accumulator's column groups (TcArgs::nstk):
 //   out[m] = D_0[m] + D_1[m + 1] + D_2[m + 2]
-// Row m + j lives j lanes further along the warp; for the last lanes it is a row of the NEXT warp's TMEM lane quarter,
-// which that warp published in xn (nmma floats each: its lane 0 of D_1, then its lanes 0 and 1 of D_2).  Lanes 0 / 1 do
-// not need their own D_1 / D_2 values (those belong to the previous warp's rows), so they load the published rows in
-// their place and a ROTATING shuffle delivers them to lanes 31 / 30, 31 -- no select, no extra registers.
-__device__ __forceinline__ void acc_load16(uint32_t taddr, int c, int nstk, int nmma, int lane, const float* xn, float* o) {
+// Row m + j lives j lanes further along the warp (a rotating shuffle).  For the last nstk - 1 lanes of a warp it is a
+// row of the NEXT warp's TMEM lane quarter, which this warp cannot read: those lanes get a wrapped (wrong) value here,
+// are stored as zeros by the caller, and are finished by the epilogue's fix-up pass from the raw pieces that the
+// boundary lanes of both warps leave in `xw` (this warp's slice of s_xchg, n = nmma floats per vector):
+//   nstk = 2: [0] D_0 of lane 31, [1] D_1 of lane 0
+//   nstk = 3: [0] D_0 of lane 30, [1] D_0 of lane 31, [2] D_1 of lane 31, [3] D_1 of lane 0, [4] D_2 of lane 0, [5] D_2 of lane 1
+// Plain vector stores by one or two lanes: no extra TMEM loads, no selects in the per-element path.
+__device__ __forceinline__ void acc16(uint32_t taddr, int c, int nstk, int n, int lane, float* xw, float* o) {
   uint32_t v0[16];
   tmem_ld16(taddr + c, v0);
   if (nstk == 1) {
@@ -327,30 +324,26 @@ __device__ __forceinline__ void acc_load16(uint32_t taddr, int c, int nstk, int 
     return;
   }
   uint32_t v1[16];
-  tmem_ld16(taddr + nmma + c, v1);
+  tmem_ld16(taddr + n + c, v1);
   if (nstk == 2) {
     tmem_ld_wait();
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(&v1[4 * k]) = *reinterpret_cast<const uint4*>(xn + c + 4 * k);
-    }
+    if (lane == 31) st_shared_f4x4(xw + c, v0);
+    if (lane == 0) st_shared_f4x4(xw + n + c, v1);
 #pragma unroll
     for (int j = 0; j < 16; ++j)
       o[j] = __uint_as_float(v0[j]) + __uint_as_float(__shfl_sync(0xffffffffu, v1[j], (lane + 1) & 31));
     return;
   }
   uint32_t v2[16];
-  tmem_ld16(taddr + 2 * nmma + c, v2);
+  tmem_ld16(taddr + 2 * n + c, v2);
   tmem_ld_wait();
-  if (lane < 2) {
-    const float* x2 = xn + nmma * (1 + lane) + c;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(&v2[4 * k]) = *reinterpret_cast<const uint4*>(x2 + 4 * k);
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(&v1[4 * k]) = *reinterpret_cast<const uint4*>(xn + c + 4 * k);
-    }
+  if (lane >= 30) st_shared_f4x4(xw + (lane - 30) * n + c, v0);
+  if (lane == 31) st_shared_f4x4(xw + 2 * n + c, v1);
+  if (lane == 0) {
+    st_shared_f4x4(xw + 3 * n + c, v1);
+    st_shared_f4x4(xw + 4 * n + c, v2);
   }
+  if (lane == 1) st_shared_f4x4(xw + 5 * n + c, v2);
 #pragma unroll
   for (int j = 0; j < 16; ++j)
     o[j] = (__uint_as_float(v0[j]) + __uint_as_float(__shfl_sync(0xffffffffu, v1[j], (lane + 1) & 31))) +
@@ -387,7 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #endif
   __shared__ uint8_t s_rown[400];  // transform group: image (relative to the tile's first) of each A-tile row, 0xff = not a pixel
   __shared__ __align__(16) float s_bias[256];
-  __shared__ __align__(16) float s_xchg[2][4][96];  // tap stacking: rows a warp needs from the next warp's lane quarter (acc_load16)
+  __shared__ __align__(16) float s_xchg[2][4][192];  // tap stacking: raw pieces of the rows that straddle two warps' lane quarters (acc16)
   __shared__ __align__(16) float s_part[2][4][3][64][2];
   // per epilogue group / warp / image slot: {sum, sumsq} of a 64-channel chunk
 
@@ -395,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_stage = smem_base + (uint32_t)p.a_slots * p.a_slot;  // epilogue staging tiles (one per epilogue group)
-  const uint32_t smem_b = smem_stage + 2u * TC_STAGE_BYTES;    // weight ring
+  const uint32_t smem_b = smem_stage + 2u * TC_STAGE_BYTES;    // weights (resident or ring)
   const ConvArgs& a = p.c;
   const int N = p.nmma;
   const int total_rows = a.nimg * (p.H + 1) * p.P;
@@ -671,6 +664,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int cC = p.coef_C[seg];
             const uint32_t sa = smem_base + as * p.a_slot;
             const bool to_bf16 = p.xf_bf16 != 0;
+            if (!to_bf16) {
+              // ---- fp16 mode: packed half2 arithmetic, four rows in flight per thread ----
+              // silu(z) = hz + hz * tanh(hz), hz = x * (scale / 2) + shift / 2: per PAIR of channels one HFMA2, one
+              // MUFU.TANH (f16x2) and one HFMA2, no conversions (the fp32 path below spends ~4.5 instructions per element;
+              // the kernel is issue-bound, profiles/notes_r02.md).  The operand is rounded to fp16 either way; the extra
+              // fp16 roundings of hz and tanh are inside the 16-bit tolerance (tests/test_gpu_parity.py).
+              const int ostride = (cC >> 3) * 2;  // uint4 per image
+              const uint4* ch = p.coef_h[seg] + (size_t)nbase * ostride + (size_t)(((p.coef_c0[seg] + cb * 64) >> 3) + oct) * 2;
+              uint32_t cur = 0xffu, nxt = 0xffu;
+              uint4 hs = make_uint4(0u, 0u, 0u, 0u), hb = hs, ns = hs, nb = hs;
+              if (work) {
+                cur = 0u;
+                hs = __ldg(ch);
+                hb = __ldg(ch + 1);
+                if (nbase + 1 < a.nimg) {
+                  nxt = 1u;
+                  ns = __ldg(ch + ostride);
+                  nb = __ldg(ch + ostride + 1);
+                }
+              }
+              if (tt == 0) mbar_wait(a_full(as), aph);
+              asm volatile("bar.sync 3, %0;" ::"n"(TC_XF_THREADS) : "memory");
+              if (tt == 0 && seg == 0 && cb == 0) TRC(4, (sti - (int)blockIdx.x) / (int)gridDim.x);
+              if (work) {
+#pragma unroll 1
+                for (int r0 = rl; r0 < rows_used; r0 += 4 * rstride) {
+                  uint32_t w4[4][4], addr[4], nr[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {  // all loads in flight before the math
+                    const int r = r0 + j * rstride;
+                    nr[j] = r < rows_used ? (uint32_t)s_rown[r] : 0xffu;
+                    addr[j] = sa + (uint32_t)r * 128u + (uint32_t)((oct ^ (r & 7)) << 4);
+                    if (nr[j] != 0xffu)
+                      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                   : "=r"(w4[j][0]), "=r"(w4[j][1]), "=r"(w4[j][2]), "=r"(w4[j][3]) : "r"(addr[j]));
+                  }
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    if (nr[j] == 0xffu) continue;  // not a pixel: the raw row is zero already (conv padding)
+                    if (nr[j] != cur) {
+                      cur = nr[j];
+                      if (cur != nxt) {  // not the prefetched image (a thread whose rows skip one): load it now
+                        ns = __ldg(ch + (size_t)cur * ostride);
+                        nb = __ldg(ch + (size_t)cur * ostride + 1);
+                      }
+                      hs = ns;
+                      hb = nb;
+                      nxt = 0xffu;
+                      if (nbase + (int)cur + 1 < a.nimg) {  // and request the one after it
+                        nxt = cur + 1u;
+                        ns = __ldg(ch + (size_t)nxt * ostride);
+                        nb = __ldg(ch + (size_t)nxt * ostride + 1);
+                      }
+                    }
+                    const uint32_t hsv[4] = {hs.x, hs.y, hs.z, hs.w}, hbv[4] = {hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      uint32_t z, t;
+                      asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(z) : "r"(w4[j][q]), "r"(hsv[q]), "r"(hbv[q]));
+                      asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(z));
+                      asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(w4[j][q]) : "r"(z), "r"(t));
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr[j]), "r"(w4[j][0]), "r"(w4[j][1]), "r"(w4[j][2]), "r"(w4[j][3]) : "memory");
+                  }
+                }
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
+              asm volatile("bar.sync 3, %0;" ::"n"(TC_XF_THREADS) : "memory");
+              if (tt == 0) mbar_arrive(a_ready(as));
+              if (tt == 0 && seg == 0 && cb == 0) TRC(5, (sti - (int)blockIdx.x) / (int)gridDim.x);
+              if (++as == a_slots) {
+                as = 0u;
+                aph ^= 1u;
+              }
+              continue;
+            }
             uint32_t cur = 0xffu, nxt = 0xffu;
             float hs[8], hb[8];  // half scale / half shift: silu(z) = hz + hz * tanh(hz), hz = z / 2
             float4 nv[4];        // raw {scale, shift} of the NEXT image of the tile, requested one image ahead: a tile of
@@ -759,15 +828,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else {
-    // ---------------- epilogue: group eg owns rows [128*eg, 128*eg+128) of every super-tile ----------------
+    // ---------------- epilogue: group eg owns the eg-th unit (UR output rows) of every super-tile ----------------
     const int eg = warp >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int et = threadIdx.x - eg * 128;
     const int wq = et >> 5;  // warp inside the group (row quarter for the column sums)
-    const int r = q * 32 + lane;  // row inside the 128-row unit
+    const int r = q * 32 + lane;  // row inside the unit's M=128 tile
     const int CP = a.CoutP;  // channel stride of the raw output (32, or a multiple of 64; channels >= nmma are written as zeros)
-    const int total_rows_alloc = p.rows_alloc;  // rows of the output tensor (direct-store bound)
     const uint32_t stg = smem_stage + (uint32_t)eg * TC_STAGE_BYTES;
+    const int nstk = p.nstk;
+    float* xw = &s_xchg[eg][q][0];
+    // rows whose D_j[m + j] sits in the next warp's lane quarter: stored as zeros by the main path, finished by the fix-up
+    const bool bnd = nstk > 1 && lane >= 33 - nstk;
+    const int g = lane >> 2, t4 = lane & 3;  // mma.sync fragment coordinates of the GroupNorm partials
     int it = 0;
     for (int sti = blockIdx.x; sti < supers; sti += gridDim.x, ++it) {
       const int st = p.descend ? supers - 1 - sti : sti;
@@ -783,10 +856,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // w == W + 1 writes the second pad column, so the half-resolution raw tensor is zero padded like every other one
       bool wr = false;
       size_t o = 0;
-      if (!p.sub && !p.tma_store && a.out_mode == OUT_RAW) {  // 32-channel raw output: every row of the unit inside the tensor
-        wr = m < total_rows_alloc && r < UR;
-        o = (size_t)m * CP;
-      }
       if (p.sub) {
         const bool inimg = (n < a.nimg) && (h <= p.H) && r < UR;
         valid = valid && !(h & 1) && !(w & 1);
@@ -796,37 +865,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           o = ((size_t)((size_t)n * (p.out_H + 1) + (h >> 1)) * (p.out_W + 2) + w2) * CP;
         }
       }
-      // one lane per warp polls (with back-off): 256 threads polling would saturate the mbarrier unit that the
-      // producer / MMA threads' waits and every arrive of the pipeline go through
-      if (lane == 0) mbar_wait_sleep(tmem_full_bar(buf), use & 1u);
+      // one lane per warp waits: 256 threads on one mbarrier would crowd the unit that the producer / MMA threads' waits
+      // and every arrive of the pipeline go through
+      if (lane == 0) mbar_wait(tmem_full_bar(buf), use & 1u);
       __syncwarp();
       tc_fence_after();
       if (threadIdx.x == 0) TRC(3, it);
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + eg) * p.ncols);
-      const int nstk = p.nstk;
-      const float* xn = &s_xchg[eg][(q + 1) & 3][0];  // published by the next warp of the group (unused rows for q == 3)
-      if (nstk > 1) {
-        // publish what the previous warp needs of this lane quarter: D_1 of lane 0, D_2 of lanes 0 and 1 (every channel).
-        // (the previous tile's readers are behind a group barrier of its epilogue)
-        for (int c = 0; c < N; c += 16) {
-          uint32_t t1[16], t2[16];
-          tmem_ld16(taddr + N + c, t1);
-          if (nstk == 3) tmem_ld16(taddr + 2 * N + c, t2);
-          tmem_ld_wait();
-          if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              *reinterpret_cast<uint4*>(&s_xchg[eg][q][c + 4 * k]) = make_uint4(t1[4 * k], t1[4 * k + 1], t1[4 * k + 2], t1[4 * k + 3]);
-          }
-          if (nstk == 3 && lane < 2) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              *reinterpret_cast<uint4*>(&s_xchg[eg][q][N * (1 + lane) + c + 4 * k]) = make_uint4(t2[4 * k], t2[4 * k + 1], t2[4 * k + 2], t2[4 * k + 3]);
-          }
-        }
-        if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
-      }
       if (a.out_mode == OUT_RAW) {
         // raw activation, 16-bit, channel stride CP; rows that are not real pixels are stored as exact zeros, so the
         // tensor doubles as a zero-padded conv operand and the per-channel sums below need no masking
@@ -835,7 +880,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int nf = fast_div(unit * UR, p.magic_R);
         const int b1 = (nf + 1) * p.R - unit * UR;
         const int b2 = b1 + p.R;
-        __half2 sat2 = __float2half2_rn(0.f);  // running max |value| before the clamp: saturation is counted, not silent
+        __half2 sat2 = __float2half2_rn(0.f);  // running max |stored value| (cvt2_f16_sat)
+        const uint32_t vm = (valid && !bnd) ? 0xffffffffu : 0u;
         for (int c0 = 0; c0 < CP; c0 += 64) {
           if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has left the buffer
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -845,11 +891,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (c0 + hh * 32 >= CP) break;  // 32-channel outputs: the upper half of the staging tile is never read
             uint32_t pk[16];
             if (c0 + hh * 32 < N) {
-              const uint32_t vm = valid ? 0xffffffffu : 0u;
 #pragma unroll
               for (int sc = 0; sc < 2; ++sc) {
                 float v[16];
-                acc_load16(taddr, c0 + hh * 32 + sc * 16, nstk, N, lane, xn, v);
+                acc16(taddr, c0 + hh * 32 + sc * 16, nstk, N, lane, xw, v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + hh * 32 + sc * 16 + 4 * j]);
@@ -868,7 +913,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
                            "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
             }
-            if (!p.tma_store && wr) {
+            if (!p.tma_store && wr) {  // stride-2 convs (never stacked): subsampled rows go straight to global memory
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<uint4*>(out16 + o + c0 + hh * 32 + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -878,6 +923,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+          }
+          if (nstk > 1 && c0 < N) {
+            // fix-up pass: the rows that straddle two warps' lane quarters (3 boundaries x (nstk - 1) rows per unit), from
+            // the raw fp32 pieces acc16 left in s_xchg -- 96 threads, one channel pair each
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (et < 96) {
+              const int b = et >> 5;
+              const int half = nstk == 3 ? ((et >> 4) & 1) : 1;  // 0: row 32b + 30 (nstk = 3 only), 1: row 32b + 31
+              const int cpair = nstk == 3 ? (et & 15) : (et & 31);
+              const int ch = c0 + 2 * cpair;
+              if (ch < N) {
+                const float* xa = &s_xchg[eg][b][0];      // the warp that owns the row
+                const float* xb = &s_xchg[eg][b + 1][0];  // the next warp: D_j of its first lanes
+                float2 sum;
+                if (nstk == 2) {
+                  const float2 d0 = *reinterpret_cast<const float2*>(xa + ch), d1 = *reinterpret_cast<const float2*>(xb + N + ch);
+                  sum = make_float2(d0.x + d1.x, d0.y + d1.y);
+                } else if (half == 0) {  // D_0[30] + D_1[31] + D_2[next 0]
+                  const float2 d0 = *reinterpret_cast<const float2*>(xa + ch), d1 = *reinterpret_cast<const float2*>(xa + 2 * N + ch),
+                               d2 = *reinterpret_cast<const float2*>(xb + 4 * N + ch);
+                  sum = make_float2((d0.x + d1.x) + d2.x, (d0.y + d1.y) + d2.y);
+                } else {                 // D_0[31] + D_1[next 0] + D_2[next 1]
+                  const float2 d0 = *reinterpret_cast<const float2*>(xa + N + ch), d1 = *reinterpret_cast<const float2*>(xb + 3 * N + ch),
+                               d2 = *reinterpret_cast<const float2*>(xb + 5 * N + ch);
+                  sum = make_float2((d0.x + d1.x) + d2.x, (d0.y + d1.y) + d2.y);
+                }
+                const int rr = 32 * b + 30 + half;
+                int n2, h2, w2;
+                const bool ok = slot_pixel(unit * UR + rr, p.H, p.P, p.magic_P, p.magic_H1, a.nimg, n2, h2, w2);
+                const uint32_t pv = cvt2_f16_sat(sum.x + s_bias[ch], sum.y + s_bias[ch + 1], ok ? 0xffffffffu : 0u, sat2);
+                const uint32_t dst = stg + (uint32_t)rr * 128u + (uint32_t)((((ch - c0) >> 3) ^ (rr & 7)) << 4) + (uint32_t)(((ch - c0) & 7) << 1);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(pv) : "memory");
+              }
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -891,29 +971,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             // GroupNorm partials of the ROUNDED values on the legacy tensor path, channels on M and image slots on N:
             //   S[ch][slot] = sum_row X[row][ch] * Ind[row][slot]   (Ind = 0/1: row belongs to image slot of the unit)
             // per warp = its 32 staged rows: 4 channel blocks x 2 row blocks of mma.sync m16n8k16, A = X^T by
-            // ldmatrix.trans from the swizzled staging tile, B = the indicator built in registers.  The squares go through
-            // a bf16 MMA (fp32 multiply, rounded to bf16: no fp16 overflow / underflow).  16 + 16 HMMAs per warp and
-            // 64-channel chunk (a [slot][row] x [row][ch] formulation needs 4x as many, and HMMA is what bounds the epilogue).
+            // ldmatrix.trans from the swizzled staging tile, B = the indicator built in registers.  The squares are
+            // fp16 too ((x / 16)^2, sq2_f16_scaled).  16 + 16 HMMAs per warp and 64-channel chunk (a [slot][row] x
+            // [row][ch] formulation needs 4x as many, and HMMA is what bounds the epilogue).
             float sm[4][4], sq[4][4];
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
               for (int e = 0; e < 4; ++e) sm[cb][e] = sq[cb][e] = 0.f;
-            const int g = lane >> 2, t4 = lane & 3;
             const int mat = lane >> 3, rrow = lane & 7;
+            const bool one_img = b1 >= UR;  // the whole unit lies inside one image (9 of 10 units at 32x32): slot 0 everywhere
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
               const int r0 = wq * 32 + kb * 16;
-              // B fragment: b0 = Ind[k0, k0+1][g], b1 = Ind[k0+8, k0+9][g], k0 = 2 * t4 (column g = image slot g)
-              uint32_t ind[4];
+              // B fragment: b0 = Ind[k0, k0+1][g], b1 = Ind[k0+8, k0+9][g], k0 = 2 * t4 (column g = image slot g), fp16 1.0 / 0.0
+              uint32_t b0h = g == 0 ? 0x3C003C00u : 0u, b1h = b0h;
+              if (!one_img) {
+                uint32_t ind[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int row = r0 + (t4 << 1) + (e & 1) + ((e >> 1) << 3);
-                const int sl = (row >= b1) + (row >= b2);
-                ind[e] = (sl == g) ? 1u : 0u;
+                for (int e = 0; e < 4; ++e) {
+                  const int row = r0 + (t4 << 1) + (e & 1) + ((e >> 1) << 3);
+                  const int sl = (row >= b1) + (row >= b2);
+                  ind[e] = (sl == g) ? 1u : 0u;
+                }
+                b0h = ind[0] * 0x3C00u + ind[1] * 0x3C000000u;
+                b1h = ind[2] * 0x3C00u + ind[3] * 0x3C000000u;
               }
-              const uint32_t b0h = ind[0] * 0x3C00u + ind[1] * 0x3C000000u, b1h = ind[2] * 0x3C00u + ind[3] * 0x3C000000u;  // fp16 1.0
-              const uint32_t b0b = ind[0] * 0x3F80u + ind[1] * 0x3F800000u, b1b = ind[2] * 0x3F80u + ind[3] * 0x3F800000u;  // bf16 1.0
               // ldmatrix.x4.trans: matrices (rows r0.., chunk 2cb), (rows r0.., chunk 2cb+1), (rows r0+8.., 2cb), (rows r0+8.., 2cb+1)
               // = A fragments a0 (ch 0-7, k 0-7), a1 (ch 8-15, k 0-7), a2 (ch 0-7, k 8-15), a3 (ch 8-15, k 8-15)
               const int lrow = r0 + ((mat >> 1) << 3) + rrow;
@@ -921,13 +1004,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int cb = 0; cb < 4; ++cb) {
                 if (c0 + cb * 16 >= N) break;  // channel blocks past the real output channels hold zeros
                 const uint32_t chunk16 = (uint32_t)(2 * cb + (mat & 1));
-                uint32_t a[4];
-                ldsm_x4_trans(stg + (uint32_t)lrow * 128u + ((chunk16 ^ (uint32_t)(lrow & 7)) << 4), a[0], a[1], a[2], a[3]);
-                mma_f16_16816(sm[cb], a, b0h, b1h);
+                uint32_t af[4];
+                ldsm_x4_trans(stg + (uint32_t)lrow * 128u + ((chunk16 ^ (uint32_t)(lrow & 7)) << 4), af[0], af[1], af[2], af[3]);
+                mma_f16_16816(sm[cb], af, b0h, b1h);
                 uint32_t a2[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) a2[e] = sq2_bf16(a[e]);
-                mma_bf16_16816(sq[cb], a2, b0b, b1b);
+                for (int e = 0; e < 4; ++e) a2[e] = sq2_f16_scaled(af[e]);
+                mma_f16_16816(sq[cb], a2, b0h, b1h);
               }
             }
             // D fragment: c0 = (ch g, slot 2*t4), c1 = (ch g, slot 2*t4+1), c2 / c3 = the same for ch g + 8
@@ -936,12 +1019,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int cb = 0; cb < 4; ++cb) {
                 if (c0 + cb * 16 >= N) break;
                 float* d0 = &s_part[eg][wq][2 * t4][cb * 16 + g][0];
-                d0[0] = sm[cb][0]; d0[1] = sq[cb][0];       // slot 2*t4, channel g
-                d0[16] = sm[cb][2]; d0[17] = sq[cb][2];     // slot 2*t4, channel g + 8
+                d0[0] = sm[cb][0]; d0[1] = 256.f * sq[cb][0];       // slot 2*t4, channel g
+                d0[16] = sm[cb][2]; d0[17] = 256.f * sq[cb][2];     // slot 2*t4, channel g + 8
                 if (t4 == 0) {
                   float* d1 = &s_part[eg][wq][1][cb * 16 + g][0];
-                  d1[0] = sm[cb][1]; d1[1] = sq[cb][1];     // slot 1
-                  d1[16] = sm[cb][3]; d1[17] = sq[cb][3];
+                  d1[0] = sm[cb][1]; d1[1] = 256.f * sq[cb][1];     // slot 1
+                  d1[16] = sm[cb][3]; d1[17] = 256.f * sq[cb][3];
                 }
               }
             }
@@ -958,23 +1041,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (threadIdx.x == 0) TRC(7, it);
         if (p.sat != nullptr) {  // rows of this tile that hit the fp16 bound (reported in diag[12]; must stay 0)
           const uint32_t sb = *reinterpret_cast<const uint32_t*>(&sat2);
-          const unsigned hit = __ballot_sync(0xffffffffu, (sb & 0x7fffu) >= 0x7c00u || (sb & 0x7fff0000u) >= 0x7c000000u);
+          const unsigned hit = __ballot_sync(0xffffffffu, (sb & 0x7fffu) >= 0x7bffu || (sb & 0x7fff0000u) >= 0x7bff0000u);
           if (hit != 0u && lane == 0) atomicAdd(p.sat, (unsigned int)__popc(hit));
         }
       } else {
-        // output conv: Cout <= 16 real channels -> NCHW velocity, or fused Euler update x += dt * v
-        float v[16];
-        acc_load16(taddr, 0, nstk, N, lane, xn, v);
+        // output conv (never stacked): Cout <= 16 real channels -> NCHW velocity, or fused Euler update x += dt * v
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
-        if (nstk > 1) {  // the next tile's exchange rows may only be written once every warp has read this tile's
-          if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-          else asm volatile("bar.sync 2, 128;" ::: "memory");
-        }
         if (valid) {
           for (int c = 0; c < a.Cout; ++c) {
-            const float val = v[c] + s_bias[c];
+            const float val = __uint_as_float(v[c]) + s_bias[c];
             const size_t oc = (((size_t)n * a.Cout + c) * p.out_H + h) * p.out_W + w;
             if (a.out_mode == OUT_NCHW)
               a.out[oc] = val;
@@ -1049,19 +1129,30 @@ static void encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const 
   RGFM_CHECK(r == CUDA_SUCCESS, std::string("cuTensorMapEncodeTiled(") + what + ") failed with code " + std::to_string((int)r));
 }
 
-// Column groups per accumulator (TcArgs::nstk) for a conv with `cout` output channels.  RGFM_TC_STACK=0 selects the
-// classic nine-tap issue everywhere (same results up to fp32 summation order; for A/B timing).
-int tc_stack_groups(int cout) {
-  static const int enable = getenv("RGFM_TC_STACK") ? atoi(getenv("RGFM_TC_STACK")) : 1;
+// Column groups per accumulator (TcArgs::nstk).  Stacking shortens the MMA phase of a tile (N = 96: 57 cycles, N = 192: 97,
+// N = 128 + 64: 115 against 3 x 49.7) but lengthens its epilogue (three / two accumulator column groups to read, the
+// lane-shifted sum, the boundary fix-up), and the epilogue is the critical role of a conv whose tile holds ONE operand
+// stage (measured, profiles/notes_r02.md: 64->64 @32x32 136 -> 191 us stacked, 192->64 339 -> 313 us).  So taps are stacked
+// only where the MMA phase dominates: stride-1 convs with a raw 16-bit output (their epilogue has the staging tile the
+// fix-up writes into) whose super-tile walks at least two operand stages -- for Cout <= 32 at least two 3x3 stages.
+// stages3 / stages: 64-channel operand blocks of the 3x3 segments / of all segments.
+// RGFM_TC_STACK=0: the classic nine-tap issue everywhere; 2: stack wherever it is legal (A/B timing; same results up to
+// fp32 summation order).
+int tc_stack_groups(int cout, int stride, bool final, int stages3, int stages) {
+  static const int mode = getenv("RGFM_TC_STACK") ? atoi(getenv("RGFM_TC_STACK")) : 1;
   const int nmma = (cout + 15) / 16 * 16;
-  if (!enable) return 1;
-  return nmma <= 32 ? 3 : (nmma <= 64 ? 2 : 1);
+  if (mode == 0 || stride != 1 || final || nmma > 64) return 1;
+  const int nstk = nmma <= 32 ? 3 : 2;
+  if (mode == 2) return nstk;
+  return (nstk == 3 ? stages3 >= 2 : stages >= 2) ? nstk : 1;
 }
-int tc_unit_rows(int cout) { return 128 - (tc_stack_groups(cout) - 1); }
+int tc_unit_rows(int cout, int stride, bool final, int stages3, int stages) {
+  return 128 - (tc_stack_groups(cout, stride, final, stages3, stages) - 1);
+}
 
-size_t tc_stats_floats(int H, int W, int chunk, int Cout, int CoutP) {
+size_t tc_stats_floats(int H, int W, int chunk, int unit_rows, int CoutP) {
   const int R = (H + 1) * (W + 2);
-  const int SR = 2 * tc_unit_rows(Cout);
+  const int SR = 2 * unit_rows;
   const size_t supers = ((size_t)chunk * R + SR - 1) / SR;
   return supers * 2 * (size_t)stats_slots_for(R) * CoutP * 2;
 }
@@ -1091,7 +1182,15 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   }
   p.nseg = d.nseg;
   p.nmma = nmma;
-  p.nstk = tc_stack_groups(d.Cout);
+  {
+    int st3 = 0, stall = 0;
+    for (int sg = 0; sg < d.nseg; ++sg) {
+      const int cb = (d.seg[sg].Cin_real + 63) / 64;
+      stall += cb;
+      if (d.seg[sg].ks == 3) st3 += cb;
+    }
+    p.nstk = tc_stack_groups(d.Cout, d.stride, d.out == nullptr && d.stride == 1, st3, stall);
+  }
   p.unit_rows = 128 - (p.nstk - 1);
   p.super_rows = 2 * p.unit_rows;
   p.ncols = (p.nstk * nmma + 31) / 32 * 32;
@@ -1115,6 +1214,7 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   // the weights stay RESIDENT (loaded once per CTA) and whatever is left deepens the A pipeline; otherwise the weights
   // stream through a ring of stages of tps taps (tps in {9, 3, 1}: as many as keep >= 3 stages in the budget).
   const uint32_t budget = TC_SMEM_BUDGET;
+  const uint32_t stage = 2u * TC_STAGE_BYTES;  // one epilogue staging tile per accumulator half
   uint32_t b_total = 0;
   for (int sg = 0; sg < d.nseg; ++sg) b_total += (uint32_t)((d.seg[sg].Cin_real + 63) / 64) * (uint32_t)(d.seg[sg].ks * d.seg[sg].ks) * p.b_bytes;
   p.b_total = b_total;
@@ -1122,20 +1222,20 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   // the weight tiles from L2 for every super-tile is what bounds the ring mode (L2 -> SM bandwidth), not load latency.
   static const int force_slots = getenv("RGFM_TC_A_SLOTS") ? atoi(getenv("RGFM_TC_A_SLOTS")) : 0;
   const uint32_t min_slots = force_slots ? (uint32_t)force_slots : 2u;
-  p.resident = (min_slots * p.a_slot + 2u * TC_STAGE_BYTES + b_total <= budget) ? 1 : 0;
+  p.resident = (min_slots * p.a_slot + stage + b_total <= budget) ? 1 : 0;
   p.tps[0] = p.tps[1] = p.tps[2] = 1;
   if (p.resident) {
-    int slots = (int)((budget - 2u * TC_STAGE_BYTES - b_total) / p.a_slot);
+    int slots = (int)((budget - stage - b_total) / p.a_slot);
     p.a_slots = slots > 4 ? 4 : slots;
     p.b_stages = 1;
     p.b_stage = p.b_bytes;
-    t->smem = (size_t)p.a_slots * p.a_slot + 2u * TC_STAGE_BYTES + b_total + 1024;
+    t->smem = (size_t)p.a_slots * p.a_slot + stage + b_total + 1024;
   } else {
     // weight ring: at least two stages of >= 1 tap must fit next to the A slots, else fall back to two slots
     uint32_t slots = min_slots;
-    while (slots > 2u && slots * p.a_slot + 2u * TC_STAGE_BYTES + 2u * p.b_bytes > budget) --slots;
+    while (slots > 2u && slots * p.a_slot + stage + 2u * p.b_bytes > budget) --slots;
     p.a_slots = (int)slots;
-    const uint32_t fixed = slots * p.a_slot + 2u * TC_STAGE_BYTES;
+    const uint32_t fixed = slots * p.a_slot + stage;
     const uint32_t ring_budget = budget - fixed;
     // Every ring stage costs the single producer / MMA threads ~500 cycles of hand-off (wait, fence, commit at one
     // dependent instruction per ~5 cycles), so stages are made as large as two of them fit: measured 6.37 -> 5.99 ms of
@@ -1167,6 +1267,8 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     const CUtensorMapDataType dt16 = seg_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     p.xform[sg] = xf ? 1 : 0;
     p.coef[sg] = reinterpret_cast<const float2*>(S.coef);
+    p.coef_h[sg] = xf ? reinterpret_cast<const uint4*>(S.coef + (size_t)d.chunk * S.coef_C * 2) : nullptr;
+    RGFM_CHECK(!xf || (S.coef_c0 % 8 == 0 && S.coef_C % 8 == 0), "tc conv: GroupNorm coefficient offsets must be multiples of 8");
     p.coef_C[sg] = S.coef_C;
     p.coef_c0[sg] = S.coef_c0;
     p.cin_real[sg] = S.Cin_real;

@@ -104,15 +104,15 @@ struct Builder {
   }
   // 16-bit zero-padded padded-linear raw activation (tcgen05 path); (Hc, Wc) is the geometry of the producing conv's
   // GEMM row space (differs from (H, W) for stride-2 convs), which is what the GroupNorm partials are indexed by
-  Act new_act_tc(int H, int Wd, int C, bool stats, int Hc, int Wc) {
+  Act new_act_tc(int H, int Wd, int C, bool stats, int Hc, int Wc, int unit_rows) {
     Act a;
     a.H = H; a.W = Wd; a.C = C; a.Cs = tc_stride(C);
     a.padded = true; a.fmt = 2;  // raw activations are fp16 in both 16-bit modes
     a.p = (float*)pool.alloc(tc_raw_rows(H, Wd, chunk) * a.Cs * 2);
     if (stats) {
-      a.stats = (float*)pool.alloc(tc_stats_floats(Hc, Wc, chunk, C, a.Cs) * sizeof(float));
+      a.stats = (float*)pool.alloc(tc_stats_floats(Hc, Wc, chunk, unit_rows, a.Cs) * sizeof(float));
       a.st.p = a.stats; a.st.mode = ST_UNITS; a.st.C = a.Cs; a.st.R = (Hc + 1) * (Wc + 2); a.st.slots = stats_slots_for(a.st.R);
-      a.st.unit_rows = tc_unit_rows(C);  // the producing conv's unit (conv_tc.cu: tap stacking shortens it)
+      a.st.unit_rows = unit_rows;  // the producing conv's unit (conv_tc.cu: tap stacking shortens it)
       a.st.magic_unit = (unsigned int)(((1ull << 32) + a.st.unit_rows - 1) / a.st.unit_rows);
     }
     return a;
@@ -248,7 +248,6 @@ struct Builder {
       PackSrc ps{};
       ps.p = srcs[i].p; ps.st = srcs[i].st; ps.C = srcs[i].C; ps.Cs = srcs[i].Cs;
       ps.padded = srcs[i].padded ? 1 : 0; ps.fmt = srcs[i].fmt;
-      RGFM_CHECK(ps.st.mode != ST_NONE, "gn_coef: GroupNorm needs the producer's partial statistics");
       a.src[i] = ps;
       C += srcs[i].C;
     }
@@ -256,12 +255,16 @@ struct Builder {
     a.Hs = a.Ho = srcs[0].H; a.Ws = a.Wo = srcs[0].W;
     a.C = C; a.norm = NORM_GN; a.act = ACT_SILU; a.spatial = SP_ID;
     a.gamma = gamma; a.beta = beta; a.groups = 8;
-    float* coef = (float*)pool.alloc((size_t)chunk * C * 2 * sizeof(float));
-    net.ops_.push_back({[a, coef](const RunCtx& c) {
+    for (int i = 0; i < a.nsrc; ++i) RGFM_CHECK(a.src[i].st.mode != ST_NONE, "gn_coef: GroupNorm needs the producer's partial statistics");
+    // {scale, shift} fp32 pairs, followed by the fp16 copy the half2 transform reads (TcSegment::coef documents the layout)
+    RGFM_CHECK(C % 8 == 0, "gn_coef: channels must be a multiple of 8");
+    float* coef = (float*)pool.alloc((size_t)chunk * C * 3 * sizeof(float));
+    void* coef_h = coef + (size_t)chunk * C * 2;
+    net.ops_.push_back({[a, coef, coef_h](const RunCtx& c) {
       PackArgs b = a;
       b.nimg = c.nimg;
-      launch_gn_coef(b, coef, c.s);
-    }, "gn_coef", 0.0, (double)C * 8.0, std::to_string(a.Hs) + "x" + std::to_string(a.Ws) + " C" + std::to_string(C)});
+      launch_gn_coef(b, coef, coef_h, c.s);
+    }, "gn_coef", 0.0, (double)C * 12.0, std::to_string(a.Hs) + "x" + std::to_string(a.Ws) + " C" + std::to_string(C)});
     return coef;
   }
   static Seg seg_of(const Packed& in, int creal, int ks, const float* w) { return Seg{in.p, in.C, creal, false, ks, w, 0, 0}; }
@@ -284,14 +287,19 @@ struct Builder {
     a.out_mode = OUT_RAW;
     Act o;
     if (!final) {
-      o = new_act_tc(Ho, Wo, cout, stats, H, Wd);
+      int st3 = 0, stall = 0;
+      for (const Seg& S : segs) {
+        stall += (S.Creal + 63) / 64;
+        if (S.ks == 3) st3 += (S.Creal + 63) / 64;
+      }
+      o = new_act_tc(Ho, Wo, cout, stats, H, Wd, tc_unit_rows(cout, stride, false, st3, stall));
       a.out = o.p;
       a.CoutP = o.Cs;
     } else {
       a.CoutP = 16;
     }
     TcConvDesc d{};
-    d.Hin = H; d.Win = Wd; d.Cout = cout; d.CoutP = a.CoutP; d.chunk = chunk; d.fp16 = fp16;
+    d.Hin = H; d.Win = Wd; d.Cout = cout; d.CoutP = a.CoutP; d.chunk = chunk; d.fp16 = fp16; d.stride = stride;
     d.nseg = (int)segs.size();
     double macs = 0.0, in_bytes = 0.0;
     for (int i = 0; i < d.nseg; ++i) {

@@ -126,6 +126,8 @@ struct TcSegment {
   int w_c0;
   // fused GroupNorm + SiLU (raw segments only): the kernel's transform warps rewrite the raw tile in shared memory as
   // silu(x * scale + shift) with coef[image][coef_C][2], channels [coef_c0, coef_c0 + Cin_real) -- no packed operand tensor
+  // coef: {scale, shift}[chunk][coef_C] fp32, immediately followed by the fp16 copy {scale / 2 x 8, shift / 2 x 8} per
+  // (image, 8-channel octet) that the fp16 mode's half2 transform reads (written by launch_gn_coef)
   const float* coef;
   int coef_C, coef_c0;
 };
@@ -133,6 +135,7 @@ struct TcConvDesc {
   int Hin, Win;          // operand image geometry (stride-1 output geometry)
   int Cout, CoutP;       // real / padded output channels
   int chunk;             // max images
+  int stride;            // 1, or 2 (computed at stride 1, stored subsampled)
   int nseg;              // 1, or 2-3 when a 1x1 skip conv / identity residual is folded in as extra K segments
   TcSegment seg[3];
   void* out;             // raw padded-linear 16-bit output buffer (TMA store) or nullptr
@@ -145,7 +148,8 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s);
 bool tc_available();
 size_t tc_operand_slots(int H, int W, int chunk);  // rows of a padded-linear operand tensor
 size_t tc_raw_rows(int H, int W, int chunk);       // rows of a padded-linear raw activation tensor
-size_t tc_stats_floats(int H, int W, int chunk, int Cout, int CoutP);  // floats of a conv's GroupNorm partials buffer
-int tc_unit_rows(int cout);  // output rows per GroupNorm-partials unit of a conv with `cout` output channels (128, 127 or 126)
+size_t tc_stats_floats(int H, int W, int chunk, int unit_rows, int CoutP);  // floats of a conv's GroupNorm partials buffer
+// output rows per GroupNorm-partials unit of a conv (128, or 127 / 126 when it stacks taps: stride 1, raw output, Cout <= 64)
+int tc_unit_rows(int cout, int stride, bool final, int stages3, int stages);  // stages: 64-channel operand blocks (3x3 segments / all)
 
 }  // namespace rgfm

@@ -643,20 +643,31 @@ void launch_pack_padded(const PackArgs& a, cudaStream_t s) {
 // operand = silu(raw * scale + shift), from the producers' partial statistics (same reduction as the pack kernels).
 // Per-image GroupNorm {scale, shift} for the conv kernel's fused GroupNorm + SiLU segments: the prologue of the pack
 // kernels on its own (one block per image), written once per layer instead of being re-derived by every consumer CTA.
-__global__ void __launch_bounds__(256) gn_coef_kernel(PackArgs a, float2* __restrict__ coef) {
+// coef_h (optional): the same coefficients halved and rounded to fp16, laid out per (image, 8-channel octet) as 8 x hs then
+// 8 x hb (32 bytes): silu(z) = hz + hz * tanh(hz) with hz = x * hs + hb is what the conv's transform warps evaluate in
+// packed half2 arithmetic (conv_tc.cu), two LDG.128 per octet instead of four and no conversions in the hot loop
+__device__ __forceinline__ void store_coef_h(__half* coef_h, int n, int C, int c, float sc, float sh) {
+  __half* q = coef_h + ((size_t)n * (C >> 3) + (c >> 3)) * 16 + (c & 7);
+  q[0] = __float2half_rn(0.5f * sc);
+  q[8] = __float2half_rn(0.5f * sh);
+}
+__global__ void __launch_bounds__(256) gn_coef_kernel(PackArgs a, float2* __restrict__ coef, __half* __restrict__ coef_h) {
   __shared__ float s_scale[PACK_MAXC];
   __shared__ float s_shift[PACK_MAXC];
   __shared__ float s_red[2][PACK_MAXC];
   __shared__ double s_grp[32][2];
   const int n = blockIdx.x;
   pack_scale_shift<12>(a, n, s_scale, s_shift, s_red, s_grp);
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) coef[(size_t)n * a.C + c] = make_float2(s_scale[c], s_shift[c]);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    coef[(size_t)n * a.C + c] = make_float2(s_scale[c], s_shift[c]);
+    if (coef_h) store_coef_h(coef_h, n, a.C, c, s_scale[c], s_shift[c]);
+  }
 }
 // C <= 256: one thread per channel, one barrier.  gamma / beta and every statistics partial are requested before anything
 // is consumed (one global round trip), each thread sums its own group from shared memory in double, and the count enters
 // as a host-computed reciprocal (no fp64 division or square root on the critical path of a ~3 us kernel that sits between
 // two convolutions 60 times per Euler step).
-__global__ void __launch_bounds__(256) gn_coef256_kernel(PackArgs a, float2* __restrict__ coef, double inv_cnt, int ipb) {
+__global__ void __launch_bounds__(256) gn_coef256_kernel(PackArgs a, float2* __restrict__ coef, __half* __restrict__ coef_h, double inv_cnt, int ipb) {
   __shared__ float s_red[2][256];
   pdl_trigger();  // the consuming conv may set up (barriers, TMEM, tensor maps) while this grid runs
   pdl_wait();     // the statistics come from the previous kernel
@@ -687,9 +698,11 @@ __global__ void __launch_bounds__(256) gn_coef256_kernel(PackArgs a, float2* __r
   double var = gss * inv_cnt - mean * mean;
   if (var < 0.0) var = 0.0;
   const float sc = rsqrtf((float)var + 1e-5f) * gam;
-  coef[(size_t)n * a.C + c] = make_float2(sc, bet - (float)mean * sc);
+  const float sh = bet - (float)mean * sc;
+  coef[(size_t)n * a.C + c] = make_float2(sc, sh);
+  if (coef_h) store_coef_h(coef_h, n, a.C, c, sc, sh);
 }
-void launch_gn_coef(const PackArgs& a, float* coef, cudaStream_t s) {
+void launch_gn_coef(const PackArgs& a, float* coef, void* coef_h, cudaStream_t s) {
   RGFM_CHECK(a.C <= PACK_MAXC && a.norm == NORM_GN && a.C % a.groups == 0, "gn_coef: GroupNorm over at most 512 channels");
 #ifdef RGFM_EXPERIMENTS  // timing-only switch that knowingly corrupts results: compiled out of the shipped library
   static const bool skip = getenv("RGFM_EXPERIMENT_SKIP_GN_COEF") != nullptr;
@@ -698,10 +711,10 @@ void launch_gn_coef(const PackArgs& a, float* coef, cudaStream_t s) {
   if (a.C <= 256) {
     const int ipb = 256 / a.C;
     launch_pdl(gn_coef256_kernel, dim3((a.nimg + ipb - 1) / ipb), dim3(256), 0, s, a, reinterpret_cast<float2*>(coef),
-               1.0 / ((double)(a.C / a.groups) * a.Hs * a.Ws), ipb);
+               reinterpret_cast<__half*>(coef_h), 1.0 / ((double)(a.C / a.groups) * a.Hs * a.Ws), ipb);
   }
   else
-    gn_coef_kernel<<<a.nimg, 256, 0, s>>>(a, reinterpret_cast<float2*>(coef));
+    gn_coef_kernel<<<a.nimg, 256, 0, s>>>(a, reinterpret_cast<float2*>(coef), reinterpret_cast<__half*>(coef_h));
   post_launch("gn_coef");
 }
 
