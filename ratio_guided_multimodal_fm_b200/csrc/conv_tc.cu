@@ -37,6 +37,11 @@ static inline void post_launch(const char* what) {
 }
 
 constexpr int TC_MAX_STAGES = 12;
+// Row-dense kernel: GroupNorm partials from the accumulator registers (quad sums + a 31-shuffle transpose-reduce) instead
+// of ldmatrix.trans + mma.sync on the staged tile.  Measured (profiles/notes_r02.md): it removes the legacy HMMAs that queue
+// behind the UMMA stream and wins on single-stage convs (165 -> 148 us), but costs ~160 issue slots per thread and unit,
+// and the multi-stage convs this mode is used for are issue-bound: 179 -> 196 us.  Off.
+constexpr bool TC_DENSE_REG_STATS = false;
 constexpr int TC_XF_THREADS = 256;        // transform group: fused GroupNorm + SiLU on the A tiles in shared memory (12 warps: no faster)
 // two epilogue groups of 4 warps, producer warp, two MMA warps (one per accumulator half), transform group
 constexpr int TC_THREADS = 2 * 128 + 96 + TC_XF_THREADS;
@@ -80,6 +85,21 @@ struct TcArgs {
   //   nstk = 1: the classic nine taps
   // A unit yields unit_rows = 128 - (nstk - 1) output rows (the last rows of the M=128 tile lack their D_j[m + j]).
   int nstk;
+  // Row-dense mode: the GEMM row space drops the two pad COLUMNS of the padded-linear layout --
+  // row m = image_row * Wt + w, image_row = n * (H + 1) + h, Wt = 8 / 16 / 32 >= W -- by loading the tile through a 3-D
+  // view [C][P][image rows] of the same tensor (box [64][Wt][rows]).  Wt divides 32, so every warp of the epilogue holds
+  // whole image rows: with all three kx taps stacked on N (one MMA per filter row, A read once, N = 3 * nmma) the output is
+  //   out[l] = D_0[l - 1] (w > 0) + D_1[l] + D_2[l + 1] (w < Wt - 1)
+  // -- intra-warp shuffles with zero fill at the image-row ends (= the conv's own zero padding), no boundary fix-up, all
+  // 128 rows of a unit are outputs, and only the pad ROW of each image is wasted (3 / 6 / 11 % at 32 / 16 / 8 pixels
+  // against 10 / 20 / 41 % of the padded-linear row space).  ky is a shift of Wt rows of the shared tile (atom aligned).
+  int dense;
+  int xchg16;           // row-dense: neighbour partial sums are exchanged as packed fp16 pairs (RGFM_TC_XCHG16, default off)
+  int Wt, wt_shift;     // tile width and its log2
+  int irs;              // image rows per super-tile (256 / Wt)
+  int w0[3];            // per segment: TMA w coordinate of tile column 0 (0 = raw tensor, 1 = packed operand)
+  int ir_off[3];        // per segment: image-row coordinate of the tile's first image row relative to the super-tile's
+  uint32_t a_bytes[3];  // per segment: bytes of the A box
   int unit_rows;        // output rows per accumulator half
   int super_rows;       // 2 * unit_rows: output rows per super-tile
   int ncols;            // TMEM columns per accumulator: nstk * nmma rounded up to 32
@@ -100,6 +120,7 @@ struct TcArgs {
   int cin_real[3];      // real channels of the segment (transform touches only those)
   int xf_bf16;          // format the transform writes: 1 = bf16, 0 = fp16 (the net's operand format)
   int exp_no_xform;     // timing experiments only (RGFM_EXPERIMENT_NO_XFORM): transform warps keep the protocol but do no work
+  int exp_no_bias;      // timing experiments only (RGFM_EXPERIMENT_NO_BIAS): the epilogue skips its shared-memory bias loads
   int l2_prefetch;      // prefetch the next super-tile's A boxes into L2 (RGFM_TC_L2_PREFETCH, default on)
   int descend;          // walk the super-tiles from the last to the first: every tensor is a little larger than L2, the
                         // packs stream in ascending order, so a conv that starts at the END of its operand finds the rows
@@ -158,6 +179,9 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
 // pull a box into L2 only (no shared-memory slot needed): the later tma_load_2d of the same box pays L2 instead of HBM latency
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -291,6 +315,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // decode padded-linear output index m' -> (image, h, w); valid iff a real pixel of an image < nimg
 __device__ __forceinline__ bool slot_pixel(int m, int H, int P, uint32_t magic_P, uint32_t magic_H1, int nimg, int& n, int& h, int& w) {
   const int hv = fast_div(m, magic_P);
@@ -300,6 +329,15 @@ __device__ __forceinline__ bool slot_pixel(int m, int H, int P, uint32_t magic_P
   return (w < P - 2) && (h < H) && (n < nimg);
 }
 
+
+// row-dense decode: m = image_row * Wt + w
+__device__ __forceinline__ bool dense_pixel(int m, int H, int W, int Wt, int wt_shift, uint32_t magic_H1, int nimg, int& n, int& h, int& w) {
+  const int ir = m >> wt_shift;
+  w = m & (Wt - 1);
+  n = fast_div(ir, magic_H1);
+  h = ir - n * (H + 1);
+  return (w < W) && (h < H) && (n < nimg);
+}
 
 __device__ __forceinline__ void st_shared_f4x4(float* dst, const uint32_t* v) {
 #pragma unroll
@@ -314,6 +352,67 @@ __device__ __forceinline__ void st_shared_f4x4(float* dst, const uint32_t* v) {
 //   nstk = 2: [0] D_0 of lane 31, [1] D_1 of lane 0
 //   nstk = 3: [0] D_0 of lane 30, [1] D_0 of lane 31, [2] D_1 of lane 31, [3] D_1 of lane 0, [4] D_2 of lane 0, [5] D_2 of lane 1
 // Plain vector stores by one or two lanes: no extra TMEM loads, no selects in the per-element path.
+// Row-dense mode: sixteen output channels [c, c + 16) from the three kx column groups, neighbours by shuffle with zero
+// fill at the ends of the image row (ml: the row has a left neighbour, mr: a right neighbour; TcArgs::dense).
+// x16: the neighbours' partial sums travel as packed fp16 pairs (one SHFL per two channels; SHFL throughput is what bounds
+// this loop) and are added to the centre tap's fp32 sum -- each neighbour term carries one extra fp16 rounding, the same
+// size as the rounding of the stored activation itself.  The output conv (fp32 velocity) exchanges fp32.
+__device__ __forceinline__ void acc16_dense(uint32_t taddr, int c, int n, bool ml, bool mr, bool x16, float* o) {
+  uint32_t v0[16], v1[16], v2[16];
+  tmem_ld16(taddr + c, v0);
+  tmem_ld16(taddr + n + c, v1);
+  tmem_ld16(taddr + 2 * n + c, v2);
+  tmem_ld_wait();
+  if (x16) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t lp, rp;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lp) : "f"(__uint_as_float(v0[2 * j + 1])), "f"(__uint_as_float(v0[2 * j])));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(rp) : "f"(__uint_as_float(v2[2 * j + 1])), "f"(__uint_as_float(v2[2 * j])));
+      lp = __shfl_up_sync(0xffffffffu, lp, 1);
+      rp = __shfl_down_sync(0xffffffffu, rp, 1);
+      lp = ml ? lp : 0u;
+      rp = mr ? rp : 0u;
+      const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lp));
+      const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rp));
+      o[2 * j] = (__uint_as_float(v1[2 * j]) + lf.x) + rf.x;
+      o[2 * j + 1] = (__uint_as_float(v1[2 * j + 1]) + lf.y) + rf.y;
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float l = __uint_as_float(__shfl_up_sync(0xffffffffu, v0[j], 1));
+    const float r = __uint_as_float(__shfl_down_sync(0xffffffffu, v2[j], 1));
+    o[j] = (__uint_as_float(v1[j]) + (ml ? l : 0.f)) + (mr ? r : 0.f);
+  }
+}
+
+// 32 values per lane -> lane L ends with the sum over the 32 lanes of value L; lanes with keep == false contribute zeros.
+// The input array is left intact (the first butterfly writes into g), so a second pass with another mask can follow.
+__device__ __forceinline__ float transpose_reduce32_masked(const float* f, bool keep, int lane) {
+  float g[16];
+  {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float a = keep ? f[i] : 0.f, b = keep ? f[i + 16] : 0.f;
+      g[i] = (hi ? b : a) + __shfl_xor_sync(0xffffffffu, hi ? a : b, 16);
+    }
+  }
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? g[i] : g[i + off];
+      const float kp = hi ? g[i + off] : g[i];
+      g[i] = kp + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return g[0];
+}
+
 __device__ __forceinline__ void acc16(uint32_t taddr, int c, int nstk, int n, int lane, float* xw, float* o) {
   uint32_t v0[16];
   tmem_ld16(taddr + c, v0);
@@ -350,6 +449,31 @@ __device__ __forceinline__ void acc16(uint32_t taddr, int c, int nstk, int n, in
            __uint_as_float(__shfl_sync(0xffffffffu, v2[j], (lane + 2) & 31));
 }
 
+// The same for 16 values (convs with at most 32 output channels): 16 shuffles, lane L ends with the total of value L >> 1.
+__device__ __forceinline__ float transpose_reduce16_masked(const float* f, bool keep, int lane) {
+  float g[8];
+  {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = keep ? f[i] : 0.f, b = keep ? f[i + 8] : 0.f;
+      g[i] = (hi ? b : a) + __shfl_xor_sync(0xffffffffu, hi ? a : b, 16);
+    }
+  }
+#pragma unroll
+  for (int off = 8; off >= 2; off >>= 1) {
+    const int half = off >> 1;  // values kept: 4, 2, 1
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = hi ? g[i] : g[i + half];
+      const float kp = hi ? g[i + half] : g[i];
+      g[i] = kp + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return g[0] + __shfl_xor_sync(0xffffffffu, g[0], 1);
+}
+
 // -DRGFM_TC_TRACE: block 0 records clock64 stamps of the first 24 super-tiles per role and prints them (debug builds only)
 #ifdef RGFM_TC_TRACE
 #define TRC(role, idx) do { if (blockIdx.x == 0 && (idx) < 12) s_trace[role][idx] = clock64() - t_start; } while (0)
@@ -357,11 +481,13 @@ __device__ __forceinline__ void acc16(uint32_t taddr, int c, int nstk, int n, in
 #define TRC(role, idx) do { } while (0)
 #endif
 
+// DENSE: the row-dense instantiation (TcArgs::dense) -- its own register allocation, none of the padded-linear stacking code
+template <bool DENSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-               const __grid_constant__ CUtensorMap tmO, const TcArgs p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmZ, const TcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bars[16 + 2 * TC_MAX_STAGES];
   const uint32_t bar_base = smem_u32(s_bars);
@@ -380,7 +506,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #endif
   __shared__ uint8_t s_rown[400];  // transform group: image (relative to the tile's first) of each A-tile row, 0xff = not a pixel
   __shared__ __align__(16) float s_bias[256];
-  __shared__ __align__(16) float s_xchg[2][4][192];  // tap stacking: raw pieces of the rows that straddle two warps' lane quarters (acc16)
+  // tap stacking: raw pieces of the rows that straddle two warps' lane quarters (acc16); row-dense mode: 4 KB of zeros, the
+  // source of the TMA store that writes the output's two pad columns
+  __shared__ __align__(128) float s_xchg[2][4][192];
   __shared__ __align__(16) float s_part[2][4][3][64][2];
   // per epilogue group / warp / image slot: {sum, sumsq} of a 64-channel chunk
 
@@ -391,7 +519,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t smem_b = smem_stage + 2u * TC_STAGE_BYTES;    // weights (resident or ring)
   const ConvArgs& a = p.c;
   const int N = p.nmma;
-  const int total_rows = a.nimg * (p.H + 1) * p.P;
+  const int total_rows = a.nimg * (p.H + 1) * (DENSE ? p.Wt : p.P);
   const int SR = p.super_rows, UR = p.unit_rows;
   const int supers = (total_rows + SR - 1) / SR;
 
@@ -407,6 +535,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
     }
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+    if (p.tma_store && DENSE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmZ)) : "memory");
     for (int s = 0; s < 4; ++s) {
       mbar_init(a_full(s), 1);
       mbar_init(a_empty(s), 2);                    // both MMA warps
@@ -431,6 +560,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlaps the previous kernel's tail; nothing
   // below may run before its writes are visible
+  if (DENSE && warp < 8) {  // the zero tile of the pad-column store (before the barrier below; generic -> async proxy fence)
+    for (int i = threadIdx.x; i < 2 * 4 * 192; i += 256) (&s_xchg[0][0][0])[i] = 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   pdl_wait();
   if (warp < 8) {
     // bias + this step's time bias: identical for every tile of the launch (t is uniform over the batch)
@@ -482,11 +615,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int cb = 0; cb < ncb; ++cb) {
             mbar_wait(a_empty(as), aph ^ 1u);
             const uint32_t half_bytes = (uint32_t)p.box_rows[seg] * 128u;
-            mbar_expect_tx(a_full(as), 2u * half_bytes);
             const uint32_t sa = smem_base + as * p.a_slot;
+            if (DENSE) {  // one 3-D box [64 channels][Wt pixels][image rows] of the padded-linear tensor: no pad columns
+              mbar_expect_tx(a_full(as), p.a_bytes[seg]);
+              tma_load_3d(sa, tA, a_full(as), cb * 64, p.w0[seg], st * p.irs + p.ir_off[seg]);
+              if (p.l2_prefetch && sti + (int)gridDim.x < supers) {
+                const int st2 = p.descend ? supers - 1 - (sti + (int)gridDim.x) : sti + (int)gridDim.x;
+                tma_prefetch_3d(tA, cb * 64, p.w0[seg], st2 * p.irs + p.ir_off[seg]);
+              }
+            } else {
+            mbar_expect_tx(a_full(as), 2u * half_bytes);
             tma_load_2d(sa, tA, a_full(as), cb * 64, ra);
             tma_load_2d(sa + half_bytes, tA, a_full(as), cb * 64, ra + p.box_rows[seg]);
-            if (p.l2_prefetch && sti + (int)gridDim.x < supers) {
+            }
+            if (!DENSE && p.l2_prefetch && sti + (int)gridDim.x < supers) {
               // The same tile of this CTA's NEXT super-tile, into L2 now: with two A slots the load -> (transform) -> MMA
               // chain of a slot is serial, and the ~1.9 us HBM latency of the load was the largest term in it.
               const int st2 = p.descend ? supers - 1 - (sti + (int)gridDim.x) : sti + (int)gridDim.x;
@@ -524,7 +666,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t hf = (uint32_t)(warp - 9);
     if (lane == 0) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-      const uint32_t rowstep = (uint32_t)p.P * 8u;
+      // 16-byte units: a filter row is P rows of the padded-linear tile, or Wt rows of the row-dense one (whose kx taps
+      // never shift the A descriptor: they are column groups of one MMA)
+      const uint32_t rowstep = DENSE ? (uint32_t)p.Wt * 8u : (uint32_t)p.P * 8u - 16u;
+      const uint32_t kxstep = DENSE ? 0u : 8u;
+      const uint32_t td_1x1 = DENSE ? (uint32_t)p.nmma : 0u;  // row-dense: a 1x1 segment adds to the centre column group
       const uint32_t b_tap16 = p.b_bytes >> 4, b_stage16 = p.b_stage >> 4;
       const uint32_t b_stages = (uint32_t)p.b_stages;
       const uint64_t dhi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;  // SBO = 1024 B, version 1, SWIZZLE_128B
@@ -575,18 +721,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 // shared memory); nothing to issue when the tap belongs to the previous group
                 const uint32_t idg = kx == 0u ? id0 : (kx == 1u ? id1 : id2);
                 if (idg != 0u) {
+                  const uint32_t tdd = ntp == 1 ? td + td_1x1 : td;
 #pragma unroll 1
                   for (int k = 0; k < ks; ++k) {
-                    tc_mma_bf16(td, dhi | (uint64_t)(a_lo + 2u * k), dhi | (uint64_t)(b_lo + 2u * k), idg, acc);
+                    tc_mma_bf16(tdd, dhi | (uint64_t)(a_lo + 2u * k), dhi | (uint64_t)(b_lo + 2u * k), idg, acc);
                     acc = 1u;
                   }
                 }
                 b_lo += b_tap16;
                 if (++kx == 3u) {  // next filter row
                   kx = 0u;
-                  a_lo += rowstep - 16u;
+                  a_lo += rowstep;
                 } else {
-                  a_lo += 8u;
+                  a_lo += kxstep;
                 }
               }
               if (resident) {
@@ -621,23 +768,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // were both slower; a single warp of this kernel runs at ~0.2 IPC, hence eight of them.
     if (p.any_xform) {
       const int tt = threadIdx.x - 11 * 32;
-      const int rows_used = SR + 2 * p.P + 2;
+      const int rows_used = DENSE ? (p.irs + 2) * p.Wt : SR + 2 * p.P + 2;
+      [[maybe_unused]] const bool wcheck = DENSE && p.Wt != p.W;
       uint32_t as = 0, aph = 0;
       const uint32_t a_slots = (uint32_t)p.a_slots;
 #pragma unroll 1
       for (int sti = blockIdx.x; sti < supers; sti += gridDim.x) {
         const int st = p.descend ? supers - 1 - sti : sti;
-        const int rbase = st * SR - (p.P + 1);  // raw row of tile row 0 (every raw segment has this row offset)
+        // raw row of tile row 0 (every raw 3x3 segment has this offset): one image row (dense) / P + 1 rows before the super-tile
+        const int rbase = DENSE ? (st * p.irs - 1) * p.Wt : st * SR - (p.P + 1);
         const int nbase = fast_div(rbase < 0 ? 0 : rbase, p.magic_R);
         // row table of the super-tile, shared by all its (segment, channel block) tiles: one division chain per row here
         // instead of one per row and tile in the hot loop
         // (the previous super-tile's readers are behind the closing barrier of its last tile; the opening barrier of the
         // first tile below publishes the new table)
+        if constexpr (DENSE) {  // one entry per image row of the tile (at most 34)
+          if (tt < p.irs + 2) {
+            const int ir = st * p.irs - 1 + tt;
+            const int n = fast_div(ir < 0 ? 0 : ir, p.magic_H1);
+            const bool ok = ir >= 0 && ir - n * (p.H + 1) < p.H && n < a.nimg;
+            s_rown[tt] = ok ? (uint8_t)(n - nbase) : (uint8_t)0xff;
+          }
+        } else {
         for (int r = tt; r < 400; r += TC_XF_THREADS) {
           int n = -1, h, w;
           const int R = rbase + r;
           const bool ok = r < rows_used && R >= 0 && slot_pixel(R, p.H, p.P, p.magic_P, p.magic_H1, a.nimg, n, h, w);
           s_rown[r] = ok ? (uint8_t)(n - nbase) : (uint8_t)0xff;
+        }
         }
 #pragma unroll 1
         for (int seg = 0; seg < p.nseg; ++seg) {
@@ -694,7 +852,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {  // all loads in flight before the math
                     const int r = r0 + j * rstride;
-                    nr[j] = r < rows_used ? (uint32_t)s_rown[r] : 0xffu;
+                    if constexpr (DENSE) {
+                      nr[j] = r < rows_used ? (uint32_t)s_rown[r >> p.wt_shift] : 0xffu;
+                      if (wcheck && (r & (p.Wt - 1)) >= p.W) nr[j] = 0xffu;  // tile wider than the image: pad / out-of-bounds pixels
+                    } else {
+                      nr[j] = r < rows_used ? (uint32_t)s_rown[r] : 0xffu;
+                    }
                     addr[j] = sa + (uint32_t)r * 128u + (uint32_t)((oct ^ (r & 7)) << 4);
                     if (nr[j] != 0xffu)
                       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
@@ -771,7 +934,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {  // both loads in flight before the math
                   const int r = r0 + j * rstride;
-                  nr[j] = s_rown[r];
+                  if constexpr (DENSE) {
+                    nr[j] = r < rows_used ? (uint32_t)s_rown[r >> p.wt_shift] : 0xffu;
+                    if (wcheck && (r & (p.Wt - 1)) >= p.W) nr[j] = 0xffu;
+                  } else {
+                    nr[j] = s_rown[r];
+                  }
                   addr[j] = sa + (uint32_t)r * 128u + (uint32_t)((oct ^ (r & 7)) << 4);
                   if (r < rows_used)
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
@@ -839,7 +1007,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int nstk = p.nstk;
     float* xw = &s_xchg[eg][q][0];
     // rows whose D_j[m + j] sits in the next warp's lane quarter: stored as zeros by the main path, finished by the fix-up
-    const bool bnd = nstk > 1 && lane >= 33 - nstk;
+    const bool bnd = !DENSE && nstk > 1 && lane >= 33 - nstk;
+    constexpr bool dense = DENSE;
+    // row-dense: lane % Wt is the pixel's w (a unit starts on an image-row boundary); the row ends have no neighbour
+    const bool ml = (lane & (p.Wt - 1)) != 0, mr = (lane & (p.Wt - 1)) != p.Wt - 1;
     const int g = lane >> 2, t4 = lane & 3;  // mma.sync fragment coordinates of the GroupNorm partials
     int it = 0;
     for (int sti = blockIdx.x; sti < supers; sti += gridDim.x, ++it) {
@@ -850,7 +1021,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int m = unit * UR + r;
       int n, h, w;
       // a real pixel of an image < nimg, and one of the UR rows this unit produces (TcArgs::unit_rows)
-      bool valid = slot_pixel(m, p.H, p.P, p.magic_P, p.magic_H1, a.nimg, n, h, w) && r < UR;
+      bool valid = (dense ? dense_pixel(m, p.H, p.W, p.Wt, p.wt_shift, p.magic_H1, a.nimg, n, h, w)
+                          : slot_pixel(m, p.H, p.P, p.magic_P, p.magic_H1, a.nimg, n, h, w)) && r < UR;
       // where this thread's row goes in a stride-2 (subsampled) output: even (h, w) rows map to (h/2, w/2) -- including
       // the pad row h == H and pad column w == W, which are written as zeros -- and the otherwise idle column
       // w == W + 1 writes the second pad column, so the half-resolution raw tensor is zero padded like every other one
@@ -859,7 +1031,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (p.sub) {
         const bool inimg = (n < a.nimg) && (h <= p.H) && r < UR;
         valid = valid && !(h & 1) && !(w & 1);
-        if (inimg && !(h & 1) && (!(w & 1) || w == p.W + 1)) {
+        if (dense) {
+          // no pad-column lanes in the row-dense space: the (otherwise idle) lanes w == 1 and w == 3 of an even image row
+          // write the two pad columns of the half-resolution tensor; the pad row h == H is part of the row space
+          if (inimg && !(h & 1) && w < p.W && (!(w & 1) || w < 4)) {
+            wr = true;
+            const int w2 = (w & 1) ? p.out_W + (w >> 1) : (w >> 1);
+            o = ((size_t)((size_t)n * (p.out_H + 1) + (h >> 1)) * (p.out_W + 2) + w2) * CP;
+          }
+        } else if (inimg && !(h & 1) && (!(w & 1) || w == p.W + 1)) {
           wr = true;
           const int w2 = (w == p.W + 1) ? p.out_W + 1 : (w >> 1);
           o = ((size_t)((size_t)n * (p.out_H + 1) + (h >> 1)) * (p.out_W + 2) + w2) * CP;
@@ -882,6 +1062,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int b2 = b1 + p.R;
         __half2 sat2 = __float2half2_rn(0.f);  // running max |stored value| (cvt2_f16_sat)
         const uint32_t vm = (valid && !bnd) ? 0xffffffffu : 0u;
+        // row-dense statistics: image slot of this row inside the unit, and of the warp's first / last row
+        const int my_slot = n - nf;
+        const int sl_lo = __shfl_sync(0xffffffffu, my_slot, 0), sl_hi = __shfl_sync(0xffffffffu, my_slot, 31);
+        float* s_dpart = &s_part[0][0][0][0][0];  // [group][warp][slot][4 blocks x 8 values]
+        [[maybe_unused]] float fq[DENSE && TC_DENSE_REG_STATS ? 32 : 1];  // per 16-channel block: sums of its four channel quads, then their sums of squares (this row)
+        if constexpr (DENSE && TC_DENSE_REG_STATS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) fq[j] = 0.f;
+        }
         for (int c0 = 0; c0 < CP; c0 += 64) {
           if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has left the buffer
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -894,12 +1083,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
               for (int sc = 0; sc < 2; ++sc) {
                 float v[16];
-                acc16(taddr, c0 + hh * 32 + sc * 16, nstk, N, lane, xw, v);
+                if constexpr (DENSE) acc16_dense(taddr, c0 + hh * 32 + sc * 16, N, ml, mr, p.xchg16 != 0, v);
+                else acc16(taddr, c0 + hh * 32 + sc * 16, nstk, N, lane, xw, v);
+                [[maybe_unused]] float f[8];  // row-dense GroupNorm partials: {sum, sum of squares} of the four channel quads of this block
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + hh * 32 + sc * 16 + 4 * j]);
-                  pk[8 * sc + 2 * j] = cvt2_f16_sat(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, vm, sat2);
-                  pk[8 * sc + 2 * j + 1] = cvt2_f16_sat(v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w, vm, sat2);
+                  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (!p.exp_no_bias) b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + hh * 32 + sc * 16 + 4 * j]);
+                  const float x0 = v[4 * j] + b4.x, x1 = v[4 * j + 1] + b4.y, x2 = v[4 * j + 2] + b4.z, x3 = v[4 * j + 3] + b4.w;
+                  pk[8 * sc + 2 * j] = cvt2_f16_sat(x0, x1, vm, sat2);
+                  pk[8 * sc + 2 * j + 1] = cvt2_f16_sat(x2, x3, vm, sat2);
+                  if constexpr (DENSE && TC_DENSE_REG_STATS) {
+                    f[j] = (x0 + x1) + (x2 + x3);
+                    f[4 + j] = fmaf(x3, x3, fmaf(x2, x2, fmaf(x1, x1, x0 * x0)));
+                  }
+                }
+                if constexpr (DENSE && TC_DENSE_REG_STATS) {  // row-dense GroupNorm partials: kept in registers until the accumulator has been released
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) fq[(hh * 2 + sc) * 8 + j] = f[j];
                 }
               }
             } else {
@@ -924,7 +1125,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
           }
-          if (nstk > 1 && c0 < N) {
+          if (nstk > 1 && !dense && c0 < N) {
             // fix-up pass: the rows that straddle two warps' lane quarters (3 boundaries x (nstk - 1) rows per unit), from
             // the raw fp32 pieces acc16 left in s_xchg -- 96 threads, one channel pair each
             if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -963,11 +1164,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
           else asm volatile("bar.sync 2, 128;" ::: "memory");
           if (p.tma_store && et == 0) {
-            tma_store_2d(&tmO, stg, c0, unit * UR);  // the box has UR rows
+            if (dense) {
+              // box [64 channels][Wt pixels][128 / Wt image rows]; when the tile is as wide as the image the two pad columns
+              // of the padded-linear tensor lie outside it and are written as zeros by a second box (w = W, W + 1)
+              tma_store_3d(&tmO, stg, c0, 0, unit * (128 >> p.wt_shift));
+              if (p.Wt == p.W) tma_store_3d(&tmZ, smem_u32(&s_xchg[0][0][0]), c0, p.W, unit * (128 >> p.wt_shift));
+            } else {
+              tma_store_2d(&tmO, stg, c0, unit * UR);  // the box has UR rows
+            }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           if (threadIdx.x == 0 && c0 == 0) TRC(6, it);
+          if constexpr (DENSE && TC_DENSE_REG_STATS) {
           if (p.stats != nullptr && c0 < N) {
+            // combine the four warps' quad sums; every channel of a quad is credited a quarter of the quad's sums, so the
+            // consumers' per-channel gather (common.h stats_channel_sums) adds up to the group sums it needs unchanged
+            // (GroupNorm groups are whole quads: 4, 8, 12, 16, 24, 32 channels)
+            // Statistics from the registers (no ldmatrix, no legacy HMMA queued behind the UMMA stream), after the
+            // accumulator went back to the MMA warps: quad sums of the stored rows, summed over the warp's 32 rows by
+            // one 31-shuffle transpose-reduce.  A warp's rows lie in at most two images (slots sl_lo / sl_hi of the unit);
+            // the second pass runs only for a warp that straddles an image boundary.
+            if (N <= 32) {  // two 16-channel blocks: 16 values
+              const float ta = transpose_reduce16_masked(fq, valid && my_slot == sl_lo, lane);
+              float tb = 0.f;
+              if (sl_hi != sl_lo) tb = transpose_reduce16_masked(fq, valid && my_slot == sl_hi, lane);
+              if (!(lane & 1)) {
+                float* sp = s_dpart + ((eg * 4 + wq) * 3) * 32 + (lane >> 1);
+                for (int sl = 0; sl < p.nslots; ++sl) sp[sl * 32] = sl == sl_lo ? ta : (sl == sl_hi ? tb : 0.f);
+              }
+            } else {
+              const float ta = transpose_reduce32_masked(fq, valid && my_slot == sl_lo, lane);
+              float tb = 0.f;
+              if (sl_hi != sl_lo) tb = transpose_reduce32_masked(fq, valid && my_slot == sl_hi, lane);
+              float* sp = s_dpart + ((eg * 4 + wq) * 3) * 32 + lane;
+              for (int sl = 0; sl < p.nslots; ++sl) sp[sl * 32] = sl == sl_lo ? ta : (sl == sl_hi ? tb : 0.f);
+            }
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (et < p.nslots * 32) {
+              const int slot = et >> 5, j = et & 31;
+              const float* sp = s_dpart + (eg * 4 * 3 + slot) * 32 + j;
+              const float tot = 0.25f * (((sp[0] + sp[3 * 32]) + sp[2 * 3 * 32]) + sp[3 * 3 * 32]);
+              const int ch = c0 + (j >> 3) * 16 + (j & 3) * 4;
+              if (ch < N) {
+                float* dst = p.stats + ((size_t)(unit * p.nslots + slot) * CP + ch) * 2 + ((j >> 2) & 1);
+                dst[0] = tot; dst[2] = tot; dst[4] = tot; dst[6] = tot;
+              }
+            }
+          }
+          } else if (p.stats != nullptr && c0 < N) {
             // GroupNorm partials of the ROUNDED values on the legacy tensor path, channels on M and image slots on N:
             //   S[ch][slot] = sum_row X[row][ch] * Ind[row][slot]   (Ind = 0/1: row belongs to image slot of the unit)
             // per warp = its 32 staged rows: 4 channel blocks x 2 row blocks of mma.sync m16n8k16, A = X^T by
@@ -1046,15 +1291,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       } else {
         // output conv (never stacked): Cout <= 16 real channels -> NCHW velocity, or fused Euler update x += dt * v
-        uint32_t v[16];
-        tmem_ld16(taddr, v);
-        tmem_ld_wait();
+        float v[16];
+        if (dense) {
+          acc16_dense(taddr, 0, N, ml, mr, false, v);
+        } else {
+          uint32_t u[16];
+          tmem_ld16(taddr, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
         if (valid) {
           for (int c = 0; c < a.Cout; ++c) {
-            const float val = __uint_as_float(v[c]) + s_bias[c];
+            const float val = v[c] + s_bias[c];
             const size_t oc = (((size_t)n * a.Cout + c) * p.out_H + h) * p.out_W + w;
             if (a.out_mode == OUT_NCHW)
               a.out[oc] = val;
@@ -1102,7 +1354,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 struct TcConv {
-  CUtensorMap tmA[3], tmB[3], tmO;
+  CUtensorMap tmA[3], tmB[3], tmO, tmZ;
   TcArgs p;
   size_t smem;
 };
@@ -1129,6 +1381,38 @@ static void encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const 
   RGFM_CHECK(r == CUDA_SUCCESS, std::string("cuTensorMapEncodeTiled(") + what + ") failed with code " + std::to_string((int)r));
 }
 
+static void encode_3d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t mid, uint64_t outer, uint32_t box_inner,
+                      uint32_t box_mid, uint32_t box_outer, CUtensorMapSwizzle swz, const char* what) {
+  cuuint64_t dims[3] = {inner, mid, outer};
+  cuuint64_t strides[2] = {inner * 2, inner * mid * 2};
+  cuuint32_t box[3] = {box_inner, box_mid, box_outer};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RGFM_CHECK(r == CUDA_SUCCESS, std::string("cuTensorMapEncodeTiled(") + what + ") failed with code " + std::to_string((int)r));
+}
+
+// Row-dense mode (TcArgs::dense): convs with at most 64 output channels (three kx column groups of an accumulator are
+// 3 * nmma <= 192 TMEM columns) whose image is at most 32 pixels wide.  It trades shared-memory operand traffic and MMA
+// instructions (a third of both) for epilogue instructions (three column groups to read, the neighbour exchange), and
+// the kernel is short of BOTH the shared-memory port and issue slots (ncu: 55..58 % of the issue slots busy with 19
+// warps, profiles/notes_r02.md): measured per layer it wins 10..20 % where a super-tile walks at least two operand
+// stages (decoder conv1s, every conv2 with its skip / identity segment) and on the output convs (N = 16: 12 instead of
+// 36 MMAs), and loses 8..25 % on single-stage convs, whose epilogue is the critical role.  Hence the rule below.
+// RGFM_TC_DENSE=0: padded-linear everywhere, 2: row-dense wherever it is legal (A/B timing).
+// stages: 64-channel operand blocks of all K segments.
+bool tc_dense(int cout, int W, bool final, int stages) {
+  static const int mode = getenv("RGFM_TC_DENSE") ? atoi(getenv("RGFM_TC_DENSE")) : 1;
+  const int nmma = (cout + 15) / 16 * 16;
+  if (mode == 0 || nmma > 64 || W > 32 || W < 4) return false;
+  return mode == 2 || final || stages >= 2;
+}
+static int tc_tile_width(int W) { return W <= 8 ? 8 : (W <= 16 ? 16 : 32); }
+// GEMM rows per image of the row space a conv's GroupNorm partials are indexed by
+int tc_rows_per_image(int cout, int H, int W, bool final, int stages) {
+  return tc_dense(cout, W, final, stages) ? (H + 1) * tc_tile_width(W) : (H + 1) * (W + 2);
+}
+
 // Column groups per accumulator (TcArgs::nstk).  Stacking shortens the MMA phase of a tile (N = 96: 57 cycles, N = 192: 97,
 // N = 128 + 64: 115 against 3 x 49.7) but lengthens its epilogue (three / two accumulator column groups to read, the
 // lane-shifted sum, the boundary fix-up), and the epilogue is the critical role of a conv whose tile holds ONE operand
@@ -1146,12 +1430,12 @@ int tc_stack_groups(int cout, int stride, bool final, int stages3, int stages) {
   if (mode == 2) return nstk;
   return (nstk == 3 ? stages3 >= 2 : stages >= 2) ? nstk : 1;
 }
-int tc_unit_rows(int cout, int stride, bool final, int stages3, int stages) {
+int tc_unit_rows(int cout, int W, int stride, bool final, int stages3, int stages) {
+  if (tc_dense(cout, W, final, stages)) return 128;
   return 128 - (tc_stack_groups(cout, stride, final, stages3, stages) - 1);
 }
 
-size_t tc_stats_floats(int H, int W, int chunk, int unit_rows, int CoutP) {
-  const int R = (H + 1) * (W + 2);
+size_t tc_stats_floats(int R, int chunk, int unit_rows, int CoutP) {
   const int SR = 2 * unit_rows;
   const size_t supers = ((size_t)chunk * R + SR - 1) / SR;
   return supers * 2 * (size_t)stats_slots_for(R) * CoutP * 2;
@@ -1169,7 +1453,20 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   std::memset(&p, 0, sizeof(p));
   const int P = d.Win + 2;
   p.H = d.Hin; p.W = d.Win; p.P = P;
-  p.R = (d.Hin + 1) * P;
+  {
+    int stall = 0;
+    for (int sg = 0; sg < d.nseg; ++sg) stall += (d.seg[sg].Cin_real + 63) / 64;
+    p.dense = tc_dense(d.Cout, d.Win, d.out == nullptr && d.stride == 1, stall) ? 1 : 0;
+  }
+  if (p.dense) {
+    RGFM_CHECK(d.seg[0].ks == 3, "tc conv: segment 0 of a row-dense conv is 3x3");
+    p.Wt = tc_tile_width(d.Win);
+    p.wt_shift = p.Wt == 8 ? 3 : (p.Wt == 16 ? 4 : 5);
+    p.irs = 256 / p.Wt;
+  }
+  static const int xchg16 = getenv("RGFM_TC_XCHG16") ? atoi(getenv("RGFM_TC_XCHG16")) : 0;  // measured: < 0.5 % of a step; off = exact fp32 exchange
+  p.xchg16 = xchg16;
+  p.R = p.dense ? (d.Hin + 1) * p.Wt : (d.Hin + 1) * P;
   {
     auto magic = [&](int dv) {
       const uint64_t nmax = (uint64_t)d.chunk * p.R + 2 * 256;
@@ -1189,16 +1486,16 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
       stall += cb;
       if (d.seg[sg].ks == 3) st3 += cb;
     }
-    p.nstk = tc_stack_groups(d.Cout, d.stride, d.out == nullptr && d.stride == 1, st3, stall);
+    p.nstk = p.dense ? 3 : tc_stack_groups(d.Cout, d.stride, d.out == nullptr && d.stride == 1, st3, stall);
   }
-  p.unit_rows = 128 - (p.nstk - 1);
+  p.unit_rows = p.dense ? 128 : 128 - (p.nstk - 1);
   p.super_rows = 2 * p.unit_rows;
   p.ncols = (p.nstk * nmma + 31) / 32 * 32;
   p.sat = d.sat;
   const int rows_needed = p.super_rows + 2 * P + 2;
   p.a_box_rows = ((rows_needed + 1) / 2 + 7) / 8 * 8;
   RGFM_CHECK(p.a_box_rows <= 256, "tc conv: A box too tall");
-  p.a_slot = 2u * p.a_box_rows * 128u;
+  p.a_slot = p.dense ? (uint32_t)(p.irs + 2) * p.Wt * 128u : 2u * p.a_box_rows * 128u;
   p.b_bytes = (uint32_t)nmma * 128u;
   p.nbuf = (4 * p.ncols <= 512) ? 2 : 1;
   uint32_t cols = 32;
@@ -1319,9 +1616,28 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
           hw[((size_t)tp * nmma + o) * S.Cin + c] = bits;
         }
     uint16_t* dw = pool.upload(hw);
+    if (p.dense) {
+      // 3-D view [Cin][P][image rows] of the same padded-linear tensor; the box takes Wt pixels of each image row (the
+      // pad columns stay behind; for W < Wt the columns past the row are pads / out of bounds = zeros).  A packed operand
+      // holds pixel (image row, w) at (image row + 1, w + 1).  3x3 segments start one image row above the super-tile.
+      const int irows = S.ks == 3 ? p.irs + 2 : p.irs;
+      p.w0[sg] = S.raw ? 0 : 1;
+      p.ir_off[sg] = (S.raw ? 0 : 1) + (S.ks == 3 ? -1 : 0);
+      p.a_bytes[sg] = (uint32_t)irows * p.Wt * 128u;
+      const uint64_t image_rows = (uint64_t)d.chunk * (d.Hin + 1) + (S.raw ? 0 : 1);
+      cuuint64_t dims[3] = {(cuuint64_t)S.Cin, (cuuint64_t)P, image_rows};
+      cuuint64_t strides[2] = {(cuuint64_t)S.Cin * 2, (cuuint64_t)S.Cin * P * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)p.Wt, (cuuint32_t)irows};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult r = encode_fn()(&t->tmA[sg], S.raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : dt16, 3, const_cast<void*>(S.in), dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      RGFM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, row-dense) failed with code " + std::to_string((int)r));
+    } else {
     // operand: 2-D [rows][Cin]; rows before the first / after the last are zero-filled by TMA
     encode_2d(&t->tmA[sg], S.raw ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : dt16, 2, S.in, (uint64_t)S.Cin,
               S.raw ? tc_raw_rows(d.Hin, d.Win, d.chunk) : tc_operand_slots(d.Hin, d.Win, d.chunk), 64, (uint32_t)p.box_rows[sg], "A");
+    }
     {
       cuuint64_t dims[3] = {(cuuint64_t)S.Cin, (cuuint64_t)nmma, (cuuint64_t)taps};
       cuuint64_t strides[2] = {(cuuint64_t)S.Cin * 2, (cuuint64_t)nmma * S.Cin * 2};
@@ -1336,13 +1652,19 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     t->tmA[sg] = t->tmA[0];
     t->tmB[sg] = t->tmB[0];
   }
-  if (p.tma_store)
+  t->tmZ = t->tmA[0];
+  if (p.tma_store && p.dense) {
+    const uint64_t image_rows = (uint64_t)d.chunk * (d.Hin + 1);
+    encode_3d(&t->tmO, d.out, (uint64_t)d.CoutP, (uint64_t)P, image_rows, 64, (uint32_t)p.Wt, (uint32_t)(128 / p.Wt), CU_TENSOR_MAP_SWIZZLE_128B, "out, row-dense");
+    encode_3d(&t->tmZ, d.out, (uint64_t)d.CoutP, (uint64_t)P, image_rows, 64, 2, (uint32_t)(128 / p.Wt), CU_TENSOR_MAP_SWIZZLE_NONE, "pad columns");
+  } else if (p.tma_store)
     encode_2d(&t->tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d.out, (uint64_t)d.CoutP, tc_raw_rows(d.Hin, d.Win, d.chunk), 64,
               (uint32_t)p.unit_rows, "out");
   else
     t->tmO = t->tmA[0];
   // per device (function attributes belong to the current context): cheap enough to set for every plan
-  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
+  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
+  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
   return t;
 }
 
@@ -1371,10 +1693,12 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
 #ifdef RGFM_EXPERIMENTS  // timing-only switches that knowingly corrupt results: compiled out of the shipped library
   static const int noxf = getenv("RGFM_EXPERIMENT_NO_XFORM") ? atoi(getenv("RGFM_EXPERIMENT_NO_XFORM")) : 0;  // 1: no work, 2: no coefficient switches
   p.exp_no_xform = noxf;
+  static const int nobias = getenv("RGFM_EXPERIMENT_NO_BIAS") ? atoi(getenv("RGFM_EXPERIMENT_NO_BIAS")) : 0;
+  p.exp_no_bias = nobias;
   static const bool no_stats = getenv("RGFM_TC_NO_STATS") != nullptr;
   if (no_stats) p.stats = nullptr;
 #endif
-  const int total_rows = a.nimg * (p.H + 1) * p.P;
+  const int total_rows = a.nimg * (p.H + 1) * (p.dense ? p.Wt : p.P);
   const int supers = (total_rows + p.super_rows - 1) / p.super_rows;
   static int num_sms = 0;  // B200 only: every device of the box has the same count
   if (!num_sms) {
@@ -1383,7 +1707,10 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = supers < num_sms ? supers : num_sms;  // persistent: one CTA per SM, static round-robin
-  launch_pdl(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, p);
+  if (p.dense)
+    launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p);
+  else
+    launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p);
   post_launch("conv_tc");
 }
 

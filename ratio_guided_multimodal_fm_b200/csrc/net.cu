@@ -104,14 +104,14 @@ struct Builder {
   }
   // 16-bit zero-padded padded-linear raw activation (tcgen05 path); (Hc, Wc) is the geometry of the producing conv's
   // GEMM row space (differs from (H, W) for stride-2 convs), which is what the GroupNorm partials are indexed by
-  Act new_act_tc(int H, int Wd, int C, bool stats, int Hc, int Wc, int unit_rows) {
+  Act new_act_tc(int H, int Wd, int C, bool stats, int R, int unit_rows) {  // R: rows per image of the producing conv's row space
     Act a;
     a.H = H; a.W = Wd; a.C = C; a.Cs = tc_stride(C);
     a.padded = true; a.fmt = 2;  // raw activations are fp16 in both 16-bit modes
     a.p = (float*)pool.alloc(tc_raw_rows(H, Wd, chunk) * a.Cs * 2);
     if (stats) {
-      a.stats = (float*)pool.alloc(tc_stats_floats(Hc, Wc, chunk, unit_rows, a.Cs) * sizeof(float));
-      a.st.p = a.stats; a.st.mode = ST_UNITS; a.st.C = a.Cs; a.st.R = (Hc + 1) * (Wc + 2); a.st.slots = stats_slots_for(a.st.R);
+      a.stats = (float*)pool.alloc(tc_stats_floats(R, chunk, unit_rows, a.Cs) * sizeof(float));
+      a.st.p = a.stats; a.st.mode = ST_UNITS; a.st.C = a.Cs; a.st.R = R; a.st.slots = stats_slots_for(a.st.R);
       a.st.unit_rows = unit_rows;  // the producing conv's unit (conv_tc.cu: tap stacking shortens it)
       a.st.magic_unit = (unsigned int)(((1ull << 32) + a.st.unit_rows - 1) / a.st.unit_rows);
     }
@@ -292,7 +292,7 @@ struct Builder {
         stall += (S.Creal + 63) / 64;
         if (S.ks == 3) st3 += (S.Creal + 63) / 64;
       }
-      o = new_act_tc(Ho, Wo, cout, stats, H, Wd, tc_unit_rows(cout, stride, false, st3, stall));
+      o = new_act_tc(Ho, Wo, cout, stats, tc_rows_per_image(cout, H, Wd, false, stall), tc_unit_rows(cout, Wd, stride, false, st3, stall));
       a.out = o.p;
       a.CoutP = o.Cs;
     } else {

@@ -148,8 +148,10 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s);
 bool tc_available();
 size_t tc_operand_slots(int H, int W, int chunk);  // rows of a padded-linear operand tensor
 size_t tc_raw_rows(int H, int W, int chunk);       // rows of a padded-linear raw activation tensor
-size_t tc_stats_floats(int H, int W, int chunk, int unit_rows, int CoutP);  // floats of a conv's GroupNorm partials buffer
-// output rows per GroupNorm-partials unit of a conv (128, or 127 / 126 when it stacks taps: stride 1, raw output, Cout <= 64)
-int tc_unit_rows(int cout, int stride, bool final, int stages3, int stages);  // stages: 64-channel operand blocks (3x3 segments / all)
+size_t tc_stats_floats(int R, int chunk, int unit_rows, int CoutP);  // floats of a conv's GroupNorm partials buffer (R: rows per image)
+// output rows per GroupNorm-partials unit of a conv (128; 127 / 126 when a padded-linear conv stacks taps: stride 1, raw output, Cout <= 64)
+int tc_unit_rows(int cout, int W, int stride, bool final, int stages3, int stages);  // stages: 64-channel operand blocks (3x3 segments / all)
+// GEMM rows per image of the conv's row space: (H + 1) * (W + 2) padded-linear, (H + 1) * Wt row-dense (conv_tc.cu, TcArgs::dense)
+int tc_rows_per_image(int cout, int H, int W, bool final, int stages);
 
 }  // namespace rgfm
