@@ -58,7 +58,7 @@ _lib = None
 EXPORTS = [
     "rgfm_last_error", "rgfm_abi_version", "rgfm_sampler_create", "rgfm_sampler_run", "rgfm_sampler_run_host",
     "rgfm_sampler_set_strength", "rgfm_sampler_run_reuse_bank", "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
-    "rgfm_unet_forward", "rgfm_unet_sample", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_log_ratio", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
+    "rgfm_unet_forward", "rgfm_unet_sample", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_create_prec", "rgfm_ratio_grad_log_ratio", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
 ]
 
 
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
     L.rgfm_ratio_log_ratio.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
     L.rgfm_classifier_logits.argtypes = [vp, vp, C.c_int32, vp, vp]
     L.rgfm_ratio_grad_create.argtypes = [C.c_int32, C.POINTER(_Weights), C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.rgfm_ratio_grad_create_prec.argtypes = [C.c_int32, C.POINTER(_Weights), C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
     L.rgfm_ratio_grad_log_ratio.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
     L.rgfm_net_destroy.argtypes = [vp]
     L.rgfm_net_destroy.restype = None
@@ -175,8 +176,9 @@ class Net:
         self.device = torch.device("cuda", _dev_index(device))
         self.h = C.c_void_p()
         w = Weights(state_dict)
-        if grad:  # forward + input-gradient program of a ratio estimator (exact fp32)
-            check(lib().rgfm_ratio_grad_create(NET_KINDS[kind], w.ref(), int(max_batch), self.device.index, C.byref(self.h)))
+        if grad:  # forward + input-gradient program of a ratio estimator (fp32: exact; 16-bit: both conv chains on the tensor cores)
+            check(lib().rgfm_ratio_grad_create_prec(NET_KINDS[kind], w.ref(), int(max_batch), PRECISION[precision], self.device.index,
+                                                    C.byref(self.h)))
         else:
             check(lib().rgfm_net_create(NET_KINDS[kind], w.ref(), int(max_batch), PRECISION[precision],
                                         self.device.index, C.byref(self.h)))

@@ -189,14 +189,20 @@ int rgfm_ratio_log_ratio(rgfm_net* net, const float* x, const float* y, int32_t 
   RGFM_API_END
 }
 
-int rgfm_ratio_grad_create(int32_t net_kind, const rgfm_weights* w, int32_t max_batch, int32_t device, rgfm_net** out) {
+int rgfm_ratio_grad_create_prec(int32_t net_kind, const rgfm_weights* w, int32_t max_batch, int32_t precision, int32_t device,
+                                rgfm_net** out) {
   RGFM_API_BEGIN
   RGFM_CHECK(out != nullptr, "rgfm_ratio_grad_create: null out");
+  RGFM_CHECK(precision == RGFM_PREC_FP32 || precision == RGFM_PREC_FP16 || precision == RGFM_PREC_BF16, "rgfm_ratio_grad_create: unknown precision");
   std::unique_ptr<rgfm_net> n(new rgfm_net());
   n->device = device;
-  n->net.reset(new rgfm::Net(net_kind, w, max_batch, RGFM_PREC_FP32, device, /*want_grad=*/true));
+  n->net.reset(new rgfm::Net(net_kind, w, max_batch, precision, device, /*want_grad=*/true));
   *out = n.release();
   RGFM_API_END
+}
+
+int rgfm_ratio_grad_create(int32_t net_kind, const rgfm_weights* w, int32_t max_batch, int32_t device, rgfm_net** out) {
+  return rgfm_ratio_grad_create_prec(net_kind, w, max_batch, RGFM_PREC_FP32, device, out);
 }
 
 int rgfm_ratio_grad_log_ratio(rgfm_net* net, const float* x, const float* y, int32_t batch, int32_t loss_type, float* grad_x,

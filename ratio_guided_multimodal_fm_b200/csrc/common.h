@@ -174,7 +174,8 @@ enum NormMode { NORM_NONE = 0, NORM_GN = 1, NORM_AFFINE = 2 };
 // SP_D2S: depth-to-space x2 of a [H][W][4*C] source whose channel (a*2+b)*C + c is output pixel (2h+a, 2w+b), channel c --
 // a ConvTranspose2d(4, stride 2, padding 1) computed as a 3x3 convolution with 4*C_out outputs (fp32 pack kernel only)
 enum SpatialMode { SP_ID = 0, SP_UP2 = 1, SP_POOL2 = 2, SP_D2S = 3 };
-enum OutMode { OUT_RAW = 0, OUT_NCHW = 1, OUT_EULER = 2 };
+// OUT_NCHW_SCALED: out = dt * val (the last dgrad conv of the 16-bit gradient chain removes its loss scale)
+enum OutMode { OUT_RAW = 0, OUT_NCHW = 1, OUT_EULER = 2, OUT_NCHW_SCALED = 3 };
 enum ActMode { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2 };
 
 // ---- kernel launch descriptors (plain structs passed by value) ----
@@ -246,8 +247,13 @@ void launch_mlp(const float* in, int ld_in, const MlpLayer* layers, int nlayers,
                 cudaStream_t s);
 void launch_mlp_bwd(const float* in, int ld_in, const MlpLayer* layers, int nlayers, int loss_type, float* scores, float* log_ratio,
                     float* dfeat, int ld_d, int nimg, cudaStream_t s);
-void launch_gap_fc_bwd(const float* dfeat, int ld, const float* w, int Cout, int HW, int C, float* dact, int nimg, cudaStream_t s);
-void launch_pack_bwd(const PackArgs& a, const float* dcur, float* draw, cudaStream_t s);
+void launch_gap_fc_bwd(const float* dfeat, int ld, const float* w, int Cout, int HW, int C, float gscale, float* dact, int nimg, cudaStream_t s);
+// storage of the gradient tensors of one pack backward: dense fp32 NHWC, or the tensor-core kernel's 16-bit padded-linear raw layout
+struct PackBwdIO {
+  int dcur_fmt = 0, dcur_padded = 0, dcur_Cs = 0;  // incoming gradient (geometry of the pack's output): 0 = fp32, 2 = fp16; channel stride
+  int draw_padded = 0, draw_Cs = 0;                // outgoing gradient (geometry of the raw activation): fp32 dense, or fp16 padded with stride Cs
+};
+void launch_pack_bwd(const PackArgs& a, const PackBwdIO& io, const float* dcur, float* draw, cudaStream_t s);
 void launch_euler_grad(float* x, const float* v, const float* g, float gamma, float dt, size_t n, cudaStream_t s);
 void launch_ratio_head(const float* scores, int loss_type, float* log_ratio, float* ratios, int n, cudaStream_t s);
 void launch_step_inc(int* step, cudaStream_t s);

@@ -1310,6 +1310,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const size_t oc = (((size_t)n * a.Cout + c) * p.out_H + h) * p.out_W + w;
             if (a.out_mode == OUT_NCHW)
               a.out[oc] = val;
+            else if (a.out_mode == OUT_NCHW_SCALED)
+              a.out[oc] = val * a.dt;
             else
               a.out[oc] = __fadd_rn(a.out[oc], __fmul_rn(val, a.dt));
           }

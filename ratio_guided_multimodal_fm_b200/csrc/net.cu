@@ -68,7 +68,11 @@ void* DevPool::persistent(size_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// loss scale of the 16-bit gradient chain (encoder(): dgrad on the tensor cores)
+constexpr float GRAD_SCALE = 1024.f;
+
 struct Builder {
+  using Op = Net::Op;
   Net& net;
   const WeightMap& W;
   DevPool& pool;
@@ -223,7 +227,12 @@ struct Builder {
     return p;
   }
 
-  static bool tc_geom_ok(int H, int Wd) { return (H + 1) * (Wd + 2) >= 64 && Wd + 2 <= 39; }
+  // GroupNorm partials index at most three images per 128-row unit (>= 64 GEMM rows per image); a conv without statistics
+  // (BatchNorm nets, gradient tensors) only needs a tile that holds its 3x3 halo
+  static bool tc_geom_ok(int H, int Wd, bool stats = true) {
+    static const bool small_off = getenv("RGFM_TC_SMALL") && atoi(getenv("RGFM_TC_SMALL")) == 0;  // A/B switch
+    return (H + 1) * (Wd + 2) >= (stats || small_off ? 64 : 16) && Wd + 2 <= 39 && H >= 2;
+  }
 
   // ---- tcgen05 convolution -------------------------------------------------------------------------------------
   // K segment of a tensor-core conv: a packed operand or a (zero-padded) raw activation, 3x3 or 1x1, with weights taken
@@ -273,9 +282,11 @@ struct Builder {
   }
 
   // (H, W): geometry of the operands (the stride-1 output geometry).  Returns the raw output (none when `final`).
+  // grad_out (final convs only): 1 / 2 = the output is the chunk's d log r / dx / dy (RunCtx::gx / gy), written as
+  // grad_scale * value (OUT_NCHW_SCALED) -- the last dgrad conv of the 16-bit gradient chain
   Act conv_tc(int H, int Wd, const std::vector<Seg>& segs, const float* bias, int cout, int stride, int temb_off, bool stats,
-              bool final, const std::string& label) {
-    RGFM_CHECK(tc_geom_ok(H, Wd), "conv_tc: image geometry is not supported by the tensor-core kernel");
+              bool final, const std::string& label, int grad_out = 0, float grad_scale = 1.f, const char* kind = "conv_tc") {
+    RGFM_CHECK(tc_geom_ok(H, Wd, stats), "conv_tc: image geometry is not supported by the tensor-core kernel");
     const int Ho = stride == 2 ? H / 2 : H, Wo = stride == 2 ? Wd / 2 : Wd;
     ConvArgs a{};
     a.Hin = H; a.Win = Wd;
@@ -317,7 +328,7 @@ struct Builder {
     Net* np = &net;
     const double flops = 2.0 * Ho * Wo * (double)cout * macs;
     const double bytes = in_bytes + (double)Ho * Wo * cout * (final ? 4.0 : 2.0);
-    net.ops_.push_back({[a, tcp, final, has_temb, np](const RunCtx& c) {
+    net.ops_.push_back({[a, tcp, final, has_temb, np, grad_out, grad_scale](const RunCtx& c) {
       ConvArgs b = a;
       b.nimg = c.nimg;
       if (has_temb) {
@@ -330,8 +341,13 @@ struct Builder {
         b.out_mode = c.out_mode;
         b.dt = c.dt;
       }
+      if (grad_out) {
+        b.out = grad_out == 2 ? c.gy : c.gx;
+        b.out_mode = OUT_NCHW_SCALED;
+        b.dt = grad_scale;
+      }
       launch_conv_tc(*tcp, b, c.s);
-    }, "conv_tc", flops, bytes, label});
+    }, kind, flops, bytes, label});
     return o;
   }
 
@@ -747,7 +763,7 @@ struct Builder {
     int hcur = img;
     for (size_t i = 0; i < L.size(); ++i) {
       sp[i] = hcur;
-      ltc[i] = tc_mode && i > 0 && tc_geom_ok(hcur, hcur);
+      ltc[i] = tc_mode && i > 0 && tc_geom_ok(hcur, hcur, gn);
       if (L[i].pool) hcur /= 2;
     }
     for (size_t i = 0; i < L.size(); ++i) {
@@ -785,45 +801,88 @@ struct Builder {
       return;
     }
     // ---- dgrad chain (appended after the score-net backward) ----
+    // 16-bit modes: the dgrad convs of the layers the tensor-core kernel takes (every layer with >= 64 GEMM rows per image,
+    // the first one included: its 1 / 3 outputs are an N = 16 output conv) run on conv_tc over fp16 gradient tensors in the
+    // padded-linear raw layout.  Gradients of log r are ~1e-5, far below fp16's normal range, so the whole chain carries a
+    // LOSS SCALE: gap_fc_bwd multiplies by GRAD_SCALE, every later op is linear in the gradient, and the last dgrad conv
+    // stores value / GRAD_SCALE (OUT_NCHW_SCALED).  Saturated rows are counted like everywhere else (diag[12]).
+    const float gscale = tc_mode ? GRAD_SCALE : 1.f;
+    std::vector<Op>& B = *bwd;
+    std::vector<bool> btc(L.size());
+    for (size_t i = 0; i < L.size(); ++i) btc[i] = tc_mode && tc_geom_ok(sp[i], sp[i], false);
     float* dcur = (float*)pool.alloc((size_t)chunk * HW * C * sizeof(float));
-    bwd->push_back({[=](const RunCtx& c) { launch_gap_fc_bwd(dfeat + feat_off, feat_ld, fw, 256, HW, C, dcur, c.nimg, c.s); }, "gap_fc_bwd",
-                    2.0 * 256 * C, (double)HW * C * 4.0});
+    B.push_back({[=](const RunCtx& c) { launch_gap_fc_bwd(dfeat + feat_off, feat_ld, fw, 256, HW, C, gscale, dcur, c.nimg, c.s); }, "gap_fc_bwd",
+                 2.0 * 256 * C, (double)HW * C * 4.0});
+    PackBwdIO io{};  // format of the gradient arriving at layer i's pack output (dense fp32 out of the GAP / fc backward)
+    io.dcur_fmt = 0; io.dcur_padded = 0; io.dcur_Cs = C;
     for (int i = (int)L.size() - 1; i >= 0; --i) {
       const EncLayer& l = L[i];
       const int H = saved[i].Hs;
-      float* draw = (float*)pool.alloc((size_t)chunk * H * H * l.cout * sizeof(float));
       const PackArgs pa = saved[i];
       const float* dc = dcur;
-      bwd->push_back({[=](const RunCtx& c) {
-        PackArgs b = pa;
-        b.nimg = c.nimg;
-        launch_pack_bwd(b, dc, draw, c.s);
-      }, "pack_bwd", 0.0, (double)H * H * l.cout * 12.0});
-      // conv dgrad: dIn[h][w][ci] = sum_{tap, co} dRaw[h + ky - 1][w + kx - 1][co] * W[co][ci][2 - ky][2 - kx]
-      const int cinP = (l.cin + 31) / 32 * 32;
-      const float* wt = W.get(pre + l.conv + ".weight", (int64_t)l.cout * l.cin * 9);
-      std::vector<float> wf((size_t)9 * l.cout * cinP, 0.f);
-      for (int co = 0; co < l.cout; ++co)
-        for (int ci = 0; ci < l.cin; ++ci)
-          for (int t = 0; t < 9; ++t) wf[((size_t)t * l.cout + co) * cinP + ci] = wt[((size_t)co * l.cin + ci) * 9 + (8 - t)];
-      ConvArgs ca{};
-      ca.in = draw; ca.Hin = H; ca.Win = H; ca.Cin = l.cout;
-      ca.w = pool.upload(wf);
-      ca.bias = pool.upload(std::vector<float>(cinP, 0.f));
-      ca.CoutP = cinP; ca.Cout = l.cin; ca.ks = 3; ca.stride = 1; ca.pad = 1;
-      ca.g = make_geom(H, H);
       const bool first = (i == 0);
-      float* dnext = first ? nullptr : (float*)pool.alloc((size_t)chunk * H * H * l.cin * sizeof(float));
-      ca.out_mode = first ? OUT_NCHW : OUT_RAW;
-      ca.out = dnext;
-      bwd->push_back({[=](const RunCtx& c) {
-        ConvArgs b = ca;
-        b.nimg = c.nimg;
-        if (first) b.out = from_y ? c.gy : c.gx;
-        launch_conv_simt(b, c.s);
-      }, "conv_dgrad", 2.0 * H * H * (double)l.cout * l.cin * 9, (double)H * H * (l.cout + l.cin) * 4.0,
-         pre + l.conv + " dgrad " + std::to_string(H) + "x" + std::to_string(H) + " " + std::to_string(l.cout) + "->" + std::to_string(l.cin)});
-      dcur = dnext;
+      // conv dgrad: dIn[h][w][ci] = sum_{tap, co} dRaw[h + ky - 1][w + kx - 1][co] * W[co][ci][2 - ky][2 - kx]
+      const float* wt = W.get(pre + l.conv + ".weight", (int64_t)l.cout * l.cin * 9);
+      const std::string lab = pre + l.conv + " dgrad " + std::to_string(H) + "x" + std::to_string(H) + " " + std::to_string(l.cout) + "->" + std::to_string(l.cin);
+      if (btc[i]) {
+        // outgoing gradient of the pack backward: fp16 padded-linear raw tensor = zero-padded operand of the dgrad conv
+        Act dr = new_act_tc(H, H, l.cout, false, 0, 128);
+        io.draw_padded = 1; io.draw_Cs = dr.Cs;
+        float* draw = dr.p;
+        const PackBwdIO iob = io;
+        B.push_back({[=](const RunCtx& c) {
+          PackArgs b = pa;
+          b.nimg = c.nimg;
+          launch_pack_bwd(b, iob, dc, draw, c.s);
+        }, "pack_bwd", 0.0, (double)H * H * l.cout * 8.0});
+        std::vector<float> wf((size_t)l.cin * l.cout * 9);  // torch layout [Cout' = cin][Cin' = cout][3][3], taps flipped
+        for (int co = 0; co < l.cout; ++co)
+          for (int ci = 0; ci < l.cin; ++ci)
+            for (int t = 0; t < 9; ++t) wf[((size_t)ci * l.cout + co) * 9 + t] = wt[((size_t)co * l.cin + ci) * 9 + (8 - t)];
+        const int coutP = first ? 16 : (l.cin + 63) / 64 * 64;
+        const size_t nops = net.ops_.size();
+        Act dn = conv_tc(H, H, {seg_of(dr, 3, wf.data())}, pool.upload(std::vector<float>(coutP, 0.f)), l.cin, 1, -1, false, first, lab,
+                         first ? (from_y ? 2 : 1) : 0, 1.f / gscale, "conv_dgrad");
+        // conv_tc() appended to the forward program: the dgrad chain runs after the score-net backward
+        B.push_back(net.ops_.back());
+        net.ops_.pop_back();
+        RGFM_CHECK(net.ops_.size() == nops, "encoder: dgrad op bookkeeping");
+        // NOTE: dr / dcur stay allocated (the backward program reuses them every call)
+        io.dcur_fmt = 2; io.dcur_padded = 1; io.dcur_Cs = dn.Cs;
+        dcur = dn.p;
+      } else {
+        float* draw = (float*)pool.alloc((size_t)chunk * H * H * l.cout * sizeof(float));
+        io.draw_padded = 0; io.draw_Cs = l.cout;
+        const PackBwdIO iob = io;
+        B.push_back({[=](const RunCtx& c) {
+          PackArgs b = pa;
+          b.nimg = c.nimg;
+          launch_pack_bwd(b, iob, dc, draw, c.s);
+        }, "pack_bwd", 0.0, (double)H * H * l.cout * 12.0});
+        const int cinP = (l.cin + 31) / 32 * 32;
+        std::vector<float> wf((size_t)9 * l.cout * cinP, 0.f);
+        for (int co = 0; co < l.cout; ++co)
+          for (int ci = 0; ci < l.cin; ++ci)
+            for (int t = 0; t < 9; ++t) wf[((size_t)t * l.cout + co) * cinP + ci] = wt[((size_t)co * l.cin + ci) * 9 + (8 - t)];
+        ConvArgs ca{};
+        ca.in = draw; ca.Hin = H; ca.Win = H; ca.Cin = l.cout;
+        ca.w = pool.upload(wf);
+        ca.bias = pool.upload(std::vector<float>(cinP, 0.f));
+        ca.CoutP = cinP; ca.Cout = l.cin; ca.ks = 3; ca.stride = 1; ca.pad = 1;
+        ca.g = make_geom(H, H);
+        float* dnext = first ? nullptr : (float*)pool.alloc((size_t)chunk * H * H * l.cin * sizeof(float));
+        ca.out_mode = first ? OUT_NCHW : OUT_RAW;
+        ca.out = dnext;
+        RGFM_CHECK(!first || gscale == 1.f, "encoder: the first dgrad conv of a 16-bit chain runs on the tensor cores");
+        B.push_back({[=](const RunCtx& c) {
+          ConvArgs b = ca;
+          b.nimg = c.nimg;
+          if (first) b.out = from_y ? c.gy : c.gx;
+          launch_conv_simt(b, c.s);
+        }, "conv_dgrad", 2.0 * H * H * (double)l.cout * l.cin * 9, (double)H * H * (l.cout + l.cin) * 4.0, lab});
+        io.dcur_fmt = 0; io.dcur_padded = 0; io.dcur_Cs = l.cin;
+        dcur = dnext;
+      }
     }
   }
 
@@ -936,11 +995,9 @@ Net::Net(int kind, const rgfm_weights* w, int chunk, int precision, int device, 
       b.build_flow28();
       break;
     case RGFM_NET_RATIO28:
-      if (want_grad) b.tc_mode = false;  // the dgrad chain is exact fp32
       b.build_ratio28(want_grad);
       break;
     case RGFM_NET_RATIO_MNIST_SVHN:
-      if (want_grad) b.tc_mode = false;
       b.build_ratio_mnist_svhn(want_grad);
       break;
     case RGFM_NET_CLF_MNIST28:

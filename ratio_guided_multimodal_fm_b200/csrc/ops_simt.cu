@@ -1196,9 +1196,10 @@ void launch_mlp_bwd(const float* in, int ld_in, const MlpLayer* layers, int nlay
   post_launch("mlp_bwd");
 }
 
-// ---- GAP + fc backward: feat = fc(mean_p act[p][c])  ->  dAct[p][c] = (W^T dfeat)[c] / HW for every pixel p
+// ---- GAP + fc backward: feat = fc(mean_p act[p][c])  ->  dAct[p][c] = gscale * (W^T dfeat)[c] / HW for every pixel p
+// gscale: the loss scale of the 16-bit gradient chain (1 in the fp32 mode); every later backward op is linear in it
 __global__ void __launch_bounds__(256) gap_fc_bwd_kernel(const float* __restrict__ dfeat, int ld, const float* __restrict__ w, int Cout,
-                                                         int HW, int C, float* __restrict__ dact) {
+                                                         int HW, int C, float gscale, float* __restrict__ dact) {
   __shared__ float dm[PACK_MAXC];
   __shared__ float df[512];
   const int n = blockIdx.x;
@@ -1207,22 +1208,26 @@ __global__ void __launch_bounds__(256) gap_fc_bwd_kernel(const float* __restrict
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (int j = 0; j < Cout; ++j) s = fmaf(w[(size_t)j * C + c], df[j], s);
-    dm[c] = s / (float)HW;
+    dm[c] = gscale * s / (float)HW;
   }
   __syncthreads();
   float* dst = dact + (size_t)n * HW * C;
   for (int i = threadIdx.x; i < HW * C; i += blockDim.x) dst[i] = dm[i % C];
 }
-void launch_gap_fc_bwd(const float* dfeat, int ld, const float* w, int Cout, int HW, int C, float* dact, int nimg, cudaStream_t s) {
+void launch_gap_fc_bwd(const float* dfeat, int ld, const float* w, int Cout, int HW, int C, float gscale, float* dact, int nimg, cudaStream_t s) {
   RGFM_CHECK(C <= PACK_MAXC && Cout <= 512, "gap_fc_bwd: sizes");
-  gap_fc_bwd_kernel<<<nimg, 256, 0, s>>>(dfeat, ld, w, Cout, HW, C, dact);
+  gap_fc_bwd_kernel<<<nimg, 256, 0, s>>>(dfeat, ld, w, Cout, HW, C, gscale, dact);
   post_launch("gap_fc_bwd");
 }
 
-// ---- pack backward (fp32 dense NHWC): cur = pool?(act(norm(raw)))  ->  dRaw from dCur.
+// ---- pack backward: cur = pool?(act(norm(raw)))  ->  dRaw from dCur.
 // Max-pool routes the gradient to the first maximum of the 2x2 window of act(norm(raw)) (recomputed); GroupNorm needs the
 // two per-(image, group) moments of gamma * dz, so one CTA per image makes two passes (the image stays in L2).
-__global__ void __launch_bounds__(256) pack_bwd_kernel(PackArgs a, const float* __restrict__ dcur, float* __restrict__ draw) {
+// Every tensor is either dense fp32 NHWC (exact mode, and the layers the tensor-core kernel does not take) or the
+// tensor-core kernel's 16-bit padded-linear raw layout (PackBwdIO): raw activations as the forward conv stored them,
+// incoming gradients as the next layer's dgrad conv stored them, and the outgoing gradient with its pad rows, columns and
+// channels written as zeros, so that the dgrad conv can use it as a zero-padded operand.
+__global__ void __launch_bounds__(256) pack_bwd_kernel(PackArgs a, PackBwdIO io, const float* __restrict__ dcur, float* __restrict__ draw) {
   __shared__ float s_scale[PACK_MAXC];
   __shared__ float s_shift[PACK_MAXC];
   __shared__ float s_red[2][PACK_MAXC];
@@ -1232,13 +1237,15 @@ __global__ void __launch_bounds__(256) pack_bwd_kernel(PackArgs a, const float* 
   pack_scale_shift(a, n, s_scale, s_shift, s_red, s_grp);  // scale = rstd * gamma (GN) | BN scale ; shift likewise
   const int C = a.C, H = a.Hs, Wd = a.Ws;
   const bool pool = a.spatial == SP_POOL2;
-  const float* raw = a.src[0].p + (size_t)n * H * Wd * C;
-  const float* dc = dcur + (size_t)n * a.Ho * a.Wo * C;
-  float* dr = draw + (size_t)n * H * Wd * C;
+  const PackSrc& S = a.src[0];
   const int cpg = C / a.groups;
+  auto raw_at = [&](int h, int w, int c) -> float { return load_raw1(S.p, raw_offset(S.padded, n, h, w, H, Wd, S.Cs) + c, S.fmt); };
+  auto dcur_at = [&](int ho, int wo, int c) -> float {
+    return load_raw1(dcur, raw_offset(io.dcur_padded, n, ho, wo, a.Ho, a.Wo, io.dcur_Cs) + c, io.dcur_fmt);
+  };
   // gradient arriving at act(norm(raw))[h][w][c]
-  auto grad_out = [&](int h, int w, int c, float av) -> float {
-    if (!pool) return dc[((size_t)h * a.Wo + w) * C + c];
+  auto grad_out = [&](int h, int w, int c) -> float {
+    if (!pool) return dcur_at(h, w, c);
     const int ho = h >> 1, wo = w >> 1;
     if (ho >= a.Ho || wo >= a.Wo) return 0.f;  // odd sizes: the last row / column is not pooled
     // first maximum of the window in scan order
@@ -1247,15 +1254,14 @@ __global__ void __launch_bounds__(256) pack_bwd_kernel(PackArgs a, const float* 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int hh = 2 * ho + (k >> 1), ww = 2 * wo + (k & 1);
-      const float z = fmaf(raw[((size_t)hh * Wd + ww) * C + c], s_scale[c], s_shift[c]);
+      const float z = fmaf(raw_at(hh, ww, c), s_scale[c], s_shift[c]);
       const float v = apply_act(z, a.act);
       if (v > best) {
         best = v;
         bi = k;
       }
     }
-    (void)av;
-    return (bi == ((h & 1) * 2 + (w & 1))) ? dc[((size_t)ho * a.Wo + wo) * C + c] : 0.f;
+    return (bi == ((h & 1) * 2 + (w & 1))) ? dcur_at(ho, wo, c) : 0.f;
   };
   auto dact = [&](float z) -> float {
     if (a.act == ACT_SILU) {
@@ -1265,43 +1271,161 @@ __global__ void __launch_bounds__(256) pack_bwd_kernel(PackArgs a, const float* 
     if (a.act == ACT_RELU) return z > 0.f ? 1.0f : 0.f;
     return 1.0f;
   };
+  // d raw of one real element
+  const float cnt = (float)cpg * H * Wd;
+  auto draw_of = [&](int h, int w, int c) -> float {
+    const float z = fmaf(raw_at(h, w, c), s_scale[c], s_shift[c]);
+    const float dz = grad_out(h, w, c) * dact(z);
+    if (a.norm != NORM_GN) return dz * s_scale[c];
+    const int g = c / cpg;
+    const float xh = (a.gamma[c] != 0.f) ? (z - a.beta[c]) / a.gamma[c] : 0.f;
+    const float rstd = (float)s_grp[g][1];
+    return rstd * (dz * a.gamma[c] - s_m1[g] / cnt - xh * s_m2[g] / cnt);
+  };
   const int total = H * Wd * C;
   if (a.norm == NORM_GN) {
-    // pass A: per-group means of gamma*dz and gamma*dz*xhat
+    // pass A: per-group sums of gamma*dz and gamma*dz*xhat
     for (int g = tid; g < a.groups; g += blockDim.x) s_m1[g] = s_m2[g] = 0.f;
     __syncthreads();
     for (int i = tid; i < total; i += blockDim.x) {
       const int c = i % C, pix = i / C, h = pix / Wd, w = pix - h * Wd;
-      const float z = fmaf(raw[i], s_scale[c], s_shift[c]);
-      const float dz = grad_out(h, w, c, 0.f) * dact(z);
+      const float z = fmaf(raw_at(h, w, c), s_scale[c], s_shift[c]);
+      const float dz = grad_out(h, w, c) * dact(z);
       const float dg = dz * a.gamma[c];
       const float xh = (a.gamma[c] != 0.f) ? (z - a.beta[c]) / a.gamma[c] : 0.f;
       atomicAdd(&s_m1[c / cpg], dg);
       atomicAdd(&s_m2[c / cpg], dg * xh);
     }
     __syncthreads();
-    const float cnt = (float)cpg * H * Wd;
+  }
+  if (!io.draw_padded) {
+    float* dr = draw + (size_t)n * H * Wd * C;
     for (int i = tid; i < total; i += blockDim.x) {
       const int c = i % C, pix = i / C, h = pix / Wd, w = pix - h * Wd;
-      const int g = c / cpg;
-      const float z = fmaf(raw[i], s_scale[c], s_shift[c]);
-      const float dz = grad_out(h, w, c, 0.f) * dact(z);
-      const float xh = (a.gamma[c] != 0.f) ? (z - a.beta[c]) / a.gamma[c] : 0.f;
-      const float rstd = (float)s_grp[g][1];
-      dr[i] = rstd * (dz * a.gamma[c] - s_m1[g] / cnt - xh * s_m2[g] / cnt);
+      dr[i] = draw_of(h, w, c);
     }
   } else {
-    for (int i = tid; i < total; i += blockDim.x) {
-      const int c = i % C, pix = i / C, h = pix / Wd, w = pix - h * Wd;
-      const float z = fmaf(raw[i], s_scale[c], s_shift[c]);
-      dr[i] = grad_out(h, w, c, 0.f) * dact(z) * s_scale[c];
+    // 16-bit padded-linear raw layout: every element of the image's (H + 1) x (W + 2) x Cs block is written (pads = 0)
+    const int Cs = io.draw_Cs, P = Wd + 2;
+    __half* dr = reinterpret_cast<__half*>(draw) + (size_t)n * (H + 1) * P * Cs;
+    const int total_p = (H + 1) * P * Cs;
+    for (int i = tid; i < total_p; i += blockDim.x) {
+      const int c = i % Cs, pix = i / Cs, h = pix / P, w = pix - h * P;
+      float v = 0.f;
+      if (h < H && w < Wd && c < C) v = draw_of(h, w, c);
+      dr[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
     }
   }
 }
-void launch_pack_bwd(const PackArgs& a, const float* dcur, float* draw, cudaStream_t s) {
-  RGFM_CHECK(a.nsrc == 1 && a.src[0].fmt == 0 && !a.src[0].padded && a.C <= PACK_MAXC && a.spatial != SP_UP2,
-             "pack_bwd: one dense fp32 source, no upsampling");
-  pack_bwd_kernel<<<a.nimg, 256, 0, s>>>(a, dcur, draw);
+// Streaming pack backward of the 16-bit gradient chain, per-channel affine norm (BatchNorm-eval) + SiLU, optional 2x2 max-pool:
+// raw activation and outgoing gradient in the fp16 padded-linear layout, one thread per (pooling window | pixel, 8-channel
+// octet), 16-byte loads and stores, the outgoing tensor's pad row / columns written as zeros by the threads of the
+// window grid's last row / column.  Algorithmic bytes per element: 2 (raw) + 2 (d raw) + 0.5..4 (incoming gradient).
+template <bool POOL>
+__global__ void __launch_bounds__(256) pack_bwd_fast_kernel(PackArgs a, PackBwdIO io, const float* __restrict__ dcur, uint16_t* __restrict__ draw) {
+  const int C = a.C, H = a.Hs, Wd = a.Ws, P = Wd + 2, Cs = io.draw_Cs, oct = Cs >> 3;
+  const PackSrc& S = a.src[0];
+  // index space: (image, window row, window column, octet); windows are 2x2 pixels (POOL) or single pixels
+  const int gh = POOL ? H / 2 + 1 : H + 1, gw = POOL ? Wd / 2 + 1 : P;
+  const long long total = (long long)a.nimg * gh * gw * oct;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o8 = (int)(i % oct);
+    long long r = i / oct;
+    const int wx = (int)(r % gw);
+    r /= gw;
+    const int hy = (int)(r % gh), n = (int)(r / gh);
+    const int c = o8 * 8;
+    float sc[8], sh[8];
+    const bool cval = c < C;  // channel padding of the tensors (C < Cs): zeros
+    if (cval) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = __ldg(a.gamma + c + j); sh[j] = __ldg(a.beta + c + j); }
+    }
+    constexpr int NP = POOL ? 4 : 1;
+    float g[8];  // incoming gradient of the window / pixel
+    bool have_g = false;
+    const int ho = hy, wo = wx;
+    if (cval && ho < a.Ho && wo < a.Wo) {
+      load_raw8(dcur, raw_offset(io.dcur_padded, n, ho, wo, a.Ho, a.Wo, io.dcur_Cs) + c, io.dcur_fmt, g);
+      have_g = true;
+    }
+    float z[NP][8];
+    bool real[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int h = POOL ? 2 * hy + (k >> 1) : hy, w = POOL ? 2 * wx + (k & 1) : wx;
+      real[k] = cval && h < H && w < Wd;
+      if (real[k]) {
+        float x[8];
+        load_raw8(S.p, raw_offset(S.padded, n, h, w, H, Wd, S.Cs) + c, S.fmt, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[k][j] = fmaf(x[j], sc[j], sh[j]);
+      }
+    }
+    int win[8];  // POOL: the first maximum of act(z) in scan order takes the window's gradient
+    if (POOL) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float best = -INFINITY;
+        int bi = 0;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          const float v = real[k] ? apply_act(z[k][j], a.act) : -INFINITY;
+          if (v > best) { best = v; bi = k; }
+        }
+        win[j] = bi;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int h = POOL ? 2 * hy + (k >> 1) : hy, w = POOL ? 2 * wx + (k & 1) : wx;
+      if (h > H || w >= P) continue;  // outside the padded image block
+      uint32_t pk[4] = {0u, 0u, 0u, 0u};
+      if (real[k] && have_g) {
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float zz = z[k][j];
+          float da = 1.0f;
+          if (a.act == ACT_SILU) {
+            const float sg = 1.0f / (1.0f + __expf(-zz));
+            da = sg * (1.0f + zz * (1.0f - sg));
+          } else if (a.act == ACT_RELU) {
+            da = zz > 0.f ? 1.0f : 0.f;
+          }
+          const float go = (!POOL || win[j] == k) ? g[j] : 0.f;
+          d[j] = fminf(fmaxf(go * da * sc[j], -65504.f), 65504.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half2 hv = __floats2half2_rn(d[2 * j], d[2 * j + 1]);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+      }
+      *reinterpret_cast<uint4*>(draw + raw_offset(1, n, h, w, H, Wd, Cs) + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+void launch_pack_bwd(const PackArgs& a, const PackBwdIO& io, const float* dcur, float* draw, cudaStream_t s) {
+  // streaming path: affine norm, fp16 padded-linear outgoing gradient, whole octets, even sizes when pooled
+  const bool fast = a.nsrc == 1 && a.norm == NORM_AFFINE && ((a.src[0].fmt == 2 && a.src[0].padded) || a.src[0].fmt == 0) && io.draw_padded && io.draw_Cs % 8 == 0 &&
+                    a.src[0].Cs % 8 == 0 && io.dcur_Cs % 8 == 0 && (io.dcur_fmt == 0 || io.dcur_fmt == 2) && a.C % 8 == 0 &&
+                    (a.spatial == SP_ID || (a.spatial == SP_POOL2 && a.Hs % 2 == 0 && a.Ws % 2 == 0)) && a.spatial != SP_UP2;
+  static const bool fast_off = getenv("RGFM_PACK_BWD_FAST") && atoi(getenv("RGFM_PACK_BWD_FAST")) == 0;  // A/B switch (same results)
+  if (fast && !fast_off) {
+    const bool pool = a.spatial == SP_POOL2;
+    const long long total = (long long)a.nimg * (pool ? (a.Hs / 2 + 1) * (a.Ws / 2 + 1) : (a.Hs + 1) * (a.Ws + 2)) * (io.draw_Cs / 8);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    if (pool) pack_bwd_fast_kernel<true><<<blocks, 256, 0, s>>>(a, io, dcur, reinterpret_cast<uint16_t*>(draw));
+    else pack_bwd_fast_kernel<false><<<blocks, 256, 0, s>>>(a, io, dcur, reinterpret_cast<uint16_t*>(draw));
+    post_launch("pack_bwd_fast");
+    return;
+  }
+  RGFM_CHECK(a.nsrc == 1 && (a.src[0].fmt == 0 || a.src[0].fmt == 2) && a.C <= PACK_MAXC && a.spatial != SP_UP2,
+             "pack_bwd: one fp32 or fp16 source, no upsampling");
+  RGFM_CHECK((io.dcur_fmt == 0 || io.dcur_fmt == 2) && (!io.draw_padded || io.draw_Cs >= a.C), "pack_bwd: gradient tensor formats");
+  pack_bwd_kernel<<<a.nimg, 256, 0, s>>>(a, io, dcur, draw);
   post_launch("pack_bwd");
 }
 

@@ -156,8 +156,10 @@ struct Sampler {
     fx.reset(new Net(kx, wx, chunk, d.precision, d.device));
     fy.reset(new Net(ky, wy, chunk, d.precision, d.device));
     if (guided) fr.reset(new Net(kr, wr, std::min(chunk, N), d.precision, d.device));
-    // gradient guidance: forward + dgrad of the estimator at the sampler's batch, every step, exact fp32, 256-image chunks
-    if (grad_guided) fr.reset(new Net(kr, wr, std::min(256, B), RGFM_PREC_FP32, d.device, /*want_grad=*/true));
+    // gradient guidance: forward + dgrad of the estimator at the sampler's batch, every step, in the plan's precision
+    // (16-bit modes: both conv chains on the tensor cores, net.cu encoder(); fp32: exact, 256-image chunks)
+    if (grad_guided)
+      fr.reset(new Net(kr, wr, d.precision == RGFM_PREC_FP32 ? std::min(256, B) : std::min(chunk, B), d.precision, d.device, /*want_grad=*/true));
     Dx = (int)fx->dim();
     Dy = (int)fy->dim();
 
