@@ -37,11 +37,12 @@ static inline void post_launch(const char* what) {
 }
 
 constexpr int TC_MAX_STAGES = 12;
-// Row-dense kernel: GroupNorm partials from the accumulator registers (quad sums + a 31-shuffle transpose-reduce) instead
-// of ldmatrix.trans + mma.sync on the staged tile.  Measured (profiles/notes_r02.md): it removes the legacy HMMAs that queue
-// behind the UMMA stream and wins on single-stage convs (165 -> 148 us), but costs ~160 issue slots per thread and unit,
-// and the multi-stage convs this mode is used for are issue-bound: 179 -> 196 us.  Off.
-constexpr bool TC_DENSE_REG_STATS = false;
+// REGSTATS kernels: GroupNorm partials from the accumulator registers (channel-quad sums of the thread's row + one 31-shuffle
+// transpose-reduce per unit, after the accumulator went back to the MMA warps) instead of ldmatrix.trans + mma.sync on the
+// staged tile.  It removes the legacy HMMAs that queue behind the UMMA stream but costs ~160 issue slots per thread and
+// unit, so it pays where the epilogue's LATENCY bounds a conv (one operand stage per super-tile: few MMAs, few instructions
+// in flight) and loses where the SM is short of issue slots (multi-stage convs; measured 179 -> 196 us, profiles/notes_r02.md).
+// Selected per conv by tc_reg_stats().
 constexpr int TC_XF_THREADS = 256;        // transform group: fused GroupNorm + SiLU on the A tiles in shared memory (12 warps: no faster)
 // two epilogue groups of 4 warps, producer warp, two MMA warps (one per accumulator half), transform group
 constexpr int TC_THREADS = 2 * 128 + 96 + TC_XF_THREADS;
@@ -94,6 +95,7 @@ struct TcArgs {
   // 128 rows of a unit are outputs, and only the pad ROW of each image is wasted (3 / 6 / 11 % at 32 / 16 / 8 pixels
   // against 10 / 20 / 41 % of the padded-linear row space).  ky is a shift of Wt rows of the shared tile (atom aligned).
   int dense;
+  int reg_stats;        // GroupNorm partials from the accumulator registers (REGSTATS kernels; tc_reg_stats())
   int xchg16;           // row-dense: neighbour partial sums are exchanged as packed fp16 pairs (RGFM_TC_XCHG16, default off)
   int Wt, wt_shift;     // tile width and its log2
   int irs;              // image rows per super-tile (256 / Wt)
@@ -482,7 +484,7 @@ __device__ __forceinline__ float transpose_reduce16_masked(const float* f, bool 
 #endif
 
 // DENSE: the row-dense instantiation (TcArgs::dense) -- its own register allocation, none of the padded-linear stacking code
-template <bool DENSE>
+template <bool DENSE, bool REGSTATS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -1066,8 +1068,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int my_slot = n - nf;
         const int sl_lo = __shfl_sync(0xffffffffu, my_slot, 0), sl_hi = __shfl_sync(0xffffffffu, my_slot, 31);
         float* s_dpart = &s_part[0][0][0][0][0];  // [group][warp][slot][4 blocks x 8 values]
-        [[maybe_unused]] float fq[DENSE && TC_DENSE_REG_STATS ? 32 : 1];  // per 16-channel block: sums of its four channel quads, then their sums of squares (this row)
-        if constexpr (DENSE && TC_DENSE_REG_STATS) {
+        [[maybe_unused]] float fq[REGSTATS ? 32 : 1];  // per 16-channel block: sums of its four channel quads, then their sums of squares (this row)
+        if constexpr (REGSTATS) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) fq[j] = 0.f;
         }
@@ -1093,12 +1095,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                   const float x0 = v[4 * j] + b4.x, x1 = v[4 * j + 1] + b4.y, x2 = v[4 * j + 2] + b4.z, x3 = v[4 * j + 3] + b4.w;
                   pk[8 * sc + 2 * j] = cvt2_f16_sat(x0, x1, vm, sat2);
                   pk[8 * sc + 2 * j + 1] = cvt2_f16_sat(x2, x3, vm, sat2);
-                  if constexpr (DENSE && TC_DENSE_REG_STATS) {
+                  if constexpr (REGSTATS) {
                     f[j] = (x0 + x1) + (x2 + x3);
                     f[4 + j] = fmaf(x3, x3, fmaf(x2, x2, fmaf(x1, x1, x0 * x0)));
                   }
                 }
-                if constexpr (DENSE && TC_DENSE_REG_STATS) {  // row-dense GroupNorm partials: kept in registers until the accumulator has been released
+                if constexpr (REGSTATS) {  // row-dense GroupNorm partials: kept in registers until the accumulator has been released
 #pragma unroll
                   for (int j = 0; j < 8; ++j) fq[(hh * 2 + sc) * 8 + j] = f[j];
                 }
@@ -1175,7 +1177,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           if (threadIdx.x == 0 && c0 == 0) TRC(6, it);
-          if constexpr (DENSE && TC_DENSE_REG_STATS) {
+          if constexpr (REGSTATS) {
           if (p.stats != nullptr && c0 < N) {
             // combine the four warps' quad sums; every channel of a quad is credited a quarter of the quad's sums, so the
             // consumers' per-channel gather (common.h stats_channel_sums) adds up to the group sums it needs unchanged
@@ -1404,7 +1406,7 @@ static void encode_3d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
 // RGFM_TC_DENSE=0: padded-linear everywhere, 2: row-dense wherever it is legal (A/B timing).
 // stages: 64-channel operand blocks of all K segments.
 bool tc_dense(int cout, int W, bool final, int stages) {
-  static const int mode = getenv("RGFM_TC_DENSE") ? atoi(getenv("RGFM_TC_DENSE")) : 1;
+  const int mode = getenv("RGFM_TC_DENSE") ? atoi(getenv("RGFM_TC_DENSE")) : 1;  // read at plan build time (tests switch it)
   const int nmma = (cout + 15) / 16 * 16;
   if (mode == 0 || nmma > 64 || W > 32 || W < 4) return false;
   return mode == 2 || final || stages >= 2;
@@ -1460,6 +1462,21 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     for (int sg = 0; sg < d.nseg; ++sg) stall += (d.seg[sg].Cin_real + 63) / 64;
     p.dense = tc_dense(d.Cout, d.Win, d.out == nullptr && d.stride == 1, stall) ? 1 : 0;
   }
+  {
+    // register statistics: convs whose super-tile walks ONE operand stage (see REGSTATS above), with at least 64 output
+    // channels, and no transform warps competing for issue slots unless the conv is wide (measured per layer, same box:
+    // upsamplers.0 128 -> 121 us, downsamplers.0 64->64 129 -> 117, enc2.conv1 64->128 79 -> 67; 32-channel convs and the
+    // fused 64->64 conv1s lose 3..8 %).  Never with taps stacked in the padded-linear row space (the boundary rows of a
+    // stacked unit are finished after the main pass).  RGFM_TC_REG_STATS=0: never, 2: wherever legal (A/B timing).
+    const int mode = getenv("RGFM_TC_REG_STATS") ? atoi(getenv("RGFM_TC_REG_STATS")) : 1;
+    int stall = 0;
+    bool xf = false;
+    for (int sg = 0; sg < d.nseg; ++sg) {
+      stall += (d.seg[sg].Cin_real + 63) / 64;
+      xf = xf || d.seg[sg].coef != nullptr;
+    }
+    p.reg_stats = (mode == 2 || (mode == 1 && stall == 1 && nmma >= 64 && (!xf || nmma >= 128))) ? 1 : 0;
+  }
   if (p.dense) {
     RGFM_CHECK(d.seg[0].ks == 3, "tc conv: segment 0 of a row-dense conv is 3x3");
     p.Wt = tc_tile_width(d.Win);
@@ -1489,6 +1506,7 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
       if (d.seg[sg].ks == 3) st3 += cb;
     }
     p.nstk = p.dense ? 3 : tc_stack_groups(d.Cout, d.stride, d.out == nullptr && d.stride == 1, st3, stall);
+    if (!p.dense && p.nstk > 1) p.reg_stats = 0;
   }
   p.unit_rows = p.dense ? 128 : 128 - (p.nstk - 1);
   p.super_rows = 2 * p.unit_rows;
@@ -1665,8 +1683,10 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   else
     t->tmO = t->tmA[0];
   // per device (function attributes belong to the current context): cheap enough to set for every plan
-  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
-  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
+  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
+  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
+  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
+  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
   return t;
 }
 
@@ -1709,10 +1729,14 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = supers < num_sms ? supers : num_sms;  // persistent: one CTA per SM, static round-robin
-  if (p.dense)
-    launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p);
-  else
-    launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p);
+#define RGFM_TC_LAUNCH(D, R) launch_pdl(conv_tc_kernel<D, R>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p)
+  const bool regs = p.reg_stats && p.stats != nullptr && a.out_mode == OUT_RAW;
+  if (p.dense) {
+    if (regs) RGFM_TC_LAUNCH(true, true); else RGFM_TC_LAUNCH(true, false);
+  } else {
+    if (regs) RGFM_TC_LAUNCH(false, true); else RGFM_TC_LAUNCH(false, false);
+  }
+#undef RGFM_TC_LAUNCH
   post_launch("conv_tc");
 }
 

@@ -287,6 +287,28 @@ def _bench_rows(B):
     return sorted(r for r in rows if 0 <= r < B)
 
 
+@pytest.mark.parametrize("kind", ["unet_mnist28", "unet_mnist32", "unet_svhn"])
+def test_conv_row_spaces_agree_with_the_oracle(kind, synth, monkeypatch):
+    """conv_tc's two row spaces on every layer they can take: RGFM_TC_DENSE=2 runs the row-dense mode (3-D TMA view, kx taps
+    stacked on N, shuffle exchange) wherever it is legal -- input convs, stride-2 convs with their subsampled stores and
+    pad-column lanes, 28x28 images in 32-wide tiles -- and =0 keeps the padded-linear row space everywhere; the default
+    mixes them per layer.  37 images, chunk 16: tiles straddle images and the last chunk is ragged."""
+    sd = synth(kind, 33)
+    c, hw = (3, 32) if kind == "unet_svhn" else (1, 28 if kind == "unet_mnist28" else 32)
+    x = torch.randn(37, c, hw, hw, generator=torch.Generator().manual_seed(6))
+    ref = O.unet_forward(sd, kind, x, torch.full((37,), 0.81))
+    scale = max(1.0, ref.abs().max().item())
+    outs = {}
+    for mode in ("2", "0", "1"):
+        monkeypatch.setenv("RGFM_TC_DENSE", mode)  # read when the plan is built
+        net = _lib.Net(kind, sd, max_batch=16, precision="fp16", device=DEV)
+        outs[mode] = net.unet_forward(x.to(DEV), 0.81).cpu()
+        net.close()
+        assert maxabs(outs[mode], ref) <= TOL_FWD["fp16"] * scale, (kind, mode, maxabs(outs[mode], ref))
+    # same arithmetic up to fp32 summation order and one fp16 rounding per layer
+    assert maxabs(outs["2"], outs["0"]) <= TOL_FWD["fp16"] * scale
+
+
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 @pytest.mark.parametrize("kind", ["unet_mnist32", "unet_svhn"])
 def test_unet_forward_bench_size(kind, prec, synth):
