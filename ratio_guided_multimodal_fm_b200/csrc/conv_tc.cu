@@ -25,6 +25,7 @@
 #include "net.h"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cmath>
 #include <cstring>
 #include <cstdlib>
 
@@ -256,15 +257,16 @@ __device__ __forceinline__ uint32_t cvt2(float a, float b, int fmt) {
 // n / d for n * (d - 1) < 2^32 with magic = ceil(2^32 / d) (checked on the host)
 __device__ __forceinline__ int fast_div(int n, uint32_t magic) { return (int)__umulhi((uint32_t)n, magic); }
 
-// two fp32 -> packed fp16, saturated to +-65504 by the conversion itself (F2FP.SATFINITE: one instruction).  `seen` keeps
-// the running max |value| of rows that are stored (vm = all ones, or zero for rows written as zeros): a tile whose max
-// reaches 0x7BFF saturated something, and the epilogue counts it (diag[12]) -- saturation is never silent.
-__device__ __forceinline__ uint32_t cvt2_f16_sat(float a, float b, uint32_t vm, __half2& seen) {
+// two fp32 -> packed fp16, saturated to +-65504 by the conversion itself (F2FP.SATFINITE: one instruction), zeroed for
+// rows that are written as zeros (vm).  `seen` keeps the running max |value| of the thread's row in fp32 (the compiler
+// folds the chain into three-input FMNMX3 with |.| modifiers: half an instruction per value, where tracking the packed
+// halves cost one): a stored row whose max reaches 65504 saturated something, and the epilogue counts it (diag[12]) --
+// saturation is never silent.
+__device__ __forceinline__ uint32_t cvt2_f16_sat(float a, float b, uint32_t vm, float& seen) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  r &= vm;
-  seen = __hmax2(seen, __habs2(*reinterpret_cast<const __half2*>(&r)));
-  return r;
+  seen = fmaxf(seen, fmaxf(fabsf(a), fabsf(b)));
+  return r & vm;
 }
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& d0, uint32_t& d1, uint32_t& d2, uint32_t& d3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -382,11 +384,15 @@ __device__ __forceinline__ void acc16_dense(uint32_t taddr, int c, int n, bool m
     }
     return;
   }
+  // the zero fill at the row ends as PREDICATED adds (no select per value: the loop is issue-bound)
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float l = __uint_as_float(__shfl_up_sync(0xffffffffu, v0[j], 1));
     const float r = __uint_as_float(__shfl_down_sync(0xffffffffu, v2[j], 1));
-    o[j] = (__uint_as_float(v1[j]) + (ml ? l : 0.f)) + (mr ? r : 0.f);
+    float acc = __uint_as_float(v1[j]);
+    if (ml) acc += l;
+    if (mr) acc += r;
+    o[j] = acc;
   }
 }
 
@@ -824,6 +830,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int cC = p.coef_C[seg];
             const uint32_t sa = smem_base + as * p.a_slot;
             const bool to_bf16 = p.xf_bf16 != 0;
+            if constexpr (DENSE) {
+              if (!to_bf16) {
+                // ---- row-dense tile, fp16 mode: the lean loop ----
+                // rstride (32 or 64 rows) is a multiple of the tile width, so a thread's rows all have the same pixel
+                // column w (threads of columns >= W idle) and its k-th row lies in tile image row a0 + k * da.  The rows of
+                // one image are one contiguous k range: loop over the tile's images (2..5), load that image's coefficients
+                // once, and run a branch-free inner loop over its rows -- no row table, no per-row validity / image tests
+                // (pad rows fall between the ranges).  ~25 instead of ~67 thread-instructions per 8-channel item, in a
+                // kernel that is short of issue slots (profiles/notes_r02.md).
+                const int sh = p.wt_shift;
+                const int a0 = rl >> sh, da = rstride >> sh;
+                const int dsh = 31 - __clz(da);
+                const bool mine = work && (rl & (p.Wt - 1)) < p.W;
+                const int H1 = p.H + 1;
+                const int ir0 = st * p.irs - 1;
+                const int ir_lo = ir0 < 0 ? 0 : ir0;
+                const int ir_hi = min(ir0 + p.irs + 2, a.nimg * H1);
+                const int ostride = (cC >> 3) * 2;  // uint4 per image
+                const uint4* ch = p.coef_h[seg] + (size_t)(((p.coef_c0[seg] + cb * 64) >> 3) + oct) * 2;
+                int n = nbase;
+                uint4 ns = make_uint4(0u, 0u, 0u, 0u), nb = ns;
+                if (mine && n * H1 < ir_hi) {  // first image: in flight while the tile is still loading
+                  ns = __ldg(ch + (size_t)n * ostride);
+                  nb = __ldg(ch + (size_t)n * ostride + 1);
+                }
+                if (tt == 0) mbar_wait(a_full(as), aph);
+                asm volatile("bar.sync 3, %0;" ::"n"(TC_XF_THREADS) : "memory");
+                if (tt == 0 && seg == 0 && cb == 0) TRC(4, (sti - (int)blockIdx.x) / (int)gridDim.x);
+                if (mine) {
+                  const uint32_t abase = sa + (uint32_t)rl * 128u + (uint32_t)((oct ^ (rl & 7)) << 4);
+                  const uint32_t astep = (uint32_t)rstride * 128u;
+#pragma unroll 1
+                  for (; n * H1 < ir_hi; ++n) {
+                    const uint4 hs = ns, hb = nb;
+                    if ((n + 1) * H1 < ir_hi) {  // the next image's coefficients, one image ahead
+                      ns = __ldg(ch + (size_t)(n + 1) * ostride);
+                      nb = __ldg(ch + (size_t)(n + 1) * ostride + 1);
+                    }
+                    const int lo = max(n * H1, ir_lo) - ir0, hi = min(n * H1 + p.H, ir_hi) - ir0;  // tile image rows of image n
+                    const int k_lo = lo <= a0 ? 0 : (lo - a0 + da - 1) >> dsh;
+                    const int k_hi = hi <= a0 ? 0 : (hi - a0 + da - 1) >> dsh;
+                    const uint32_t hsv[4] = {hs.x, hs.y, hs.z, hs.w}, hbv[4] = {hb.x, hb.y, hb.z, hb.w};
+#pragma unroll 1
+                    for (int k = k_lo; k < k_hi; k += 4) {
+                      uint32_t w4[4][4];
+                      const uint32_t ad = abase + (uint32_t)k * astep;
+#pragma unroll
+                      for (int j = 0; j < 4; ++j)  // all loads in flight before the math
+                        if (k + j < k_hi)
+                          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                       : "=r"(w4[j][0]), "=r"(w4[j][1]), "=r"(w4[j][2]), "=r"(w4[j][3]) : "r"(ad + (uint32_t)j * astep));
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) {
+                        if (k + j >= k_hi) break;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                          uint32_t z, t;
+                          asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(z) : "r"(w4[j][q]), "r"(hsv[q]), "r"(hbv[q]));
+                          asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(z));
+                          asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(w4[j][q]) : "r"(z), "r"(t));
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad + (uint32_t)j * astep), "r"(w4[j][0]), "r"(w4[j][1]),
+                                     "r"(w4[j][2]), "r"(w4[j][3]) : "memory");
+                      }
+                    }
+                  }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core (async proxy) reads
+                asm volatile("bar.sync 3, %0;" ::"n"(TC_XF_THREADS) : "memory");
+                if (tt == 0) mbar_arrive(a_ready(as));
+                if (tt == 0 && seg == 0 && cb == 0) TRC(5, (sti - (int)blockIdx.x) / (int)gridDim.x);
+                if (++as == a_slots) {
+                  as = 0u;
+                  aph ^= 1u;
+                }
+                continue;
+              }
+            }
             if (!to_bf16) {
               // ---- fp16 mode: packed half2 arithmetic, four rows in flight per thread ----
               // silu(z) = hz + hz * tanh(hz), hz = x * (scale / 2) + shift / 2: per PAIR of channels one HFMA2, one
@@ -1062,7 +1146,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int nf = fast_div(unit * UR, p.magic_R);
         const int b1 = (nf + 1) * p.R - unit * UR;
         const int b2 = b1 + p.R;
-        __half2 sat2 = __float2half2_rn(0.f);  // running max |stored value| (cvt2_f16_sat)
+        float sat2 = 0.f;  // running max |value| of this row (cvt2_f16_sat)
+        float sat_fix = 0.f;  // the same for the boundary rows this thread finishes in the fix-up pass (stacked padded-linear units)
         const uint32_t vm = (valid && !bnd) ? 0xffffffffu : 0u;
         // row-dense statistics: image slot of this row inside the unit, and of the warp's first / last row
         const int my_slot = n - nf;
@@ -1156,7 +1241,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const int rr = 32 * b + 30 + half;
                 int n2, h2, w2;
                 const bool ok = slot_pixel(unit * UR + rr, p.H, p.P, p.magic_P, p.magic_H1, a.nimg, n2, h2, w2);
-                const uint32_t pv = cvt2_f16_sat(sum.x + s_bias[ch], sum.y + s_bias[ch + 1], ok ? 0xffffffffu : 0u, sat2);
+                float satb = 0.f;
+                const uint32_t pv = cvt2_f16_sat(sum.x + s_bias[ch], sum.y + s_bias[ch + 1], ok ? 0xffffffffu : 0u, satb);
+                if (ok) sat_fix = fmaxf(sat_fix, satb);
                 const uint32_t dst = stg + (uint32_t)rr * 128u + (uint32_t)((((ch - c0) >> 3) ^ (rr & 7)) << 4) + (uint32_t)(((ch - c0) & 7) << 1);
                 asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(pv) : "memory");
               }
@@ -1287,8 +1374,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (threadIdx.x == 0) TRC(7, it);
         if (p.sat != nullptr) {  // rows of this tile that hit the fp16 bound (reported in diag[12]; must stay 0)
-          const uint32_t sb = *reinterpret_cast<const uint32_t*>(&sat2);
-          const unsigned hit = __ballot_sync(0xffffffffu, (sb & 0x7fffu) >= 0x7bffu || (sb & 0x7fff0000u) >= 0x7bff0000u);
+          const unsigned hit = __ballot_sync(0xffffffffu, (vm != 0u && sat2 >= 65504.f) || sat_fix >= 65504.f);
           if (hit != 0u && lane == 0) atomicAdd(p.sat, (unsigned int)__popc(hit));
         }
       } else {
@@ -1625,6 +1711,8 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
         for (int tp = 0; tp < taps; ++tp) {
           const int wct = S.w_cin_total > 0 ? S.w_cin_total : S.Cin_real;
           const float wv = S.w_oihw ? S.w_oihw[((size_t)o * wct + S.w_c0 + c) * taps + tp] : (o == c ? 1.0f : 0.0f);
+          // an operand outside the 16-bit format's range would become inf and poison every output it touches
+          RGFM_CHECK(std::isfinite(wv) && (!seg_fp16 || std::fabs(wv) <= 65504.f), "tc conv: a weight is not finite or outside fp16's range");
           uint16_t bits;
           if (seg_fp16) {
             const __half hv = __float2half_rn(wv);

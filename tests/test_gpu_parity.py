@@ -287,6 +287,29 @@ def _bench_rows(B):
     return sorted(r for r in rows if 0 <= r < B)
 
 
+def test_fp16_saturation_is_counted(synth):
+    """A checkpoint whose activations leave fp16's range must not corrupt samples silently: the tensor-core epilogue clamps
+    to +-65504 and counts the rows it clamped in diag[12] (both row spaces: the 64-channel input conv runs padded-linear,
+    the blocks behind it row-dense)."""
+    sdx, sdy = dict(synth("unet_mnist32", 12)), dict(synth("unet_svhn", 13))
+    sdy["input_conv.weight"] = sdy["input_conv.weight"] * 1e5   # weights stay inside fp16, |activation| ~ 1e5 > 65504
+    sdx["encoder_blocks.0.conv2.weight"] = sdx["encoder_blocks.0.conv2.weight"] * 2e5
+    B = 4
+    g = torch.Generator().manual_seed(2)
+    x0, y0 = torch.randn(B, 1, 32, 32, generator=g), torch.randn(B, 3, 32, 32, generator=g)
+    plan = _lib.SamplerPlan("mnist_svhn", sdx, sdy, None, guidance_method="none", guidance_strength=0.0, num_samples=B, num_steps=1,
+                            mc_batch_size=4, precision="fp16", device=DEV)
+    _, _, diag = plan.run(x0.to(DEV), y0.to(DEV), want_diag=True)
+    torch.cuda.synchronize()
+    assert float(diag[12]) > 0
+    plan.close()
+    # weights outside fp16's range are refused when the plan is built (they would turn into inf operands)
+    sdy["input_conv.weight"] = sdy["input_conv.weight"] * 1e3
+    with pytest.raises(_lib.RgfmError):
+        _lib.SamplerPlan("mnist_svhn", sdx, sdy, None, guidance_method="none", guidance_strength=0.0, num_samples=B, num_steps=1,
+                         mc_batch_size=4, precision="fp16", device=DEV)
+
+
 @pytest.mark.parametrize("kind", ["unet_mnist28", "unet_mnist32", "unet_svhn"])
 def test_conv_row_spaces_agree_with_the_oracle(kind, synth, monkeypatch):
     """conv_tc's two row spaces on every layer they can take: RGFM_TC_DENSE=2 runs the row-dense mode (3-D TMA view, kx taps
