@@ -490,7 +490,9 @@ __device__ __forceinline__ float transpose_reduce16_masked(const float* f, bool 
 #endif
 
 // DENSE: the row-dense instantiation (TcArgs::dense) -- its own register allocation, none of the padded-linear stacking code
-template <bool DENSE, bool REGSTATS>
+// XBF16: format the transform group writes (bf16 mode: fp32 arithmetic; fp16 mode: packed half2) -- compile time, so that a
+// kernel carries one transform loop: code size is felt by the single-thread roles, whose instruction-cache misses nobody shares
+template <bool DENSE, bool REGSTATS, bool XBF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -829,7 +831,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const float2* cf = p.coef[seg] + (size_t)nbase * p.coef_C[seg] + p.coef_c0[seg] + cb * 64 + oct * 8;
             const int cC = p.coef_C[seg];
             const uint32_t sa = smem_base + as * p.a_slot;
-            const bool to_bf16 = p.xf_bf16 != 0;
+            constexpr bool to_bf16 = XBF16;
             if constexpr (DENSE) {
               if (!to_bf16) {
                 // ---- row-dense tile, fp16 mode: the lean loop ----
@@ -1771,10 +1773,10 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   else
     t->tmO = t->tmA[0];
   // per device (function attributes belong to the current context): cheap enough to set for every plan
-  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
-  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
-  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
-  RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024));
+#define RGFM_TC_ATTR(D, R, X) RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<D, R, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024))
+  RGFM_TC_ATTR(false, false, false); RGFM_TC_ATTR(false, true, false); RGFM_TC_ATTR(true, false, false); RGFM_TC_ATTR(true, true, false);
+  RGFM_TC_ATTR(false, false, true); RGFM_TC_ATTR(false, true, true); RGFM_TC_ATTR(true, false, true); RGFM_TC_ATTR(true, true, true);
+#undef RGFM_TC_ATTR
   return t;
 }
 
@@ -1817,13 +1819,16 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = supers < num_sms ? supers : num_sms;  // persistent: one CTA per SM, static round-robin
-#define RGFM_TC_LAUNCH(D, R) launch_pdl(conv_tc_kernel<D, R>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p)
+#define RGFM_TC_LAUNCH(D, R, X) launch_pdl(conv_tc_kernel<D, R, X>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p)
+#define RGFM_TC_LAUNCH2(D, R) do { if (xb) RGFM_TC_LAUNCH(D, R, true); else RGFM_TC_LAUNCH(D, R, false); } while (0)
   const bool regs = p.reg_stats && p.stats != nullptr && a.out_mode == OUT_RAW;
+  const bool xb = p.any_xform && p.xf_bf16;
   if (p.dense) {
-    if (regs) RGFM_TC_LAUNCH(true, true); else RGFM_TC_LAUNCH(true, false);
+    if (regs) RGFM_TC_LAUNCH2(true, true); else RGFM_TC_LAUNCH2(true, false);
   } else {
-    if (regs) RGFM_TC_LAUNCH(false, true); else RGFM_TC_LAUNCH(false, false);
+    if (regs) RGFM_TC_LAUNCH2(false, true); else RGFM_TC_LAUNCH2(false, false);
   }
+#undef RGFM_TC_LAUNCH2
 #undef RGFM_TC_LAUNCH
   post_launch("conv_tc");
 }
