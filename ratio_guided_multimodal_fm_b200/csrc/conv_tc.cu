@@ -492,7 +492,9 @@ __device__ __forceinline__ float transpose_reduce16_masked(const float* f, bool 
 // DENSE: the row-dense instantiation (TcArgs::dense) -- its own register allocation, none of the padded-linear stacking code
 // XBF16: format the transform group writes (bf16 mode: fp32 arithmetic; fp16 mode: packed half2) -- compile time, so that a
 // kernel carries one transform loop: code size is felt by the single-thread roles, whose instruction-cache misses nobody shares
-template <bool DENSE, bool REGSTATS, bool XBF16>
+// FINAL: the output conv (NCHW velocity / fused Euler update / scaled gradient) -- its kernels carry no raw-activation epilogue
+// STACKED: padded-linear units that stack kx taps (lane-shifted sums, boundary fix-up pass); nstk == 1 kernels carry none of it
+template <bool DENSE, bool REGSTATS, bool XBF16, bool FINAL, bool STACKED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -1092,7 +1094,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int r = q * 32 + lane;  // row inside the unit's M=128 tile
     const int CP = a.CoutP;  // channel stride of the raw output (32, or a multiple of 64; channels >= nmma are written as zeros)
     const uint32_t stg = smem_stage + (uint32_t)eg * TC_STAGE_BYTES;
-    const int nstk = p.nstk;
+    const int nstk = STACKED ? p.nstk : 1;
     float* xw = &s_xchg[eg][q][0];
     // rows whose D_j[m + j] sits in the next warp's lane quarter: stored as zeros by the main path, finished by the fix-up
     const bool bnd = !DENSE && nstk > 1 && lane >= 33 - nstk;
@@ -1140,7 +1142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tc_fence_after();
       if (threadIdx.x == 0) TRC(3, it);
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + eg) * p.ncols);
-      if (a.out_mode == OUT_RAW) {
+      if constexpr (!FINAL) {
         // raw activation, 16-bit, channel stride CP; rows that are not real pixels are stored as exact zeros, so the
         // tensor doubles as a zero-padded conv operand and the per-channel sums below need no masking
         uint16_t* out16 = reinterpret_cast<uint16_t*>(a.out);
@@ -1773,9 +1775,12 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   else
     t->tmO = t->tmA[0];
   // per device (function attributes belong to the current context): cheap enough to set for every plan
-#define RGFM_TC_ATTR(D, R, X) RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<D, R, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024))
-  RGFM_TC_ATTR(false, false, false); RGFM_TC_ATTR(false, true, false); RGFM_TC_ATTR(true, false, false); RGFM_TC_ATTR(true, true, false);
-  RGFM_TC_ATTR(false, false, true); RGFM_TC_ATTR(false, true, true); RGFM_TC_ATTR(true, false, true); RGFM_TC_ATTR(true, true, true);
+#define RGFM_TC_ATTR(D, R, X, F, S) RGFM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<D, R, X, F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 1024))
+#define RGFM_TC_ATTR4(X, F) RGFM_TC_ATTR(false, false, X, F, false); RGFM_TC_ATTR(true, false, X, F, false)
+  RGFM_TC_ATTR4(false, false); RGFM_TC_ATTR4(true, false); RGFM_TC_ATTR4(false, true); RGFM_TC_ATTR4(true, true);
+  RGFM_TC_ATTR(false, true, false, false, false); RGFM_TC_ATTR(true, true, false, false, false); RGFM_TC_ATTR(false, true, true, false, false); RGFM_TC_ATTR(true, true, true, false, false);
+  RGFM_TC_ATTR(false, false, false, false, true); RGFM_TC_ATTR(false, false, true, false, true);  // stacked padded-linear units (RGFM_TC_DENSE=0)
+#undef RGFM_TC_ATTR4
 #undef RGFM_TC_ATTR
   return t;
 }
@@ -1819,14 +1824,19 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = supers < num_sms ? supers : num_sms;  // persistent: one CTA per SM, static round-robin
-#define RGFM_TC_LAUNCH(D, R, X) launch_pdl(conv_tc_kernel<D, R, X>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p)
-#define RGFM_TC_LAUNCH2(D, R) do { if (xb) RGFM_TC_LAUNCH(D, R, true); else RGFM_TC_LAUNCH(D, R, false); } while (0)
-  const bool regs = p.reg_stats && p.stats != nullptr && a.out_mode == OUT_RAW;
+#define RGFM_TC_LAUNCH(D, R, X, F, S) launch_pdl(conv_tc_kernel<D, R, X, F, S>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p)
+#define RGFM_TC_LAUNCH2(D, R, F, S) do { if (xb) RGFM_TC_LAUNCH(D, R, true, F, S); else RGFM_TC_LAUNCH(D, R, false, F, S); } while (0)
+  const bool final_out = a.out_mode != OUT_RAW;
+  const bool regs = p.reg_stats && p.stats != nullptr && !final_out;
   const bool xb = p.any_xform && p.xf_bf16;
-  if (p.dense) {
-    if (regs) RGFM_TC_LAUNCH2(true, true); else RGFM_TC_LAUNCH2(true, false);
+  if (final_out) {  // no statistics: one kernel per row space
+    if (p.dense) RGFM_TC_LAUNCH2(true, false, true, false); else RGFM_TC_LAUNCH2(false, false, true, false);
+  } else if (p.dense) {
+    if (regs) RGFM_TC_LAUNCH2(true, true, false, false); else RGFM_TC_LAUNCH2(true, false, false, false);
+  } else if (p.nstk > 1) {  // register statistics are never combined with stacked padded-linear units (make_tc_conv)
+    RGFM_TC_LAUNCH2(false, false, false, true);
   } else {
-    if (regs) RGFM_TC_LAUNCH2(false, true); else RGFM_TC_LAUNCH2(false, false);
+    if (regs) RGFM_TC_LAUNCH2(false, true, false, false); else RGFM_TC_LAUNCH2(false, false, false, false);
   }
 #undef RGFM_TC_LAUNCH2
 #undef RGFM_TC_LAUNCH
