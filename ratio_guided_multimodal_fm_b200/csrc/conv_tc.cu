@@ -38,6 +38,9 @@ static inline void post_launch(const char* what) {
 }
 
 constexpr int TC_MAX_STAGES = 12;
+// row-dense neighbour exchange as packed fp16 pairs (half the shuffles, one extra fp16 rounding per neighbour term):
+// measured < 0.5 % of a step; off = exact fp32 exchange.  Compile time: the kernels carry one exchange loop.
+constexpr bool TC_XCHG16 = false;
 // REGSTATS kernels: GroupNorm partials from the accumulator registers (channel-quad sums of the thread's row + one 31-shuffle
 // transpose-reduce per unit, after the accumulator went back to the MMA warps) instead of ldmatrix.trans + mma.sync on the
 // staged tile.  It removes the legacy HMMAs that queue behind the UMMA stream but costs ~160 issue slots per thread and
@@ -97,7 +100,6 @@ struct TcArgs {
   // against 10 / 20 / 41 % of the padded-linear row space).  ky is a shift of Wt rows of the shared tile (atom aligned).
   int dense;
   int reg_stats;        // GroupNorm partials from the accumulator registers (REGSTATS kernels; tc_reg_stats())
-  int xchg16;           // row-dense: neighbour partial sums are exchanged as packed fp16 pairs (RGFM_TC_XCHG16, default off)
   int Wt, wt_shift;     // tile width and its log2
   int irs;              // image rows per super-tile (256 / Wt)
   int w0[3];            // per segment: TMA w coordinate of tile column 0 (0 = raw tensor, 1 = packed operand)
@@ -1166,7 +1168,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has left the buffer
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
           else asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll
+#pragma unroll 1
           for (int hh = 0; hh < 2; ++hh) {
             if (c0 + hh * 32 >= CP) break;  // 32-channel outputs: the upper half of the staging tile is never read
             uint32_t pk[16];
@@ -1174,7 +1176,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
               for (int sc = 0; sc < 2; ++sc) {
                 float v[16];
-                if constexpr (DENSE) acc16_dense(taddr, c0 + hh * 32 + sc * 16, N, ml, mr, p.xchg16 != 0, v);
+                if constexpr (DENSE) acc16_dense(taddr, c0 + hh * 32 + sc * 16, N, ml, mr, TC_XCHG16, v);
                 else acc16(taddr, c0 + hh * 32 + sc * 16, nstk, N, lane, xw, v);
                 [[maybe_unused]] float f[8];  // row-dense GroupNorm partials: {sum, sum of squares} of the four channel quads of this block
 #pragma unroll
@@ -1573,8 +1575,6 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     p.wt_shift = p.Wt == 8 ? 3 : (p.Wt == 16 ? 4 : 5);
     p.irs = 256 / p.Wt;
   }
-  static const int xchg16 = getenv("RGFM_TC_XCHG16") ? atoi(getenv("RGFM_TC_XCHG16")) : 0;  // measured: < 0.5 % of a step; off = exact fp32 exchange
-  p.xchg16 = xchg16;
   p.R = p.dense ? (d.Hin + 1) * p.Wt : (d.Hin + 1) * P;
   {
     auto magic = [&](int dv) {
