@@ -1168,50 +1168,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has left the buffer
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
           else asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll 1
-          for (int hh = 0; hh < 2; ++hh) {
-            if (c0 + hh * 32 >= CP) break;  // 32-channel outputs: the upper half of the staging tile is never read
-            uint32_t pk[16];
-            if (c0 + hh * 32 < N) {
+          // one 16-channel block at a time: accumulator (+ neighbour exchange) -> + bias -> saturating fp16 -> two 16-byte
+          // pieces of the 128B-swizzled staging tile [128 rows x 64 channels x 2 B].  The loop stays rolled unless the
+          // statistics live in registers (static indexing): the epilogue's code size is felt in the instruction caches.
+          auto block = [&](const int blk) {
+            const int cc = c0 + blk * 16;
+            uint32_t pk[8];
+            if (cc < N) {
+              float v[16];
+              if constexpr (DENSE) acc16_dense(taddr, cc, N, ml, mr, TC_XCHG16, v);
+              else acc16(taddr, cc, nstk, N, lane, xw, v);
+              [[maybe_unused]] float f[8];  // GroupNorm partials in registers: {sum, sum of squares} of the block's four channel quads
 #pragma unroll
-              for (int sc = 0; sc < 2; ++sc) {
-                float v[16];
-                if constexpr (DENSE) acc16_dense(taddr, c0 + hh * 32 + sc * 16, N, ml, mr, TC_XCHG16, v);
-                else acc16(taddr, c0 + hh * 32 + sc * 16, nstk, N, lane, xw, v);
-                [[maybe_unused]] float f[8];  // row-dense GroupNorm partials: {sum, sum of squares} of the four channel quads of this block
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (!p.exp_no_bias) b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + hh * 32 + sc * 16 + 4 * j]);
-                  const float x0 = v[4 * j] + b4.x, x1 = v[4 * j + 1] + b4.y, x2 = v[4 * j + 2] + b4.z, x3 = v[4 * j + 3] + b4.w;
-                  pk[8 * sc + 2 * j] = cvt2_f16_sat(x0, x1, vm, sat2);
-                  pk[8 * sc + 2 * j + 1] = cvt2_f16_sat(x2, x3, vm, sat2);
-                  if constexpr (REGSTATS) {
-                    f[j] = (x0 + x1) + (x2 + x3);
-                    f[4 + j] = fmaf(x3, x3, fmaf(x2, x2, fmaf(x1, x1, x0 * x0)));
-                  }
+              for (int j = 0; j < 4; ++j) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!p.exp_no_bias) b4 = *reinterpret_cast<const float4*>(&s_bias[cc + 4 * j]);
+                const float x0 = v[4 * j] + b4.x, x1 = v[4 * j + 1] + b4.y, x2 = v[4 * j + 2] + b4.z, x3 = v[4 * j + 3] + b4.w;
+                pk[2 * j] = cvt2_f16_sat(x0, x1, vm, sat2);
+                pk[2 * j + 1] = cvt2_f16_sat(x2, x3, vm, sat2);
+                if constexpr (REGSTATS) {
+                  f[j] = (x0 + x1) + (x2 + x3);
+                  f[4 + j] = fmaf(x3, x3, fmaf(x2, x2, fmaf(x1, x1, x0 * x0)));
                 }
-                if constexpr (REGSTATS) {  // row-dense GroupNorm partials: kept in registers until the accumulator has been released
+              }
+              if constexpr (REGSTATS) {  // kept in registers until the accumulator has been released
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) fq[(hh * 2 + sc) * 8 + j] = f[j];
-                }
+                for (int j = 0; j < 8; ++j) fq[blk * 8 + j] = f[j];
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = 0u;
+              for (int j = 0; j < 8; ++j) pk[j] = 0u;
             }
-            // registers -> 128B-swizzled staging tile [128 rows x 64 channels x 2 B]
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t dst = stg + (uint32_t)r * 128u + (uint32_t)(((hh * 4 + j) ^ (r & 7)) << 4);
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t dst = stg + (uint32_t)r * 128u + (uint32_t)(((blk * 2 + j) ^ (r & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
                            "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
             }
             if (!p.tma_store && wr) {  // stride-2 convs (never stacked): subsampled rows go straight to global memory
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(out16 + o + c0 + hh * 32 + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<uint4*>(out16 + o + cc + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
+          };
+          const int nblk = min(4, (CP - c0) >> 4);  // 32-channel outputs: the upper half of the staging tile is never read
+          if constexpr (REGSTATS) {
+#pragma unroll
+            for (int blk = 0; blk < 4; ++blk)
+              if (blk < nblk) block(blk);
+          } else {
+#pragma unroll 1
+            for (int blk = 0; blk < nblk; ++blk) block(blk);
           }
           if (c0 + 64 >= N) {  // last chunk that reads TMEM: hand the accumulator back to the MMA warps (one arrival per warp)
             tc_fence_before();
