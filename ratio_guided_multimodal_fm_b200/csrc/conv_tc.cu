@@ -1137,11 +1137,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           o = ((size_t)((size_t)n * (p.out_H + 1) + (h >> 1)) * (p.out_W + 2) + w2) * CP;
         }
       }
-      // one lane per warp waits: 256 threads on one mbarrier would crowd the unit that the producer / MMA threads' waits
-      // and every arrive of the pipeline go through
-      if (lane == 0) mbar_wait(tmem_full_bar(buf), use & 1u);
-      __syncwarp();
-      tc_fence_after();
+      // ONE thread per group waits for the accumulator (every poll of an mbarrier.try_wait loop is ~8 issued instructions
+      // and the pollers were 7 % of all warp-instructions); the group barrier publishes it.  The raw-activation path has that
+      // barrier anyway (the staging tile's previous TMA store must have been read out before it is overwritten).
+      if constexpr (FINAL) {
+        if (et == 0) mbar_wait(tmem_full_bar(buf), use & 1u);
+        if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        tc_fence_after();
+      }
       if (threadIdx.x == 0) TRC(3, it);
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + eg) * p.ncols);
       if constexpr (!FINAL) {
@@ -1165,9 +1169,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int j = 0; j < 32; ++j) fq[j] = 0.f;
         }
         for (int c0 = 0; c0 < CP; c0 += 64) {
-          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has left the buffer
+          if (et == 0) {
+            if (c0 == 0) mbar_wait(tmem_full_bar(buf), use & 1u);                  // this tile's accumulator is complete
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");         // previous store has left the buffer
+          }
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
           else asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (c0 == 0) tc_fence_after();
           // one 16-channel block at a time: accumulator (+ neighbour exchange) -> + bias -> saturating fp16 -> two 16-byte
           // pieces of the 128B-swizzled staging tile [128 rows x 64 channels x 2 B].  The loop stays rolled unless the
           // statistics live in registers (static indexing): the epilogue's code size is felt in the instruction caches.
