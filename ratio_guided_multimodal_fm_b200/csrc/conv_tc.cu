@@ -99,6 +99,15 @@ struct TcArgs {
   // 128 rows of a unit are outputs, and only the pad ROW of each image is wasted (3 / 6 / 11 % at 32 / 16 / 8 pixels
   // against 10 / 20 / 41 % of the padded-linear row space).  ky is a shift of Wt rows of the shared tile (atom aligned).
   int dense;
+  // One-unit tiles (row-dense convs with 64 output channels and resident weights): three column groups of 64 are 192 TMEM
+  // columns per unit, so the two units of a 256-row super-tile fill TMEM single-buffered and the MMAs of tile i + 1 wait
+  // for the epilogue's reads of tile i.  With upt == 1 a tile is ONE unit (128 rows + halo), MMA warp / epilogue group
+  // (tile & 1) owns it and TMEM buffer (tile & 1): the accumulators are double buffered again.  The halo costs 1.5x instead
+  // of 1.25x operand rows at 32 pixels; the weights must be resident (a ring would stream them per 128 rows).
+  // An MMA warp WAITS on the operand stages of the other warp's tiles without using them: a parity wait only tells apart
+  // two consecutive phases of a barrier, so every phase of every slot has to be observed by both warps.
+  int upt;              // units per tile: 2, or 1
+  int stages_total;     // operand stages (64-channel blocks of all segments) per tile
   int reg_stats;        // GroupNorm partials from the accumulator registers (REGSTATS kernels; tc_reg_stats())
   int Wt, wt_shift;     // tile width and its log2
   int irs;              // image rows per super-tile (256 / Wt)
@@ -552,12 +561,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (p.tma_store && DENSE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmZ)) : "memory");
     for (int s = 0; s < 4; ++s) {
       mbar_init(a_full(s), 1);
-      mbar_init(a_empty(s), 2);                    // both MMA warps
+      mbar_init(a_empty(s), p.upt == 1 ? 1 : 2);   // both MMA warps (one-unit tiles: the tile's own MMA warp)
       mbar_init(a_ready(s), 1);  // transform group -> MMA warps
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(tmem_full_bar(s), 2);   // both MMA warps
-      mbar_init(tmem_empty_bar(s), 8);  // one arrival per epilogue warp
+      mbar_init(tmem_full_bar(s), p.upt == 1 ? 1 : 2);   // both MMA warps (one-unit tiles: per MMA warp / epilogue group)
+      mbar_init(tmem_empty_bar(s), p.upt == 1 ? 4 : 8);  // one arrival per epilogue warp
     }
     for (int s = 0; s < (p.resident ? 1 : p.b_stages); ++s) {
       mbar_init(b_full(s), 1);
@@ -694,12 +703,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         mbar_wait(b_full(0), 0u);
         tc_fence_after();
       }
+      const bool upt1 = p.upt == 1;
+      const uint32_t a_unit = upt1 ? 0u : hf * ((uint32_t)UR * 128u);  // this warp's rows inside the A tile
       int it = 0;
 #pragma unroll 1
       for (int st = blockIdx.x; st < supers; st += gridDim.x, ++it) {
-        const int buf = (p.nbuf == 2) ? (it & 1) : 0;
-        const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
-        mbar_wait(tmem_empty_bar(buf), (use & 1u) ^ 1u);  // both epilogue groups drained this accumulator pair
+        if (upt1 && ((uint32_t)it & 1u) != hf) {
+          // The other MMA warp's tile: step over its operand stages -- but OBSERVE each of them.  A parity wait only tells
+          // apart two consecutive phases of a barrier: a warp that skipped a slot's first fill and then waited for its
+          // second one could pass while the first is still in flight (seen as a deadlock with the slower bf16 transform).
+          for (int k = 0; k < p.stages_total; ++k) {
+            mbar_wait(p.any_xform ? a_ready(as) : a_full(as), aph);
+            if (++as == a_slots) {
+              as = 0u;
+              aph ^= 1u;
+            }
+          }
+          continue;
+        }
+        const int buf = (!upt1 && p.nbuf == 2) ? (it & 1) : 0;
+        const uint32_t use = (upt1 || p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+        const uint32_t tb = upt1 ? hf : (uint32_t)buf;  // barrier pair: per buffer, or per MMA warp with one-unit tiles
+        mbar_wait(tmem_empty_bar(tb), (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t td = tmem_d + (uint32_t)((buf * 2 + (int)hf) * p.ncols);
         uint32_t acc = 0;  // the first MMA of the super-tile overwrites the accumulator
@@ -719,7 +744,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (hf == 0 && seg == 0 && cb == 0) TRC(1, it);
             const int ks = p.ksteps[seg][cb];
             // descriptor low word of the current filter row (a 1x1 segment's tile starts at the super-tile's own first row)
-            uint32_t a_lo = (smem_base + as * p.a_slot + hf * ((uint32_t)UR * 128u)) >> 4;
+            uint32_t a_lo = (smem_base + as * p.a_slot + a_unit) >> 4;
             uint32_t kx = 0;
 #pragma unroll 1
             for (int tap = 0; tap < ntp; tap += tps) {
@@ -767,7 +792,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           }
         }
-        tc_commit(tmem_full_bar(buf));
+        tc_commit(tmem_full_bar(tb));
         if (hf == 0) TRC(2, it);
       }
     }
@@ -1107,9 +1132,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int it = 0;
     for (int sti = blockIdx.x; sti < supers; sti += gridDim.x, ++it) {
       const int st = p.descend ? supers - 1 - sti : sti;
-      const int buf = (p.nbuf == 2) ? (it & 1) : 0;
-      const uint32_t use = (p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
-      const int unit = st * 2 + eg;  // unit index: UR output rows each
+      const bool upt1 = p.upt == 1;
+      if (upt1 && (it & 1) != eg) continue;  // one-unit tiles: the other group's tile
+      const int buf = (!upt1 && p.nbuf == 2) ? (it & 1) : 0;
+      const uint32_t use = (upt1 || p.nbuf == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+      const int tb = upt1 ? eg : buf;  // TMEM barrier pair
+      const int unit = upt1 ? st : st * 2 + eg;  // unit index: UR output rows each
       const int m = unit * UR + r;
       int n, h, w;
       // a real pixel of an image < nimg, and one of the UR rows this unit produces (TcArgs::unit_rows)
@@ -1141,7 +1169,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // and the pollers were 7 % of all warp-instructions); the group barrier publishes it.  The raw-activation path has that
       // barrier anyway (the staging tile's previous TMA store must have been read out before it is overwritten).
       if constexpr (FINAL) {
-        if (et == 0) mbar_wait(tmem_full_bar(buf), use & 1u);
+        if (et == 0) mbar_wait(tmem_full_bar(tb), use & 1u);
         if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         tc_fence_after();
@@ -1170,7 +1198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         for (int c0 = 0; c0 < CP; c0 += 64) {
           if (et == 0) {
-            if (c0 == 0) mbar_wait(tmem_full_bar(buf), use & 1u);                  // this tile's accumulator is complete
+            if (c0 == 0) mbar_wait(tmem_full_bar(tb), use & 1u);                   // this tile's accumulator is complete
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");         // previous store has left the buffer
           }
           if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -1231,7 +1259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (c0 + 64 >= N) {  // last chunk that reads TMEM: hand the accumulator back to the MMA warps (one arrival per warp)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+            if (lane == 0) mbar_arrive(tmem_empty_bar(tb));
           }
           if (nstk > 1 && !dense && c0 < N) {
             // fix-up pass: the rows that straddle two warps' lane quarters (3 boundaries x (nstk - 1) rows per unit), from
@@ -1412,7 +1440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+        if (lane == 0) mbar_arrive(tmem_empty_bar(tb));
         if (valid) {
           for (int c = 0; c < a.Cout; ++c) {
             const float val = v[c] + s_bias[c];
@@ -1584,11 +1612,21 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     }
     p.reg_stats = (mode == 2 || (mode == 1 && stall == 1 && nmma >= 64 && (!xf || nmma >= 128))) ? 1 : 0;
   }
+  p.upt = 2;
+  for (int sg = 0; sg < d.nseg; ++sg) p.stages_total += (d.seg[sg].Cin_real + 63) / 64;
   if (p.dense) {
     RGFM_CHECK(d.seg[0].ks == 3, "tc conv: segment 0 of a row-dense conv is 3x3");
     p.Wt = tc_tile_width(d.Win);
     p.wt_shift = p.Wt == 8 ? 3 : (p.Wt == 16 ? 4 : 5);
-    p.irs = 256 / p.Wt;
+    // one-unit tiles (TcArgs::upt): N = 64 and every weight tile resident next to two 128-row A slots and the staging tiles
+    uint32_t wbytes = 0;
+    for (int sg = 0; sg < d.nseg; ++sg) wbytes += (uint32_t)((d.seg[sg].Cin_real + 63) / 64) * (uint32_t)(d.seg[sg].ks * d.seg[sg].ks) * (uint32_t)nmma * 128u;
+    const uint32_t slot1 = (uint32_t)(128 / p.Wt + 2) * p.Wt * 128u;
+    const int upt_mode = getenv("RGFM_TC_UPT") ? atoi(getenv("RGFM_TC_UPT")) : 1;  // 0: never (A/B timing)
+    // measured per layer (same box): -4..-8 % on the two-stage convs (conv2 + identity residual), +19..24 % on the convs
+    // with three or four stages per tile (conv2 + 1x1 skip over a concatenation: more stages than A slots) -> two stages only
+    if (upt_mode != 0 && nmma == 64 && p.stages_total == 2 && 2u * slot1 + 2u * TC_STAGE_BYTES + wbytes <= TC_SMEM_BUDGET) p.upt = 1;
+    p.irs = (p.upt == 1 ? 128 : 256) / p.Wt;
   }
   p.R = p.dense ? (d.Hin + 1) * p.Wt : (d.Hin + 1) * P;
   {
@@ -1614,7 +1652,7 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
     if (!p.dense && p.nstk > 1) p.reg_stats = 0;
   }
   p.unit_rows = p.dense ? 128 : 128 - (p.nstk - 1);
-  p.super_rows = 2 * p.unit_rows;
+  p.super_rows = p.upt * p.unit_rows;
   p.ncols = (p.nstk * nmma + 31) / 32 * 32;
   p.sat = d.sat;
   const int rows_needed = p.super_rows + 2 * P + 2;
@@ -1622,7 +1660,7 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   RGFM_CHECK(p.a_box_rows <= 256, "tc conv: A box too tall");
   p.a_slot = p.dense ? (uint32_t)(p.irs + 2) * p.Wt * 128u : 2u * p.a_box_rows * 128u;
   p.b_bytes = (uint32_t)nmma * 128u;
-  p.nbuf = (4 * p.ncols <= 512) ? 2 : 1;
+  p.nbuf = (4 * p.ncols <= 512) ? 2 : 1;  // (one-unit tiles: one accumulator per MMA warp, 2 * ncols columns, see TcArgs::upt)
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.nbuf * p.ncols)) cols <<= 1;
   p.tmem_cols = cols;
@@ -1645,6 +1683,7 @@ TcPtr make_tc_conv(const TcConvDesc& d, DevPool& pool) {
   static const int force_slots = getenv("RGFM_TC_A_SLOTS") ? atoi(getenv("RGFM_TC_A_SLOTS")) : 0;
   const uint32_t min_slots = force_slots ? (uint32_t)force_slots : 2u;
   p.resident = (min_slots * p.a_slot + stage + b_total <= budget) ? 1 : 0;
+  RGFM_CHECK(p.upt == 2 || p.resident, "tc conv: one-unit tiles need resident weights");
   p.tps[0] = p.tps[1] = p.tps[2] = 1;
   if (p.resident) {
     int slots = (int)((budget - stage - b_total) / p.a_slot);
