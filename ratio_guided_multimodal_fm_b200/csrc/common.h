@@ -303,6 +303,10 @@ struct McfArgs {
 };
 size_t mcf_scratch_floats(int B, int N, int Dx, int Dy, int* ksx, int* ksy);
 void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof = nullptr);
+// the two halves of launch_mcf: distances + stabilised weights depend only on the state (x_t, y_t) and the bank, so the
+// sampler's graph runs them on a third branch beside the two U-Nets; the fused guidance sum + blend + Euler update needs v
+void launch_mcf_prep(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof = nullptr);
+void launch_mcf_apply(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof = nullptr);
 struct DiagArgs {
   int B, Dx, Dy, N;
   const float *vx, *vy, *gx, *gy, *zbuf;

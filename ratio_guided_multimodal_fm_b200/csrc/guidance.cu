@@ -340,6 +340,11 @@ size_t mcf_scratch_floats(int B, int N, int Dx, int Dy, int* ksx, int* ksy) {
 }
 
 void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof) {
+  launch_mcf_prep(a, s, prof);
+  launch_mcf_apply(a, s, prof);
+}
+
+void launch_mcf_prep(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof) {
   RGFM_CHECK(a.Dx % DK == 0 && a.Dy % DK == 0, "mc_feng: D must be a multiple of 16");
   RGFM_CHECK(a.N * sizeof(float) <= 48 * 1024, "mc_feng: mc_batch_size too large (max 12288)");
   const double BN = (double)a.B * a.N, D = (double)a.Dx + a.Dy;
@@ -355,6 +360,10 @@ void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof) {
     mcf_weights_kernel<<<a.B, 128, a.N * sizeof(float), s>>>(a);
     post_launch("mcf_weights");
   }
+}
+
+void launch_mcf_apply(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof) {
+  const double BN = (double)a.B * a.N, D = (double)a.Dx + a.Dy;
   {
     // fused guidance-sum + blend + Euler update: algorithmic bytes = read x, v, write x (+ bank and weights once)
     // one of the two paths runs per launch (device-side switch on the longest weight list, no host round trip); the

@@ -36,7 +36,8 @@ struct Sampler {
   int first_guided = 0;  // first step with t > eps
   int ksx = 1, ksy = 1;
   cudaStream_t cap = nullptr, cap2 = nullptr;   // capture streams: the x- and y-network forwards are independent branches
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t cap3 = nullptr;                  // third branch of a guided step: mc_feng distances + weights (need x_t, y_t only)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
   Graph g_pre, g_ratio, g_plain, g_guided, g_grad;
   int64_t launches = 0;
   float *hx = nullptr, *hy = nullptr, *hmx = nullptr, *hmy = nullptr;  // pinned staging for run_host
@@ -46,6 +47,8 @@ struct Sampler {
     cudaSetDevice(d.device);
     if (cap) cudaStreamDestroy(cap);
     if (cap2) cudaStreamDestroy(cap2);
+    if (cap3) cudaStreamDestroy(cap3);
+    if (ev_join3) cudaEventDestroy(ev_join3);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (hx) cudaFreeHost(hx);
@@ -211,6 +214,8 @@ struct Sampler {
     }
     RGFM_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
     RGFM_CUDA(cudaStreamCreateWithFlags(&cap2, cudaStreamNonBlocking));
+    RGFM_CUDA(cudaStreamCreateWithFlags(&cap3, cudaStreamNonBlocking));
+    RGFM_CUDA(cudaEventCreateWithFlags(&ev_join3, cudaEventDisableTiming));
     RGFM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     RGFM_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     // fork / join inside a capture: the second stream becomes a parallel branch of the graph, so the tail of one
@@ -240,13 +245,22 @@ struct Sampler {
         launch_ratio_head(scores, d.loss_type, nullptr, ratios, N, s);
         launch_ratio_stats(ratios, N, diag + 9, s);
       });
+      // RGFM_MCF_BRANCH=0: distances + weights after the U-Nets on the main branch (A/B timing; same results)
+      static const bool mcf_branch = !(getenv("RGFM_MCF_BRANCH") && atoi(getenv("RGFM_MCF_BRANCH")) == 0);
       capture(g_guided, [&](cudaStream_t s) {
+        McfArgs a = mcf_args();
         fork(s);
+        if (mcf_branch) {  // third branch: the importance weights depend on (x_t, y_t) only -- beside the U-Nets
+          RGFM_CUDA(cudaStreamWaitEvent(cap3, ev_fork, 0));
+          launch_mcf_prep(a, cap3);
+          RGFM_CUDA(cudaEventRecord(ev_join3, cap3));
+        }
         fx->forward(s, B, x, nullptr, vx, OUT_NCHW, dtf, step);
         fy->forward(cap2, B, y, nullptr, vy, OUT_NCHW, dtf, step);
         join(s);
-        McfArgs a = mcf_args();
-        launch_mcf(a, s);
+        if (mcf_branch) RGFM_CUDA(cudaStreamWaitEvent(s, ev_join3, 0));
+        else launch_mcf_prep(a, s);
+        launch_mcf_apply(a, s);
         DiagArgs da{B, Dx, Dy, N, vx, vy, gx, gy, a.zbuf, sc, step, (int)(0.3 * steps), diag};
         launch_diag(da, s);
         launch_step_inc(step, s);
