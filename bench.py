@@ -295,13 +295,18 @@ def other_configs(dev, world, rank, prec, dist, gather_pairs):
                                 mc_batch_size=N_MC, loss_type="disc", precision=prec, device=dev)
         plan.run(x0, y0, m0, n0)  # warm
         evaluate_coherence_mnist_svhn(x0[:64], y0[:64], cm, cs, dev)  # builds the classifier nets
-        coh = {}
+        # the evaluator is fused into the sampler's tail: classifier forwards + argmax match on the device, count in diag[15]
+        from ratio_guided_multimodal_fm_b200 import evaluate as _ev
+        plan.attach_evaluators(_ev._net(cm, x0.shape, dev), _ev._net(cs, y0.shape, dev))
+        coh, dg = {}, {}
 
         def sweep():
             for i, gm in enumerate(gammas):
                 plan.set_strength(gm)
-                x1, y1 = plan.run(x0, y0, m0, n0) if i == 0 else plan.run(x0, y0, reuse_bank=True)
-                coh[str(gm)] = evaluate_coherence_mnist_svhn(x1, y1, cm, cs, dev)["coherence_acc"]
+                r = plan.run(x0, y0, m0, n0, want_diag=True) if i == 0 else plan.run(x0, y0, reuse_bank=True, want_diag=True)
+                dg[str(gm)] = r[2]
+            for k, v in dg.items():  # one scalar per gamma crosses to the host
+                coh[k] = float(v[15]) / B
         s, _ = _timed(sweep)
         plan.close()
         out["configs[2]"] = dict(workload=f"MNIST32-SVHN gamma sweep {gammas}, B=4096 per gamma, N_mc=256, 100 steps, shared MC bank, "

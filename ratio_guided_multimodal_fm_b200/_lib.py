@@ -58,7 +58,7 @@ _lib = None
 EXPORTS = [
     "rgfm_last_error", "rgfm_abi_version", "rgfm_sampler_create", "rgfm_sampler_run", "rgfm_sampler_run_host",
     "rgfm_sampler_set_strength", "rgfm_sampler_run_reuse_bank", "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
-    "rgfm_unet_forward", "rgfm_unet_sample", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_create_prec", "rgfm_ratio_grad_log_ratio", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
+    "rgfm_unet_forward", "rgfm_unet_sample", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_create_prec", "rgfm_ratio_grad_log_ratio", "rgfm_coherence_matches", "rgfm_sampler_attach_evaluators", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
 ]
 
 
@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
     L.rgfm_classifier_logits.argtypes = [vp, vp, C.c_int32, vp, vp]
     L.rgfm_ratio_grad_create.argtypes = [C.c_int32, C.POINTER(_Weights), C.c_int32, C.c_int32, C.POINTER(vp)]
     L.rgfm_ratio_grad_create_prec.argtypes = [C.c_int32, C.POINTER(_Weights), C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.rgfm_coherence_matches.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp, vp]
+    L.rgfm_sampler_attach_evaluators.argtypes = [vp, vp, vp, C.c_int32]
     L.rgfm_ratio_grad_log_ratio.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
     L.rgfm_net_destroy.argtypes = [vp]
     L.rgfm_net_destroy.restype = None
@@ -165,6 +167,22 @@ def _dev_index(device) -> int:
 
 def _f32c(t: torch.Tensor, device) -> torch.Tensor:
     return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+TRANSFORMS = {"identity": 0, "none": 0, "rotate90": 1, "rotate180": 2, "rotate270": 3, "invert": 4, "flip_h": 5, "flip_v": 6}
+
+
+def coherence_matches(clf_a: "Net", clf_b: "Net", xa: torch.Tensor, xb: torch.Tensor, matches: torch.Tensor = None) -> torch.Tensor:
+    """Number of pairs whose classifier predictions agree, as ONE device float that is added to (rgfm_coherence_matches):
+    both classifier forwards, argmax and the comparison stay on the device."""
+    dev = clf_a.device
+    xa, xb = _f32c(xa, dev), _f32c(xb, dev)
+    assert xa.shape[0] == xb.shape[0] and xa.shape[0] >= 1
+    if matches is None:
+        matches = torch.zeros(1, device=dev, dtype=torch.float32)
+    scratch = torch.empty(20 * xa.shape[0], device=dev, dtype=torch.float32)
+    check(lib().rgfm_coherence_matches(clf_a.h, clf_b.h, _ptr(xa), _ptr(xb), xa.shape[0], _ptr(scratch), _ptr(matches), _stream_ptr(dev)))
+    return matches
 
 
 class Net:
@@ -286,6 +304,16 @@ class SamplerPlan:
     @property
     def launch_count(self) -> int:
         return int(lib().rgfm_sampler_launch_count(self.h))
+
+    def attach_evaluators(self, clf_x: "Net" = None, clf_y: "Net" = None, transform_type: str = None):
+        """Fuse the coherence evaluator into the plan's tail (evaluate_mnist_svhn.py:28-57 / evaluate.py:56-90): every run
+        classifies its finished pairs on the device and reports the number of coherent pairs in diag[15].
+        transform_type: the 28x28 pair's transform, undone on y before its classifier.  None, None detaches."""
+        code = TRANSFORMS.get(transform_type or "identity")
+        if code is None:
+            raise ValueError(f"Unknown transform_type: {transform_type}")
+        check(lib().rgfm_sampler_attach_evaluators(self.h, clf_x.h if clf_x else None, clf_y.h if clf_y else None, code))
+        self._evaluators = (clf_x, clf_y)  # keep the nets alive as long as the plan uses them
 
     def set_strength(self, guidance_strength: float):
         """Change gamma in place (mc_feng / unguided plans): the graphs read it from a device table."""

@@ -13,6 +13,8 @@ void sampler_get_bank(Sampler*, float*, float*, float*, cudaStream_t);
 int64_t sampler_launches(const Sampler*);
 void sampler_run_reuse_bank(Sampler*, const float*, const float*, float*, float*, float*, cudaStream_t);
 void sampler_set_strength(Sampler*, double, cudaStream_t);
+void sampler_attach_evaluators(Sampler*, Net*, Net*, int);
+void launch_argmax_match(const float*, const float*, int, float*, cudaStream_t);
 int sampler_profile(Sampler*, rgfm_prof_entry*, int);
 }  // namespace rgfm
 
@@ -92,6 +94,30 @@ int rgfm_sampler_set_strength(rgfm_sampler* s, double guidance_strength, void* s
   RGFM_API_BEGIN
   RGFM_CHECK(s != nullptr, "rgfm_sampler_set_strength: null plan");
   rgfm::sampler_set_strength(reinterpret_cast<rgfm::Sampler*>(s), guidance_strength, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_sampler_attach_evaluators(rgfm_sampler* s, rgfm_net* clf_x, rgfm_net* clf_y, int32_t inverse_transform) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(s != nullptr, "rgfm_sampler_attach_evaluators: null plan");
+  rgfm::sampler_attach_evaluators(reinterpret_cast<rgfm::Sampler*>(s), clf_x ? clf_x->net.get() : nullptr, clf_y ? clf_y->net.get() : nullptr,
+                                  inverse_transform);
+  RGFM_API_END
+}
+
+int rgfm_coherence_matches(rgfm_net* clf_a, rgfm_net* clf_b, const float* xa, const float* xb, int32_t batch, float* logits_scratch,
+                           float* matches, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(clf_a && clf_b && xa && xb && logits_scratch && matches && batch >= 1, "rgfm_coherence_matches: null argument");
+  for (rgfm_net* n : {clf_a, clf_b})
+    RGFM_CHECK(n->net->kind() >= RGFM_NET_CLF_MNIST28 && n->net->kind() <= RGFM_NET_CLF_SVHN, "rgfm_coherence_matches: not a classifier");
+  RGFM_CUDA(cudaSetDevice(clf_a->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* la = logits_scratch;
+  float* lb = logits_scratch + (size_t)batch * 10;
+  clf_a->net->forward(st, batch, xa, nullptr, la, 0, 0.f, nullptr);
+  clf_b->net->forward(st, batch, xb, nullptr, lb, 0, 0.f, nullptr);
+  rgfm::launch_argmax_match(la, lb, batch, matches, st);
   RGFM_API_END
 }
 

@@ -317,6 +317,10 @@ struct DiagArgs {
 };
 void launch_diag(const DiagArgs& a, cudaStream_t s);
 void launch_sat_report(const unsigned int* a, const unsigned int* b, const unsigned int* c, float* out, cudaStream_t s);
+// count += #{i : argmax la[i] == argmax lb[i]} over [n][10] logits (first maximum, like torch.argmax)
+void launch_argmax_match(const float* la, const float* lb, int n, float* count, cudaStream_t s);
+// the inverse of a 28x28 pair transform (0 identity, 1 rotate90, 2 rotate180, 3 rotate270, 4 invert, 5 flip_h, 6 flip_v)
+void launch_inverse_transform(const float* in, float* out, int n, int H, int code, cudaStream_t s);
 void launch_ratio_stats(const float* ratios, int n, float* diag3, cudaStream_t s);
 
 // Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains; it must execute

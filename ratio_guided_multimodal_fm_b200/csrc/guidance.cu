@@ -461,6 +461,55 @@ void launch_sat_report(const unsigned int* a, const unsigned int* b, const unsig
   post_launch("sat_report");
 }
 
+// ---- pair coherence (evaluate_mnist_svhn.py:28-57, evaluate.py:56-90): argmax agreement of two classifiers ----
+// logits [n][10] each; torch.argmax returns the FIRST maximum, so the scan keeps the earliest index (strict >).
+__global__ void __launch_bounds__(256) argmax_match_kernel(const float* __restrict__ la, const float* __restrict__ lb, int n, float* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int hit = 0;
+  if (i < n) {
+    int ia = 0, ib = 0;
+    float ma = la[(size_t)i * 10], mb = lb[(size_t)i * 10];
+#pragma unroll
+    for (int c = 1; c < 10; ++c) {
+      const float va = la[(size_t)i * 10 + c], vb = lb[(size_t)i * 10 + c];
+      if (va > ma) { ma = va; ia = c; }
+      if (vb > mb) { mb = vb; ib = c; }
+    }
+    hit = ia == ib;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (float)__popc(m));  // integers below 2^24: exact in fp32
+}
+void launch_argmax_match(const float* la, const float* lb, int n, float* count, cudaStream_t s) {
+  argmax_match_kernel<<<(n + 255) / 256, 256, 0, s>>>(la, lb, n, count);
+  post_launch("argmax_match");
+}
+
+// inverse of the pair's transform on [n][1][H][H] images (evaluate.py:30-53; quarter turns and flips are pixel
+// permutations: TF.rotate(img, 90) is a counter-clockwise quarter turn = torch.rot90(k=1))
+__global__ void inverse_transform_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int H, int code) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * H * H) return;
+  const int px = (int)(i % ((size_t)H * H)), r = px / H, c = px % H;
+  const float* img = in + (i - px);
+  float v;
+  switch (code) {
+    case 1: v = img[c * H + (H - 1 - r)]; break;            // rotate90  -> rot90(k=1):  out[r][c] = in[c][H-1-r]
+    case 2: v = img[(H - 1 - r) * H + (H - 1 - c)]; break;  // rotate180 -> rot90(k=2)
+    case 3: v = img[(H - 1 - c) * H + r]; break;            // rotate270 -> rot90(k=-1): out[r][c] = in[H-1-c][r]
+    case 4: v = -img[px]; break;                            // invert
+    case 5: v = img[r * H + (H - 1 - c)]; break;            // flip_h
+    case 6: v = img[(H - 1 - r) * H + c]; break;            // flip_v
+    default: v = img[px];
+  }
+  out[i] = v;
+}
+void launch_inverse_transform(const float* in, float* out, int n, int H, int code, cudaStream_t s) {
+  const size_t tot = (size_t)n * H * H;
+  inverse_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(in, out, n, H, code);
+  post_launch("inverse_transform");
+}
+
 void launch_diag(const DiagArgs& a, cudaStream_t s) {
   diag_kernel<<<1, 1024, 0, s>>>(a);
   post_launch("diag");

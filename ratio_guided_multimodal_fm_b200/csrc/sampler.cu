@@ -41,6 +41,11 @@ struct Sampler {
   Graph g_pre, g_ratio, g_plain, g_guided, g_grad;
   int64_t launches = 0;
   float *hx = nullptr, *hy = nullptr, *hmx = nullptr, *hmy = nullptr;  // pinned staging for run_host
+  // evaluators attached to the plan (rgfm_sampler_attach_evaluators): classifier forwards + argmax match on the finished
+  // pairs at the end of every run, count in diag[15].  The nets are the caller's (they must outlive the plan's runs).
+  Net *clf_x = nullptr, *clf_y = nullptr;
+  int clf_transform = 0;
+  float *clf_lx = nullptr, *clf_ly = nullptr, *clf_ty = nullptr;
   std::vector<float*> stage;  // device staging for run_host
 
   ~Sampler() {
@@ -338,6 +343,16 @@ struct Sampler {
     RGFM_CUDA(cudaMemcpyAsync(x1, x, (size_t)B * Dx * sizeof(float), cudaMemcpyDeviceToDevice, s));
     RGFM_CUDA(cudaMemcpyAsync(y1, y, (size_t)B * Dy * sizeof(float), cudaMemcpyDeviceToDevice, s));
     launch_sat_report(fx->sat_counter(), fy->sat_counter(), fr ? fr->sat_counter() : nullptr, diag + 12, s);
+    if (clf_x) {  // fused evaluator tail: the pairs are still in HBM / L2, nothing goes back to Python but the count
+      const float* ys = y;
+      if (clf_transform != 0) {
+        launch_inverse_transform(y, clf_ty, B, fy->img(), clf_transform, s);
+        ys = clf_ty;
+      }
+      clf_x->forward(s, B, x, nullptr, clf_lx, 0, 0.f, nullptr);
+      clf_y->forward(s, B, ys, nullptr, clf_ly, 0, 0.f, nullptr);
+      launch_argmax_match(clf_lx, clf_ly, B, diag + 15, s);
+    }
     if (diag_out) RGFM_CUDA(cudaMemcpyAsync(diag_out, diag, RGFM_DIAG_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
 };
@@ -359,6 +374,25 @@ void sampler_run_reuse_bank(Sampler* s, const float* x0, const float* y0, float*
   s->run(x0, y0, nullptr, nullptr, x1, y1, diag, st, /*reuse_bank=*/true);
 }
 void sampler_set_strength(Sampler* s, double gamma, cudaStream_t st) { s->set_strength(gamma, st); }
+void sampler_attach_evaluators(Sampler* s, Net* cx, Net* cy, int inverse_transform) {
+  RGFM_CHECK((cx == nullptr) == (cy == nullptr), "rgfm_sampler_attach_evaluators: both classifiers or none");
+  if (cx) {
+    RGFM_CHECK(cx->kind() >= RGFM_NET_CLF_MNIST28 && cx->kind() <= RGFM_NET_CLF_SVHN && cy->kind() >= RGFM_NET_CLF_MNIST28 &&
+                   cy->kind() <= RGFM_NET_CLF_SVHN, "rgfm_sampler_attach_evaluators: not classifiers");
+    RGFM_CHECK(cx->dim() == (size_t)s->Dx && cy->dim() == (size_t)s->Dy, "rgfm_sampler_attach_evaluators: classifier input shapes do not match the pair");
+    RGFM_CHECK(inverse_transform >= 0 && inverse_transform <= 6, "rgfm_sampler_attach_evaluators: unknown transform");
+    RGFM_CHECK(inverse_transform == 0 || s->fy->in_ch() == 1, "rgfm_sampler_attach_evaluators: transforms apply to single-channel pairs");
+    RGFM_CUDA(cudaSetDevice(s->d.device));
+    if (!s->clf_lx) {
+      s->clf_lx = (float*)s->pool.persistent((size_t)s->B * 10 * sizeof(float));
+      s->clf_ly = (float*)s->pool.persistent((size_t)s->B * 10 * sizeof(float));
+      s->clf_ty = (float*)s->pool.persistent((size_t)s->B * s->Dy * sizeof(float));
+    }
+  }
+  s->clf_x = cx;
+  s->clf_y = cy;
+  s->clf_transform = inverse_transform;
+}
 int64_t sampler_launches(const Sampler* s) { return s->launches; }
 
 void sampler_run_host(Sampler* s, const float* x0, const float* y0, const float* mx0, const float* my0, float* x1,

@@ -53,6 +53,21 @@ def classifier_predictions(classifier, samples: torch.Tensor, device) -> torch.T
     return torch.cat(preds) if preds else torch.empty(0, dtype=torch.int64, device=device)
 
 
+def _matches(clf_a, clf_b, xa: torch.Tensor, xb: torch.Tensor, device) -> torch.Tensor:
+    """#{i : argmax clf_a(xa_i) == argmax clf_b(xb_i)} as one device scalar: classifier forwards, argmax and the comparison in
+    one C-ABI call per chunk (rgfm_coherence_matches), nothing but the final count crosses to the host."""
+    clf_a.eval()
+    clf_b.eval()
+    device = torch.device(device)
+    cnt = torch.zeros(1, device=device, dtype=torch.float32)
+    if xa.shape[0] == 0:
+        return cnt
+    na, nb = _net(clf_a, xa.shape, device), _net(clf_b, xb.shape, device)
+    for i in range(0, xa.shape[0], _CHUNK):
+        _lib.coherence_matches(na, nb, xa[i:i + _CHUNK].to(device), xb[i:i + _CHUNK].to(device), cnt)
+    return cnt
+
+
 def get_inverse_transform(transform_type):
     """evaluate.py:30-53.  The reference uses torchvision's rotate / flips; for these exact quarter turns they are
     pixel permutations (TF.rotate(img, 90) is a counter-clockwise quarter turn = torch.rot90(k=1))."""
@@ -71,8 +86,8 @@ def get_inverse_transform(transform_type):
     return lambda img: img
 
 
-def _coherence(pred_a: torch.Tensor, pred_b: torch.Tensor, total: int, shard: bool, group) -> Dict[str, float]:
-    cnt = (pred_a == pred_b).sum().to(torch.int64).reshape(1)
+def _coherence(cnt: torch.Tensor, total: int, shard: bool, group) -> Dict[str, float]:
+    cnt = cnt.to(torch.int64).reshape(1)
     if shard:
         import torch.distributed as dist
         dist.all_reduce(cnt, group=group)
@@ -88,9 +103,7 @@ def evaluate_coherence(samples_x, samples_y, classifier, device, transform_type=
         import torch.distributed as dist
         lo, hi = shard_bounds(n, dist.get_world_size(group), dist.get_rank(group))
     inv = get_inverse_transform(transform_type)
-    px = classifier_predictions(classifier, samples_x[lo:hi], device)
-    py = classifier_predictions(classifier, inv(samples_y[lo:hi]).contiguous(), device)
-    return _coherence(px, py, n, shard, group)
+    return _coherence(_matches(classifier, classifier, samples_x[lo:hi], inv(samples_y[lo:hi]).contiguous(), device), n, shard, group)
 
 
 def evaluate_coherence_mnist_svhn(samples_mnist, samples_svhn, mnist_classifier, svhn_classifier, device, *,
@@ -101,6 +114,4 @@ def evaluate_coherence_mnist_svhn(samples_mnist, samples_svhn, mnist_classifier,
     if shard:
         import torch.distributed as dist
         lo, hi = shard_bounds(n, dist.get_world_size(group), dist.get_rank(group))
-    pm = classifier_predictions(mnist_classifier, samples_mnist[lo:hi], device)
-    ps = classifier_predictions(svhn_classifier, samples_svhn[lo:hi], device)
-    return _coherence(pm, ps, n, shard, group)
+    return _coherence(_matches(mnist_classifier, svhn_classifier, samples_mnist[lo:hi], samples_svhn[lo:hi], device), n, shard, group)

@@ -179,7 +179,7 @@ def sample_bimodal_guided_mnist_svhn(fm_mnist, fm_svhn, ratio_estimator=None, gu
 
 def sample_guidance_sweep(pair, fm_x, fm_y, ratio_estimator, guidance_strengths, num_samples=16, num_steps=100,
                           device='cuda', mc_batch_size=64, *, precision: Optional[str] = None, same_prior: bool = False,
-                          chunk: int = 0):
+                          chunk: int = 0, evaluators=None, transform_type: Optional[str] = None, coherence_out: Optional[dict] = None):
     """mc_feng pairs for SEVERAL guidance strengths from ONE plan and ONE MC bank.
 
     The reference's evaluators call the sampler once per gamma (src/evaluate.py:189-199,
@@ -188,6 +188,10 @@ def sample_guidance_sweep(pair, fm_x, fm_y, ratio_estimator, guidance_strengths,
     runs the full call, and every further gamma only rewrites the per-step scalar table and runs the main loop.
     pair: "pair28" (1x28x28, 1x28x28) or "mnist_svhn" (1x32x32, 3x32x32).  A fresh prior (x0, y0) is drawn per gamma,
     in call order like the reference would, unless same_prior=True (paired comparison across gammas).
+    evaluators=(classifier_x, classifier_y) fuses the coherence evaluation (evaluate_mnist_svhn.py:28-57, evaluate.py:56-90)
+    into the sampler's tail: the classifiers run on the finished pairs while they are still on the device and
+    coherence_out[gamma] = {'coherence_acc', 'num_samples'} is filled from ONE device scalar per gamma (diag[15]);
+    transform_type is the 28x28 pair's transform (undone on y before its classifier).
     Returns {gamma: (samples_x, samples_y)}."""
     shapes = {"pair28": ((1, 28, 28), (1, 28, 28)), "mnist_svhn": ((1, 32, 32), (3, 32, 32))}
     if pair not in shapes:
@@ -213,6 +217,14 @@ def sample_guidance_sweep(pair, fm_x, fm_y, ratio_estimator, guidance_strengths,
                             precision=precision or default_precision(), device=device, chunk=chunk)
     try:
         x0 = y0 = None
+        diags = {}
+        if evaluators is not None:
+            from . import evaluate as _ev  # classifier nets are cached by weight content there
+            cx, cy = evaluators
+            cx.eval()
+            cy.eval()
+            plan.attach_evaluators(_ev._net(cx, (num_samples,) + shape_x, device), _ev._net(cy, (num_samples,) + shape_y, device),
+                                   transform_type)
         for i, g in enumerate(gammas):
             if x0 is None or not same_prior:
                 x0 = torch.randn(num_samples, *shape_x, device=device)
@@ -220,11 +232,16 @@ def sample_guidance_sweep(pair, fm_x, fm_y, ratio_estimator, guidance_strengths,
             if i == 0:
                 mc_x0 = torch.randn(mc_batch_size, *shape_x, device=device)
                 mc_y0 = torch.randn(mc_batch_size, *shape_y, device=device)
-                out[g] = plan.run(x0, y0, mc_x0, mc_y0)
+                r = plan.run(x0, y0, mc_x0, mc_y0, want_diag=True)
             else:
                 plan.set_strength(g)
-                out[g] = plan.run(x0, y0, reuse_bank=True)
+                r = plan.run(x0, y0, reuse_bank=True, want_diag=True)
+            out[g] = (r[0], r[1])
+            diags[g] = r[2]
         torch.cuda.current_stream(device).synchronize()
+        if evaluators is not None and coherence_out is not None:
+            for g in gammas:
+                coherence_out[g] = {"coherence_acc": float(diags[g][15]) / float(max(num_samples, 1)), "num_samples": int(num_samples)}
     finally:
         plan.close()
     return out

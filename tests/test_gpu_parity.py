@@ -457,6 +457,52 @@ def test_coherence_evaluators_match_oracle(synth):
     assert abs(ours["coherence_acc"] - float((px == py).double().mean())) < 1e-9
 
 
+def test_fused_evaluator_tail(synth):
+    """rgfm_sampler_attach_evaluators: the classifier forwards + argmax match run at the end of the sampler call on the pairs
+    still on the device and report the count in diag[15]; it equals the evaluators' count and the oracle's argmax agreement
+    on the returned pairs (exact: fp32 classifiers on identical inputs) -- MNIST32/SVHN, and the 28x28 pair with every
+    transform's inverse (evaluate.py:30-53)."""
+    from ratio_guided_multimodal_fm_b200 import evaluate_coherence, evaluate_coherence_mnist_svhn, evaluate as ev
+    B, N, steps = 48, 8, 3
+    gen = torch.Generator().manual_seed(9)
+    # MNIST32 <-> SVHN
+    sdx, sdy, sdr = synth("unet_mnist32", 12), synth("unet_svhn", 13), synth("ratio_mnist_svhn", 22)
+    cm = synthetic.StateDictModule("clf_mnist32", synth("clf_mnist32", 31))
+    cs = synthetic.StateDictModule("clf_svhn", synth("clf_svhn", 32))
+    x0, y0 = torch.randn(B, 1, 32, 32, generator=gen), torch.randn(B, 3, 32, 32, generator=gen)
+    m0, n0 = torch.randn(N, 1, 32, 32, generator=gen), torch.randn(N, 3, 32, 32, generator=gen)
+    plan = _lib.SamplerPlan("mnist_svhn", sdx, sdy, sdr, guidance_method="mc_feng", guidance_strength=0.5, num_samples=B, num_steps=steps,
+                            mc_batch_size=N, precision="fp16", device=DEV)
+    plan.attach_evaluators(ev._net(cm, x0.shape, torch.device(DEV)), ev._net(cs, y0.shape, torch.device(DEV)))
+    x1, y1, diag = plan.run(x0.to(DEV), y0.to(DEV), m0.to(DEV), n0.to(DEV), want_diag=True)
+    torch.cuda.synchronize()
+    pm = O.classifier_logits(cm.state_dict(), "clf_mnist32", x1.cpu()).argmax(1)
+    ps = O.classifier_logits(cs.state_dict(), "clf_svhn", y1.cpu()).argmax(1)
+    assert float(diag[15]) == float((pm == ps).sum())
+    assert float(diag[15]) == round(evaluate_coherence_mnist_svhn(x1, y1, cm, cs, DEV)["coherence_acc"] * B)
+    plan.attach_evaluators(None, None)  # detach: the slot reads 0 again
+    _, _, diag = plan.run(x0.to(DEV), y0.to(DEV), m0.to(DEV), n0.to(DEV), want_diag=True)
+    assert float(diag[15]) == 0.0
+    plan.close()
+    # 28x28 pair, every transform
+    sdx, sdy, sdr = synth("unet_mnist28", 11), synth("unet_mnist28", 14), synth("ratio28", 21)
+    c28 = synthetic.StateDictModule("clf_mnist28", synth("clf_mnist28", 33))
+    x0, y0 = torch.randn(B, 1, 28, 28, generator=gen), torch.randn(B, 1, 28, 28, generator=gen)
+    m0, n0 = torch.randn(N, 1, 28, 28, generator=gen), torch.randn(N, 1, 28, 28, generator=gen)
+    plan = _lib.SamplerPlan("pair28", sdx, sdy, sdr, guidance_method="mc_feng", guidance_strength=0.5, num_samples=B, num_steps=steps,
+                            mc_batch_size=N, precision="fp16", device=DEV)
+    net28 = ev._net(c28, x0.shape, torch.device(DEV))
+    for tt in ("rotate90", "rotate180", "rotate270", "invert", "flip_h", "flip_v", "identity"):
+        plan.attach_evaluators(net28, net28, tt)
+        x1, y1, diag = plan.run(x0.to(DEV), y0.to(DEV), m0.to(DEV), n0.to(DEV), want_diag=True)
+        torch.cuda.synchronize()
+        want = evaluate_coherence(x1, y1, c28, DEV, transform_type=tt)["coherence_acc"] * B
+        assert float(diag[15]) == round(want), (tt, float(diag[15]), want)
+    with pytest.raises(ValueError):
+        plan.attach_evaluators(net28, net28, "shear")
+    plan.close()
+
+
 @pytest.mark.parametrize("gamma", [0.0, 0.5, 2.0, 5.0])
 def test_guidance_strength_sweep_coherence(gamma, synth):
     """BASELINE configs[2] shape at a CPU-oracle-sized batch: gamma sweep incl. the extrapolating 2 and 5, pair coherence
