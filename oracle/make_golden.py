@@ -133,6 +133,46 @@ def case_ratio(kind, seed, B):
     save(f"{kind}_forward", seed=seed, x=x, y=y, grad_x_disc=gx, grad_y_disc=gy, digest=sd_digest(sd), **out)
 
 
+def case_ratio_train(kind, seed, B, loss_type):
+    """One RatioTrainer.train_step's loss + param.grad through the UNMODIFIED reference module and loss classes
+    (trainer.py:36-52, losses.py:27-133), with the two training-mode effects pinned: fixed dropout masks are replayed by
+    forward hooks on the nn.Dropout modules of a module in eval mode (= training mode with those masks and frozen BatchNorm)."""
+    from src.utils.losses import get_ratio_loss
+    shp = {"ratio28": ((1, 28, 28), (1, 28, 28)), "ratio_mnist_svhn": ((1, 32, 32), (3, 32, 32))}[kind]
+    widths = {"ratio28": (512, 256), "ratio_mnist_svhn": (512, 512)}[kind]
+    g = torch.Generator().manual_seed(3000 + seed)
+    x = torch.randn(B, *shp[0], generator=g)
+    y = torch.randn(B, *shp[1], generator=g)
+    is_real = (torch.arange(B) % 3 != 1).float()          # uneven split: ~2/3 real
+    masks = [torch.bernoulli(torch.full((B, w), 0.9), generator=g) / 0.9 for w in widths]
+    m, sd = ref_module(kind, seed, loss_type)
+    drops = [mod for mod in m.score_net if isinstance(mod, torch.nn.Dropout)]
+    assert len(drops) == len(masks)
+    hooks = [d.register_forward_hook(lambda mod, inp, out, mk=mk: out * mk) for d, mk in zip(drops, masks)]
+    loss_fn = get_ratio_loss(loss_type)
+    m.zero_grad()
+    scores = m(x, y)
+    loss, metrics = loss_fn(scores[is_real == 1], scores[is_real == 0])
+    loss.backward()
+    for h in hooks:
+        h.remove()
+    lam = getattr(loss_fn, "lambda_penalty", 0.0)
+    oloss, ometrics, ograds = O.ratio_train_grads(sd, kind, x, y, is_real, loss_type, lam, masks)
+    exact(loss.detach(), oloss, kind + " train loss " + loss_type)
+    for k in metrics:
+        assert metrics[k] == ometrics[k], (k, metrics[k], ometrics[k])
+    out = {}
+    for name, p in m.named_parameters():
+        exact(p.grad, ograds[name], f"{kind} grad {name} ({loss_type})")
+        flat = p.grad.flatten()
+        idx = torch.linspace(0, flat.numel() - 1, min(flat.numel(), 64)).long()
+        out["g:" + name] = torch.cat([flat.norm().reshape(1), flat.sum().reshape(1), flat[idx]])
+    assert set(ograds) == {n for n, _ in m.named_parameters()}
+    save(f"{kind}_train_{loss_type}", seed=seed, x=x, y=y, is_real=is_real, loss=loss.detach(), lambda_penalty=lam,
+         metric_names=np.array(sorted(metrics)), metric_values=np.array([metrics[k] for k in sorted(metrics)]),
+         digest=sd_digest(sd), **{f"mask{i}": mk for i, mk in enumerate(masks)}, **out)
+
+
 def case_classifier(kind, seed, B):
     m, sd = ref_module(kind, seed)
     shp = {"clf_mnist28": (1, 28, 28), "clf_mnist32": (1, 32, 32), "clf_svhn": (3, 32, 32)}[kind]
@@ -220,6 +260,10 @@ def main():
         ("flow28", lambda: case_unet("flow28", 15, 3)),
         ("ratio28", lambda: case_ratio("ratio28", 21, 4)),
         ("ratio_mnist_svhn", lambda: case_ratio("ratio_mnist_svhn", 22, 4)),
+        ("ratio28_train_disc", lambda: case_ratio_train("ratio28", 21, 6, "disc")),
+        ("ratio28_train_rulsif", lambda: case_ratio_train("ratio28", 21, 6, "rulsif")),
+        ("ratio_mnist_svhn_train_disc", lambda: case_ratio_train("ratio_mnist_svhn", 22, 6, "disc")),
+        ("ratio_mnist_svhn_train_rulsif", lambda: case_ratio_train("ratio_mnist_svhn", 22, 6, "rulsif")),
         ("clf_mnist28", lambda: case_classifier("clf_mnist28", 31, 4)),
         ("clf_mnist32", lambda: case_classifier("clf_mnist32", 32, 4)),
         ("clf_svhn", lambda: case_classifier("clf_svhn", 33, 4)),

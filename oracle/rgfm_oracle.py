@@ -191,26 +191,73 @@ def _encoder_svhn(sd: StateDict, p: str, x: Tensor) -> Tensor:
     return F.linear(h, sd[p + "fc.weight"], sd[p + "fc.bias"])
 
 
-def _score_net(sd: StateDict, feats: Tensor, linear_ln: Tuple[Tuple[int, int], ...], last: int) -> Tensor:
+def _score_net(sd: StateDict, feats: Tensor, linear_ln: Tuple[Tuple[int, int], ...], last: int, masks=None) -> Tensor:
+    """Linear -> LayerNorm -> SiLU -> Dropout per hidden layer (ratio_estimator.py:125-135).  Dropout is the identity in eval
+    mode; `masks` (training step, one [B, width] tensor of 0 | 1/(1-p) per hidden layer) multiplies where nn.Dropout would."""
     h = feats
-    for li, ni in linear_ln:
+    for i, (li, ni) in enumerate(linear_ln):
         h = F.linear(h, sd[f"score_net.{li}.weight"], sd[f"score_net.{li}.bias"])
         h = F.layer_norm(h, (h.shape[-1],), sd[f"score_net.{ni}.weight"], sd[f"score_net.{ni}.bias"])
         h = F.silu(h)
+        if masks is not None and i < len(masks):  # ratio_flexible.py:332-345 has no Dropout after the third hidden layer
+            h = h * masks[i]
     return F.linear(h, sd[f"score_net.{last}.weight"], sd[f"score_net.{last}.bias"]).squeeze(-1)
 
 
-def ratio_scores(sd: StateDict, kind: str, x: Tensor, y: Tensor) -> Tensor:
+def ratio_scores(sd: StateDict, kind: str, x: Tensor, y: Tensor, masks=None) -> Tensor:
     """T_theta(x, y).  reference: ratio_estimator.py:137-158, ratio_flexible.py:347-364."""
     if kind == "ratio28":
         fx = _encoder28(sd, "encoder_x.", x)
         fy = _encoder28(sd, "encoder_y.", y)
-        return _score_net(sd, torch.cat([fx, fy], dim=1), ((0, 1), (4, 5)), 8)
+        return _score_net(sd, torch.cat([fx, fy], dim=1), ((0, 1), (4, 5)), 8, masks)
     if kind == "ratio_mnist_svhn":
         fx = _encoder_mnist32(sd, "encoder_mnist.", x)
         fy = _encoder_svhn(sd, "encoder_svhn.", y)
-        return _score_net(sd, torch.cat([fx, fy], dim=1), ((0, 1), (4, 5), (8, 9)), 11)
+        return _score_net(sd, torch.cat([fx, fy], dim=1), ((0, 1), (4, 5), (8, 9)), 11, masks)
     raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------
+# Training side (SURVEY.md section 8 f-4): the ratio losses and one step's parameter gradients
+# ----------------------------------------------------------------------------
+def ratio_loss(scores_real: Tensor, scores_fake: Tensor, loss_type: str, lambda_penalty: float = 0.1):
+    """(loss, metrics) of DiscriminatorLoss.forward (losses.py:41-65) / RuLSIFLoss.forward (losses.py:93-130; `alpha` is
+    stored by the reference but not used by its forward)."""
+    if loss_type == "disc":
+        loss = (F.binary_cross_entropy_with_logits(scores_real, torch.ones_like(scores_real))
+                + F.binary_cross_entropy_with_logits(scores_fake, torch.zeros_like(scores_fake)))
+        with torch.no_grad():
+            m = {"loss": loss.item(), "acc_real": (scores_real > 0).float().mean().item(),
+                 "acc_fake": (scores_fake < 0).float().mean().item()}
+        return loss, m
+    if loss_type == "rulsif":
+        w_real, w_fake = F.softplus(scores_real), F.softplus(scores_fake)
+        w_mix = torch.cat([w_real, w_fake])
+        constraint = lambda_penalty * (w_mix.mean() - 1.0).pow(2)
+        loss = 0.5 * w_mix.pow(2).mean() - w_real.mean() + constraint
+        with torch.no_grad():
+            m = {"loss": loss.item(), "mean_w_real": w_real.mean().item(), "mean_w_fake": w_fake.mean().item(),
+                 "constraint_term": constraint.item()}
+        return loss, m
+    raise ValueError(f"Unknown loss_type: {loss_type}")
+
+
+TRAIN_BUFFERS = ("running_mean", "running_var", "num_batches_tracked")
+
+
+def ratio_train_grads(sd: StateDict, kind: str, x: Tensor, y: Tensor, is_real: Tensor, loss_type: str,
+                      lambda_penalty: float = 0.1, masks=None):
+    """What RatioTrainer.train_step (trainer.py:36-52) leaves in param.grad: scores = model(x, y); split by is_real;
+    loss_fn; backward.  BatchNorm uses its running statistics (frozen) and dropout is `masks` -- the two training-mode
+    effects that are not a pure function of (weights, batch).  Returns (loss, metrics, {name: grad})."""
+    with torch.enable_grad():
+        p = {k: (v.detach().clone().requires_grad_(True) if v.dtype.is_floating_point and not k.endswith(TRAIN_BUFFERS) else v)
+             for k, v in sd.items()}
+        scores = ratio_scores(p, kind, x, y, masks)
+        loss, metrics = ratio_loss(scores[is_real == 1], scores[is_real == 0], loss_type, lambda_penalty)
+        names = [k for k, v in p.items() if v.requires_grad]
+        grads = torch.autograd.grad(loss, [p[k] for k in names])
+    return loss.detach(), metrics, dict(zip(names, grads))
 
 
 def ratio_log_ratio(sd: StateDict, kind: str, x: Tensor, y: Tensor, loss_type: str) -> Tensor:

@@ -4,8 +4,10 @@ from .sampler import (sample_bimodal_guided, sample_bimodal_guided_mnist_svhn, s
 from .flow import CFMSchedule
 from .evaluate import (evaluate_coherence, evaluate_coherence_mnist_svhn, classifier_predictions,
                        get_inverse_transform)
-from .synthetic import synthetic_module, state_dict as synthetic_state_dict, StateDictModule
+from .synthetic import synthetic_module, state_dict as synthetic_state_dict, StateDictModule, TrainableModule
+from .train import RatioTrainer, RatioTrainPlan, ratio_loss
 
 __all__ = ["sample_bimodal_guided", "sample_bimodal_guided_mnist_svhn", "sample_guidance_sweep", "CFMSchedule", "shard_bounds", "gather_pairs",
            "clear_plan_cache", "evaluate_coherence", "evaluate_coherence_mnist_svhn", "classifier_predictions",
-           "get_inverse_transform", "synthetic_module", "synthetic_state_dict", "StateDictModule"]
+           "get_inverse_transform", "synthetic_module", "synthetic_state_dict", "StateDictModule", "TrainableModule",
+           "RatioTrainer", "RatioTrainPlan", "ratio_loss"]

@@ -59,6 +59,7 @@ EXPORTS = [
     "rgfm_last_error", "rgfm_abi_version", "rgfm_sampler_create", "rgfm_sampler_run", "rgfm_sampler_run_host",
     "rgfm_sampler_set_strength", "rgfm_sampler_run_reuse_bank", "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
     "rgfm_unet_forward", "rgfm_unet_sample", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_create_prec", "rgfm_ratio_grad_log_ratio", "rgfm_coherence_matches", "rgfm_sampler_attach_evaluators", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
+    "rgfm_ratio_trainer_create", "rgfm_ratio_trainer_step", "rgfm_ratio_trainer_destroy", "rgfm_ratio_loss",
 ]
 
 
@@ -98,6 +99,11 @@ def lib() -> C.CDLL:
     L.rgfm_net_destroy.argtypes = [vp]
     L.rgfm_net_destroy.restype = None
     L.rgfm_mc_feng_step.argtypes = [C.c_int32] * 4 + [vp] * 7 + [C.c_double] * 3 + [vp] * 5 + [vp]
+    L.rgfm_ratio_trainer_create.argtypes = [C.c_int32, C.POINTER(_Weights), C.POINTER(_Weights), C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.rgfm_ratio_trainer_step.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_float, C.POINTER(vp), C.c_int32, vp, vp]
+    L.rgfm_ratio_trainer_destroy.argtypes = [vp]
+    L.rgfm_ratio_trainer_destroy.restype = None
+    L.rgfm_ratio_loss.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_float, vp, vp, vp]
     if L.rgfm_abi_version() != ABI_VERSION:
         raise RgfmError("librgfm.so ABI version mismatch; rebuild")
     _lib = L
@@ -128,6 +134,33 @@ class Weights:
             self.arr[i].data = a.ctypes.data_as(C.POINTER(C.c_float))
             self.arr[i].numel = a.size
         self.w = _Weights(self.arr, len(items))
+
+    def ref(self):
+        return C.byref(self.w)
+
+
+class DeviceWeights:
+    """name -> DEVICE fp32 tensor table as rgfm_weights (the training entry points read parameters and write gradients in
+    place).  The tensors must stay alive and must not move while the handle built from this table exists."""
+
+    def __init__(self, tensors: Dict[str, torch.Tensor], device):
+        self._keep = []
+        items = []
+        for k, v in tensors.items():
+            if not torch.is_tensor(v) or not v.dtype.is_floating_point:
+                continue
+            if v.dtype != torch.float32 or not v.is_contiguous() or v.device.type != "cuda" or v.device.index != _dev_index(device):
+                raise RgfmError(f"training tensors must be contiguous fp32 on {device}: {k} is {v.dtype} on {v.device}")
+            items.append((k.encode(), v))
+        self.arr = (_Tensor * len(items))()
+        for i, (k, v) in enumerate(items):
+            self._keep.append(k)
+            self._keep.append(v)
+            self.arr[i].name = k
+            self.arr[i].data = C.cast(C.c_void_p(v.data_ptr()), C.POINTER(C.c_float))
+            self.arr[i].numel = v.numel()
+        self.w = _Weights(self.arr, len(items))
+        self.ptrs = tuple(v.data_ptr() for _, v in items)
 
     def ref(self):
         return C.byref(self.w)

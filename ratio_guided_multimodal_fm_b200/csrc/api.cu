@@ -18,6 +18,15 @@ void launch_argmax_match(const float*, const float*, int, float*, cudaStream_t);
 int sampler_profile(Sampler*, rgfm_prof_entry*, int);
 }  // namespace rgfm
 
+struct rgfm_ratio_trainer;
+namespace rgfm {
+rgfm_ratio_trainer* ratio_trainer_create(int, const rgfm_weights*, const rgfm_weights*, int, int);
+void ratio_trainer_step(rgfm_ratio_trainer*, const float*, const float*, const float*, int, int, float, const float* const*, int, float*,
+                        cudaStream_t);
+void ratio_trainer_destroy(rgfm_ratio_trainer*);
+void launch_ratio_loss(const float*, const float*, int, int, float, float*, float*, cudaStream_t);
+}  // namespace rgfm
+
 static thread_local std::string g_err;
 
 // Every entry point works on the plan's / net's device (cudaSetDevice inside) and puts the caller's current device back
@@ -297,6 +306,41 @@ int rgfm_mc_feng_step(int32_t batch, int32_t n_mc, int32_t dx, int32_t dy, const
   }
   cudaFree(scratch);
   cudaFree(dsc);
+  RGFM_API_END
+}
+
+int rgfm_ratio_trainer_create(int32_t net_kind, const rgfm_weights* params, const rgfm_weights* grads, int32_t max_batch,
+                              int32_t device, rgfm_ratio_trainer** out) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(out != nullptr && params != nullptr && grads != nullptr, "rgfm_ratio_trainer_create: null argument");
+  *out = rgfm::ratio_trainer_create(net_kind, params, grads, max_batch, device);
+  RGFM_API_END
+}
+
+int rgfm_ratio_trainer_step(rgfm_ratio_trainer* t, const float* x, const float* y, const float* is_real, int32_t batch,
+                            int32_t loss_type, float lambda_penalty, const float* const* dropout_masks, int32_t n_masks,
+                            float* out8, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(t && x && y && is_real && out8 && batch >= 1, "rgfm_ratio_trainer_step: null argument");
+  RGFM_CHECK(loss_type == RGFM_LOSS_DISC || loss_type == RGFM_LOSS_RULSIF, "Unknown loss_type");
+  RGFM_CHECK(n_masks == 0 || dropout_masks != nullptr, "rgfm_ratio_trainer_step: null dropout_masks");
+  for (int i = 0; i < n_masks; ++i) RGFM_CHECK(dropout_masks[i] != nullptr, "rgfm_ratio_trainer_step: null dropout mask");
+  rgfm::ratio_trainer_step(t, x, y, is_real, batch, loss_type, lambda_penalty, dropout_masks, n_masks, out8, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+void rgfm_ratio_trainer_destroy(rgfm_ratio_trainer* t) {
+  DeviceRestore _restore;
+  rgfm::ratio_trainer_destroy(t);
+}
+
+int rgfm_ratio_loss(const float* scores, const float* is_real, int32_t n, int32_t loss_type, float lambda_penalty, float* out8,
+                    float* dscore, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(scores && is_real && out8 && dscore && n >= 1, "rgfm_ratio_loss: null argument");
+  RGFM_CHECK(loss_type == RGFM_LOSS_DISC || loss_type == RGFM_LOSS_RULSIF, "Unknown loss_type");
+  set_device_of(scores);
+  rgfm::launch_ratio_loss(scores, is_real, n, loss_type, lambda_penalty, out8, dscore, (cudaStream_t)stream);
   RGFM_API_END
 }
 

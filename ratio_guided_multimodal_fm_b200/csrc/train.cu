@@ -1,0 +1,892 @@
+// Training-side reuse: the loss and parameter gradients of one ratio-estimator optimisation step,
+// i.e. what `loss.backward()` leaves in `param.grad` inside RatioTrainer.train_step (src/utils/trainer.py:26-56) for the
+// losses of src/utils/losses.py:27-133 (DiscriminatorLoss, RuLSIFLoss).
+//
+// The step reuses the sampler's fp32 kernels for everything that already exists -- forward convs and the input-gradient
+// (dgrad) convs on conv_simt, GroupNorm / BatchNorm-affine + SiLU + max-pool packs and their backward, GAP + fc and its
+// backward -- and adds what only training needs: the loss heads with their score gradients, weight gradients of the
+// convs (a deterministic split-K outer-product kernel), of the linears and of the normalisation affines, and the
+// score-net backward with caller-supplied dropout masks.
+//
+// Parameters are read IN PLACE from the caller's live parameter tensors (device pointers in torch layout) and gradients
+// are written straight into the caller's gradient tensors: no host round trip and no plan rebuild after an optimiser
+// step.  The conv kernels' [tap][Cin][CoutP] weight layouts are refreshed by a repack kernel at the start of every step
+// (3.3 M floats at most).  Everything is fp32; summation orders are fixed, so a step is bit-reproducible.
+//
+// Not covered (stated in DESIGN.md): BatchNorm in training mode (batch statistics) -- RatioEstimatorMNISTSVHN is
+// trained here with frozen running statistics; the U-Nets' flow-matching step (needs a U-Net backward chain).
+#include "net.h"
+#include "simt_device.cuh"
+#include <cmath>
+
+namespace rgfm {
+
+static inline void post_launch_t(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw Error(std::string(what) + " launch failed: " + cudaGetErrorString(e));
+  ++g_launch_counter;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight refresh: torch [Cout][Cin][3][3] -> conv_simt layouts
+//   forward  wf[tap][ci][co]            (ci < CinP, co < CoutP, zero padded)
+//   dgrad    wb[tap][co][ci] = W[co][ci][8 - tap]   (rows = Cout, columns padded to CinB; net.cu encoder())
+// ------------------------------------------------------------------------------------------------
+__global__ void repack_conv_w_kernel(const float* __restrict__ w, int cout, int cin, int CinP, int CoutP, int CinB,
+                                     float* __restrict__ wf, float* __restrict__ wb) {
+  const int nf = 9 * CinP * CoutP, nb = wb ? 9 * cout * CinB : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const int co = i % CoutP, ci = (i / CoutP) % CinP, t = i / (CoutP * CinP);
+      wf[i] = (co < cout && ci < cin) ? w[((size_t)co * cin + ci) * 9 + t] : 0.f;
+    } else {
+      const int j = i - nf;
+      const int ci = j % CinB, co = (j / CinB) % cout, t = j / (CinB * cout);
+      wb[j] = (ci < cin) ? w[((size_t)co * cin + ci) * 9 + (8 - t)] : 0.f;
+    }
+  }
+}
+__global__ void pad_vec_kernel(const float* __restrict__ v, int n, int nP, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nP) out[i] = i < n ? v[i] : 0.f;
+}
+// BatchNorm with frozen running statistics as a per-channel affine (ratio_flexible.py:217-226 in eval mode)
+__global__ void bn_affine_kernel(const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ m,
+                                 const float* __restrict__ v, int C, float* __restrict__ scale, float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) {
+    const float inv = 1.0f / sqrtf(v[i] + 1e-5f);
+    const float sc = g[i] * inv;
+    scale[i] = sc;
+    shift[i] = b[i] - m[i] * sc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loss heads (losses.py:27-133) over the scores of one batch; is_real[i] in {0, 1}.  One CTA, fixed summation order.
+//   disc:   L = mean_real softplus(-s) + mean_fake softplus(s)                    (BCE with logits, targets 1 / 0)
+//   rulsif: w = softplus(s);  L = 0.5 mean_all w^2 - mean_real w + lambda (mean_all w - 1)^2   (alpha is unused by the
+//           reference's forward: "treat concatenated samples as mixture", losses.py:108-121)
+// out[0] = loss; disc: out[1] = acc_real, out[2] = acc_fake; rulsif: out[1] = mean_w_real, out[2] = mean_w_fake,
+// out[3] = constraint term.  dscore[i] = dL / ds_i.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // F.softplus (threshold 20)
+__device__ __forceinline__ float sigmoid_t(float x) { return 1.0f / (1.0f + expf(-x)); }
+// softplus without the threshold shortcut, the way binary_cross_entropy_with_logits evaluates it
+__device__ __forceinline__ float softplus_stable(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+__global__ void __launch_bounds__(256) ratio_loss_kernel(const float* __restrict__ s, const float* __restrict__ is_real, int n,
+                                                         int loss_type, float lambda, float* __restrict__ out,
+                                                         float* __restrict__ dscore) {
+  __shared__ float red[8];
+  const int tid = threadIdx.x;
+  float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // n_real | disc: sum_r sp(-s), sum_f sp(s), #r(s>0), #f(s<0) | rulsif: sum_r w, sum_f w, sum w^2
+  for (int i = tid; i < n; i += 256) {
+    const bool r = is_real[i] != 0.f;
+    const float v = s[i];
+    a[0] += r ? 1.f : 0.f;
+    if (loss_type == RGFM_LOSS_DISC) {
+      if (r) { a[1] += softplus_stable(-v); a[3] += v > 0.f ? 1.f : 0.f; }
+      else   { a[2] += softplus_stable(v);  a[4] += v < 0.f ? 1.f : 0.f; }
+    } else {
+      const float w = softplus_t(v);
+      if (r) a[1] += w; else a[2] += w;
+      a[3] = fmaf(w, w, a[3]);
+    }
+  }
+  float t[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) t[k] = block_sum256(a[k], red);
+  const float nr = t[0], nf = (float)n - t[0], nn = (float)n;
+  if (loss_type == RGFM_LOSS_DISC) {
+    if (tid == 0) {
+      out[0] = t[1] / nr + t[2] / nf;
+      out[1] = t[3] / nr;
+      out[2] = t[4] / nf;
+      out[3] = 0.f;
+    }
+    for (int i = tid; i < n; i += 256) {
+      const float v = s[i];
+      dscore[i] = is_real[i] != 0.f ? -sigmoid_t(-v) / nr : sigmoid_t(v) / nf;
+    }
+  } else {
+    const float m = (t[1] + t[2]) / nn;
+    const float cons = lambda * (m - 1.f) * (m - 1.f);
+    if (tid == 0) {
+      out[0] = 0.5f * t[3] / nn - t[1] / nr + cons;
+      out[1] = t[1] / nr;
+      out[2] = t[2] / nf;
+      out[3] = cons;
+    }
+    const float dm = 2.f * lambda * (m - 1.f) / nn;
+    for (int i = tid; i < n; i += 256) {
+      const float v = s[i];
+      const float w = softplus_t(v);
+      const float dw = w / nn - (is_real[i] != 0.f ? 1.f / nr : 0.f) + dm;
+      dscore[i] = dw * (v > 20.f ? 1.f : sigmoid_t(v));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Score net in training mode: Linear -> LayerNorm -> SiLU -> Dropout per hidden layer, then Linear -> 1
+// (ratio_estimator.py:125-135, ratio_flexible.py:332-345).  One CTA per sample keeps every intermediate in shared memory.
+// Dropout is a caller-supplied mask per hidden layer (values 0 or 1 / (1 - p); null = no dropout).
+// dscore == nullptr: forward only (scores).  Otherwise the backward from dL/dscore: the feature gradient and, per layer,
+// what the weight-gradient reductions need: dh (gradient at the Linear output), the layer input, and for the LayerNorm
+// affine dz * xhat and dz.
+// ------------------------------------------------------------------------------------------------
+struct MlpTrainIO {
+  const float* mask[3];
+  float* a_in[4];   // a_in[0] unused (the features themselves)
+  float* dh[4];
+  float* dzx[3];
+  float* dz[3];
+};
+struct MlpPackT {
+  MlpLayer l[4];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) mlp_train_kernel(const float* __restrict__ in, int ld_in, MlpPackT mp, MlpTrainIO io,
+                                                        const float* __restrict__ dscore, float* __restrict__ scores,
+                                                        float* __restrict__ dfeat, int ld_d) {
+  extern __shared__ float sm[];
+  __shared__ float red[8];
+  __shared__ float s_mean[4], s_rstd[4];
+  const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* act[5];
+  float* pre[4];
+  int off = 0;
+  act[0] = sm;
+  off += mp.l[0].in;
+  for (int li = 0; li < mp.n; ++li) {
+    pre[li] = sm + off; off += mp.l[li].out;
+    act[li + 1] = sm + off; off += mp.l[li].out;
+  }
+  float* gcur = sm + off; off += 512;
+  float* gnext = sm + off;
+  for (int i = tid; i < mp.l[0].in; i += 256) act[0][i] = in[(size_t)n * ld_in + i];
+  __syncthreads();
+  for (int li = 0; li < mp.n; ++li) {
+    const MlpLayer L = mp.l[li];
+    for (int j = warp; j < L.out; j += 8) {
+      const float* wr = L.w + (size_t)j * L.in;
+      float s = 0.f;
+      for (int c = lane; c < L.in; c += 32) s = fmaf(wr[c], act[li][c], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) pre[li][j] = s + L.b[j];
+    }
+    __syncthreads();
+    if (L.ln_g) {
+      float s = 0.f;
+      for (int c = tid; c < L.out; c += 256) s += pre[li][c];
+      const float mean = block_sum256(s, red) / (float)L.out;
+      float v = 0.f;
+      for (int c = tid; c < L.out; c += 256) {
+        const float d = pre[li][c] - mean;
+        v = fmaf(d, d, v);
+      }
+      const float rstd = rsqrtf(block_sum256(v, red) / (float)L.out + 1e-5f);
+      if (tid == 0) {
+        s_mean[li] = mean;
+        s_rstd[li] = rstd;
+      }
+      const float* mk = io.mask[li];
+      for (int c = tid; c < L.out; c += 256) {
+        const float z = (pre[li][c] - mean) * rstd * L.ln_g[c] + L.ln_b[c];
+        float a = silu_f(z);
+        if (mk) a *= mk[(size_t)n * L.out + c];
+        act[li + 1][c] = a;
+      }
+    } else {
+      for (int c = tid; c < L.out; c += 256) act[li + 1][c] = pre[li][c];
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && scores) scores[n] = act[mp.n][0];
+  if (!dscore) return;
+  // ---- backward ----
+  for (int c = tid; c < mp.l[mp.n - 1].out; c += 256) gcur[c] = (c == 0) ? dscore[n] : 0.f;
+  __syncthreads();
+  for (int li = mp.n - 1; li >= 0; --li) {
+    const MlpLayer L = mp.l[li];
+    if (L.ln_g) {
+      const float mean = s_mean[li], rstd = s_rstd[li];
+      const float* mk = io.mask[li];
+      float s1 = 0.f, s2 = 0.f;
+      for (int c = tid; c < L.out; c += 256) {
+        const float xh = (pre[li][c] - mean) * rstd;
+        const float z = xh * L.ln_g[c] + L.ln_b[c];
+        float dz = gcur[c];
+        if (mk) dz *= mk[(size_t)n * L.out + c];
+        const float sg = 1.0f / (1.0f + expf(-z));
+        dz *= sg * (1.0f + z * (1.0f - sg));
+        io.dzx[li][(size_t)n * L.out + c] = dz * xh;
+        io.dz[li][(size_t)n * L.out + c] = dz;
+        const float dg = dz * L.ln_g[c];
+        gcur[c] = dg;
+        s1 += dg;
+        s2 = fmaf(dg, xh, s2);
+      }
+      const float m1 = block_sum256(s1, red) / (float)L.out;
+      const float m2 = block_sum256(s2, red) / (float)L.out;
+      for (int c = tid; c < L.out; c += 256) {
+        const float xh = (pre[li][c] - mean) * rstd;
+        gcur[c] = rstd * (gcur[c] - m1 - xh * m2);
+      }
+    }
+    __syncthreads();
+    for (int c = tid; c < L.out; c += 256) io.dh[li][(size_t)n * L.out + c] = gcur[c];
+    if (li > 0)
+      for (int i = tid; i < L.in; i += 256) io.a_in[li][(size_t)n * L.in + i] = act[li][i];
+    for (int i = tid; i < L.in; i += 256) {
+      float s = 0.f;
+      for (int j = 0; j < L.out; ++j) s = fmaf(L.w[(size_t)j * L.in + i], gcur[j], s);
+      gnext[i] = s;
+    }
+    __syncthreads();
+    float* t = gcur;
+    gcur = gnext;
+    gnext = t;
+  }
+  for (int i = tid; i < mp.l[0].in; i += 256) dfeat[(size_t)n * ld_d + i] = gcur[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// dW[j][i] = sum_n A[n][j] * B[n][i]   (j < J, i < I; row strides lda / ldb): weight gradient of a Linear.
+// 32 x 32 outputs per CTA, samples walked in order (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ A, int lda, int J, const float* __restrict__ B,
+                                                           int ldb, int I, int N, float* __restrict__ dW) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int j0 = blockIdx.y * 32, i0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int ti = tid & 31, tj = tid >> 5;  // outputs (j0 + tj + 8 q, i0 + ti), q = 0..3
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    for (int e = tid; e < 1024; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      const int n = n0 + r;
+      As[r][c] = (n < N && j0 + c < J) ? A[(size_t)n * lda + j0 + c] : 0.f;
+      Bs[r][c] = (n < N && i0 + c < I) ? B[(size_t)n * ldb + i0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float b = Bs[r][ti];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(As[r][tj + 8 * q], b, acc[q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = j0 + tj + 8 * q, i = i0 + ti;
+    if (j < J && i < I) dW[(size_t)j * I + i] = acc[q];
+  }
+}
+
+// out[split][c] = sum over the split's rows of M[r][c]  (column sums, two deterministic stages: call again on `out`)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ M, int ld, int C, long long rows, int rows_per_split,
+                                                     float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tc = threadIdx.x & 31, tr = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tc;
+  const long long r0 = (long long)blockIdx.y * rows_per_split;
+  const long long r1 = r0 + rows_per_split < rows ? r0 + rows_per_split : rows;
+  float s = 0.f;
+  if (c < C)
+    for (long long r = r0 + tr; r < r1; r += 8) s += M[(size_t)r * ld + c];
+  red[tr][tc] = s;
+  __syncthreads();
+  if (tr == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][tc];
+    out[(size_t)blockIdx.y * C + c] = t;
+  }
+}
+
+// mean over the pixels of the last packed activation: gap[n][c]  (the fc layer's input, ratio_estimator.py:88-90)
+__global__ void __launch_bounds__(256) gap_kernel(const float* __restrict__ in, int HW, int C, float* __restrict__ out) {
+  const int n = blockIdx.x;
+  const float* src = in + (size_t)n * HW * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += src[(size_t)p * C + c];
+    out[(size_t)n * C + c] = s / (float)HW;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Normalisation affine gradients of one layer, per image: part[n][c] = {sum_p dz * u, sum_p dz} where dz is the gradient
+// at the norm's output (incoming gradient routed through the max-pool to the first maximum and through SiLU', exactly
+// as pack_bwd_kernel does) and u = xhat (GroupNorm) or the raw activation (per-channel affine).  C must divide 256, so
+// that a thread owns one channel; the 256 / C threads of a channel are combined in a fixed order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) norm_param_grad_kernel(PackArgs a, const float* __restrict__ dcur, float* __restrict__ part) {
+  __shared__ float s_scale[PACK_MAXC];
+  __shared__ float s_shift[PACK_MAXC];
+  __shared__ float s_red[2][PACK_MAXC];
+  __shared__ double s_grp[32][2];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  pack_scale_shift(a, n, s_scale, s_shift, s_red, s_grp);
+  const int C = a.C, H = a.Hs, Wd = a.Ws;
+  const bool pool = a.spatial == SP_POOL2;
+  const float* raw = a.src[0].p + (size_t)n * H * Wd * C;
+  const float* dc = dcur + (size_t)n * a.Ho * a.Wo * C;
+  const int c = tid % C, cpg = C / a.groups;
+  const float sc = s_scale[c], sh = s_shift[c];
+  const float mean = a.norm == NORM_GN ? (float)s_grp[c / cpg][0] : 0.f, rstd = a.norm == NORM_GN ? (float)s_grp[c / cpg][1] : 1.f;
+  float s0 = 0.f, s1 = 0.f;
+  for (int pix = tid / C; pix < H * Wd; pix += 256 / C) {
+    const int h = pix / Wd, w = pix - h * Wd;
+    const float r = raw[(size_t)pix * C + c];
+    const float z = fmaf(r, sc, sh);
+    float g;
+    if (!pool) {
+      g = dc[(size_t)pix * C + c];
+    } else {
+      const int ho = h >> 1, wo = w >> 1;
+      g = 0.f;
+      if (ho < a.Ho && wo < a.Wo) {
+        float best = -INFINITY;
+        int bi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int hh = 2 * ho + (k >> 1), ww = 2 * wo + (k & 1);
+          const float v = silu_f(fmaf(raw[((size_t)hh * Wd + ww) * C + c], sc, sh));
+          if (v > best) {
+            best = v;
+            bi = k;
+          }
+        }
+        if (bi == ((h & 1) * 2 + (w & 1))) g = dc[((size_t)ho * a.Wo + wo) * C + c];
+      }
+    }
+    const float sg = 1.0f / (1.0f + expf(-z));
+    const float dz = g * sg * (1.0f + z * (1.0f - sg));
+    const float u = a.norm == NORM_GN ? (r - mean) * rstd : r;
+    s0 = fmaf(dz, u, s0);
+    s1 += dz;
+  }
+  __syncthreads();
+  s_red[0][tid] = s0;
+  s_red[1][tid] = s1;
+  __syncthreads();
+  if (tid < C) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int j = tid; j < 256; j += C) {
+      t0 += s_red[0][j];
+      t1 += s_red[1][j];
+    }
+    part[((size_t)n * C + tid) * 2] = t0;
+    part[((size_t)n * C + tid) * 2 + 1] = t1;
+  }
+}
+// sums[c][2] (over the images) -> the affine's parameter gradients.  GroupNorm: d gamma = sums[c][0], d beta = sums[c][1].
+// Frozen BatchNorm y = (x - rm) * inv * w + b:  d w = inv * (sum dz x - rm sum dz), d b = sum dz.
+__global__ void norm_grad_finish_kernel(const float* __restrict__ sums, int C, const float* __restrict__ rm, const float* __restrict__ rv,
+                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float a = sums[2 * c], b = sums[2 * c + 1];
+  if (rm) {
+    const float inv = 1.0f / sqrtf(rv[c] + 1e-5f);
+    dgamma[c] = inv * (a - rm[c] * b);
+  } else {
+    dgamma[c] = a;
+  }
+  dbeta[c] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Conv weight gradient: dW[co][ci][ky][kx] = sum_{n,h,w} dY[n][h][w][co] * X[n][h + ky - 1][w + kx - 1][ci]
+// X: the conv's fp32 NHWC operand (channel stride CinP), dY: dense fp32 NHWC gradient of the raw output.
+// A CTA owns a (16 CI x 64) tile of (ci, co) for all nine taps and a contiguous range of (image, row) pairs; per row it
+// stages the three operand rows (zero halo) and the gradient row in shared memory and accumulates 9 x CI x 4 outer-product
+// terms per thread.  Partials part[split][tap][ci][co] are summed in split order by conv_wgrad_reduce_kernel, which also
+// transposes to the torch layout: deterministic, no atomics.
+// ------------------------------------------------------------------------------------------------
+template <int CI>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ X, int CinP, const float* __restrict__ dY, int Cout,
+                                                         int H, int W, int nimg, int rows_per_split, float* __restrict__ part) {
+  constexpr int TCI = 16 * CI, TCO = 64;
+  extern __shared__ __align__(16) float smw[];
+  float* Xs = smw;                          // [3][W + 2][TCI]
+  float* Ys = smw + 3 * (W + 2) * TCI;      // [W][TCO]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int co_tiles = (Cout + TCO - 1) / TCO;
+  const int cot = blockIdx.x % co_tiles, cit = blockIdx.x / co_tiles;
+  const int ci0 = cit * TCI, co0 = cot * TCO;
+  float acc[9][CI][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < CI; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][c][j] = 0.f;
+  const int total = nimg * H;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(r0 + rows_per_split, total);
+  for (int r = r0; r < r1; ++r) {
+    const int n = r / H, h = r - n * H;
+    __syncthreads();
+    for (int i = tid; i < 3 * (W + 2) * (TCI / 4); i += 256) {
+      const int c4 = i % (TCI / 4), q = i / (TCI / 4), wq = q % (W + 2), ky = q / (W + 2);
+      const int hh = h + ky - 1, ww = wq - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+        v = __ldg(reinterpret_cast<const float4*>(X + (((size_t)n * H + hh) * W + ww) * CinP + ci0 + c4 * 4));
+      *reinterpret_cast<float4*>(Xs + (size_t)(ky * (W + 2) + wq) * TCI + c4 * 4) = v;
+    }
+    for (int i = tid; i < W * (TCO / 4); i += 256) {
+      const int c4 = i % (TCO / 4), w = i / (TCO / 4), co = co0 + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co < Cout) v = __ldg(reinterpret_cast<const float4*>(dY + (((size_t)n * H + h) * W + w) * Cout + co));
+      *reinterpret_cast<float4*>(Ys + (size_t)w * TCO + c4 * 4) = v;
+    }
+    __syncthreads();
+    for (int w = 0; w < W; ++w) {
+      const float4 y = *reinterpret_cast<const float4*>(Ys + (size_t)w * TCO + tx * 4);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float* xp = Xs + (size_t)((t / 3) * (W + 2) + w + (t % 3)) * TCI + ty * CI;
+        float x[CI];
+        if (CI == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(xp);
+          x[0] = v.x; x[1 % CI] = v.y; x[2 % CI] = v.z; x[3 % CI] = v.w;
+        } else if (CI == 2) {
+          const float2 v = *reinterpret_cast<const float2*>(xp);
+          x[0] = v.x; x[1 % CI] = v.y;
+        } else {
+          x[0] = xp[0];
+        }
+#pragma unroll
+        for (int c = 0; c < CI; ++c) {
+          acc[t][c][0] = fmaf(x[c], y.x, acc[t][c][0]);
+          acc[t][c][1] = fmaf(x[c], y.y, acc[t][c][1]);
+          acc[t][c][2] = fmaf(x[c], y.z, acc[t][c][2]);
+          acc[t][c][3] = fmaf(x[c], y.w, acc[t][c][3]);
+        }
+      }
+    }
+  }
+  const int co = co0 + tx * 4;
+  if (co < Cout) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int c = 0; c < CI; ++c) {
+        const int ci = ci0 + ty * CI + c;
+        *reinterpret_cast<float4*>(part + (((size_t)blockIdx.y * 9 + t) * CinP + ci) * Cout + co) =
+            make_float4(acc[t][c][0], acc[t][c][1], acc[t][c][2], acc[t][c][3]);
+      }
+  }
+}
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int CinP, int Cout, int cin,
+                                         float* __restrict__ dW) {
+  const int total = Cout * cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // thread order follows the partials' layout (co fastest) so the reads coalesce; the store is the transposition
+    const int co = i % Cout, ci = (i / Cout) % cin, t = i / (Cout * cin);
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += part[(((size_t)k * 9 + t) * CinP + ci) * Cout + co];
+    dW[((size_t)co * cin + ci) * 9 + t] = s;
+  }
+}
+
+void launch_ratio_loss(const float* scores, const float* is_real, int n, int loss_type, float lambda, float* out8, float* dscore,
+                       cudaStream_t s) {
+  ratio_loss_kernel<<<1, 256, 0, s>>>(scores, is_real, n, loss_type, lambda, out8, dscore);
+  post_launch_t("ratio_loss");
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct TrainLayer { std::string conv, norm; int cin, cout; bool pool; };
+
+struct TrainEncoder {
+  std::string pre;
+  std::vector<TrainLayer> L;
+  bool gn = false, from_y = false;
+  int in_ch = 1, img = 28, feat_off = 0, fc_in = 128;
+  // per layer
+  std::vector<int> sp, cinP;
+  std::vector<float*> opnd, raw, stats, draw, dopnd, wf, wb, biasP, scale, shift;
+  std::vector<PackArgs> pa;
+  float *cur_last = nullptr, *dcur_last = nullptr, *gap = nullptr, *zero_bias = nullptr;
+  int HWl = 0;
+};
+
+class RatioTrainer {
+ public:
+  RatioTrainer(int kind, const rgfm_weights* params, const rgfm_weights* grads, int max_batch, int device)
+      : kind_(kind), B_(max_batch), device_(device), P_(params), G_(grads) {
+    RGFM_CHECK(kind == RGFM_NET_RATIO28 || kind == RGFM_NET_RATIO_MNIST_SVHN, "ratio trainer: not a ratio estimator kind");
+    RGFM_CHECK(max_batch >= 1, "ratio trainer: max_batch");
+    RGFM_CUDA(cudaSetDevice(device));
+    if (kind == RGFM_NET_RATIO28) {
+      std::vector<TrainLayer> L{{"conv1", "gn1", 1, 32, true}, {"conv2", "gn2", 32, 64, true}, {"conv3", "gn3", 64, 128, true}, {"conv4", "gn4", 128, 128, false}};
+      add_encoder("encoder_x.", L, true, 1, 28, false, 0, 128);
+      add_encoder("encoder_y.", L, true, 1, 28, true, 256, 128);
+      add_mlp({{0, 1}, {4, 5}}, 8, {512, 256});
+    } else {
+      std::vector<TrainLayer> M{{"conv1", "bn1", 1, 32, true}, {"conv2", "bn2", 32, 64, true}, {"conv3", "bn3", 64, 128, true}, {"conv4", "bn4", 128, 128, false}};
+      std::vector<TrainLayer> S{{"conv1a", "bn1a", 3, 64, false},   {"conv1b", "bn1b", 64, 64, true},   {"conv2a", "bn2a", 64, 128, false},
+                                {"conv2b", "bn2b", 128, 128, true}, {"conv3a", "bn3a", 128, 256, false}, {"conv3b", "bn3b", 256, 256, true},
+                                {"conv4a", "bn4a", 256, 256, false}, {"conv4b", "bn4b", 256, 256, true}};
+      add_encoder("encoder_mnist.", M, false, 1, 32, false, 0, 128);
+      add_encoder("encoder_svhn.", S, false, 3, 32, true, 256, 256);
+      add_mlp({{0, 1}, {4, 5}, {8, 9}}, 11, {512, 512, 256});
+    }
+    feat_ = dalloc((size_t)B_ * 512);
+    dfeat_ = dalloc((size_t)B_ * 512);
+    scores_ = dalloc(B_);
+    dscore_ = dalloc(B_);
+    out_ = dalloc(8);
+    // scratch for the two-stage column sums and the conv weight-gradient partials
+    colsum_scratch_ = dalloc((size_t)kColSplits * 512);
+    size_t wmax = 0;
+    for (auto& e : enc_)
+      for (size_t i = 0; i < e.L.size(); ++i) wmax = std::max(wmax, (size_t)wgrad_splits(e, (int)i) * 9 * e.cinP[i] * e.L[i].cout);
+    wpart_ = dalloc(wmax);
+    size_t npmax = 0;
+    for (auto& e : enc_)
+      for (auto& l : e.L) npmax = std::max(npmax, (size_t)B_ * l.cout * 2);
+    npart_ = dalloc(npmax);
+    nsum_ = dalloc(1024);
+  }
+  ~RatioTrainer() {
+    cudaSetDevice(device_);
+    for (void* p : owned_) cudaFree(p);
+  }
+  int device() const { return device_; }
+  int max_batch() const { return B_; }
+  size_t dim_x() const { return (size_t)enc_[0].in_ch * enc_[0].img * enc_[0].img; }
+  size_t dim_y() const { return (size_t)enc_[1].in_ch * enc_[1].img * enc_[1].img; }
+  int hidden_layers() const { return nmlp_ - 1; }
+  int hidden_width(int i) const { return mlp_[i].out; }
+
+  // One step: forward in training mode, loss, backward into the caller's gradient tensors.  out8 (device, 8 floats) gets
+  // {loss, metric1, metric2, metric3} (ratio_loss_kernel).  masks: one device pointer per hidden layer or null.
+  void step(const float* x, const float* y, const float* is_real, int nb, int loss_type, float lambda, const float* const* masks,
+            int n_masks, float* out8, cudaStream_t s) {
+    RGFM_CHECK(nb >= 1 && nb <= B_, "ratio trainer: batch exceeds max_batch");
+    RGFM_CHECK(n_masks >= 0 && n_masks <= nmlp_ - 1, "ratio trainer: at most one dropout mask per hidden layer of the score net");
+    refresh(s);
+    for (auto& e : enc_) forward_encoder(e, e.from_y ? y : x, nb, s);
+    MlpPackT mp;
+    mp.n = nmlp_;
+    for (int i = 0; i < nmlp_; ++i) mp.l[i] = mlp_[i];
+    MlpTrainIO io{};
+    for (int i = 0; i < nmlp_; ++i) {
+      io.a_in[i] = a_in_[i];
+      io.dh[i] = dh_[i];
+      if (i < nmlp_ - 1) {
+        io.dzx[i] = dzx_[i];
+        io.dz[i] = dz_[i];
+        io.mask[i] = i < n_masks ? masks[i] : nullptr;
+      }
+    }
+    mlp_train_kernel<<<nb, 256, mlp_smem_, s>>>(feat_, 512, mp, io, nullptr, scores_, nullptr, 0);
+    post_launch_t("mlp_train(forward)");
+    ratio_loss_kernel<<<1, 256, 0, s>>>(scores_, is_real, nb, loss_type, lambda, out_, dscore_);
+    post_launch_t("ratio_loss");
+    mlp_train_kernel<<<nb, 256, mlp_smem_, s>>>(feat_, 512, mp, io, dscore_, nullptr, dfeat_, 512);
+    post_launch_t("mlp_train(backward)");
+    // score-net parameter gradients
+    for (int i = 0; i < nmlp_; ++i) {
+      const MlpLayer& L = mlp_[i];
+      const float* ain = i == 0 ? feat_ : a_in_[i];
+      const int lda = L.out, ldb = i == 0 ? 512 : L.in;
+      dim3 grid((L.in + 31) / 32, (L.out + 31) / 32);
+      linear_wgrad_kernel<<<grid, 256, 0, s>>>(dh_[i], lda, L.out, ain, ldb, L.in, nb, mlp_gw_[i]);
+      post_launch_t("linear_wgrad");
+      colsum(dh_[i], L.out, L.out, nb, mlp_gb_[i], s);
+      if (i < nmlp_ - 1) {
+        colsum(dzx_[i], L.out, L.out, nb, mlp_gln_g_[i], s);
+        colsum(dz_[i], L.out, L.out, nb, mlp_gln_b_[i], s);
+      }
+    }
+    for (auto& e : enc_) backward_encoder(e, nb, s);
+    RGFM_CUDA(cudaMemcpyAsync(out8, out_, 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+
+ private:
+  static constexpr int kColSplits = 256;
+  int kind_, B_, device_;
+  WeightMap P_, G_;
+  std::vector<void*> owned_;
+  std::vector<TrainEncoder> enc_;
+  MlpLayer mlp_[4];
+  int nmlp_ = 0;
+  size_t mlp_smem_ = 0;
+  float *a_in_[4] = {}, *dh_[4] = {}, *dzx_[3] = {}, *dz_[3] = {};
+  float *mlp_gw_[4] = {}, *mlp_gb_[4] = {}, *mlp_gln_g_[3] = {}, *mlp_gln_b_[3] = {};
+  float *feat_ = nullptr, *dfeat_ = nullptr, *scores_ = nullptr, *dscore_ = nullptr, *out_ = nullptr;
+  float *colsum_scratch_ = nullptr, *wpart_ = nullptr, *npart_ = nullptr, *nsum_ = nullptr;
+
+  float* dalloc(size_t floats) {
+    void* p = nullptr;
+    floats = std::max<size_t>(floats, 4);
+    RGFM_CUDA(cudaMalloc(&p, floats * sizeof(float)));
+    RGFM_CUDA(cudaMemset(p, 0, floats * sizeof(float)));
+    owned_.push_back(p);
+    return (float*)p;
+  }
+  const float* param(const std::string& name, int64_t n) const { return P_.get(name, n); }
+  float* grad(const std::string& name, int64_t n) const { return const_cast<float*>(G_.get(name, n)); }
+
+  void add_encoder(const std::string& pre, const std::vector<TrainLayer>& L, bool gn, int in_ch, int img, bool from_y, int feat_off,
+                   int fc_in) {
+    TrainEncoder e;
+    e.pre = pre; e.L = L; e.gn = gn; e.in_ch = in_ch; e.img = img; e.from_y = from_y; e.feat_off = feat_off; e.fc_in = fc_in;
+    int h = img;
+    const size_t nl = L.size();
+    e.sp.resize(nl); e.cinP.resize(nl);
+    e.opnd.resize(nl); e.raw.resize(nl); e.stats.assign(nl, nullptr); e.draw.resize(nl); e.dopnd.assign(nl, nullptr);
+    e.wf.resize(nl); e.wb.assign(nl, nullptr); e.biasP.resize(nl); e.scale.assign(nl, nullptr); e.shift.assign(nl, nullptr);
+    e.pa.resize(nl);
+    int cmax = 0;
+    for (size_t i = 0; i < nl; ++i) {
+      const TrainLayer& l = L[i];
+      RGFM_CHECK(256 % l.cout == 0, "ratio trainer: channel counts must divide 256");
+      e.sp[i] = h;
+      e.cinP[i] = i == 0 ? 16 : l.cin;
+      const int coutP = (l.cout + 31) / 32 * 32, cinB = (l.cin + 31) / 32 * 32;
+      e.opnd[i] = dalloc((size_t)B_ * h * h * e.cinP[i]);
+      e.raw[i] = dalloc((size_t)B_ * h * h * l.cout);
+      e.draw[i] = dalloc((size_t)B_ * h * h * l.cout);
+      if (i > 0) e.dopnd[i] = dalloc((size_t)B_ * h * h * l.cin);
+      const TileGeom g = make_geom(h, h);
+      if (gn) e.stats[i] = dalloc((size_t)B_ * g.parts * l.cout * 2);
+      e.wf[i] = dalloc((size_t)9 * e.cinP[i] * coutP);
+      if (i > 0) e.wb[i] = dalloc((size_t)9 * l.cout * cinB);
+      e.biasP[i] = dalloc(coutP);
+      if (!gn) {
+        e.scale[i] = dalloc(l.cout);
+        e.shift[i] = dalloc(l.cout);
+      }
+      cmax = std::max(cmax, cinB);
+      if (l.pool) h /= 2;
+    }
+    e.HWl = h * h;
+    const int C = L.back().cout;
+    RGFM_CHECK(C == fc_in, "ratio trainer: fc input width");
+    e.cur_last = dalloc((size_t)B_ * e.HWl * C);
+    e.dcur_last = dalloc((size_t)B_ * e.HWl * C);
+    e.gap = dalloc((size_t)B_ * C);
+    e.zero_bias = dalloc(cmax);
+    // pack descriptors (norm + SiLU [+ max-pool] of layer i's raw output into layer i + 1's operand)
+    for (size_t i = 0; i < nl; ++i) {
+      const TrainLayer& l = L[i];
+      PackArgs a{};
+      PackSrc ps{};
+      ps.p = e.raw[i]; ps.C = l.cout; ps.Cs = l.cout; ps.padded = 0; ps.fmt = 0;
+      if (gn) {
+        ps.st.p = e.stats[i]; ps.st.mode = ST_PARTS; ps.st.C = l.cout; ps.st.parts = make_geom(e.sp[i], e.sp[i]).parts;
+      }
+      a.src[0] = ps; a.src[1] = ps; a.nsrc = 1;
+      a.Hs = a.Ws = e.sp[i];
+      a.Ho = a.Wo = l.pool ? e.sp[i] / 2 : e.sp[i];
+      a.C = l.cout; a.norm = gn ? NORM_GN : NORM_AFFINE; a.act = ACT_SILU; a.spatial = l.pool ? SP_POOL2 : SP_ID;
+      if (gn) {
+        a.gamma = param(pre + l.norm + ".weight", l.cout);
+        a.beta = param(pre + l.norm + ".bias", l.cout);
+      } else {
+        a.gamma = e.scale[i];
+        a.beta = e.shift[i];
+      }
+      a.groups = 8;
+      a.out = (i + 1 < nl) ? e.opnd[i + 1] : e.cur_last;
+      a.out_bf16 = 0;
+      a.Cpad = l.cout;
+      e.pa[i] = a;
+    }
+    enc_.push_back(std::move(e));
+  }
+
+  void add_mlp(const std::vector<std::pair<int, int>>& lin_ln, int last, const std::vector<int>& dims) {
+    int in = 512;
+    size_t floats = 512 + 2 * 512;
+    for (size_t i = 0; i < lin_ln.size(); ++i) {
+      MlpLayer l{};
+      const std::string a = "score_net." + std::to_string(lin_ln[i].first), n = "score_net." + std::to_string(lin_ln[i].second);
+      l.in = in; l.out = dims[i];
+      l.w = param(a + ".weight", (int64_t)l.in * l.out); l.b = param(a + ".bias", l.out);
+      l.ln_g = param(n + ".weight", l.out); l.ln_b = param(n + ".bias", l.out);
+      l.act = ACT_SILU;
+      mlp_gw_[i] = grad(a + ".weight", (int64_t)l.in * l.out); mlp_gb_[i] = grad(a + ".bias", l.out);
+      mlp_gln_g_[i] = grad(n + ".weight", l.out); mlp_gln_b_[i] = grad(n + ".bias", l.out);
+      mlp_[nmlp_++] = l;
+      in = l.out;
+    }
+    MlpLayer f{};
+    const std::string a = "score_net." + std::to_string(last);
+    f.in = in; f.out = 1; f.w = param(a + ".weight", in); f.b = param(a + ".bias", 1); f.act = ACT_NONE;
+    mlp_gw_[nmlp_] = grad(a + ".weight", in); mlp_gb_[nmlp_] = grad(a + ".bias", 1);
+    mlp_[nmlp_++] = f;
+    for (int i = 0; i < nmlp_; ++i) {
+      RGFM_CHECK(mlp_[i].in <= 512 && mlp_[i].out <= 512, "ratio trainer: score-net width");
+      floats += 2 * (size_t)mlp_[i].out;
+      a_in_[i] = dalloc((size_t)B_ * mlp_[i].in);
+      dh_[i] = dalloc((size_t)B_ * mlp_[i].out);
+      if (i < nmlp_ - 1) {
+        dzx_[i] = dalloc((size_t)B_ * mlp_[i].out);
+        dz_[i] = dalloc((size_t)B_ * mlp_[i].out);
+      }
+    }
+    mlp_smem_ = floats * sizeof(float);
+    RGFM_CHECK(mlp_smem_ <= 48 * 1024, "ratio trainer: score-net shared memory");
+  }
+
+  void refresh(cudaStream_t s) {
+    for (auto& e : enc_)
+      for (size_t i = 0; i < e.L.size(); ++i) {
+        const TrainLayer& l = e.L[i];
+        const int coutP = (l.cout + 31) / 32 * 32, cinB = (l.cin + 31) / 32 * 32;
+        const int total = 9 * e.cinP[i] * coutP + (e.wb[i] ? 9 * l.cout * cinB : 0);
+        repack_conv_w_kernel<<<std::min((total + 255) / 256, 1024), 256, 0, s>>>(param(e.pre + l.conv + ".weight", (int64_t)l.cout * l.cin * 9),
+                                                                                  l.cout, l.cin, e.cinP[i], coutP, cinB, e.wf[i], e.wb[i]);
+        post_launch_t("repack_conv_w");
+        pad_vec_kernel<<<(coutP + 255) / 256, 256, 0, s>>>(param(e.pre + l.conv + ".bias", l.cout), l.cout, coutP, e.biasP[i]);
+        post_launch_t("pad_vec");
+        if (!e.gn) {
+          const std::string p = e.pre + l.norm;
+          bn_affine_kernel<<<(l.cout + 255) / 256, 256, 0, s>>>(param(p + ".weight", l.cout), param(p + ".bias", l.cout),
+                                                                 param(p + ".running_mean", l.cout), param(p + ".running_var", l.cout),
+                                                                 l.cout, e.scale[i], e.shift[i]);
+          post_launch_t("bn_affine");
+        }
+      }
+  }
+
+  void forward_encoder(TrainEncoder& e, const float* img, int nb, cudaStream_t s) {
+    launch_pack_nchw(img, e.in_ch, e.img, e.img, 16, e.opnd[0], 0, nb, s);
+    for (size_t i = 0; i < e.L.size(); ++i) {
+      const TrainLayer& l = e.L[i];
+      ConvArgs a{};
+      a.in = e.opnd[i]; a.Hin = a.Win = e.sp[i]; a.Cin = e.cinP[i];
+      a.w = e.wf[i]; a.bias = e.biasP[i];
+      a.CoutP = (l.cout + 31) / 32 * 32; a.Cout = l.cout; a.ks = 3; a.stride = 1; a.pad = 1;
+      a.g = make_geom(e.sp[i], e.sp[i]);
+      a.nimg = nb; a.out_mode = OUT_RAW; a.out = e.raw[i]; a.stats = e.stats[i];
+      launch_conv_simt(a, s);
+      PackArgs p = e.pa[i];
+      p.nimg = nb;
+      launch_pack(p, s);
+    }
+    const int C = e.L.back().cout;
+    launch_gap_fc(e.cur_last, e.HWl, C, param(e.pre + "fc.weight", (int64_t)256 * C), param(e.pre + "fc.bias", 256), 256,
+                  feat_ + e.feat_off, 512, nb, s);
+  }
+
+  // out[c] = sum over `rows` rows of M[r][c]
+  void colsum(const float* M, int ld, int C, long long rows, float* out, cudaStream_t s) {
+    RGFM_CHECK(C <= 512, "colsum: width");
+    int splits = (int)std::min<long long>(kColSplits, (rows + 63) / 64);
+    const int rps = (int)((rows + splits - 1) / splits);
+    splits = (int)((rows + rps - 1) / rps);
+    if (splits == 1) {
+      colsum_kernel<<<dim3((C + 31) / 32, 1), 256, 0, s>>>(M, ld, C, rows, rps, out);
+    } else {
+      colsum_kernel<<<dim3((C + 31) / 32, splits), 256, 0, s>>>(M, ld, C, rows, rps, colsum_scratch_);
+      colsum_kernel<<<dim3((C + 31) / 32, 1), 256, 0, s>>>(colsum_scratch_, C, C, splits, splits, out);
+    }
+    post_launch_t("colsum");
+  }
+
+  int wgrad_splits(const TrainEncoder& e, int i) const {
+    const TrainLayer& l = e.L[i];
+    const int tci = e.cinP[i] >= 64 ? 64 : e.cinP[i];
+    const int tiles = (e.cinP[i] / tci) * ((l.cout + 63) / 64);
+    const int rows = B_ * e.sp[i];
+    return std::max(1, std::min(rows, (148 * 3 + tiles - 1) / tiles));
+  }
+
+  void backward_encoder(TrainEncoder& e, int nb, cudaStream_t s) {
+    const int nl = (int)e.L.size(), C = e.L.back().cout;
+    const float* fw = param(e.pre + "fc.weight", (int64_t)256 * C);
+    launch_gap_fc_bwd(dfeat_ + e.feat_off, 512, fw, 256, e.HWl, C, 1.f, e.dcur_last, nb, s);
+    gap_kernel<<<nb, 256, 0, s>>>(e.cur_last, e.HWl, C, e.gap);
+    post_launch_t("gap");
+    linear_wgrad_kernel<<<dim3((C + 31) / 32, 256 / 32), 256, 0, s>>>(dfeat_ + e.feat_off, 512, 256, e.gap, C, C, nb,
+                                                                       grad(e.pre + "fc.weight", (int64_t)256 * C));
+    post_launch_t("linear_wgrad");
+    colsum(dfeat_ + e.feat_off, 512, 256, nb, grad(e.pre + "fc.bias", 256), s);
+    for (int i = nl - 1; i >= 0; --i) {
+      const TrainLayer& l = e.L[i];
+      const int H = e.sp[i];
+      const float* dcur = (i == nl - 1) ? e.dcur_last : e.dopnd[i + 1];
+      PackArgs p = e.pa[i];
+      p.nimg = nb;
+      PackBwdIO io{};
+      io.dcur_fmt = 0; io.dcur_padded = 0; io.dcur_Cs = l.cout; io.draw_padded = 0; io.draw_Cs = l.cout;
+      // affine gradients of the norm (before pack_bwd only by convention: both read the same tensors)
+      norm_param_grad_kernel<<<nb, 256, 0, s>>>(p, dcur, npart_);
+      post_launch_t("norm_param_grad");
+      colsum(npart_, 2 * l.cout, 2 * l.cout, nb, nsum_, s);
+      const std::string np = e.pre + l.norm;
+      norm_grad_finish_kernel<<<(l.cout + 255) / 256, 256, 0, s>>>(nsum_, l.cout, e.gn ? nullptr : param(np + ".running_mean", l.cout),
+                                                                   e.gn ? nullptr : param(np + ".running_var", l.cout),
+                                                                   grad(np + ".weight", l.cout), grad(np + ".bias", l.cout));
+      post_launch_t("norm_grad_finish");
+      launch_pack_bwd(p, io, dcur, e.draw[i], s);
+      // conv bias and weight gradients
+      colsum(e.draw[i], l.cout, l.cout, (long long)nb * H * H, grad(e.pre + l.conv + ".bias", l.cout), s);
+      {
+        const int cinP = e.cinP[i];
+        const int tci = cinP >= 64 ? 64 : cinP;
+        const int tiles = (cinP / tci) * ((l.cout + 63) / 64);
+        const int rows = nb * H;
+        int splits = std::max(1, std::min(rows, (148 * 3 + tiles - 1) / tiles));
+        const int rps = (rows + splits - 1) / splits;
+        splits = (rows + rps - 1) / rps;
+        const size_t smem = ((size_t)3 * (H + 2) * tci + (size_t)H * 64) * sizeof(float);
+        dim3 grid(tiles, splits);
+        if (tci == 64) conv_wgrad_kernel<4><<<grid, 256, smem, s>>>(e.opnd[i], cinP, e.draw[i], l.cout, H, H, nb, rps, wpart_);
+        else if (tci == 32) conv_wgrad_kernel<2><<<grid, 256, smem, s>>>(e.opnd[i], cinP, e.draw[i], l.cout, H, H, nb, rps, wpart_);
+        else conv_wgrad_kernel<1><<<grid, 256, smem, s>>>(e.opnd[i], cinP, e.draw[i], l.cout, H, H, nb, rps, wpart_);
+        post_launch_t("conv_wgrad");
+        const int total = l.cout * l.cin * 9;
+        conv_wgrad_reduce_kernel<<<std::min((total + 255) / 256, 2048), 256, 0, s>>>(wpart_, splits, cinP, l.cout, l.cin,
+                                                                                      grad(e.pre + l.conv + ".weight", (int64_t)total));
+        post_launch_t("conv_wgrad_reduce");
+      }
+      if (i > 0) {  // input gradient of the conv = gradient at the previous layer's pack output
+        ConvArgs a{};
+        a.in = e.draw[i]; a.Hin = a.Win = H; a.Cin = l.cout;
+        a.w = e.wb[i]; a.bias = e.zero_bias;
+        a.CoutP = (l.cin + 31) / 32 * 32; a.Cout = l.cin; a.ks = 3; a.stride = 1; a.pad = 1;
+        a.g = make_geom(H, H);
+        a.nimg = nb; a.out_mode = OUT_RAW; a.out = e.dopnd[i];
+        launch_conv_simt(a, s);
+      }
+    }
+  }
+};
+
+}  // namespace rgfm
+
+// ---- C ABI (include/rgfm.h) ----
+struct rgfm_ratio_trainer {
+  std::unique_ptr<rgfm::RatioTrainer> t;
+};
+namespace rgfm {
+rgfm_ratio_trainer* ratio_trainer_create(int kind, const rgfm_weights* params, const rgfm_weights* grads, int max_batch, int device) {
+  std::unique_ptr<rgfm_ratio_trainer> h(new rgfm_ratio_trainer());
+  h->t.reset(new RatioTrainer(kind, params, grads, max_batch, device));
+  return h.release();
+}
+void ratio_trainer_step(rgfm_ratio_trainer* h, const float* x, const float* y, const float* is_real, int nb, int loss_type, float lambda,
+                        const float* const* masks, int n_masks, float* out8, cudaStream_t s) {
+  RGFM_CUDA(cudaSetDevice(h->t->device()));
+  h->t->step(x, y, is_real, nb, loss_type, lambda, masks, n_masks, out8, s);
+}
+void ratio_trainer_destroy(rgfm_ratio_trainer* h) {
+  if (h) cudaSetDevice(h->t->device());
+  delete h;
+}
+}  // namespace rgfm

@@ -218,5 +218,27 @@ class StateDictModule:
         return self._sd
 
 
+class TrainableModule(torch.nn.Module):
+    """A real nn.Module whose parameters / buffers carry the reference's state_dict key names (nested containers), for the
+    training-side entry points: `.parameters()` feed a stock optimiser, `.state_dict(keep_vars=True)` hands the live
+    tensors to the trainer plan.  It has no forward of its own -- the forward / backward run in librgfm.so."""
+
+    def __init__(self, kind: str, sd: Dict[str, torch.Tensor], loss_type: str = "disc"):
+        super().__init__()
+        self.rgfm_kind = kind
+        self.loss_type = loss_type
+        for k, v in sd.items():
+            parts = k.split(".")
+            m = self
+            for part in parts[:-1]:
+                if part not in m._modules:
+                    m.add_module(part, torch.nn.Module())
+                m = m._modules[part]
+            if parts[-1].startswith("running_") or parts[-1] == "num_batches_tracked" or not v.dtype.is_floating_point:
+                m.register_buffer(parts[-1], v.clone())
+            else:
+                m.register_parameter(parts[-1], torch.nn.Parameter(v.clone()))
+
+
 def synthetic_module(kind: str, seed: int, loss_type: str = "disc") -> StateDictModule:
     return StateDictModule(kind, state_dict(kind, seed), loss_type)

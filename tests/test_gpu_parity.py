@@ -704,3 +704,105 @@ def test_sampler_with_original_flow_model(prec, synth):
     x1, y1 = plan.run(T(g["x0"]).to(DEV), T(g["y0"]).to(DEV), T(g["mc_x0"]).to(DEV), T(g["mc_y0"]).to(DEV))
     plan.close()
     assert maxabs(x1, T(g["x1"])) <= TOL_FINAL[prec] and maxabs(y1, T(g["y1"])) <= TOL_FINAL[prec], (maxabs(x1, T(g["x1"])), maxabs(y1, T(g["y1"])))
+
+
+# ---- training-side reuse: RatioTrainer.train_step's loss + param.grad on the library's kernels ----
+def _train_case(kind, loss_type, synth):
+    g = load_golden(f"{kind}_train_{loss_type}")
+    sd = synth(kind, g["seed"])
+    masks = [T(g[k]) for k in sorted(k for k in g if k.startswith("mask"))]
+    return g, sd, T(g["x"]), T(g["y"]), T(g["is_real"]), masks, float(g["lambda_penalty"])
+
+
+@pytest.mark.parametrize("loss_type", ["disc", "rulsif"])
+def test_ratio_loss_heads(loss_type):
+    """losses.py:27-133 on the device: loss, metrics and dL/dscore vs the restated losses; saturated scores included."""
+    from ratio_guided_multimodal_fm_b200 import ratio_loss
+    gen = torch.Generator().manual_seed(9)
+    s = torch.randn(37, generator=gen) * 3
+    s[0], s[1], s[2] = 25.0, -30.0, 0.0  # softplus threshold / underflow / tie
+    r = (torch.arange(37) % 4 != 0).float()
+    sg = s.clone().requires_grad_(True)
+    loss, metrics = O.ratio_loss(sg[r == 1], sg[r == 0], loss_type, 0.1)
+    (ds_ref,) = torch.autograd.grad(loss, sg)
+    out8, ds = ratio_loss(s.to(DEV), r.to(DEV), loss_type, 0.1)
+    torch.cuda.synchronize()
+    o = out8.cpu().tolist()
+    assert abs(o[0] - loss.item()) <= 2e-6 * max(1.0, abs(loss.item()))
+    names = ["acc_real", "acc_fake"] if loss_type == "disc" else ["mean_w_real", "mean_w_fake", "constraint_term"]
+    for i, k in enumerate(names):
+        assert abs(o[1 + i] - metrics[k]) <= 2e-6 * max(1.0, abs(metrics[k])), k
+    assert maxabs(ds, ds_ref) <= 1e-7 + 2e-6 * ds_ref.abs().max().item()
+    with pytest.raises(ValueError):
+        ratio_loss(s.to(DEV), r.to(DEV), "nope")
+
+
+@pytest.mark.parametrize("loss_type", ["disc", "rulsif"])
+@pytest.mark.parametrize("kind", ["ratio28", "ratio_mnist_svhn"])
+def test_ratio_train_step_grads(kind, loss_type, synth):
+    """One step's loss, metrics and EVERY parameter gradient (conv / norm affine / fc / score net) vs autograd through the
+    restated estimator (pinned to the unmodified reference module + losses at max-abs 0.0 by oracle/make_golden.py), with
+    the fixture's dropout masks.  fp32 on both sides, different summation orders: relative L2 2e-4 per tensor."""
+    from ratio_guided_multimodal_fm_b200 import RatioTrainPlan
+    g, sd, x, y, r, masks, lam = _train_case(kind, loss_type, synth)
+    oloss, ometrics, ograds = O.ratio_train_grads(sd, kind, x, y, r, loss_type, lam, masks)
+    params = {k: v.to(DEV).contiguous() for k, v in sd.items() if v.dtype.is_floating_point}
+    plan = RatioTrainPlan(kind, params, max_batch=8, device=DEV)
+    for rep in range(2):  # the second step must reproduce the first bit for bit (fixed summation orders, no atomics)
+        out8, grads = plan.step(x.to(DEV), y.to(DEV), r.to(DEV), loss_type, lam, [m.to(DEV) for m in masks])
+        torch.cuda.synchronize()
+        if rep == 0:
+            first = {k: v.clone() for k, v in grads.items()}
+    assert all(torch.equal(first[k], grads[k]) for k in grads)
+    o = out8.cpu().tolist()
+    assert abs(o[0] - oloss.item()) <= 1e-5 * max(1.0, abs(oloss.item())), (o[0], oloss.item())
+    assert set(grads) == set(ograds)
+    worst = ("", 0.0)
+    for k, ref in ograds.items():
+        ours = grads[k].cpu()
+        assert ours.shape == ref.shape and torch.isfinite(ours).all(), k
+        denom = ref.norm().item()
+        rel = (ours - ref).norm().item() / denom if denom > 0 else (ours - ref).norm().item()
+        if rel > worst[1]:
+            worst = (k, rel)
+        assert rel <= 2e-4, (k, rel, denom)
+    # the golden digest (written from the reference itself) agrees too
+    for k in (k for k in g if k.startswith("g:")):
+        flat = grads[k[2:]].flatten().cpu()
+        ref = T(g[k])
+        assert abs(flat.norm().item() - ref[0].item()) <= 2e-4 * max(ref[0].item(), 1e-12), k
+    with pytest.raises(ValueError):
+        plan.step(x.to(DEV), y.to(DEV), r.to(DEV), "nope")
+    plan.close()
+
+
+def test_ratio_trainer_dropin_three_steps(synth):
+    """RatioTrainer (mirror of src/utils/trainer.py) for three SGD steps with clipping vs the same loop on the oracle:
+    parameters read in place after every optimiser step (no re-upload), gradients through param.grad."""
+    from ratio_guided_multimodal_fm_b200 import RatioTrainer, TrainableModule
+    kind, loss_type = "ratio28", "rulsif"
+    g, sd, x, y, r, masks, lam = _train_case(kind, loss_type, synth)
+    model = TrainableModule(kind, sd, loss_type).to(DEV)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+
+    class _Loss:  # stands for losses.RuLSIFLoss (alpha unused by its forward)
+        lambda_penalty = lam
+    tr = RatioTrainer(model, _Loss(), opt, device=DEV, max_batch=8)
+    # oracle loop
+    op = {k: v.clone() for k, v in sd.items()}
+    losses = []
+    for step in range(3):
+        m = tr.train_step({"x": x, "y": y, "is_real": r}, dropout_masks=[mk.to(DEV) for mk in masks])
+        oloss, om, ograds = O.ratio_train_grads(op, kind, x, y, r, loss_type, lam, masks)
+        total = torch.sqrt(sum(gv.pow(2).sum() for gv in ograds.values()))
+        clip = min(1.0, 1.0 / (total.item() + 1e-6))
+        for k, gv in ograds.items():
+            op[k] = op[k] - 0.05 * clip * gv
+        assert abs(m["loss"] - oloss.item()) <= 1e-4 * max(1.0, abs(oloss.item())), (step, m["loss"], oloss.item())
+        assert set(m) == set(om)
+        losses.append(m["loss"])
+    new = model.state_dict()
+    for k, v in op.items():
+        if v.dtype.is_floating_point:
+            assert maxabs(new[k], v) <= 1e-5 * max(1.0, v.abs().max().item()), k
+    assert losses[2] != losses[0]  # the parameters moved and the plan saw them

@@ -45,6 +45,32 @@ def test_ratio_golden(kind, synth):
     close(gy, g["grad_y_disc"], 1e-4)
 
 
+@pytest.mark.parametrize("loss_type", ["disc", "rulsif"])
+@pytest.mark.parametrize("kind", ["ratio28", "ratio_mnist_svhn"])
+def test_ratio_train_golden(kind, loss_type, synth):
+    """Training side: loss, metrics and every parameter gradient of one RatioTrainer.train_step vs the
+    fixture written from the UNMODIFIED reference module + loss classes (digest per parameter: norm, sum, 64 samples)."""
+    g = load_golden(f"{kind}_train_{loss_type}")
+    sd = synth(kind, g["seed"])
+    assert sd_digest(sd) == str(g["digest"])
+    masks = [T(g[k]) for k in sorted(k for k in g if k.startswith("mask"))]
+    loss, metrics, grads = O.ratio_train_grads(sd, kind, T(g["x"]), T(g["y"]), T(g["is_real"]), loss_type,
+                                               float(g["lambda_penalty"]), masks)
+    close(loss, g["loss"], 1e-5)
+    for name, val in zip(g["metric_names"], g["metric_values"]):
+        assert abs(metrics[str(name)] - float(val)) <= 1e-5
+    gkeys = [k for k in g if k.startswith("g:")]
+    assert {k[2:] for k in gkeys} == set(grads)
+    for k in gkeys:
+        flat = grads[k[2:]].flatten()
+        idx = torch.linspace(0, flat.numel() - 1, min(flat.numel(), 64)).long()
+        mine = torch.cat([flat.norm().reshape(1), flat.sum().reshape(1), flat[idx]])
+        ref = T(g[k])
+        assert (mine - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), k
+    with pytest.raises(ValueError):
+        O.ratio_loss(torch.zeros(2), torch.zeros(2), "nope")
+
+
 @pytest.mark.parametrize("kind", ["clf_mnist28", "clf_mnist32", "clf_svhn"])
 def test_classifier_golden(kind, synth):
     g = load_golden(f"{kind}_forward")
