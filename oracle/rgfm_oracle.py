@@ -333,8 +333,10 @@ def flow_sample(sd: StateDict, kind: str, x0: Tensor, num_steps: int) -> Tensor:
 def sample_pair(sd_x: StateDict, sd_y: StateDict, sd_r: Optional[StateDict], pair: str,
                 guidance_method: str, guidance_strength: float, num_steps: int,
                 x0: Tensor, y0: Tensor, mc_x0: Optional[Tensor] = None, mc_y0: Optional[Tensor] = None,
-                loss_type: str = "disc", return_aux: bool = False, bank=None):
+                loss_type: str = "disc", return_aux: bool = False, bank=None, gamma_schedule=None):
     """Coupled guided Euler sampler on explicit noise.
+    gamma_schedule: optional per-step strengths (time-dependent guidance, SURVEY.md 8f-2: an extension, the reference's
+    gamma is constant); step k uses gamma_schedule[k] where the reference uses guidance_strength.
     bank: optional precomputed (mc_x, mc_y, mc_ratios) -- the full-size parity tests check a row subset of a large
     batch against the bank the CUDA path computed, instead of paying the 256-sample CPU pre-pass.
     reference: flow_utils.py:178-375 and sample_mnist_svhn.py:39-177 (same algorithm, different shapes).
@@ -352,6 +354,8 @@ def sample_pair(sd_x: StateDict, sd_y: StateDict, sd_r: Optional[StateDict], pai
     aux = {}
     for step in range(num_steps):
         t = step * dt
+        if gamma_schedule is not None:
+            guidance_strength = float(gamma_schedule[step])
         tb = torch.full((B,), t)
         v_x = unet_forward(sd_x, kx, x_t, tb)
         v_y = unet_forward(sd_y, ky, y_t, tb)

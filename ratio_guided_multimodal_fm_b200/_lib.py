@@ -57,9 +57,9 @@ _lib = None
 # every symbol include/rgfm.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     "rgfm_last_error", "rgfm_abi_version", "rgfm_sampler_create", "rgfm_sampler_run", "rgfm_sampler_run_host",
-    "rgfm_sampler_set_strength", "rgfm_sampler_run_reuse_bank", "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
+    "rgfm_sampler_set_strength", "rgfm_sampler_set_strength_schedule", "rgfm_sampler_run_reuse_bank", "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
     "rgfm_unet_forward", "rgfm_unet_sample", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_create_prec", "rgfm_ratio_grad_log_ratio", "rgfm_coherence_matches", "rgfm_sampler_attach_evaluators", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
-    "rgfm_ratio_trainer_create", "rgfm_ratio_trainer_step", "rgfm_ratio_trainer_destroy", "rgfm_ratio_loss",
+    "rgfm_ratio_trainer_create", "rgfm_ratio_trainer_step", "rgfm_ratio_trainer_destroy", "rgfm_ratio_loss", "rgfm_cfm_add_noise", "rgfm_fm_mse_loss",
 ]
 
 
@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
     L.rgfm_sampler_run.argtypes = [vp] + [vp] * 7 + [vp]
     L.rgfm_sampler_run_host.argtypes = [vp] + [vp] * 7
     L.rgfm_sampler_set_strength.argtypes = [vp, C.c_double, vp]
+    L.rgfm_sampler_set_strength_schedule.argtypes = [vp, C.POINTER(C.c_double), C.c_int32, vp]
     L.rgfm_sampler_run_reuse_bank.argtypes = [vp] + [vp] * 5 + [vp]
     L.rgfm_sampler_get_bank.argtypes = [vp, vp, vp, vp, vp]
     L.rgfm_sampler_profile_step.argtypes = [vp, C.POINTER(_ProfEntry), C.c_int32, C.POINTER(C.c_int32)]
@@ -104,6 +105,8 @@ def lib() -> C.CDLL:
     L.rgfm_ratio_trainer_destroy.argtypes = [vp]
     L.rgfm_ratio_trainer_destroy.restype = None
     L.rgfm_ratio_loss.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_float, vp, vp, vp]
+    L.rgfm_cfm_add_noise.argtypes = [vp, vp, vp, C.c_int32, C.c_int64, vp, vp, vp]
+    L.rgfm_fm_mse_loss.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
     if L.rgfm_abi_version() != ABI_VERSION:
         raise RgfmError("librgfm.so ABI version mismatch; rebuild")
     _lib = L
@@ -331,6 +334,7 @@ class SamplerPlan:
         self.h = C.c_void_p()
         check(lib().rgfm_sampler_create(C.byref(d), wx.ref(), wy.ref(), wr.ref() if wr else None, C.byref(self.h)))
         self.guidance_strength = float(guidance_strength)
+        self.schedule = None
         self.shape_x, self.shape_y = {"pair28": ((1, 28, 28), (1, 28, 28)),
                                       "mnist_svhn": ((1, 32, 32), (3, 32, 32))}[pair]
 
@@ -349,9 +353,17 @@ class SamplerPlan:
         self._evaluators = (clf_x, clf_y)  # keep the nets alive as long as the plan uses them
 
     def set_strength(self, guidance_strength: float):
-        """Change gamma in place (mc_feng / unguided plans): the graphs read it from a device table."""
+        """Change gamma in place: the graphs read it from a device table."""
         check(lib().rgfm_sampler_set_strength(self.h, float(guidance_strength), _stream_ptr(self.device)))
         self.guidance_strength = float(guidance_strength)
+        self.schedule = None
+
+    def set_strength_schedule(self, gammas):
+        """Time-dependent guidance: one strength per Euler step (gamma_k at t_k = k / num_steps)."""
+        g = [float(v) for v in gammas]
+        arr = (C.c_double * len(g))(*g)
+        check(lib().rgfm_sampler_set_strength_schedule(self.h, arr, len(g), _stream_ptr(self.device)))
+        self.schedule = tuple(g)
 
     def run(self, x0, y0, mc_x0=None, mc_y0=None, want_diag: bool = False, reuse_bank: bool = False):
         """Device-resident run on the current stream; returns fresh tensors (inputs are not mutated).

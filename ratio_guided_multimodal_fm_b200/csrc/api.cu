@@ -13,6 +13,7 @@ void sampler_get_bank(Sampler*, float*, float*, float*, cudaStream_t);
 int64_t sampler_launches(const Sampler*);
 void sampler_run_reuse_bank(Sampler*, const float*, const float*, float*, float*, float*, cudaStream_t);
 void sampler_set_strength(Sampler*, double, cudaStream_t);
+void sampler_set_schedule(Sampler*, const double*, int, cudaStream_t);
 void sampler_attach_evaluators(Sampler*, Net*, Net*, int);
 void launch_argmax_match(const float*, const float*, int, float*, cudaStream_t);
 int sampler_profile(Sampler*, rgfm_prof_entry*, int);
@@ -25,6 +26,8 @@ void ratio_trainer_step(rgfm_ratio_trainer*, const float*, const float*, const f
                         cudaStream_t);
 void ratio_trainer_destroy(rgfm_ratio_trainer*);
 void launch_ratio_loss(const float*, const float*, int, int, float, float*, float*, cudaStream_t);
+void launch_cfm_interp(const float*, const float*, const float*, int, size_t, float*, float*, cudaStream_t);
+void launch_fm_mse(const float*, const float*, size_t, float*, float*, float*, cudaStream_t);
 }  // namespace rgfm
 
 static thread_local std::string g_err;
@@ -96,6 +99,13 @@ int rgfm_sampler_run_host(rgfm_sampler* s, const float* x0, const float* y0, con
   RGFM_API_BEGIN
   RGFM_CHECK(s != nullptr, "rgfm_sampler_run_host: null plan");
   rgfm::sampler_run_host(reinterpret_cast<rgfm::Sampler*>(s), x0, y0, mc_x0, mc_y0, x1, y1, diag);
+  RGFM_API_END
+}
+
+int rgfm_sampler_set_strength_schedule(rgfm_sampler* s, const double* guidance_strengths, int32_t num_steps, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(s != nullptr, "rgfm_sampler_set_strength_schedule: null plan");
+  rgfm::sampler_set_schedule(reinterpret_cast<rgfm::Sampler*>(s), guidance_strengths, num_steps, (cudaStream_t)stream);
   RGFM_API_END
 }
 
@@ -341,6 +351,23 @@ int rgfm_ratio_loss(const float* scores, const float* is_real, int32_t n, int32_
   RGFM_CHECK(loss_type == RGFM_LOSS_DISC || loss_type == RGFM_LOSS_RULSIF, "Unknown loss_type");
   set_device_of(scores);
   rgfm::launch_ratio_loss(scores, is_real, n, loss_type, lambda_penalty, out8, dscore, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_cfm_add_noise(const float* x1, const float* x0, const float* t, int32_t batch, int64_t dim, float* x_t, float* u_t,
+                       void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(x1 && x0 && t && x_t && u_t && batch >= 1 && dim >= 1, "rgfm_cfm_add_noise: null argument");
+  set_device_of(x1);
+  rgfm::launch_cfm_interp(x1, x0, t, batch, (size_t)dim, x_t, u_t, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_fm_mse_loss(const float* v, const float* u, int64_t n, float* loss, float* dv, float* scratch, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(v && u && loss && scratch && n >= 1, "rgfm_fm_mse_loss: null argument");
+  set_device_of(v);
+  rgfm::launch_fm_mse(v, u, (size_t)n, loss, dv, scratch, (cudaStream_t)stream);
   RGFM_API_END
 }
 

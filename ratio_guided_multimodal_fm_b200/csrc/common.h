@@ -252,9 +252,14 @@ void launch_gap_fc_bwd(const float* dfeat, int ld, const float* w, int Cout, int
 struct PackBwdIO {
   int dcur_fmt = 0, dcur_padded = 0, dcur_Cs = 0;  // incoming gradient (geometry of the pack's output): 0 = fp32, 2 = fp16; channel stride
   int draw_padded = 0, draw_Cs = 0;                // outgoing gradient (geometry of the raw activation): fp32 dense, or fp16 padded with stride Cs
+  // training step (train.cu): per-(image, slice, channel) {sum dz * xhat, sum dz} already computed by norm_param_grad_kernel;
+  // the GroupNorm group moments are formed from them, so the image is split over `yslices` CTAs with no second pass
+  const float* chan_sums = nullptr;
+  int nslices = 0;   // slices of chan_sums
+  int yslices = 1;   // CTAs per image of the dense fp32 generic kernel
 };
 void launch_pack_bwd(const PackArgs& a, const PackBwdIO& io, const float* dcur, float* draw, cudaStream_t s);
-void launch_euler_grad(float* x, const float* v, const float* g, float gamma, float dt, size_t n, cudaStream_t s);
+
 void launch_ratio_head(const float* scores, int loss_type, float* log_ratio, float* ratios, int n, cudaStream_t s);
 void launch_step_inc(int* step, cudaStream_t s);
 void launch_euler(float* x, const float* v, float dt, size_t n, cudaStream_t s);
@@ -301,6 +306,7 @@ struct McfArgs {
   int ksplit_x, ksplit_y;
   int g_step;             // write gx / gy only at this step (diagnostics); < 0 = always
 };
+void launch_euler_grad(float* x, const float* v, const float* g, const StepScalars* sc, const int* step, float dt, size_t n, cudaStream_t s);
 size_t mcf_scratch_floats(int B, int N, int Dx, int Dy, int* ksx, int* ksy);
 void launch_mcf(const McfArgs& a, cudaStream_t s, std::vector<ProfRec>* prof = nullptr);
 // the two halves of launch_mcf: distances + stabilised weights depend only on the state (x_t, y_t) and the bank, so the

@@ -1165,7 +1165,29 @@ __global__ void __launch_bounds__(256) pack_bwd_kernel(PackArgs a, PackBwdIO io,
     // pass A: per-group sums of gamma*dz and gamma*dz*xhat
     for (int g = tid; g < a.groups; g += blockDim.x) s_m1[g] = s_m2[g] = 0.f;
     __syncthreads();
-    if (256 % C == 0 && blockDim.x == 256) {
+    if (io.chan_sums) {
+      // group moments of gamma * dz from the per-channel sums the training step already has
+      for (int c = tid; c < C; c += blockDim.x) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int sl = 0; sl < io.nslices; ++sl) {
+          const float2 q = __ldg(reinterpret_cast<const float2*>(io.chan_sums + (((size_t)n * io.nslices + sl) * C + c) * 2));
+          a0 += q.x;
+          a1 += q.y;
+        }
+        s_red[0][c] = a.gamma[c] * a1;
+        s_red[1][c] = a.gamma[c] * a0;
+      }
+      __syncthreads();
+      for (int g = tid; g < a.groups; g += blockDim.x) {
+        float u1 = 0.f, u2 = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+          u1 += s_red[0][c];
+          u2 += s_red[1][c];
+        }
+        s_m1[g] = u1;
+        s_m2[g] = u2;
+      }
+    } else if (256 % C == 0 && blockDim.x == 256) {
       // a thread owns ONE channel (i = tid + 256 k keeps i % C): register sums, then a fixed-order combine per group --
       // deterministic, unlike the shared-memory atomics of the general case below
       const int c = tid % C;
@@ -1207,7 +1229,7 @@ __global__ void __launch_bounds__(256) pack_bwd_kernel(PackArgs a, PackBwdIO io,
   }
   if (!io.draw_padded) {
     float* dr = draw + (size_t)n * H * Wd * C;
-    for (int i = tid; i < total; i += blockDim.x) {
+    for (int i = tid + blockIdx.y * blockDim.x; i < total; i += blockDim.x * gridDim.y) {
       const int c = i % C, pix = i / C, h = pix / Wd, w = pix - h * Wd;
       dr[i] = draw_of(h, w, c);
     }
@@ -1332,15 +1354,19 @@ void launch_pack_bwd(const PackArgs& a, const PackBwdIO& io, const float* dcur, 
   RGFM_CHECK(a.nsrc == 1 && (a.src[0].fmt == 0 || a.src[0].fmt == 2) && a.C <= PACK_MAXC && a.spatial != SP_UP2,
              "pack_bwd: one fp32 or fp16 source, no upsampling");
   RGFM_CHECK((io.dcur_fmt == 0 || io.dcur_fmt == 2) && (!io.draw_padded || io.draw_Cs >= a.C), "pack_bwd: gradient tensor formats");
-  pack_bwd_kernel<<<a.nimg, 256, 0, s>>>(a, io, dcur, draw);
+  // several CTAs per image only where no CTA needs a pass over the whole image (no GroupNorm, or its sums are supplied)
+  const int ys = (!io.draw_padded && (a.norm != NORM_GN || io.chan_sums)) ? std::max(1, io.yslices) : 1;
+  pack_bwd_kernel<<<dim3(a.nimg, ys), 256, 0, s>>>(a, io, dcur, draw);
   post_launch("pack_bwd");
 }
 
-// x <- x + dt * (v + gamma * g)   (README.md:163: v_guided = v_ind + gamma * grad log r)
-__global__ void euler_grad_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ g, float gamma, float dt,
-                                  size_t n4) {
+// x <- x + dt * (v + gamma_t * g)   (README.md:163: v_guided = v_ind + gamma * grad log r); gamma_t is read from the plan's
+// per-step scalar table, so a constant strength, a sweep and a time-dependent schedule gamma(t) are the same kernel
+__global__ void euler_grad_kernel(float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ g,
+                                  const StepScalars* __restrict__ sc, const int* __restrict__ step, float dt, size_t n4) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
+  const float gamma = sc[step ? *step : 0].gamma;
   float4 a = reinterpret_cast<float4*>(x)[i];
   const float4 b = __ldg(reinterpret_cast<const float4*>(v) + i);
   const float4 c = __ldg(reinterpret_cast<const float4*>(g) + i);
@@ -1350,10 +1376,11 @@ __global__ void euler_grad_kernel(float* __restrict__ x, const float* __restrict
   a.w = __fadd_rn(a.w, __fmul_rn(__fadd_rn(b.w, __fmul_rn(gamma, c.w)), dt));
   reinterpret_cast<float4*>(x)[i] = a;
 }
-void launch_euler_grad(float* x, const float* v, const float* g, float gamma, float dt, size_t n, cudaStream_t s) {
+void launch_euler_grad(float* x, const float* v, const float* g, const StepScalars* sc, const int* step, float dt, size_t n,
+                       cudaStream_t s) {
   RGFM_CHECK(n % 4 == 0, "euler_grad: n % 4");
   const size_t n4 = n / 4;
-  euler_grad_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(x, v, g, gamma, dt, n4);
+  euler_grad_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(x, v, g, sc, step, dt, n4);
   post_launch("euler_grad");
 }
 

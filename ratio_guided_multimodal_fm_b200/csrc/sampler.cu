@@ -273,7 +273,6 @@ struct Sampler {
     }
     if (grad_guided) {
       // v = v_ind + gamma * grad log r(x_t, y_t) (README.md:163), then x += v * dt; every step, no MC bank
-      const float gam = (float)d.guidance_strength;
       const int lt = d.loss_type;
       capture(g_grad, [&](cudaStream_t s) {
         fork(s);
@@ -281,8 +280,8 @@ struct Sampler {
         fy->forward(cap2, B, y, nullptr, vy, OUT_NCHW, dtf, step);
         join(s);
         fr->grad_log_ratio(s, B, x, y, lt, gx, gy, nullptr);
-        launch_euler_grad(x, vx, gx, gam, dtf, (size_t)B * Dx, s);
-        launch_euler_grad(y, vy, gy, gam, dtf, (size_t)B * Dy, s);
+        launch_euler_grad(x, vx, gx, sc, step, dtf, (size_t)B * Dx, s);
+        launch_euler_grad(y, vy, gy, sc, step, dtf, (size_t)B * Dy, s);
         launch_step_inc(step, s);
       });
     }
@@ -300,18 +299,22 @@ struct Sampler {
       launches += grad_guided ? g_grad.kernels : ((guided && s >= first_guided) ? g_guided.kernels : g_plain.kernels);
   }
 
-  // gamma lives in the per-step scalar table the kernels read through a pointer: a sweep over guidance strengths needs
-  // no new plan and no graph re-capture.  (grad_log_ratio bakes gamma into its update kernel's arguments.)
-  void set_strength(double gamma, cudaStream_t s) {
-    RGFM_CHECK(!grad_guided, "rgfm_sampler_set_strength: not supported for grad_log_ratio plans (build a new plan)");
+  // gamma lives in the per-step scalar table the kernels read through a pointer: a sweep over guidance strengths -- or a
+  // time-dependent schedule gamma(t_k), one value per Euler step -- needs no new plan and no graph re-capture.
+  void set_schedule(const double* gammas, int n, cudaStream_t s) {
+    RGFM_CHECK(gammas != nullptr && n == (int)hsc.size(), "rgfm_sampler_set_strength_schedule: one strength per Euler step");
     RGFM_CUDA(cudaSetDevice(d.device));
-    d.guidance_strength = gamma;
-    for (auto& h : hsc) {
-      h.one_minus_gamma = (float)(1.0 - gamma);
-      h.gamma = (float)gamma;
+    for (int k = 0; k < n; ++k) {
+      hsc[k].one_minus_gamma = (float)(1.0 - gammas[k]);
+      hsc[k].gamma = (float)gammas[k];
     }
     RGFM_CUDA(cudaMemcpyAsync(sc, hsc.data(), hsc.size() * sizeof(StepScalars), cudaMemcpyHostToDevice, s));
     RGFM_CUDA(cudaStreamSynchronize(s));  // hsc may change again before an asynchronous copy has read it
+  }
+  void set_strength(double gamma, cudaStream_t s) {
+    d.guidance_strength = gamma;
+    std::vector<double> g(hsc.size(), gamma);
+    set_schedule(g.data(), (int)g.size(), s);
   }
 
   // reuse_bank: skip the MC pre-pass and the ratio pass and guide with the bank of the previous run on this plan
@@ -374,6 +377,7 @@ void sampler_run_reuse_bank(Sampler* s, const float* x0, const float* y0, float*
   s->run(x0, y0, nullptr, nullptr, x1, y1, diag, st, /*reuse_bank=*/true);
 }
 void sampler_set_strength(Sampler* s, double gamma, cudaStream_t st) { s->set_strength(gamma, st); }
+void sampler_set_schedule(Sampler* s, const double* g, int n, cudaStream_t st) { s->set_schedule(g, n, st); }
 void sampler_attach_evaluators(Sampler* s, Net* cx, Net* cy, int inverse_transform) {
   RGFM_CHECK((cx == nullptr) == (cy == nullptr), "rgfm_sampler_attach_evaluators: both classifiers or none");
   if (cx) {

@@ -18,6 +18,7 @@
 #include "net.h"
 #include "simt_device.cuh"
 #include <cmath>
+#include <algorithm>
 
 namespace rgfm {
 
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(256) gap_kernel(const float* __restrict__ in, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Normalisation affine gradients of one layer, per image: part[n][c] = {sum_p dz * u, sum_p dz} where dz is the gradient
+// Normalisation affine gradients of one layer, per image and pixel slice (blockIdx.y): part[n][slice][c] = {sum_p dz * u, sum_p dz} where dz is the gradient
 // at the norm's output (incoming gradient routed through the max-pool to the first maximum and through SiLU', exactly
 // as pack_bwd_kernel does) and u = xhat (GroupNorm) or the raw activation (per-channel affine).  C must divide 256, so
 // that a thread owns one channel; the 256 / C threads of a channel are combined in a fixed order.
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(256) norm_param_grad_kernel(PackArgs a, const 
   const float sc = s_scale[c], sh = s_shift[c];
   const float mean = a.norm == NORM_GN ? (float)s_grp[c / cpg][0] : 0.f, rstd = a.norm == NORM_GN ? (float)s_grp[c / cpg][1] : 1.f;
   float s0 = 0.f, s1 = 0.f;
-  for (int pix = tid / C; pix < H * Wd; pix += 256 / C) {
+  for (int pix = blockIdx.y * (256 / C) + tid / C; pix < H * Wd; pix += gridDim.y * (256 / C)) {
     const int h = pix / Wd, w = pix - h * Wd;
     const float r = raw[(size_t)pix * C + c];
     const float z = fmaf(r, sc, sh);
@@ -381,8 +382,9 @@ __global__ void __launch_bounds__(256) norm_param_grad_kernel(PackArgs a, const 
       t0 += s_red[0][j];
       t1 += s_red[1][j];
     }
-    part[((size_t)n * C + tid) * 2] = t0;
-    part[((size_t)n * C + tid) * 2 + 1] = t1;
+    float* q = part + (((size_t)n * gridDim.y + blockIdx.y) * C + tid) * 2;
+    q[0] = t0;
+    q[1] = t1;
   }
 }
 // sums[c][2] (over the images) -> the affine's parameter gradients.  GroupNorm: d gamma = sums[c][0], d beta = sums[c][1].
@@ -502,6 +504,68 @@ void launch_ratio_loss(const float* scores, const float* is_real, int n, int los
   post_launch_t("ratio_loss");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Flow-matching step, data side (train_flow_matching_epoch, flow_utils.py:131-142): the rectified-flow interpolation of
+// CFMSchedule.add_noise (flow_utils.py:40-66) in one pass, and F.mse_loss(v, u) with its gradient dL/dv = 2 (v - u) / n.
+// HBM-bound streaming kernels: 128-bit loads and stores, each tensor touched once.  x_t is rounded like the reference
+// (two products, one sum, no FMA); u = x_1 - x_0 is exact.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cfm_interp_kernel(const float4* __restrict__ x1, const float4* __restrict__ x0,
+                                                         const float* __restrict__ t, size_t d4, size_t n4,
+                                                         float4* __restrict__ xt, float4* __restrict__ u) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float tb = __ldg(t + i / d4), om = __fsub_rn(1.0f, tb);
+    const float4 a = __ldg(x1 + i), b = __ldg(x0 + i);
+    float4 r, v;
+    r.x = __fadd_rn(__fmul_rn(om, b.x), __fmul_rn(tb, a.x)); v.x = __fsub_rn(a.x, b.x);
+    r.y = __fadd_rn(__fmul_rn(om, b.y), __fmul_rn(tb, a.y)); v.y = __fsub_rn(a.y, b.y);
+    r.z = __fadd_rn(__fmul_rn(om, b.z), __fmul_rn(tb, a.z)); v.z = __fsub_rn(a.z, b.z);
+    r.w = __fadd_rn(__fmul_rn(om, b.w), __fmul_rn(tb, a.w)); v.w = __fsub_rn(a.w, b.w);
+    xt[i] = r;
+    u[i] = v;
+  }
+}
+// part[block] = sum over the block's elements of (v - u)^2 ; dv = 2 (v - u) / n
+__global__ void __launch_bounds__(256) fm_mse_kernel(const float4* __restrict__ v, const float4* __restrict__ u, size_t n4, float scale,
+                                                     float4* __restrict__ dv, float* __restrict__ part) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(v + i), b = __ldg(u + i);
+    const float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    s = fmaf(d.x, d.x, s); s = fmaf(d.y, d.y, s); s = fmaf(d.z, d.z, s); s = fmaf(d.w, d.w, s);
+    if (dv) dv[i] = make_float4(scale * d.x, scale * d.y, scale * d.z, scale * d.w);
+  }
+  const float t = block_sum256(s, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(256) fm_mse_finish_kernel(const float* __restrict__ part, int nparts, float inv_n, float* __restrict__ loss) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 256) s += part[i];
+  const float t = block_sum256(s, red);
+  if (threadIdx.x == 0) *loss = t * inv_n;
+}
+void launch_cfm_interp(const float* x1, const float* x0, const float* t, int batch, size_t dim, float* xt, float* u, cudaStream_t s) {
+  RGFM_CHECK(dim % 4 == 0, "cfm_add_noise: sample size must be a multiple of 4");
+  const size_t n4 = (size_t)batch * dim / 4;
+  const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
+  cfm_interp_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(x1), reinterpret_cast<const float4*>(x0), t, dim / 4, n4,
+                                            reinterpret_cast<float4*>(xt), reinterpret_cast<float4*>(u));
+  post_launch_t("cfm_interp");
+}
+// scratch: 148 * 8 floats
+void launch_fm_mse(const float* v, const float* u, size_t n, float* loss, float* dv, float* scratch, cudaStream_t s) {
+  RGFM_CHECK(n % 4 == 0 && n > 0, "fm_mse: element count must be a positive multiple of 4");
+  const size_t n4 = n / 4;
+  const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
+  fm_mse_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(v), reinterpret_cast<const float4*>(u), n4, 2.0f / (float)n,
+                                        reinterpret_cast<float4*>(dv), scratch);
+  post_launch_t("fm_mse");
+  fm_mse_finish_kernel<<<1, 256, 0, s>>>(scratch, blocks, 1.0f / (float)n, loss);
+  post_launch_t("fm_mse_finish");
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -554,7 +618,7 @@ class RatioTrainer {
     wpart_ = dalloc(wmax);
     size_t npmax = 0;
     for (auto& e : enc_)
-      for (auto& l : e.L) npmax = std::max(npmax, (size_t)B_ * l.cout * 2);
+      for (auto& l : e.L) npmax = std::max(npmax, (size_t)B_ * kMaxSlices * l.cout * 2);
     npart_ = dalloc(npmax);
     nsum_ = dalloc(1024);
   }
@@ -616,6 +680,7 @@ class RatioTrainer {
 
  private:
   static constexpr int kColSplits = 256;
+  static constexpr int kMaxSlices = 32;
   int kind_, B_, device_;
   WeightMap P_, G_;
   std::vector<void*> owned_;
@@ -825,9 +890,17 @@ class RatioTrainer {
       PackBwdIO io{};
       io.dcur_fmt = 0; io.dcur_padded = 0; io.dcur_Cs = l.cout; io.draw_padded = 0; io.draw_Cs = l.cout;
       // affine gradients of the norm (before pack_bwd only by convention: both read the same tensors)
-      norm_param_grad_kernel<<<nb, 256, 0, s>>>(p, dcur, npart_);
+      // pixel slices per image: enough CTAs to fill the GPU on small batches, at least 64 pixels each
+      // pixel slices per image: about eight elements per thread (the kernels are latency-bound: several exp and dependent loads per element)
+      const int slices = std::max(1, std::min(kMaxSlices, (H * H * l.cout + 2047) / 2048));
+      norm_param_grad_kernel<<<dim3(nb, slices), 256, 0, s>>>(p, dcur, npart_);
       post_launch_t("norm_param_grad");
-      colsum(npart_, 2 * l.cout, 2 * l.cout, nb, nsum_, s);
+      colsum(npart_, 2 * l.cout, 2 * l.cout, (long long)nb * slices, nsum_, s);
+      if (e.gn) {  // GroupNorm's group moments come from the same sums (u = xhat): pack_bwd needs no pass of its own
+        io.chan_sums = npart_;
+        io.nslices = slices;
+      }
+      io.yslices = slices;
       const std::string np = e.pre + l.norm;
       norm_grad_finish_kernel<<<(l.cout + 255) / 256, 256, 0, s>>>(nsum_, l.cout, e.gn ? nullptr : param(np + ".running_mean", l.cout),
                                                                    e.gn ? nullptr : param(np + ".running_var", l.cout),

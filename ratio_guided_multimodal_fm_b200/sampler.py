@@ -27,12 +27,11 @@ def _fingerprint(module) -> tuple:
     return () if module is None else _lib.content_fingerprint(module.state_dict())
 
 
-def _get_plan(pair, fm_x, fm_y, ratio, method, gamma, B, steps, N, loss_type, precision, device, chunk):
-    """Plans are cached by weight CONTENT (see _lib.content_fingerprint) and shape.  gamma is not part of the key for
-    mc_feng / unguided plans: the kernels read it from a device table, so a hit only rewrites that table
-    (rgfm_sampler_set_strength); grad_log_ratio plans bake gamma into their update kernel and keep it in the key."""
-    baked = float(gamma) if method == "grad_log_ratio" else None
-    key = (pair, _fingerprint(fm_x), _fingerprint(fm_y), _fingerprint(ratio), method, baked, B, steps, N,
+def _get_plan(pair, fm_x, fm_y, ratio, method, gamma, B, steps, N, loss_type, precision, device, chunk, schedule=None):
+    """Plans are cached by weight CONTENT (see _lib.content_fingerprint) and shape.  gamma is not part of the key: every
+    guidance kernel reads it from a device table, so a hit only rewrites that table (rgfm_sampler_set_strength, or
+    rgfm_sampler_set_strength_schedule for a time-dependent gamma(t))."""
+    key = (pair, _fingerprint(fm_x), _fingerprint(fm_y), _fingerprint(ratio), method, B, steps, N,
            loss_type, precision, str(device), chunk)
     plan = _PLAN_CACHE.get(key)
     if plan is None:
@@ -43,7 +42,10 @@ def _get_plan(pair, fm_x, fm_y, ratio, method, gamma, B, steps, N, loss_type, pr
                                 guidance_method=method, guidance_strength=gamma, num_samples=B, num_steps=steps,
                                 mc_batch_size=N, loss_type=loss_type, precision=precision, device=device, chunk=chunk)
         _PLAN_CACHE[key] = plan
-    elif baked is None and plan.guidance_strength != float(gamma):
+    if schedule is not None:
+        if plan.schedule != tuple(schedule):
+            plan.set_strength_schedule(schedule)
+    elif plan.schedule is not None or plan.guidance_strength != float(gamma):
         plan.set_strength(gamma)
     return plan
 
@@ -60,6 +62,34 @@ def _check_saturation(diag, precision):
             warnings.warn(msg)
         else:
             raise _lib.RgfmError(msg)
+
+
+SCHEDULES = ("constant", "linear_decay", "linear_ramp", "cosine_decay")
+
+
+def strength_schedule(guidance_schedule, guidance_strength: float, num_steps: int):
+    """Time-dependent guidance strength: gamma_k used by Euler step k at t_k = k / num_steps.
+    None / 'constant' -> None (the reference's behaviour); 'linear_decay' gamma (1 - t); 'linear_ramp' gamma t;
+    'cosine_decay' gamma (1 + cos(pi t)) / 2; a callable t -> gamma(t); or a sequence of num_steps values."""
+    if guidance_schedule is None or guidance_schedule == "constant":
+        return None
+    ts = [k / num_steps for k in range(num_steps)]
+    g = float(guidance_strength)
+    if callable(guidance_schedule):
+        return tuple(float(guidance_schedule(t)) for t in ts)
+    if isinstance(guidance_schedule, str):
+        if guidance_schedule == "linear_decay":
+            return tuple(g * (1.0 - t) for t in ts)
+        if guidance_schedule == "linear_ramp":
+            return tuple(g * t for t in ts)
+        if guidance_schedule == "cosine_decay":
+            import math
+            return tuple(g * 0.5 * (1.0 + math.cos(math.pi * t)) for t in ts)
+        raise ValueError(f"Unknown guidance_schedule: {guidance_schedule}")
+    vals = tuple(float(v) for v in guidance_schedule)
+    if len(vals) != num_steps:
+        raise ValueError(f"guidance_schedule must have num_steps = {num_steps} entries (got {len(vals)})")
+    return vals
 
 
 def clear_plan_cache():
@@ -93,7 +123,7 @@ def gather_pairs(x_local: torch.Tensor, y_local: torch.Tensor, num_samples: int,
 
 
 def _sample(pair, shape_x, shape_y, fm_x, fm_y, ratio_estimator, guidance_method, guidance_strength, num_samples,
-            num_steps, device, mc_batch_size, precision, shard, group, chunk, verbose, noise=None):
+            num_steps, device, mc_batch_size, precision, shard, group, chunk, verbose, noise=None, guidance_schedule=None):
     fm_x.eval()
     fm_y.eval()
     if ratio_estimator is not None:
@@ -132,7 +162,8 @@ def _sample(pair, shape_x, shape_y, fm_x, fm_y, ratio_estimator, guidance_method
     if n_local > 0:
         use_ratio = guided or grad_guided
         plan = _get_plan(pair, fm_x, fm_y, ratio_estimator if use_ratio else None, guidance_method if use_ratio else "none",
-                         guidance_strength, n_local, num_steps, mc_batch_size, loss_type, precision, device, chunk)
+                         guidance_strength, n_local, num_steps, mc_batch_size, loss_type, precision, device, chunk,
+                         strength_schedule(guidance_schedule, guidance_strength, num_steps) if use_ratio else None)
         x1, y1, diag = plan.run(x0[lo:hi], y0[lo:hi], mc_x0, mc_y0, want_diag=True)
     else:
         x1 = torch.empty((0,) + shape_x, device=device)
@@ -160,21 +191,22 @@ def _sample(pair, shape_x, shape_y, fm_x, fm_y, ratio_estimator, guidance_method
 def sample_bimodal_guided(fm_x, fm_y, ratio_estimator=None, guidance_method='none', guidance_strength=0.0,
                           num_samples=16, num_steps=100, device='cuda', mc_batch_size=64, *,
                           precision: Optional[str] = None, shard: bool = False, group=None, chunk: int = 0,
-                          verbose: bool = True, _noise=None):
-    """(MNIST, transformed-MNIST) 1x28x28 pairs.  Returns (samples_x [N,1,28,28], samples_y [N,1,28,28])."""
+                          verbose: bool = True, _noise=None, guidance_schedule=None):
+    """(MNIST, transformed-MNIST) 1x28x28 pairs.  Returns (samples_x [N,1,28,28], samples_y [N,1,28,28]).
+    guidance_schedule (extension, see strength_schedule): time-dependent gamma(t) for mc_feng / grad_log_ratio."""
     return _sample("pair28", (1, 28, 28), (1, 28, 28), fm_x, fm_y, ratio_estimator, guidance_method,
                    guidance_strength, num_samples, num_steps, device, mc_batch_size, precision, shard, group, chunk,
-                   verbose, _noise)
+                   verbose, _noise, guidance_schedule)
 
 
 def sample_bimodal_guided_mnist_svhn(fm_mnist, fm_svhn, ratio_estimator=None, guidance_method='none',
                                      guidance_strength=0.0, num_samples=16, num_steps=100, device='cuda',
                                      mc_batch_size=64, *, precision: Optional[str] = None, shard: bool = False,
-                                     group=None, chunk: int = 0, verbose: bool = True, _noise=None):
+                                     group=None, chunk: int = 0, verbose: bool = True, _noise=None, guidance_schedule=None):
     """(MNIST 1x32x32, SVHN 3x32x32) pairs.  Returns (samples_mnist [N,1,32,32], samples_svhn [N,3,32,32])."""
     return _sample("mnist_svhn", (1, 32, 32), (3, 32, 32), fm_mnist, fm_svhn, ratio_estimator, guidance_method,
                    guidance_strength, num_samples, num_steps, device, mc_batch_size, precision, shard, group, chunk,
-                   verbose, _noise)
+                   verbose, _noise, guidance_schedule)
 
 
 def sample_guidance_sweep(pair, fm_x, fm_y, ratio_estimator, guidance_strengths, num_samples=16, num_steps=100,

@@ -649,16 +649,11 @@ def test_guidance_sweep_shares_one_bank(synth):
     for g in gammas:
         ox, oy = O.sample_pair(sdx, sdy, sdr, "pair28", "mc_feng", g, steps, x0.cpu(), y0.cpu(), m0.cpu(), n0.cpu(), "disc")
         assert maxabs(out[g][0], ox) <= 1e-3 and maxabs(out[g][1], oy) <= 1e-3, g
-    # error behaviour: no bank yet / gradient plans bake gamma
+    # error behaviour: no bank yet (gradient plans read gamma from the table too: test_time_dependent_guidance_schedule)
     plan = _lib.SamplerPlan("pair28", sdx, sdy, sdr, guidance_method="mc_feng", guidance_strength=0.5, num_samples=B,
                             num_steps=steps, mc_batch_size=N, precision="fp32", device=DEV)
     with pytest.raises(_lib.RgfmError):
         plan.run(x0, y0, reuse_bank=True)
-    plan.close()
-    plan = _lib.SamplerPlan("pair28", sdx, sdy, sdr, guidance_method="grad_log_ratio", guidance_strength=0.5,
-                            num_samples=B, num_steps=steps, mc_batch_size=N, precision="fp32", device=DEV)
-    with pytest.raises(_lib.RgfmError):
-        plan.set_strength(1.0)
     plan.close()
 
 
@@ -806,3 +801,70 @@ def test_ratio_trainer_dropin_three_steps(synth):
         if v.dtype.is_floating_point:
             assert maxabs(new[k], v) <= 1e-5 * max(1.0, v.abs().max().item()), k
     assert losses[2] != losses[0]  # the parameters moved and the plan saw them
+
+
+@pytest.mark.parametrize("method", ["mc_feng", "grad_log_ratio"])
+def test_time_dependent_guidance_schedule(method, synth):
+    """gamma(t) schedules: one strength per Euler step from the device table, vs the oracle loop with the same
+    per-step strengths; then back to a constant strength on the same plan (no rebuild)."""
+    from ratio_guided_multimodal_fm_b200.sampler import strength_schedule
+    pair, kinds = "pair28", ("unet_mnist28", "unet_mnist28", "ratio28")
+    sdx, sdy, sdr = synth(kinds[0], 11), synth(kinds[1], 14), synth(kinds[2], 21)
+    B, N, steps, gamma = 4, 6, 6, 0.8
+    gen = torch.Generator().manual_seed(23)
+    x0, y0 = torch.randn(B, 1, 28, 28, generator=gen), torch.randn(B, 1, 28, 28, generator=gen)
+    mcx, mcy = torch.randn(N, 1, 28, 28, generator=gen), torch.randn(N, 1, 28, 28, generator=gen)
+    sched = strength_schedule("linear_decay", gamma, steps)
+    assert sched == tuple(gamma * (1 - k / steps) for k in range(steps))
+    assert strength_schedule(None, gamma, steps) is None and strength_schedule(lambda t: 2 * t, gamma, 2) == (0.0, 1.0)
+    with pytest.raises(ValueError):
+        strength_schedule("nope", gamma, steps)
+    with pytest.raises(ValueError):
+        strength_schedule([0.1, 0.2], gamma, steps)
+    ox, oy = O.sample_pair(sdx, sdy, sdr, pair, method, gamma, steps, x0, y0, mcx, mcy, "disc", gamma_schedule=sched)
+    cx, cy = O.sample_pair(sdx, sdy, sdr, pair, method, gamma, steps, x0, y0, mcx, mcy, "disc")
+    if method == "mc_feng":
+        assert maxabs(ox, cx) > 1e-4  # the schedule changes the result
+    plan = _lib.SamplerPlan(pair, sdx, sdy, sdr, guidance_method=method, guidance_strength=gamma, num_samples=B, num_steps=steps,
+                            mc_batch_size=N, loss_type="disc", precision="fp32", device=DEV)
+    plan.set_strength_schedule(sched)
+    x1, y1 = plan.run(x0.to(DEV), y0.to(DEV), mcx.to(DEV), mcy.to(DEV))
+    torch.cuda.synchronize()
+    assert maxabs(x1, ox) <= TOL_CONTRACT["fp32"] and maxabs(y1, oy) <= TOL_CONTRACT["fp32"], (maxabs(x1, ox), maxabs(y1, oy))
+    plan.set_strength(gamma)  # constant again, grad_log_ratio plans included (gamma is no longer baked into a kernel argument)
+    x2, y2 = plan.run(x0.to(DEV), y0.to(DEV), mcx.to(DEV), mcy.to(DEV))
+    torch.cuda.synchronize()
+    assert maxabs(x2, cx) <= TOL_CONTRACT["fp32"] and maxabs(y2, cy) <= TOL_CONTRACT["fp32"]
+    with pytest.raises(_lib.RgfmError):
+        plan.set_strength_schedule(sched[:-1])
+    plan.close()
+    # through the drop-in function (plan cache: same plan, table rewritten)
+    fx = synthetic.StateDictModule(kinds[0], sdx); fy = synthetic.StateDictModule(kinds[1], sdy)
+    fr = synthetic.StateDictModule(kinds[2], sdr)
+    a = sample_bimodal_guided(fx, fy, fr, guidance_method=method, guidance_strength=gamma, num_samples=B, num_steps=steps, device=DEV,
+                              mc_batch_size=N, precision="fp32", verbose=False, _noise=(x0.to(DEV), y0.to(DEV), mcx.to(DEV), mcy.to(DEV)),
+                              guidance_schedule="linear_decay")
+    assert maxabs(a[0], ox) <= TOL_CONTRACT["fp32"] and maxabs(a[1], oy) <= TOL_CONTRACT["fp32"]
+
+
+def test_flow_matching_step_data_side():
+    """train_flow_matching_epoch's non-network half (flow_utils.py:131-142): CFMSchedule.add_noise bit-exact against the
+    reference formula on the same prior draw, F.mse_loss and its gradient within fp32 summation-order noise."""
+    from ratio_guided_multimodal_fm_b200 import CFMSchedule
+    torch.manual_seed(4); torch.cuda.manual_seed_all(4)
+    B = 37
+    x1 = torch.randn(B, 3, 32, 32, device=DEV)
+    t = torch.rand(B, device=DEV)
+    torch.cuda.manual_seed_all(77)
+    x_t, u = CFMSchedule().add_noise(x1, t)
+    torch.cuda.manual_seed_all(77)
+    x0 = torch.randn_like(x1)  # the draw add_noise made
+    tb = t.view(B, 1, 1, 1)
+    assert torch.equal(x_t, (1 - tb) * x0 + tb * x1) and torch.equal(u, x1 - x0)
+    v = torch.randn_like(u).requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(v, u)
+    (gref,) = torch.autograd.grad(ref, v)
+    loss, dv = CFMSchedule.fm_mse_loss(v.detach(), u)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * ref.item()
+    assert maxabs(dv, gref) <= 1e-9 + 1e-6 * gref.abs().max().item()
