@@ -193,6 +193,34 @@ class CpuArm:
         return dict(config=f"sample_bimodal_guided_mnist_svhn(B={B}, N_mc={n_mc}, steps={steps}) on the host CPU, unmodified reference",
                     measured_s=real, composed_s=pred, composition_error=(pred - real) / real, finite=bool(torch.isfinite(x1).all()))
 
+    def train_step(self, dev=None):
+        """The UNMODIFIED reference trainer (src/utils/trainer.py RatioTrainer + src/utils/losses.py) for the training-step
+        numbers in `configs.train_step`: same batch and optimiser, on the host cores and -- as the fair comparator of the
+        GPU path -- with stock PyTorch on the same GPU."""
+        if self.ns is None:
+            return None
+        from src.utils.trainer import RatioTrainer as RefTrainer
+        from src.utils.losses import get_ratio_loss
+        res = {}
+        for kind, seed, loss in (("ratio28", 21, "disc"), ("ratio_mnist_svhn", 22, "rulsif")):
+            res[kind] = {}
+            for where in (["cpu"] + ([str(dev)] if dev is not None else [])):
+                m = self.ns.classes[kind](loss)
+                m.load_state_dict(self.S.state_dict(kind, seed), strict=True)
+                m = m.to(where).train()
+                tr = RefTrainer(m, get_ratio_loss(loss), torch.optim.Adam(m.parameters(), lr=1e-4), where)
+                b = train_batch(kind)
+                warm, reps = (1, 2) if where == "cpu" else (3, 10)
+                for _ in range(warm):
+                    tr.train_step(b)
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    tr.train_step(b)  # its metrics' .item() calls synchronise
+                res[kind]["cpu_ms" if where == "cpu" else "same_gpu_stock_pytorch_ms"] = 1e3 * (time.perf_counter() - t0) / reps
+        res["note"] = ("unmodified reference RatioTrainer.train_step, batch 128, Adam; BatchNorm in TRAINING mode (batch statistics) "
+                       "as the reference trains it -- the library step freezes them; cuDNN may use TF32 for the GPU comparator")
+        return res
+
     @torch.no_grad()
     def config0_full(self):
         """BASELINE configs[0] (28x28, mc_feng, B=64, N_mc=128, 100 steps, disc) executed ONCE in full by the unmodified
@@ -258,6 +286,52 @@ def _timed(fn, reps=1):
     return e0.elapsed_time(e1) * 1e-3 / reps, out
 
 
+TRAIN_B = 128  # --batch_size default of src/train_ratio.py:32 and src/train_ratio_mnist_svhn.py:85
+
+
+def train_batch(kind, B=TRAIN_B, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    sy = (1, 28, 28) if kind == "ratio28" else (3, 32, 32)
+    hw = 28 if kind == "ratio28" else 32
+    return dict(x=torch.randn(B, 1, hw, hw, generator=g), y=torch.randn(B, *sy, generator=g), is_real=(torch.arange(B) % 2 == 0).float())
+
+
+def train_step_numbers(dev):
+    """Training-side reuse: RatioTrainer.train_step (src/utils/trainer.py:26-56) on the library's fp32
+    kernels, batch 128, Adam, gradient clipping, dropout on.  `e2e_ms`: through the drop-in trainer with a HOST batch (H2D
+    of x, y, is_real, the step, clipping + Adam in torch, metrics D2H); `device_ms`: the C-ABI step alone on resident data."""
+    from ratio_guided_multimodal_fm_b200 import RatioTrainer, TrainableModule, synthetic as S
+    res = dict(workload=f"RatioTrainer.train_step, batch {TRAIN_B}, Adam lr 1e-4, clip_grad_norm 1.0, dropout 0.1 (masks drawn on the device), "
+                        "fp32 CUDA-core kernels, frozen BatchNorm statistics")
+    for kind, seed, loss in (("ratio28", 21, "disc"), ("ratio_mnist_svhn", 22, "rulsif")):
+        model = TrainableModule(kind, S.state_dict(kind, seed), loss).to(dev)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+
+        class _L:
+            pass
+        lf = _L()
+        if loss == "rulsif":
+            lf.lambda_penalty = 0.1
+        tr = RatioTrainer(model, lf, opt, device=dev, max_batch=TRAIN_B)
+        hb = {k: v.pin_memory() for k, v in train_batch(kind).items()}
+        for _ in range(3):
+            m = tr.train_step(hb)
+        t0 = time.perf_counter()
+        reps = 10
+        for _ in range(reps):
+            m = tr.train_step(hb)  # ends with the metrics' D2H (a synchronisation)
+        e2e = (time.perf_counter() - t0) / reps
+        db = {k: v.to(dev) for k, v in hb.items()}
+        plan = tr._plan
+        masks = [torch.ones(TRAIN_B, w, device=dev) for w in ((512, 256) if kind == "ratio28" else (512, 512))]
+        s, _ = _timed(lambda: plan.step(db["x"], db["y"], db["is_real"], loss, 0.1, masks), reps=10)
+        res[kind] = dict(loss_type=loss, e2e_ms=1e3 * e2e, device_ms=1e3 * s, pairs_per_s=TRAIN_B / e2e, loss=m["loss"],
+                         finite=bool(np.isfinite(m["loss"])))
+        plan.close()
+    return res
+
+
 def other_configs(dev, world, rank, prec, dist, gather_pairs):
     """The BASELINE configs bench.py's timed region does not cover; every number is one warm call, CUDA-event timed, on
     this rank's shard (max over ranks for the multi-GPU legs)."""
@@ -312,6 +386,8 @@ def other_configs(dev, world, rank, prec, dist, gather_pairs):
         out["configs[2]"] = dict(workload=f"MNIST32-SVHN gamma sweep {gammas}, B=4096 per gamma, N_mc=256, 100 steps, shared MC bank, "
                                           "MNISTClassifier32 / SVHNClassifier pair coherence (synthetic untrained classifiers)",
                                  pairs_per_s=B * len(gammas) / s, s_per_sweep=s, coherence_acc=coh)
+    if rank == 0:
+        out["train_step"] = train_step_numbers(dev)
     if world > 1:
         # configs[3]: 65536 pairs sharded over the ranks (strong scaling), NCCL all-gather of the pairs inside the timed call
         total = 65536
@@ -480,6 +556,8 @@ def run_gpu(args):
             cpu_v, _, parts = arm.sample()
             cpu_base = dict(value=cpu_v, unit="pairs/s", cores=arm.cores, kind=arm.kind, sample=arm.describe(), pieces=parts,
                             validation=arm.validate())
+            if not args.skip_configs:
+                cpu_base["train_step_reference"] = arm.train_step(dev)
         line = dict(metric=METRIC, value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[prec], data="synthetic",

@@ -759,7 +759,9 @@ void launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
   RGFM_CHECK(a.Cin % 16 == 0, "conv_simt: Cin must be a multiple of 16");
   RGFM_CHECK(a.CoutP % 32 == 0, "conv_simt: padded Cout must be a multiple of 32");
   const int tiles = a.g.tiles(a.nimg);
-  if (a.CoutP % 64 == 0) {
+  // 64-channel tiles unless they would leave SMs idle (deep layers at 4x4 / 2x2 with small batches): the 32-channel
+  // variant doubles the CTAs; every output's summation order is the same, so results do not depend on the choice
+  if (a.CoutP % 64 == 0 && tiles * (a.CoutP / 64) >= 148) {
     dim3 grid(tiles, a.CoutP / 64);
     conv_simt_kernel<64><<<grid, 256, 0, s>>>(a);
   } else {

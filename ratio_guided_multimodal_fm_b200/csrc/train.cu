@@ -19,6 +19,8 @@
 #include "simt_device.cuh"
 #include <cmath>
 #include <algorithm>
+#include <cstring>
+#include <tuple>
 
 namespace rgfm {
 
@@ -131,128 +133,129 @@ __global__ void __launch_bounds__(256) ratio_loss_kernel(const float* __restrict
 
 // ------------------------------------------------------------------------------------------------
 // Score net in training mode: Linear -> LayerNorm -> SiLU -> Dropout per hidden layer, then Linear -> 1
-// (ratio_estimator.py:125-135, ratio_flexible.py:332-345).  One CTA per sample keeps every intermediate in shared memory.
-// Dropout is a caller-supplied mask per hidden layer (values 0 or 1 / (1 - p); null = no dropout).
-// dscore == nullptr: forward only (scores).  Otherwise the backward from dL/dscore: the feature gradient and, per layer,
-// what the weight-gradient reductions need: dh (gradient at the Linear output), the layer input, and for the LayerNorm
-// affine dz * xhat and dz.
+// (ratio_estimator.py:125-135, ratio_flexible.py:332-345), as BATCHED layer kernels: a tiled GEMM per Linear (forward
+// Y = X W^T + b, backward dX = dY W) and one warp per sample row for LayerNorm + SiLU + dropout and their backward.
+// Dropout is a caller-supplied mask per hidden layer (values 0 or 1 / (1 - p); null = no dropout).  The backward also
+// leaves what the parameter-gradient reductions need: dh (gradient at each Linear output) and, for the LayerNorm affine,
+// dz * xhat and dz per element.  Fixed summation orders: deterministic.
 // ------------------------------------------------------------------------------------------------
-struct MlpTrainIO {
-  const float* mask[3];
-  float* a_in[4];   // a_in[0] unused (the features themselves)
-  float* dh[4];
-  float* dzx[3];
-  float* dz[3];
-};
-struct MlpPackT {
-  MlpLayer l[4];
-  int n;
-};
-
-__global__ void __launch_bounds__(256) mlp_train_kernel(const float* __restrict__ in, int ld_in, MlpPackT mp, MlpTrainIO io,
-                                                        const float* __restrict__ dscore, float* __restrict__ scores,
-                                                        float* __restrict__ dfeat, int ld_d) {
-  extern __shared__ float sm[];
-  __shared__ float red[8];
-  __shared__ float s_mean[4], s_rstd[4];
-  const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* act[5];
-  float* pre[4];
-  int off = 0;
-  act[0] = sm;
-  off += mp.l[0].in;
-  for (int li = 0; li < mp.n; ++li) {
-    pre[li] = sm + off; off += mp.l[li].out;
-    act[li + 1] = sm + off; off += mp.l[li].out;
-  }
-  float* gcur = sm + off; off += 512;
-  float* gnext = sm + off;
-  for (int i = tid; i < mp.l[0].in; i += 256) act[0][i] = in[(size_t)n * ld_in + i];
-  __syncthreads();
-  for (int li = 0; li < mp.n; ++li) {
-    const MlpLayer L = mp.l[li];
-    for (int j = warp; j < L.out; j += 8) {
-      const float* wr = L.w + (size_t)j * L.in;
-      float s = 0.f;
-      for (int c = lane; c < L.in; c += 32) s = fmaf(wr[c], act[li][c], s);
+// Y[n][j] = b[j] + sum_i X[n][i] W[j][i]      (32 x 32 outputs per CTA)
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
+                                                         const float* __restrict__ b, int I, int J, int N, float* __restrict__ Y, int ldy) {
+  __shared__ float Xs[32][33], Ws[32][33];
+  const int n0 = blockIdx.y * 32, j0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int tj = tid & 31, tn = tid >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < I; k0 += 32) {
+    for (int e = tid; e < 1024; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      Xs[r][c] = (n0 + r < N && k0 + c < I) ? X[(size_t)(n0 + r) * ldx + k0 + c] : 0.f;
+      Ws[r][c] = (j0 + r < J && k0 + c < I) ? W[(size_t)(j0 + r) * I + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float w = Ws[tj][k];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) pre[li][j] = s + L.b[j];
-    }
-    __syncthreads();
-    if (L.ln_g) {
-      float s = 0.f;
-      for (int c = tid; c < L.out; c += 256) s += pre[li][c];
-      const float mean = block_sum256(s, red) / (float)L.out;
-      float v = 0.f;
-      for (int c = tid; c < L.out; c += 256) {
-        const float d = pre[li][c] - mean;
-        v = fmaf(d, d, v);
-      }
-      const float rstd = rsqrtf(block_sum256(v, red) / (float)L.out + 1e-5f);
-      if (tid == 0) {
-        s_mean[li] = mean;
-        s_rstd[li] = rstd;
-      }
-      const float* mk = io.mask[li];
-      for (int c = tid; c < L.out; c += 256) {
-        const float z = (pre[li][c] - mean) * rstd * L.ln_g[c] + L.ln_b[c];
-        float a = silu_f(z);
-        if (mk) a *= mk[(size_t)n * L.out + c];
-        act[li + 1][c] = a;
-      }
-    } else {
-      for (int c = tid; c < L.out; c += 256) act[li + 1][c] = pre[li][c];
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(Xs[tn + 8 * q][k], w, acc[q]);
     }
     __syncthreads();
   }
-  if (tid == 0 && scores) scores[n] = act[mp.n][0];
-  if (!dscore) return;
-  // ---- backward ----
-  for (int c = tid; c < mp.l[mp.n - 1].out; c += 256) gcur[c] = (c == 0) ? dscore[n] : 0.f;
-  __syncthreads();
-  for (int li = mp.n - 1; li >= 0; --li) {
-    const MlpLayer L = mp.l[li];
-    if (L.ln_g) {
-      const float mean = s_mean[li], rstd = s_rstd[li];
-      const float* mk = io.mask[li];
-      float s1 = 0.f, s2 = 0.f;
-      for (int c = tid; c < L.out; c += 256) {
-        const float xh = (pre[li][c] - mean) * rstd;
-        const float z = xh * L.ln_g[c] + L.ln_b[c];
-        float dz = gcur[c];
-        if (mk) dz *= mk[(size_t)n * L.out + c];
-        const float sg = 1.0f / (1.0f + expf(-z));
-        dz *= sg * (1.0f + z * (1.0f - sg));
-        io.dzx[li][(size_t)n * L.out + c] = dz * xh;
-        io.dz[li][(size_t)n * L.out + c] = dz;
-        const float dg = dz * L.ln_g[c];
-        gcur[c] = dg;
-        s1 += dg;
-        s2 = fmaf(dg, xh, s2);
-      }
-      const float m1 = block_sum256(s1, red) / (float)L.out;
-      const float m2 = block_sum256(s2, red) / (float)L.out;
-      for (int c = tid; c < L.out; c += 256) {
-        const float xh = (pre[li][c] - mean) * rstd;
-        gcur[c] = rstd * (gcur[c] - m1 - xh * m2);
-      }
-    }
-    __syncthreads();
-    for (int c = tid; c < L.out; c += 256) io.dh[li][(size_t)n * L.out + c] = gcur[c];
-    if (li > 0)
-      for (int i = tid; i < L.in; i += 256) io.a_in[li][(size_t)n * L.in + i] = act[li][i];
-    for (int i = tid; i < L.in; i += 256) {
-      float s = 0.f;
-      for (int j = 0; j < L.out; ++j) s = fmaf(L.w[(size_t)j * L.in + i], gcur[j], s);
-      gnext[i] = s;
-    }
-    __syncthreads();
-    float* t = gcur;
-    gcur = gnext;
-    gnext = t;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int n = n0 + tn + 8 * q, j = j0 + tj;
+    if (n < N && j < J) Y[(size_t)n * ldy + j] = acc[q] + b[j];
   }
-  for (int i = tid; i < mp.l[0].in; i += 256) dfeat[(size_t)n * ld_d + i] = gcur[i];
+}
+// dX[n][i] = sum_j dY[n][j] W[j][i]
+__global__ void __launch_bounds__(256) linear_bwd_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ W, int I, int J,
+                                                         int N, float* __restrict__ dX, int ldx) {
+  __shared__ float Ys[32][33], Ws[32][33];
+  const int n0 = blockIdx.y * 32, i0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int ti = tid & 31, tn = tid >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < J; k0 += 32) {
+    for (int e = tid; e < 1024; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      Ys[r][c] = (n0 + r < N && k0 + c < J) ? dY[(size_t)(n0 + r) * ldy + k0 + c] : 0.f;
+      Ws[r][c] = (k0 + r < J && i0 + c < I) ? W[(size_t)(k0 + r) * I + i0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float w = Ws[k][ti];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(Ys[tn + 8 * q][k], w, acc[q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int n = n0 + tn + 8 * q, i = i0 + ti;
+    if (n < N && i < I) dX[(size_t)n * ldx + i] = acc[q];
+  }
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// one warp per row: act = mask * silu(LN(pre));  stat[n] = {mean, rstd}
+__global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restrict__ pre, int C, int N, const float* __restrict__ g,
+                                                          const float* __restrict__ b, const float* __restrict__ mask,
+                                                          float* __restrict__ act, float2* __restrict__ stat) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* p = pre + (size_t)n * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += p[c];
+  const float mean = warp_sum(s) / (float)C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = p[c] - mean;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)C + 1e-5f);
+  if (lane == 0) stat[n] = make_float2(mean, rstd);
+  for (int c = lane; c < C; c += 32) {
+    float a = silu_f((p[c] - mean) * rstd * g[c] + b[c]);
+    if (mask) a *= mask[(size_t)n * C + c];
+    act[(size_t)n * C + c] = a;
+  }
+}
+// one warp per row: gradient at the activation -> dh (gradient at the Linear output), plus dz * xhat and dz
+__global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restrict__ dact, const float* __restrict__ pre, int C, int N,
+                                                          const float* __restrict__ g, const float* __restrict__ b,
+                                                          const float* __restrict__ mask, const float2* __restrict__ stat,
+                                                          float* __restrict__ dh, float* __restrict__ dzx, float* __restrict__ dzo) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float2 st = stat[n];
+  const size_t r = (size_t)n * C;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float xh = (pre[r + c] - st.x) * st.y;
+    const float z = xh * g[c] + b[c];
+    float dz = dact[r + c];
+    if (mask) dz *= mask[r + c];
+    const float sg = 1.0f / (1.0f + expf(-z));
+    dz *= sg * (1.0f + z * (1.0f - sg));
+    dzx[r + c] = dz * xh;
+    dzo[r + c] = dz;
+    const float dg = dz * g[c];
+    s1 += dg;
+    s2 = fmaf(dg, xh, s2);
+  }
+  const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
+  for (int c = lane; c < C; c += 32) {
+    const float xh = (pre[r + c] - st.x) * st.y;
+    dh[r + c] = st.y * (dzo[r + c] * g[c] - m1 - xh * m2);
+  }
+}
+// scores[n] = pre_last[n][0]
+__global__ void copy_col0_kernel(const float* __restrict__ src, int ld, int N, float* __restrict__ dst) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) dst[n] = src[(size_t)n * ld];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -406,18 +409,18 @@ __global__ void norm_grad_finish_kernel(const float* __restrict__ sums, int C, c
 // ------------------------------------------------------------------------------------------------
 // Conv weight gradient: dW[co][ci][ky][kx] = sum_{n,h,w} dY[n][h][w][co] * X[n][h + ky - 1][w + kx - 1][ci]
 // X: the conv's fp32 NHWC operand (channel stride CinP), dY: dense fp32 NHWC gradient of the raw output.
-// A CTA owns a (16 CI x 64) tile of (ci, co) for all nine taps and a contiguous range of (image, row) pairs; per row it
-// stages the three operand rows (zero halo) and the gradient row in shared memory and accumulates 9 x CI x 4 outer-product
-// terms per thread.  Partials part[split][tap][ci][co] are summed in split order by conv_wgrad_reduce_kernel, which also
+// A CTA owns a (16 CI x 64) tile of (ci, co) for all nine taps and a contiguous range of (image, row block) units; per unit
+// (RB rows, about 32 pixels) it stages the RB + 2 operand rows (zero halo) and the RB gradient rows in shared memory and
+// accumulates 9 x CI x 4 outer-product terms per thread and pixel.  Partials part[split][tap][ci][co] are summed in split order by conv_wgrad_reduce_kernel, which also
 // transposes to the torch layout: deterministic, no atomics.
 // ------------------------------------------------------------------------------------------------
 template <int CI>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ X, int CinP, const float* __restrict__ dY, int Cout,
-                                                         int H, int W, int nimg, int rows_per_split, float* __restrict__ part) {
+                                                         int H, int W, int RB, int nimg, int units_per_split, float* __restrict__ part) {
   constexpr int TCI = 16 * CI, TCO = 64;
   extern __shared__ __align__(16) float smw[];
-  float* Xs = smw;                          // [3][W + 2][TCI]
-  float* Ys = smw + 3 * (W + 2) * TCI;      // [W][TCO]
+  float* Xs = smw;                                // [RB + 2][W + 2][TCI]
+  float* Ys = smw + (RB + 2) * (W + 2) * TCI;     // [RB][W][TCO]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int co_tiles = (Cout + TCO - 1) / TCO;
   const int cot = blockIdx.x % co_tiles, cit = blockIdx.x / co_tiles;
@@ -429,50 +432,53 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
     for (int c = 0; c < CI; ++c)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[t][c][j] = 0.f;
-  const int total = nimg * H;
-  const int r0 = blockIdx.y * rows_per_split, r1 = min(r0 + rows_per_split, total);
-  for (int r = r0; r < r1; ++r) {
-    const int n = r / H, h = r - n * H;
+  // work unit = (image, block of RB consecutive rows)
+  const int nblk = (H + RB - 1) / RB;
+  const int total = nimg * nblk;
+  const int u0 = blockIdx.y * units_per_split, u1 = min(u0 + units_per_split, total);
+  for (int u = u0; u < u1; ++u) {
+    const int n = u / nblk, h0 = (u - n * nblk) * RB;
     __syncthreads();
-    for (int i = tid; i < 3 * (W + 2) * (TCI / 4); i += 256) {
+    for (int i = tid; i < (RB + 2) * (W + 2) * (TCI / 4); i += 256) {
       const int c4 = i % (TCI / 4), q = i / (TCI / 4), wq = q % (W + 2), ky = q / (W + 2);
-      const int hh = h + ky - 1, ww = wq - 1;
+      const int hh = h0 + ky - 1, ww = wq - 1;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (hh >= 0 && hh < H && ww >= 0 && ww < W)
         v = __ldg(reinterpret_cast<const float4*>(X + (((size_t)n * H + hh) * W + ww) * CinP + ci0 + c4 * 4));
       *reinterpret_cast<float4*>(Xs + (size_t)(ky * (W + 2) + wq) * TCI + c4 * 4) = v;
     }
-    for (int i = tid; i < W * (TCO / 4); i += 256) {
-      const int c4 = i % (TCO / 4), w = i / (TCO / 4), co = co0 + c4 * 4;
+    for (int i = tid; i < RB * W * (TCO / 4); i += 256) {
+      const int c4 = i % (TCO / 4), pq = i / (TCO / 4), w = pq % W, rr = pq / W, co = co0 + c4 * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (co < Cout) v = __ldg(reinterpret_cast<const float4*>(dY + (((size_t)n * H + h) * W + w) * Cout + co));
-      *reinterpret_cast<float4*>(Ys + (size_t)w * TCO + c4 * 4) = v;
+      if (co < Cout && h0 + rr < H) v = __ldg(reinterpret_cast<const float4*>(dY + (((size_t)n * H + h0 + rr) * W + w) * Cout + co));
+      *reinterpret_cast<float4*>(Ys + (size_t)pq * TCO + c4 * 4) = v;
     }
     __syncthreads();
-    for (int w = 0; w < W; ++w) {
-      const float4 y = *reinterpret_cast<const float4*>(Ys + (size_t)w * TCO + tx * 4);
+    for (int rr = 0; rr < RB; ++rr)
+      for (int w = 0; w < W; ++w) {
+        const float4 y = *reinterpret_cast<const float4*>(Ys + (size_t)(rr * W + w) * TCO + tx * 4);
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const float* xp = Xs + (size_t)((t / 3) * (W + 2) + w + (t % 3)) * TCI + ty * CI;
-        float x[CI];
-        if (CI == 4) {
-          const float4 v = *reinterpret_cast<const float4*>(xp);
-          x[0] = v.x; x[1 % CI] = v.y; x[2 % CI] = v.z; x[3 % CI] = v.w;
-        } else if (CI == 2) {
-          const float2 v = *reinterpret_cast<const float2*>(xp);
-          x[0] = v.x; x[1 % CI] = v.y;
-        } else {
-          x[0] = xp[0];
-        }
+        for (int t = 0; t < 9; ++t) {
+          const float* xp = Xs + (size_t)((rr + t / 3) * (W + 2) + w + (t % 3)) * TCI + ty * CI;
+          float x[CI];
+          if (CI == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(xp);
+            x[0] = v.x; x[1 % CI] = v.y; x[2 % CI] = v.z; x[3 % CI] = v.w;
+          } else if (CI == 2) {
+            const float2 v = *reinterpret_cast<const float2*>(xp);
+            x[0] = v.x; x[1 % CI] = v.y;
+          } else {
+            x[0] = xp[0];
+          }
 #pragma unroll
-        for (int c = 0; c < CI; ++c) {
-          acc[t][c][0] = fmaf(x[c], y.x, acc[t][c][0]);
-          acc[t][c][1] = fmaf(x[c], y.y, acc[t][c][1]);
-          acc[t][c][2] = fmaf(x[c], y.z, acc[t][c][2]);
-          acc[t][c][3] = fmaf(x[c], y.w, acc[t][c][3]);
+          for (int c = 0; c < CI; ++c) {
+            acc[t][c][0] = fmaf(x[c], y.x, acc[t][c][0]);
+            acc[t][c][1] = fmaf(x[c], y.y, acc[t][c][1]);
+            acc[t][c][2] = fmaf(x[c], y.z, acc[t][c][2]);
+            acc[t][c][3] = fmaf(x[c], y.w, acc[t][c][3]);
+          }
         }
       }
-    }
   }
   const int co = co0 + tx * 4;
   if (co < Cout) {
@@ -605,6 +611,11 @@ class RatioTrainer {
       add_encoder("encoder_svhn.", S, false, 3, 32, true, 256, 256);
       add_mlp({{0, 1}, {4, 5}, {8, 9}}, 11, {512, 512, 256});
     }
+    RGFM_CUDA(cudaStreamCreateWithFlags(&cap_, cudaStreamNonBlocking));
+    sx_ = dalloc((size_t)B_ * dim_x());
+    sy_ = dalloc((size_t)B_ * dim_y());
+    sr_ = dalloc(B_);
+    for (int i = 0; i < nmlp_ - 1; ++i) smask_[i] = dalloc((size_t)B_ * mlp_[i].out);
     feat_ = dalloc((size_t)B_ * 512);
     dfeat_ = dalloc((size_t)B_ * 512);
     scores_ = dalloc(B_);
@@ -624,6 +635,8 @@ class RatioTrainer {
   }
   ~RatioTrainer() {
     cudaSetDevice(device_);
+    for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+    if (cap_) cudaStreamDestroy(cap_);
     for (void* p : owned_) cudaFree(p);
   }
   int device() const { return device_; }
@@ -639,56 +652,112 @@ class RatioTrainer {
             int n_masks, float* out8, cudaStream_t s) {
     RGFM_CHECK(nb >= 1 && nb <= B_, "ratio trainer: batch exceeds max_batch");
     RGFM_CHECK(n_masks >= 0 && n_masks <= nmlp_ - 1, "ratio trainer: at most one dropout mask per hidden layer of the score net");
+    // The ~250 launches of a step are captured ONCE per (batch, loss, masks) into a CUDA graph over plan-owned staging
+    // buffers: a training loop hands in fresh tensors every step, so the inputs are copied in (0.8 .. 2 MB, device to
+    // device) and the graph's pointers never change.  Parameters are read through their live pointers either way.
+    RGFM_CUDA(cudaMemcpyAsync(sx_, x, (size_t)nb * dim_x() * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    RGFM_CUDA(cudaMemcpyAsync(sy_, y, (size_t)nb * dim_y() * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    RGFM_CUDA(cudaMemcpyAsync(sr_, is_real, (size_t)nb * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    for (int i = 0; i < n_masks; ++i)
+      RGFM_CUDA(cudaMemcpyAsync(smask_[i], masks[i], (size_t)nb * mlp_[i].out * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    static const bool graphs_on = !(getenv("RGFM_TRAIN_GRAPH") && atoi(getenv("RGFM_TRAIN_GRAPH")) == 0);  // A/B switch (same results)
+    if (!graphs_on) {
+      body(nb, loss_type, lambda, n_masks, s);
+    } else {
+      uint32_t lbits;
+      memcpy(&lbits, &lambda, 4);
+      const std::tuple<int, int, int, uint32_t> key(nb, loss_type, n_masks, lbits);
+      auto it = graphs_.find(key);
+      if (it == graphs_.end()) {
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ex = nullptr;
+        RGFM_CUDA(cudaStreamBeginCapture(cap_, cudaStreamCaptureModeThreadLocal));
+        try {
+          body(nb, loss_type, lambda, n_masks, cap_);
+        } catch (...) {
+          cudaStreamEndCapture(cap_, &g);
+          if (g) cudaGraphDestroy(g);
+          throw;
+        }
+        RGFM_CUDA(cudaStreamEndCapture(cap_, &g));
+        cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) throw Error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(e));
+        it = graphs_.emplace(key, ex).first;
+      }
+      RGFM_CUDA(cudaGraphLaunch(it->second, s));
+    }
+    RGFM_CUDA(cudaMemcpyAsync(out8, out_, 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+
+ private:
+  void body(int nb, int loss_type, float lambda, int n_masks, cudaStream_t s) {
+    const float *x = sx_, *y = sy_, *is_real = sr_;
     refresh(s);
     for (auto& e : enc_) forward_encoder(e, e.from_y ? y : x, nb, s);
-    MlpPackT mp;
-    mp.n = nmlp_;
-    for (int i = 0; i < nmlp_; ++i) mp.l[i] = mlp_[i];
-    MlpTrainIO io{};
+    float* const* mk = smask_;
+    auto mask_of = [&](int i) -> const float* { return i < n_masks ? mk[i] : nullptr; };
+    // forward: act[0] = feat; act_[i + 1] = dropout(silu(LN(pre_[i]))); the last Linear's output is the score
     for (int i = 0; i < nmlp_; ++i) {
-      io.a_in[i] = a_in_[i];
-      io.dh[i] = dh_[i];
+      const MlpLayer& L = mlp_[i];
+      const float* ain = i == 0 ? feat_ : act_[i];
+      linear_fwd_kernel<<<dim3((L.out + 31) / 32, (nb + 31) / 32), 256, 0, s>>>(ain, i == 0 ? 512 : L.in, L.w, L.b, L.in, L.out, nb, pre_[i], L.out);
+      post_launch_t("linear_fwd");
       if (i < nmlp_ - 1) {
-        io.dzx[i] = dzx_[i];
-        io.dz[i] = dz_[i];
-        io.mask[i] = i < n_masks ? masks[i] : nullptr;
+        ln_silu_fwd_kernel<<<(nb + 7) / 8, 256, 0, s>>>(pre_[i], L.out, nb, L.ln_g, L.ln_b, mask_of(i), act_[i + 1], reinterpret_cast<float2*>(stat_[i]));
+        post_launch_t("ln_silu_fwd");
       }
     }
-    mlp_train_kernel<<<nb, 256, mlp_smem_, s>>>(feat_, 512, mp, io, nullptr, scores_, nullptr, 0);
-    post_launch_t("mlp_train(forward)");
+    copy_col0_kernel<<<(nb + 255) / 256, 256, 0, s>>>(pre_[nmlp_ - 1], 1, nb, scores_);
+    post_launch_t("copy_col0");
     ratio_loss_kernel<<<1, 256, 0, s>>>(scores_, is_real, nb, loss_type, lambda, out_, dscore_);
     post_launch_t("ratio_loss");
-    mlp_train_kernel<<<nb, 256, mlp_smem_, s>>>(feat_, 512, mp, io, dscore_, nullptr, dfeat_, 512);
-    post_launch_t("mlp_train(backward)");
+    // backward: dh_[i] = gradient at the output of Linear i; dact_[i] = gradient at its input
+    for (int i = nmlp_ - 1; i >= 0; --i) {
+      const MlpLayer& L = mlp_[i];
+      const float* dhp = dscore_;  // the last Linear's output IS the score
+      if (i < nmlp_ - 1) {
+        ln_silu_bwd_kernel<<<(nb + 7) / 8, 256, 0, s>>>(dact_[i + 1], pre_[i], L.out, nb, L.ln_g, L.ln_b, mask_of(i),
+                                                        reinterpret_cast<const float2*>(stat_[i]), dh_[i], dzx_[i], dz_[i]);
+        post_launch_t("ln_silu_bwd");
+        dhp = dh_[i];
+      }
+      dh_ptr_[i] = dhp;
+      linear_bwd_kernel<<<dim3((L.in + 31) / 32, (nb + 31) / 32), 256, 0, s>>>(dhp, L.out, L.w, L.in, L.out, nb, i == 0 ? dfeat_ : dact_[i],
+                                                                               i == 0 ? 512 : L.in);
+      post_launch_t("linear_bwd");
+    }
     // score-net parameter gradients
     for (int i = 0; i < nmlp_; ++i) {
       const MlpLayer& L = mlp_[i];
-      const float* ain = i == 0 ? feat_ : a_in_[i];
+      const float* ain = i == 0 ? feat_ : act_[i];
       const int lda = L.out, ldb = i == 0 ? 512 : L.in;
       dim3 grid((L.in + 31) / 32, (L.out + 31) / 32);
-      linear_wgrad_kernel<<<grid, 256, 0, s>>>(dh_[i], lda, L.out, ain, ldb, L.in, nb, mlp_gw_[i]);
+      linear_wgrad_kernel<<<grid, 256, 0, s>>>(dh_ptr_[i], lda, L.out, ain, ldb, L.in, nb, mlp_gw_[i]);
       post_launch_t("linear_wgrad");
-      colsum(dh_[i], L.out, L.out, nb, mlp_gb_[i], s);
+      colsum(dh_ptr_[i], L.out, L.out, nb, mlp_gb_[i], s);
       if (i < nmlp_ - 1) {
         colsum(dzx_[i], L.out, L.out, nb, mlp_gln_g_[i], s);
         colsum(dz_[i], L.out, L.out, nb, mlp_gln_b_[i], s);
       }
     }
     for (auto& e : enc_) backward_encoder(e, nb, s);
-    RGFM_CUDA(cudaMemcpyAsync(out8, out_, 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
 
- private:
+  std::map<std::tuple<int, int, int, uint32_t>, cudaGraphExec_t> graphs_;
+  cudaStream_t cap_ = nullptr;
+  float *sx_ = nullptr, *sy_ = nullptr, *sr_ = nullptr, *smask_[3] = {};
   static constexpr int kColSplits = 256;
   static constexpr int kMaxSlices = 32;
+
   int kind_, B_, device_;
   WeightMap P_, G_;
   std::vector<void*> owned_;
   std::vector<TrainEncoder> enc_;
   MlpLayer mlp_[4];
   int nmlp_ = 0;
-  size_t mlp_smem_ = 0;
-  float *a_in_[4] = {}, *dh_[4] = {}, *dzx_[3] = {}, *dz_[3] = {};
+  float *act_[5] = {}, *pre_[4] = {}, *dact_[5] = {}, *stat_[3] = {}, *dh_[4] = {}, *dzx_[3] = {}, *dz_[3] = {};
+  const float* dh_ptr_[4] = {};
   float *mlp_gw_[4] = {}, *mlp_gb_[4] = {}, *mlp_gln_g_[3] = {}, *mlp_gln_b_[3] = {};
   float *feat_ = nullptr, *dfeat_ = nullptr, *scores_ = nullptr, *dscore_ = nullptr, *out_ = nullptr;
   float *colsum_scratch_ = nullptr, *wpart_ = nullptr, *npart_ = nullptr, *nsum_ = nullptr;
@@ -775,7 +844,6 @@ class RatioTrainer {
 
   void add_mlp(const std::vector<std::pair<int, int>>& lin_ln, int last, const std::vector<int>& dims) {
     int in = 512;
-    size_t floats = 512 + 2 * 512;
     for (size_t i = 0; i < lin_ln.size(); ++i) {
       MlpLayer l{};
       const std::string a = "score_net." + std::to_string(lin_ln[i].first), n = "score_net." + std::to_string(lin_ln[i].second);
@@ -795,16 +863,18 @@ class RatioTrainer {
     mlp_[nmlp_++] = f;
     for (int i = 0; i < nmlp_; ++i) {
       RGFM_CHECK(mlp_[i].in <= 512 && mlp_[i].out <= 512, "ratio trainer: score-net width");
-      floats += 2 * (size_t)mlp_[i].out;
-      a_in_[i] = dalloc((size_t)B_ * mlp_[i].in);
-      dh_[i] = dalloc((size_t)B_ * mlp_[i].out);
+      pre_[i] = dalloc((size_t)B_ * mlp_[i].out);
+      if (i > 0) {
+        act_[i] = dalloc((size_t)B_ * mlp_[i].in);
+        dact_[i] = dalloc((size_t)B_ * mlp_[i].in);
+      }
       if (i < nmlp_ - 1) {
+        dh_[i] = dalloc((size_t)B_ * mlp_[i].out);
         dzx_[i] = dalloc((size_t)B_ * mlp_[i].out);
         dz_[i] = dalloc((size_t)B_ * mlp_[i].out);
+        stat_[i] = dalloc((size_t)B_ * 2);
       }
     }
-    mlp_smem_ = floats * sizeof(float);
-    RGFM_CHECK(mlp_smem_ <= 48 * 1024, "ratio trainer: score-net shared memory");
   }
 
   void refresh(cudaStream_t s) {
@@ -863,6 +933,7 @@ class RatioTrainer {
     post_launch_t("colsum");
   }
 
+  static int wgrad_rb(int H) { return std::max(1, std::min(H, 32 / H)); }  // rows per unit: about 32 pixels
   int wgrad_splits(const TrainEncoder& e, int i) const {
     const TrainLayer& l = e.L[i];
     const int tci = e.cinP[i] >= 64 ? 64 : e.cinP[i];
@@ -913,15 +984,16 @@ class RatioTrainer {
         const int cinP = e.cinP[i];
         const int tci = cinP >= 64 ? 64 : cinP;
         const int tiles = (cinP / tci) * ((l.cout + 63) / 64);
-        const int rows = nb * H;
-        int splits = std::max(1, std::min(rows, (148 * 3 + tiles - 1) / tiles));
-        const int rps = (rows + splits - 1) / splits;
-        splits = (rows + rps - 1) / rps;
-        const size_t smem = ((size_t)3 * (H + 2) * tci + (size_t)H * 64) * sizeof(float);
+        const int RB = wgrad_rb(H);
+        const int units = nb * ((H + RB - 1) / RB);
+        int splits = std::max(1, std::min(units, (148 * 3 + tiles - 1) / tiles));
+        const int ups = (units + splits - 1) / splits;
+        splits = (units + ups - 1) / ups;
+        const size_t smem = ((size_t)(RB + 2) * (H + 2) * tci + (size_t)RB * H * 64) * sizeof(float);
         dim3 grid(tiles, splits);
-        if (tci == 64) conv_wgrad_kernel<4><<<grid, 256, smem, s>>>(e.opnd[i], cinP, e.draw[i], l.cout, H, H, nb, rps, wpart_);
-        else if (tci == 32) conv_wgrad_kernel<2><<<grid, 256, smem, s>>>(e.opnd[i], cinP, e.draw[i], l.cout, H, H, nb, rps, wpart_);
-        else conv_wgrad_kernel<1><<<grid, 256, smem, s>>>(e.opnd[i], cinP, e.draw[i], l.cout, H, H, nb, rps, wpart_);
+        if (tci == 64) conv_wgrad_kernel<4><<<grid, 256, smem, s>>>(e.opnd[i], cinP, e.draw[i], l.cout, H, H, RB, nb, ups, wpart_);
+        else if (tci == 32) conv_wgrad_kernel<2><<<grid, 256, smem, s>>>(e.opnd[i], cinP, e.draw[i], l.cout, H, H, RB, nb, ups, wpart_);
+        else conv_wgrad_kernel<1><<<grid, 256, smem, s>>>(e.opnd[i], cinP, e.draw[i], l.cout, H, H, RB, nb, ups, wpart_);
         post_launch_t("conv_wgrad");
         const int total = l.cout * l.cin * 9;
         conv_wgrad_reduce_kernel<<<std::min((total + 255) / 256, 2048), 256, 0, s>>>(wpart_, splits, cinP, l.cout, l.cin,
