@@ -659,42 +659,64 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
 #pragma unroll
     for (int j = 0; j < CPT; ++j) acc[i][j] = 0.0f;
 
+  // K loop over (tap, 16-channel chunk) with a register prefetch: the global loads of step it + 1 are in flight while
+  // step it is multiplied out of shared memory (same summation order as a plain loop, so results do not change)
   const int ntaps = a.ks * a.ks;
-  for (int tap = 0; tap < ntaps; ++tap) {
+  const int nchunk = a.Cin / KC, nit = ntaps * nchunk;
+  auto load_g = [&](int it, float4 (&va)[2], float4& vb) {
+    const int tap = it / nchunk, c0 = (it - tap * nchunk) * KC;
     const int ky = tap / a.ks, kx = tap - ky * a.ks;
-    for (int c0 = 0; c0 < a.Cin; c0 += KC) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int idx = tid + j * 256;
-        const int px = idx >> 2, c4 = idx & 3;
-        const int hi = lh[j] + ky, wi = lw[j] + kx;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lv[j] && hi >= 0 && hi < a.Hin && wi >= 0 && wi < a.Win)
-          v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)ln[j] * a.Hin + hi) * a.Win + wi) * a.Cin + c0 + c4 * 4));
-        As[c4 * 4 + 0][px] = v.x;
-        As[c4 * 4 + 1][px] = v.y;
-        As[c4 * 4 + 2][px] = v.z;
-        As[c4 * 4 + 3][px] = v.w;
-      }
-      if (tid < KC * TN / 4) {
-        const int k = tid / (TN / 4), c4b = tid % (TN / 4);
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(a.w + ((size_t)tap * a.Cin + c0 + k) * a.CoutP + n0 + c4b * 4));
-        *reinterpret_cast<float4*>(&Bs[k][c4b * 4]) = wv;
-      }
-      __syncthreads();
+    for (int j = 0; j < 2; ++j) {
+      const int c4 = (tid + j * 256) & 3;
+      const int hi = lh[j] + ky, wi = lw[j] + kx;
+      va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lv[j] && hi >= 0 && hi < a.Hin && wi >= 0 && wi < a.Win)
+        va[j] = __ldg(reinterpret_cast<const float4*>(in + (((size_t)ln[j] * a.Hin + hi) * a.Win + wi) * a.Cin + c0 + c4 * 4));
+    }
+    if (tid < KC * TN / 4) {
+      const int k = tid / (TN / 4), c4b = tid % (TN / 4);
+      vb = __ldg(reinterpret_cast<const float4*>(a.w + ((size_t)tap * a.Cin + c0 + k) * a.CoutP + n0 + c4b * 4));
+    }
+  };
+  auto store_s = [&](const float4 (&va)[2], const float4& vb) {
 #pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(&As[k][pg * 8]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&As[k][pg * 8 + 4]);
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        float bv[CPT];
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + j * 256;
+      const int px = idx >> 2, c4 = idx & 3;
+      As[c4 * 4 + 0][px] = va[j].x;
+      As[c4 * 4 + 1][px] = va[j].y;
+      As[c4 * 4 + 2][px] = va[j].z;
+      As[c4 * 4 + 3][px] = va[j].w;
+    }
+    if (tid < KC * TN / 4) {
+      const int k = tid / (TN / 4), c4b = tid % (TN / 4);
+      *reinterpret_cast<float4*>(&Bs[k][c4b * 4]) = vb;
+    }
+  };
+  float4 pa[2], pb = make_float4(0.f, 0.f, 0.f, 0.f);
+  load_g(0, pa, pb);
+  store_s(pa, pb);
+  __syncthreads();
+  for (int it = 0; it < nit; ++it) {
+    const bool more = it + 1 < nit;
+    if (more) load_g(it + 1, pa, pb);
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) bv[j] = Bs[k][cg * CPT + j];
+    for (int k = 0; k < KC; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][pg * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][pg * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[CPT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+      for (int j = 0; j < CPT; ++j) bv[j] = Bs[k][cg * CPT + j];
 #pragma unroll
-          for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-      }
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (more) {
+      store_s(pa, pb);
       __syncthreads();
     }
   }
