@@ -68,6 +68,17 @@ def _worker(rank, world, port, n, q):
         pb = torch.zeros(hi - lo, dtype=torch.int64)
         res = _coherence((pa == pb).sum(), n, True, None)  # per-rank match count (on a GPU: the fused C-ABI count)
         ok = ok and res["num_samples"] == n and abs(res["coherence_acc"] - float(((torch.arange(n) % 3) == 0).sum()) / n) < 1e-12
+        # data-parallel training: per-rank gradients of batch shards averaged over the flat gradient arena with one all-reduce
+        # equal the gradient of the mean loss over the whole batch (equal shard sizes)
+        from ratio_guided_multimodal_fm_b200.train import average_gradients
+        gen = torch.Generator().manual_seed(3)
+        w = torch.randn(7, generator=gen)
+        data = torch.randn(4 * world, 7, generator=gen)
+        full = (2 * (data @ w)[:, None] * data).mean(0)               # d/dw mean_i (x_i . w)^2 over the whole batch
+        mine = data[rank * 4:(rank + 1) * 4]
+        flat = (2 * (mine @ w)[:, None] * mine).mean(0).clone()
+        average_gradients(flat)
+        ok = ok and torch.allclose(flat, full, atol=1e-6)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
