@@ -353,5 +353,10 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 }
 
 extern thread_local int64_t g_launch_counter;  // incremented by every launch_* (graph build-time kernel count)
+// CTA cap of the persistent tcgen05 conv launches issued by this thread (0 = one CTA per SM).  The sampler sets it while it
+// captures two INDEPENDENT network chains as parallel graph branches, so that the two chains' kernels own disjoint sets of
+// SMs and run side by side instead of alternating: the pipeline fill / drain of one chain's launch (~5..10 us per launch
+// and SM) is then covered by the other chain's steady state (sampler.cu, profiles/notes_r02.md section 14).
+extern thread_local int g_tc_cta_cap;
 
 }  // namespace rgfm

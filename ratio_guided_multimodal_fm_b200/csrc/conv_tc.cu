@@ -1544,7 +1544,10 @@ bool tc_dense(int cout, int W, bool final, int stages) {
   const int mode = getenv("RGFM_TC_DENSE") ? atoi(getenv("RGFM_TC_DENSE")) : 1;  // read at plan build time (tests switch it)
   const int nmma = (cout + 15) / 16 * 16;
   if (mode == 0 || nmma > 64 || W > 32 || W < 4) return false;
-  return mode == 2 || final || stages >= 2;
+  // Cout <= 32 (third session, after the instruction diet: the lean per-image transform loop exists for row-dense tiles
+  // only): single-stage 32->32 convs 88.6 -> 78.8 us, the 32->32 stride-2 conv 80.1 -> 68.1 us, the 1->32 input conv
+  // 66.2 -> 68.5 us (profiles/policy_matrix_r02.txt)
+  return mode == 2 || final || stages >= 2 || nmma <= 32;
 }
 static int tc_tile_width(int W) { return W <= 8 ? 8 : (W <= 16 ? 16 : 32); }
 // GEMM rows per image of the row space a conv's GroupNorm partials are indexed by
@@ -1877,7 +1880,8 @@ void launch_conv_tc(TcConv& tc, const ConvArgs& a, cudaStream_t s) {
     RGFM_CUDA(cudaGetDevice(&dev));
     RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = supers < num_sms ? supers : num_sms;  // persistent: one CTA per SM, static round-robin
+  const int cap = (g_tc_cta_cap > 0 && g_tc_cta_cap < num_sms) ? g_tc_cta_cap : num_sms;  // see common.h
+  const int grid = supers < cap ? supers : cap;  // persistent: one CTA per SM, static round-robin
 #define RGFM_TC_LAUNCH(D, R, X, F, S) launch_pdl(conv_tc_kernel<D, R, X, F, S>, dim3(grid), dim3(TC_THREADS), tc.smem, s, tc.tmA[0], tc.tmB[0], tc.tmA[1], tc.tmB[1], tc.tmA[2], tc.tmB[2], tc.tmO, tc.tmZ, p)
 #define RGFM_TC_LAUNCH2(D, R, F, S) do { if (xb) RGFM_TC_LAUNCH(D, R, true, F, S); else RGFM_TC_LAUNCH(D, R, false, F, S); } while (0)
   const bool final_out = a.out_mode != OUT_RAW;

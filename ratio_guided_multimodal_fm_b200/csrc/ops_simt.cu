@@ -9,6 +9,7 @@
 namespace rgfm {
 
 thread_local int64_t g_launch_counter = 0;
+thread_local int g_tc_cta_cap = 0;
 
 bool pdl_enabled() {
   // measured on B200 (round 1): 890 pairs/s with programmatic edges vs 896 without -- off unless RGFM_PDL=1

@@ -234,14 +234,36 @@ struct Sampler {
       RGFM_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
     };
 
+    // SM split between the two U-Net chains (common.h g_tc_cta_cap): the x-network's conv launches take `sx` CTAs, the
+    // y-network's the remaining SMs, so the two branches of a step run side by side instead of alternating and the
+    // pipeline fill / drain of every launch (~10 us per launch of a step that has 68 of them) is covered by the other chain.
+    // It pays where that fixed cost is a large share of a launch, i.e. at small batches -- the MC pre-pass (N_mc = 256:
+    // 205 -> 190 ms per call, plateau at 40..46 of 148 SMs for the MNIST32 chain = its share of the step's conv time; 36 or
+    // 56 lose it again) -- and costs 0..4 % at B = 1024, where the launches are long (profiles/notes_r02.md section 14).
+    // Rule: graphs whose batch is at most 512 images are split, by the chains' share of the conv time (identical networks:
+    // half).  RGFM_SPLIT_PRE / RGFM_SPLIT_MAIN override the x chain's CTA count per graph family (0 = no split).
+    int num_sms = 148;
+    RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, d.device));
+    const bool tc_mode = d.precision != RGFM_PREC_FP32;
+    const int sx_rule = d.pair == RGFM_PAIR_MNIST_SVHN ? (num_sms * 2 + 3) / 7 : num_sms / 2;
+    const int split_pre = getenv("RGFM_SPLIT_PRE") ? atoi(getenv("RGFM_SPLIT_PRE")) : ((tc_mode && N <= 512) ? sx_rule : 0);
+    const int split_main = getenv("RGFM_SPLIT_MAIN") ? atoi(getenv("RGFM_SPLIT_MAIN")) : ((tc_mode && B <= 512) ? sx_rule : 0);
+    auto both = [&](int sx, cudaStream_t s, int n, const float* xi, float* xo, const float* yi, float* yo, int mode) {
+      const bool on = sx > 0 && sx < num_sms;
+      g_tc_cta_cap = on ? sx : 0;
+      fx->forward(s, n, xi, nullptr, xo, mode, dtf, step);
+      g_tc_cta_cap = on ? num_sms - sx : 0;
+      fy->forward(cap2, n, yi, nullptr, yo, mode, dtf, step);
+      g_tc_cta_cap = 0;
+    };
+
     // ---- graphs ----
     if (guided) {
       // mc_x += fm_x(mc_x, t) * dt and mc_y += fm_y(mc_y, t) * dt (flow_utils.py:236-250): the reference runs the two
       // chains one after the other; they are independent, so step s of both runs concurrently here
       capture(g_pre, [&](cudaStream_t s) {
         fork(s);
-        fx->forward(s, N, mcx, nullptr, mcx, OUT_EULER, dtf, step);
-        fy->forward(cap2, N, mcy, nullptr, mcy, OUT_EULER, dtf, step);
+        both(split_pre, s, N, mcx, mcx, mcy, mcy, OUT_EULER);
         join(s);
         launch_step_inc(step, s);
       });
@@ -260,8 +282,7 @@ struct Sampler {
           launch_mcf_prep(a, cap3);
           RGFM_CUDA(cudaEventRecord(ev_join3, cap3));
         }
-        fx->forward(s, B, x, nullptr, vx, OUT_NCHW, dtf, step);
-        fy->forward(cap2, B, y, nullptr, vy, OUT_NCHW, dtf, step);
+        both(split_main, s, B, x, vx, y, vy, OUT_NCHW);
         join(s);
         if (mcf_branch) RGFM_CUDA(cudaStreamWaitEvent(s, ev_join3, 0));
         else launch_mcf_prep(a, s);
@@ -276,8 +297,7 @@ struct Sampler {
       const int lt = d.loss_type;
       capture(g_grad, [&](cudaStream_t s) {
         fork(s);
-        fx->forward(s, B, x, nullptr, vx, OUT_NCHW, dtf, step);
-        fy->forward(cap2, B, y, nullptr, vy, OUT_NCHW, dtf, step);
+        both(split_main, s, B, x, vx, y, vy, OUT_NCHW);
         join(s);
         fr->grad_log_ratio(s, B, x, y, lt, gx, gy, nullptr);
         launch_euler_grad(x, vx, gx, sc, step, dtf, (size_t)B * Dx, s);
@@ -287,8 +307,7 @@ struct Sampler {
     }
     capture(g_plain, [&](cudaStream_t s) {  // x += fm_x(x, t) * dt ; y += fm_y(y, t) * dt
       fork(s);
-      fx->forward(s, B, x, nullptr, x, OUT_EULER, dtf, step);
-      fy->forward(cap2, B, y, nullptr, y, OUT_EULER, dtf, step);
+      both(split_main, s, B, x, x, y, y, OUT_EULER);
       join(s);
       launch_step_inc(step, s);
     });
