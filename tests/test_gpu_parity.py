@@ -332,6 +332,35 @@ def test_conv_row_spaces_agree_with_the_oracle(kind, synth, monkeypatch):
     assert maxabs(outs["2"], outs["0"]) <= TOL_FWD["fp16"] * scale
 
 
+@pytest.mark.parametrize("pair", ["mnist_svhn", "pair28"])
+def test_sm_split_between_the_chains_does_not_change_results(pair, synth, monkeypatch):
+    """Small-batch graphs give the two U-Net chains disjoint SM sets (sampler.cu, g_tc_cta_cap: a CTA cap on the persistent
+    conv launches).  A tile's arithmetic does not depend on which CTA walks it, so the pairs must be BIT-identical with the
+    rule (default), without it, and with a lopsided split where one chain's CTAs walk many tiles each."""
+    if pair == "pair28":
+        sds, shx, shy = (synth("unet_mnist28", 11), synth("unet_mnist28", 14), synth("ratio28", 21)), (1, 28, 28), (1, 28, 28)
+    else:
+        sds, shx, shy = (synth("unet_mnist32", 12), synth("unet_svhn", 13), synth("ratio_mnist_svhn", 22)), (1, 32, 32), (3, 32, 32)
+    B, N, steps = 96, 48, 4
+    g = torch.Generator().manual_seed(17)
+    x0, y0 = torch.randn(B, *shx, generator=g), torch.randn(B, *shy, generator=g)
+    m0, n0 = torch.randn(N, *shx, generator=g), torch.randn(N, *shy, generator=g)
+    outs = []
+    for env in ({}, {"RGFM_SPLIT_PRE": "0", "RGFM_SPLIT_MAIN": "0"}, {"RGFM_SPLIT_PRE": "5", "RGFM_SPLIT_MAIN": "141"}):
+        for k in ("RGFM_SPLIT_PRE", "RGFM_SPLIT_MAIN"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)  # read when the plan is built
+        plan = _lib.SamplerPlan(pair, *sds, guidance_method="mc_feng", guidance_strength=0.5, num_samples=B, num_steps=steps,
+                                mc_batch_size=N, precision="fp16", device=DEV)
+        x1, y1 = plan.run(x0.to(DEV), y0.to(DEV), m0.to(DEV), n0.to(DEV))
+        outs.append((x1.cpu(), y1.cpu()))
+        plan.close()
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
+    for x1, y1 in outs[1:]:
+        assert torch.equal(x1, outs[0][0]) and torch.equal(y1, outs[0][1])
+
+
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 @pytest.mark.parametrize("kind", ["unet_mnist32", "unet_svhn"])
 def test_unet_forward_bench_size(kind, prec, synth):
