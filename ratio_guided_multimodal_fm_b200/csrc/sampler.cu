@@ -240,14 +240,17 @@ struct Sampler {
     // It pays where that fixed cost is a large share of a launch, i.e. at small batches -- the MC pre-pass (N_mc = 256:
     // 205 -> 190 ms per call, plateau at 40..46 of 148 SMs for the MNIST32 chain = its share of the step's conv time; 36 or
     // 56 lose it again) -- and costs 0..4 % at B = 1024, where the launches are long (profiles/notes_r02.md section 14).
-    // Rule: graphs whose batch is at most 512 images are split, by the chains' share of the conv time (identical networks:
-    // half).  RGFM_SPLIT_PRE / RGFM_SPLIT_MAIN override the x chain's CTA count per graph family (0 = no split).
+    // Rule: identical networks (28x28 pair) are always split in half (a balanced split still gains 1.5..2 % at B = 1024 /
+    // 2048); the MNIST32-SVHN pair by the chains' share of the conv time when the batch is at most 768 images (B = 768:
+    // 548 -> 540 ms; B = 1024: 709 vs 714 ms).  RGFM_SPLIT_PRE / RGFM_SPLIT_MAIN override the x chain's CTA count per graph
+    // family (0 = no split).
     int num_sms = 148;
     RGFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, d.device));
     const bool tc_mode = d.precision != RGFM_PREC_FP32;
-    const int sx_rule = d.pair == RGFM_PAIR_MNIST_SVHN ? (num_sms * 2 + 3) / 7 : num_sms / 2;
-    const int split_pre = getenv("RGFM_SPLIT_PRE") ? atoi(getenv("RGFM_SPLIT_PRE")) : ((tc_mode && N <= 512) ? sx_rule : 0);
-    const int split_main = getenv("RGFM_SPLIT_MAIN") ? atoi(getenv("RGFM_SPLIT_MAIN")) : ((tc_mode && B <= 512) ? sx_rule : 0);
+    const bool twins = d.pair != RGFM_PAIR_MNIST_SVHN;
+    const int sx_rule = twins ? num_sms / 2 : (num_sms * 2 + 3) / 7;
+    const int split_pre = getenv("RGFM_SPLIT_PRE") ? atoi(getenv("RGFM_SPLIT_PRE")) : ((tc_mode && (twins || N <= 768)) ? sx_rule : 0);
+    const int split_main = getenv("RGFM_SPLIT_MAIN") ? atoi(getenv("RGFM_SPLIT_MAIN")) : ((tc_mode && (twins || B <= 768)) ? sx_rule : 0);
     auto both = [&](int sx, cudaStream_t s, int n, const float* xi, float* xo, const float* yi, float* yo, int mode) {
       const bool on = sx > 0 && sx < num_sms;
       g_tc_cta_cap = on ? sx : 0;
