@@ -12,8 +12,8 @@
 // stride-2 convs read them directly.  Stride-2 convolutions are computed at stride 1 and stored subsampled.
 //
 // Persistent kernel, one CTA per SM, static round-robin over super-tiles, 608 threads: warps 0..7 = two epilogue groups
-// (one per 128-row unit; TMEM lane quarter = warp & 3), warp 8 = TMA producer (one thread) + TMEM allocator, warps
-// 9..10 = MMA issuers (one thread each), warps 11..18 = transform group.  Weights are RESIDENT in shared memory when
+// (one per 128-row unit; TMEM lane quarter = warp & 3), warp 8 = TMA producer (one thread; it also initialises the barriers), warps
+// 9..10 = MMA issuers (one thread each; warp 9 allocates TMEM), warps 11..18 = transform group.  Weights are RESIDENT in shared memory when
 // they fit (loaded once per CTA), otherwise they stream through a two-stage ring; A tiles use 2..4 slots; TMEM
 // accumulators are double buffered when 4 * N <= 512 columns so the epilogue of tile i overlaps the MMAs of tile i + 1.
 // Fused GroupNorm + SiLU: a K segment may be a RAW activation with per-image {scale, shift} coefficients; the transform
@@ -525,6 +525,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __shared__ uint32_t tmem_slot;
 #ifdef RGFM_TC_TRACE
   __shared__ long long s_trace[8][12];
+  __shared__ long long s_tp[2];  // prologue end (after the block-wide barrier), resident weights landed
   const long long t_start = clock64();
 #endif
   __shared__ uint8_t s_rown[400];  // transform group: image (relative to the tile's first) of each A-tile row, 0xff = not a pixel
@@ -546,19 +547,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int SR = p.super_rows, UR = p.unit_rows;
   const int supers = (total_rows + SR - 1) / SR;
 
-  if (threadIdx.x == 0) {
+  // Barriers are initialised by the PRODUCER's own thread (warp 8, lane 0), which then leaves the block-wide barrier below
+  // with a non-blocking arrive and issues the launch's first operand load at once: the other 18 warps reach that barrier
+  // ~1350 cycles into the kernel and the producer's cold start (instruction and constant-cache misses of a role one
+  // thread walks) used to begin only there -- first TMA at ~3000 cycles (trace build; profiles/notes_r02.md section 15).
+  if (warp == 8 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB0)) : "memory");
-    if (p.nseg > 1) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA1)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB1)) : "memory");
-    }
-    if (p.nseg > 2) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
-    }
-    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
-    if (p.tma_store && DENSE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmZ)) : "memory");
     for (int s = 0; s < 4; ++s) {
       mbar_init(a_full(s), 1);
       mbar_init(a_empty(s), p.upt == 1 ? 1 : 2);   // both MMA warps (one-unit tiles: the tile's own MMA warp)
@@ -574,10 +569,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x == 0) {
+    if (p.nseg > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA1)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB1)) : "memory");
+    }
+    if (p.nseg > 2) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
+    }
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+    if (p.tma_store && DENSE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmZ)) : "memory");
+  }
   // Warp roles.  The hardware arbiter favours HIGHER warp ids, so the latency-critical single-thread roles sit at the
-  // top: warps 0..7 = two epilogue groups (TMEM lane quarter = warp & 3), warp 8 = TMA producer (+ TMEM allocator),
+  // top: warps 0..7 = two epilogue groups (TMEM lane quarter = warp & 3), warp 8 = TMA producer (+ barrier init),
   // warps 9, 10 = MMA issuers of the two accumulator halves.
-  if (warp == 8) {
+  if (warp == 9) {  // TMEM allocator = the first MMA warp (the producer has its first load to issue)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -588,19 +595,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   pdl_wait();
+  tc_fence_before();
+  // the producer warp arrives without waiting (its barriers are its own work and it never touches TMEM); everybody else
+  // needs the barriers and the TMEM address published
+  if (warp == 8) asm volatile("bar.arrive 0, %0;" ::"n"(TC_THREADS) : "memory");
+  else asm volatile("bar.sync 0, %0;" ::"n"(TC_THREADS) : "memory");
+  tc_fence_after();
+  const uint32_t tmem_d = warp == 8 ? 0u : tmem_slot;  // (the producer left the barrier early and never touches TMEM)
+#ifdef RGFM_TC_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) s_tp[0] = clock64() - t_start;
+#endif
   if (warp < 8) {
-    // bias + this step's time bias: identical for every tile of the launch (t is uniform over the batch)
+    // bias + this step's time bias: identical for every tile of the launch (t is uniform over the batch).  AFTER the
+    // block-wide barrier, among the epilogue warps only: the chain step -> time-bias row -> value is ~1500 cycles of
+    // dependent global loads, and the producer's first operand load used to wait for it at the barrier (the first
+    // accumulator is thousands of cycles away: the epilogue has the time).
     const float* tb = a.temb ? a.temb + (size_t)(a.step ? *a.step : 0) * a.temb_stride + a.temb_off : nullptr;
     for (int c = threadIdx.x; c < N; c += 256) {
       float b = a.bias[c];
       if (tb && c < a.Cout) b += tb[c];
       s_bias[c] = b;
     }
+    asm volatile("bar.sync 4, 256;" ::: "memory");
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = tmem_slot;
 
   if (warp == 8) {
     // ------------------------------- TMA producer -------------------------------
@@ -611,18 +628,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0) {
       uint32_t as = 0, aph = 0, bs = 0, bph = 0;
       const uint32_t a_slots = (uint32_t)p.a_slots;
-      if (p.resident) {  // every weight tile of the conv, once: (segment, channel block, tap) order
-        mbar_expect_tx(b_full(0), p.b_total);
-        uint32_t dst = smem_b;
-#pragma unroll 1
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          const CUtensorMap* tB = seg == 0 ? &tmB0 : (seg == 1 ? &tmB1 : &tmB2);
-#pragma unroll 1
-          for (int cb = 0; cb < p.cblocks[seg]; ++cb)
-#pragma unroll 1
-            for (int tap = 0; tap < p.ntaps[seg]; ++tap, dst += p.b_bytes) tma_load_3d(dst, tB, b_full(0), cb * 64, 0, tap);
-        }
-      }
+      // resident weights (every weight tile of the conv, once, (segment, channel block, tap) order) are requested right
+      // AFTER the launch's first operand tile: the transform group needs that tile long before the MMA warps need weights
+      bool want_w = p.resident != 0;
 #pragma unroll 1
       for (int sti = blockIdx.x; sti < supers; sti += gridDim.x) {
         const int st = p.descend ? supers - 1 - sti : sti;  // see TcArgs::descend
@@ -664,6 +672,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               as = 0u;
               aph ^= 1u;
             }
+            if (want_w) {
+              want_w = false;
+              mbar_expect_tx(b_full(0), p.b_total);
+              uint32_t dst = smem_b;
+#pragma unroll 1
+              for (int sg = 0; sg < p.nseg; ++sg) {
+                const CUtensorMap* tW = sg == 0 ? &tmB0 : (sg == 1 ? &tmB1 : &tmB2);
+#pragma unroll 1
+                for (int c2 = 0; c2 < p.cblocks[sg]; ++c2)
+#pragma unroll 1
+                  for (int tap = 0; tap < p.ntaps[sg]; ++tap, dst += p.b_bytes) tma_load_3d(dst, tW, b_full(0), c2 * 64, 0, tap);
+              }
+            }
             if (p.resident) continue;
 #pragma unroll 1
             for (int tap = 0; tap < ntp; tap += tps) {
@@ -702,6 +723,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (resident) {
         mbar_wait(b_full(0), 0u);
         tc_fence_after();
+#ifdef RGFM_TC_TRACE
+        if (blockIdx.x == 0 && hf == 0) s_tp[1] = clock64() - t_start;
+#endif
       }
       const bool upt1 = p.upt == 1;
       const uint32_t a_unit = upt1 ? 0u : hf * ((uint32_t)UR * 128u);  // this warp's rows inside the A tile
@@ -1462,6 +1486,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     printf("TRACE nmma=%d nstk=%d nseg=%d cblocks=%d taps=%d resident=%d a_slots=%d supers=%d xform=%d end=%lld\n",
            p.nmma, p.nstk, p.nseg, p.cblocks[0], p.ntaps[0], p.resident, p.a_slots, supers, p.any_xform, clock64() - t_start);
+    printf("  prologue end %lld, resident weights landed %lld, dense=%d\n", s_tp[0], p.resident ? s_tp[1] : 0ll, (int)DENSE);
     for (int i = 0; i < 12 && blockIdx.x + i * gridDim.x < supers; ++i)
       printf("  st%2d prodA %7lld | xform wake %7lld done %7lld | mma a_ready %7lld committed %7lld | epi tmem_full %7lld stored %7lld done %7lld\n", i,
              s_trace[0][i], s_trace[4][i], s_trace[5][i], s_trace[1][i], s_trace[2][i], s_trace[3][i], s_trace[6][i], s_trace[7][i]);
@@ -1469,7 +1494,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #endif
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols) : "memory");
   }
