@@ -28,6 +28,8 @@ void ratio_trainer_destroy(rgfm_ratio_trainer*);
 void launch_ratio_loss(const float*, const float*, int, int, float, float*, float*, cudaStream_t);
 void launch_cfm_interp(const float*, const float*, const float*, int, size_t, float*, float*, cudaStream_t);
 void launch_fm_mse(const float*, const float*, size_t, float*, float*, float*, cudaStream_t);
+void conv3x3_forward(const float*, int, int, int, int, const float*, const float*, int, int, float*, cudaStream_t);
+void conv3x3_backward(const float*, const float*, int, int, int, int, const float*, int, int, float*, float*, float*, cudaStream_t);
 }  // namespace rgfm
 
 static thread_local std::string g_err;
@@ -368,6 +370,24 @@ int rgfm_fm_mse_loss(const float* v, const float* u, int64_t n, float* loss, flo
   RGFM_CHECK(v && u && loss && scratch && n >= 1, "rgfm_fm_mse_loss: null argument");
   set_device_of(v);
   rgfm::launch_fm_mse(v, u, (size_t)n, loss, dv, scratch, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_conv3x3_forward(const float* x, int32_t n, int32_t H, int32_t W, int32_t Cin, const float* w, const float* bias, int32_t Cout,
+                         int32_t stride, float* y, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(x && w && y, "rgfm_conv3x3_forward: null argument");
+  set_device_of(x);
+  rgfm::conv3x3_forward(x, n, H, W, Cin, w, bias, Cout, stride, y, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_conv3x3_backward(const float* x, const float* dy, int32_t n, int32_t H, int32_t W, int32_t Cin, const float* w, int32_t Cout,
+                          int32_t stride, float* dx, float* dw, float* db, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(dy, "rgfm_conv3x3_backward: null argument");
+  set_device_of(dy);
+  rgfm::conv3x3_backward(x, dy, n, H, W, Cin, w, Cout, stride, dx, dw, db, (cudaStream_t)stream);
   RGFM_API_END
 }
 

@@ -1013,6 +1013,203 @@ class RatioTrainer {
   }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Convolution ops for the flow-matching training step (flow_utils.py:103-156 trains the U-Nets of
+// unet.py / unet_flexible.py): forward, input gradient, weight gradient and bias gradient of nn.Conv2d(k = 3, padding = 1,
+// stride 1 or 2) on dense fp32 NHWC tensors (torch "channels_last" memory) with the weight in torch's own
+// [Cout][Cin][3][3] layout, so that a torch.autograd.Function can hand over its tensors as they are (fm_train.py).
+// The same kernels as the ratio trainer: conv_simt_kernel for the forward and -- on the flipped / transposed filter --
+// the input gradient, conv_wgrad_kernel + a fixed-order reduction for dW, colsum_kernel for db.  A stride-2 conv
+// (Downsample, unet.py:99-107) is differentiated on the full-resolution grid: its output gradient with zeros inserted
+// at the odd positions turns both gradients into those of a stride-1 conv.  Scratch is stream-ordered
+// (cudaMallocAsync / cudaFreeAsync: the driver's pool, no synchronisation).  Exact fp32, deterministic.
+// ------------------------------------------------------------------------------------------------
+__global__ void pad_channels_kernel(const float* __restrict__ src, int Cs, float* __restrict__ dst, int Cd, size_t rows) {
+  const size_t total = rows * (size_t)Cd;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / Cd;
+    const int c = (int)(i - r * Cd);
+    dst[i] = c < Cs ? src[r * Cs + c] : 0.f;
+  }
+}
+// dst[n][2h][2w][c] = src[n][h][w][c] (c < Cs), zeros elsewhere; dst is [n][2 Ho][2 Wo][Cd]
+__global__ void zero_insert_kernel(const float* __restrict__ src, int Ho, int Wo, int Cs, float* __restrict__ dst, int Cd, int nimg) {
+  const int H = 2 * Ho, W = 2 * Wo;
+  const size_t total = (size_t)nimg * H * W * Cd;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cd);
+    size_t q = i / Cd;
+    const int w = (int)(q % W);
+    q /= W;
+    const int h = (int)(q % H);
+    const int n = (int)(q / H);
+    float v = 0.f;
+    if (c < Cs && !(h & 1) && !(w & 1)) v = src[(((size_t)n * Ho + (h >> 1)) * Wo + (w >> 1)) * Cs + c];
+    dst[i] = v;
+  }
+}
+// forward filter wf[tap][ci][co] (ci < CinP, co < CoutP, zero padded)
+__global__ void repack_w_fwd_kernel(const float* __restrict__ w, int cout, int cin, int CinP, int CoutP, float* __restrict__ wf) {
+  const int total = 9 * CinP * CoutP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % CoutP, ci = (i / CoutP) % CinP, t = i / (CoutP * CinP);
+    wf[i] = (co < cout && ci < cin) ? w[((size_t)co * cin + ci) * 9 + t] : 0.f;
+  }
+}
+// input-gradient filter wb[tap][co][ci] = W[co][ci][8 - tap] (co < CoutK rows = the dgrad conv's K, ci < CinB its output channels)
+__global__ void repack_w_bwd_kernel(const float* __restrict__ w, int cout, int cin, int CoutK, int CinB, float* __restrict__ wb) {
+  const int total = 9 * CoutK * CinB;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % CinB, co = (i / CinB) % CoutK, t = i / (CinB * CoutK);
+    wb[i] = (co < cout && ci < cin) ? w[((size_t)co * cin + ci) * 9 + (8 - t)] : 0.f;
+  }
+}
+// like conv_wgrad_reduce_kernel with a padded channel stride of the partials (CoutS >= cout)
+__global__ void conv_wgrad_reduce_padded_kernel(const float* __restrict__ part, int nsplit, int CinP, int CoutS, int cin, int cout,
+                                                float* __restrict__ dW) {
+  const int total = cout * cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cout, ci = (i / cout) % cin, t = i / (cout * cin);
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += part[(((size_t)k * 9 + t) * CinP + ci) * CoutS + co];
+    dW[((size_t)co * cin + ci) * 9 + t] = s;
+  }
+}
+
+namespace {
+struct StreamScratch {  // stream-ordered scratch of one op call
+  cudaStream_t s;
+  std::vector<void*> ptrs;
+  explicit StreamScratch(cudaStream_t st) : s(st) {}
+  float* get(size_t floats) {
+    void* p = nullptr;
+    RGFM_CUDA(cudaMallocAsync(&p, std::max<size_t>(floats, 4) * sizeof(float), s));
+    ptrs.push_back(p);
+    return (float*)p;
+  }
+  ~StreamScratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, s);
+  }
+};
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline unsigned blocks_for(size_t n) { return (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16); }
+}  // namespace
+
+void conv3x3_forward(const float* x, int n, int H, int W, int Cin, const float* w, const float* bias, int Cout, int stride, float* y,
+                     cudaStream_t s) {
+  RGFM_CHECK(x && w && y && n >= 1 && H >= 1 && W >= 1 && Cin >= 1 && Cout >= 1, "rgfm_conv3x3_forward: bad argument");
+  RGFM_CHECK(stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0), "rgfm_conv3x3_forward: stride 1, or stride 2 on even sizes");
+  StreamScratch sc(s);
+  const int CinP = round_up(Cin, 16), CoutP = round_up(Cout, 32);
+  const float* xp = x;
+  if (CinP != Cin) {
+    float* t = sc.get((size_t)n * H * W * CinP);
+    pad_channels_kernel<<<blocks_for((size_t)n * H * W * CinP), 256, 0, s>>>(x, Cin, t, CinP, (size_t)n * H * W);
+    post_launch_t("pad_channels");
+    xp = t;
+  }
+  float* wf = sc.get((size_t)9 * CinP * CoutP);
+  repack_w_fwd_kernel<<<blocks_for((size_t)9 * CinP * CoutP), 256, 0, s>>>(w, Cout, Cin, CinP, CoutP, wf);
+  post_launch_t("repack_w_fwd");
+  float* bp = sc.get(CoutP);
+  if (bias) {
+    pad_vec_kernel<<<(CoutP + 255) / 256, 256, 0, s>>>(bias, Cout, CoutP, bp);
+    post_launch_t("pad_vec");
+  } else {
+    RGFM_CUDA(cudaMemsetAsync(bp, 0, CoutP * sizeof(float), s));
+  }
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  ConvArgs a{};
+  a.in = xp; a.Hin = H; a.Win = W; a.Cin = CinP;
+  a.w = wf; a.bias = bp;
+  a.CoutP = CoutP; a.Cout = Cout; a.ks = 3; a.stride = stride; a.pad = 1;
+  a.g = make_geom(Ho, Wo);
+  a.nimg = n; a.out_mode = OUT_RAW; a.out = y;
+  launch_conv_simt(a, s);
+}
+
+void conv3x3_backward(const float* x, const float* dy, int n, int H, int W, int Cin, const float* w, int Cout, int stride, float* dx,
+                      float* dw, float* db, cudaStream_t s) {
+  RGFM_CHECK(dy && n >= 1 && H >= 1 && W >= 1 && Cin >= 1 && Cout >= 1, "rgfm_conv3x3_backward: bad argument");
+  RGFM_CHECK(stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0), "rgfm_conv3x3_backward: stride 1, or stride 2 on even sizes");
+  RGFM_CHECK((!dw || x) && (!dx || w), "rgfm_conv3x3_backward: dw needs x, dx needs w");
+  StreamScratch sc(s);
+  const int Ho = H / stride, Wo = W / stride;
+  const size_t rows_o = (size_t)n * Ho * Wo, rows = (size_t)n * H * W;
+  if (db) {  // bias gradient: column sums of dy in a fixed two-stage order
+    int splits = (int)std::min<size_t>(64, (rows_o + 63) / 64);
+    const int rps = (int)((rows_o + splits - 1) / splits);
+    splits = (int)((rows_o + rps - 1) / rps);
+    if (splits == 1) {
+      colsum_kernel<<<dim3((Cout + 31) / 32, 1), 256, 0, s>>>(dy, Cout, Cout, (long long)rows_o, rps, db);
+    } else {
+      float* tmp = sc.get((size_t)splits * Cout);
+      colsum_kernel<<<dim3((Cout + 31) / 32, splits), 256, 0, s>>>(dy, Cout, Cout, (long long)rows_o, rps, tmp);
+      colsum_kernel<<<dim3((Cout + 31) / 32, 1), 256, 0, s>>>(tmp, Cout, Cout, splits, splits, db);
+    }
+    post_launch_t("colsum");
+  }
+  if (!dw && !dx) return;
+  // the output gradient on the full-resolution grid, channels padded to a multiple of 16 (the dgrad conv's K, float4 loads of wgrad)
+  const int CoQ = round_up(Cout, 16);
+  const float* g = dy;
+  if (stride == 2) {
+    float* t = sc.get(rows * CoQ);
+    zero_insert_kernel<<<blocks_for(rows * CoQ), 256, 0, s>>>(dy, Ho, Wo, Cout, t, CoQ, n);
+    post_launch_t("zero_insert");
+    g = t;
+  } else if (CoQ != Cout) {
+    float* t = sc.get(rows * CoQ);
+    pad_channels_kernel<<<blocks_for(rows * CoQ), 256, 0, s>>>(dy, Cout, t, CoQ, rows);
+    post_launch_t("pad_channels");
+    g = t;
+  }
+  if (dw) {
+    const int CinP = round_up(Cin, 16);
+    const float* xp = x;
+    if (CinP != Cin) {
+      float* t = sc.get(rows * CinP);
+      pad_channels_kernel<<<blocks_for(rows * CinP), 256, 0, s>>>(x, Cin, t, CinP, rows);
+      post_launch_t("pad_channels");
+      xp = t;
+    }
+    const int tci = CinP % 64 == 0 ? 64 : (CinP % 32 == 0 ? 32 : 16);
+    const int tiles = (CinP / tci) * ((CoQ + 63) / 64);
+    const int RB = std::max(1, std::min(H, 32 / std::max(1, W)));  // rows per unit: about 32 pixels
+    const int units = n * ((H + RB - 1) / RB);
+    int splits = std::max(1, std::min(units, (148 * 3 + tiles - 1) / tiles));
+    const int ups = (units + splits - 1) / splits;
+    splits = (units + ups - 1) / ups;
+    const size_t smem = ((size_t)(RB + 2) * (W + 2) * tci + (size_t)RB * W * 64) * sizeof(float);
+    RGFM_CHECK(smem <= 48 * 1024, "rgfm_conv3x3_backward: image too wide for the weight-gradient tile");
+    float* part = sc.get((size_t)splits * 9 * CinP * CoQ);
+    dim3 grid(tiles, splits);
+    if (tci == 64) conv_wgrad_kernel<4><<<grid, 256, smem, s>>>(xp, CinP, g, CoQ, H, W, RB, n, ups, part);
+    else if (tci == 32) conv_wgrad_kernel<2><<<grid, 256, smem, s>>>(xp, CinP, g, CoQ, H, W, RB, n, ups, part);
+    else conv_wgrad_kernel<1><<<grid, 256, smem, s>>>(xp, CinP, g, CoQ, H, W, RB, n, ups, part);
+    post_launch_t("conv_wgrad");
+    const int total = Cout * Cin * 9;
+    conv_wgrad_reduce_padded_kernel<<<std::min((total + 255) / 256, 2048), 256, 0, s>>>(part, splits, CinP, CoQ, Cin, Cout, dw);
+    post_launch_t("conv_wgrad_reduce");
+  }
+  if (dx) {
+    const int CinB = round_up(Cin, 32);
+    float* wb = sc.get((size_t)9 * CoQ * CinB);
+    repack_w_bwd_kernel<<<blocks_for((size_t)9 * CoQ * CinB), 256, 0, s>>>(w, Cout, Cin, CoQ, CinB, wb);
+    post_launch_t("repack_w_bwd");
+    float* zb = sc.get(CinB);
+    RGFM_CUDA(cudaMemsetAsync(zb, 0, CinB * sizeof(float), s));
+    ConvArgs a{};
+    a.in = g; a.Hin = H; a.Win = W; a.Cin = CoQ;
+    a.w = wb; a.bias = zb;
+    a.CoutP = CinB; a.Cout = Cin; a.ks = 3; a.stride = 1; a.pad = 1;
+    a.g = make_geom(H, W);
+    a.nimg = n; a.out_mode = OUT_RAW; a.out = dx;
+    launch_conv_simt(a, s);
+  }
+}
+
 }  // namespace rgfm
 
 // ---- C ABI (include/rgfm.h) ----

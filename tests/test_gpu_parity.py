@@ -929,3 +929,126 @@ def test_ratio_train_step_at_training_batch_size(kind, loss_type, synth):
             tight = any(t in k for t in ("conv4", "fc.", "score_net", "gn4", "bn4"))
             assert rel <= (2e-5 if tight else 5e-3), (B, k, rel)
     plan.close()
+
+
+# ---- flow-matching training step (FM side): 3x3 convs forward / dgrad / wgrad on the library ----
+CONV_CASES = [  # (n, Cin, Cout, H, W, stride)
+    (3, 1, 32, 28, 28, 1), (2, 3, 64, 32, 32, 1), (2, 32, 32, 32, 32, 2), (3, 64, 64, 14, 14, 2), (2, 96, 32, 16, 16, 1),
+    (2, 192, 64, 8, 8, 1), (4, 64, 128, 7, 7, 1), (2, 32, 1, 28, 28, 1), (2, 64, 3, 32, 32, 1), (1, 128, 128, 16, 16, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3x3_ops_against_float64_autograd(case):
+    """rgfm_conv3x3_forward / _backward (fm_train.conv3x3) vs F.conv2d + autograd in float64 on the CPU: output, input
+    gradient, weight gradient, bias gradient; channel counts that need padding (1, 3, 96), stride 2, odd sizes (7)."""
+    from ratio_guided_multimodal_fm_b200.fm_train import conv3x3
+    n, cin, cout, H, W, stride = case
+    g = torch.Generator().manual_seed(sum(case))
+    x, w, b = torch.randn(n, cin, H, W, generator=g), torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5), torch.randn(cout, generator=g)
+    dy = torch.randn(n, cout, H // stride, W // stride, generator=g)
+    xd, wd, bd = (t.double().requires_grad_() for t in (x, w, b))
+    yr = torch.nn.functional.conv2d(xd, wd, bd, stride=stride, padding=1)
+    yr.backward(dy.double())
+    xg, wg, bg = (t.to(DEV).requires_grad_() for t in (x, w, b))
+    y = conv3x3(xg, wg, bg, stride)
+    y.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    for name, got, ref in (("y", y, yr), ("dx", xg.grad, xd.grad), ("dw", wg.grad, wd.grad), ("db", bg.grad, bd.grad)):
+        ref = ref.detach().float()
+        rel = ((got.detach().cpu().float() - ref).norm() / ref.norm()).item()
+        assert rel <= 2e-6, (case, name, rel)
+    # bias-free, and no input gradient wanted (the U-Net's input conv)
+    y2 = conv3x3(x.to(DEV), wg, None, stride)
+    assert maxabs(y2, (yr - bd.view(1, -1, 1, 1)).detach().float()) <= 1e-4
+
+
+@pytest.mark.parametrize("kind", ["unet_mnist28", "unet_mnist32", "unet_svhn"])
+def test_flow_matching_step_grads(kind, synth):
+    """loss = F.mse_loss(model(x_t, t), u) and loss.backward() (flow_utils.py:139-147) with every 3x3 convolution of the
+    U-Net on the library (fm_train.library_convs over the module tree of the reference) vs autograd through the CPU
+    oracle: loss and every parameter gradient, per-sample times."""
+    from oracle.unet_module import UNet, fm_loss_and_grads  # checker / test infrastructure
+    from ratio_guided_multimodal_fm_b200.fm_train import library_convs, fm_mse
+    sd = synth(kind, 12)
+    c, hw = (3, 32) if kind == "unet_svhn" else (1, 28 if kind == "unet_mnist28" else 32)
+    B = 6
+    g = torch.Generator().manual_seed(31)
+    x_t, t, u = torch.randn(B, c, hw, hw, generator=g), torch.rand(B, generator=g), torch.randn(B, c, hw, hw, generator=g)
+    oloss, ograds = fm_loss_and_grads(sd, kind, x_t, t, u)
+    model = UNet(kind).eval()  # eval: dropout off (its masks are torch's own random stream, not part of the parity claim)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV)
+    # the stock-PyTorch remainder (1x1 skip convs through cuDNN, the time MLP's Linears through cuBLAS) in exact fp32 too:
+    # cuDNN's default lets 1x1 convs run in TF32, which alone puts the deep gradients 1e-4 away from float64
+    old_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with library_convs(model) as nconv:
+            v = model(x_t.to(DEV), t.to(DEV))
+            loss = fm_mse(v, u.to(DEV))
+            loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    assert nconv == sum(1 for k in sd if k.endswith("weight") and sd[k].dim() == 4 and sd[k].shape[-1] == 3)
+    assert abs(loss.item() - oloss.item()) <= 1e-5 * max(1.0, abs(oloss.item())), (loss.item(), oloss.item())
+    # Yardstick: the same gradients in float64.  Two fp32 evaluations of a 30-conv network differ by their summation orders;
+    # the bound is relative L2 <= 1e-3 against float64 and no more than 4x as far from it as the fp32 oracle (= the
+    # reference's own arithmetic) is itself.
+    _, egrads = fm_loss_and_grads(sd, kind, x_t, t, u, dtype=torch.float64)
+    worst = worst_ref = 0.0
+    for k, p in model.named_parameters():
+        exact = egrads[k]
+        rel = ((p.grad.cpu().double() - exact).norm() / exact.norm().clamp_min(1e-30)).item()
+        rel_ref = ((ograds[k].double() - exact).norm() / exact.norm().clamp_min(1e-30)).item()
+        worst, worst_ref = max(worst, rel), max(worst_ref, rel_ref)
+        assert rel <= 1e-3 and rel <= 4.0 * rel_ref + 2e-5, (k, rel, rel_ref)
+    print(f"fm step {kind}: loss {loss.item():.6f} (oracle {oloss.item():.6f}); worst relative L2 against float64 over {len(ograds)} "
+          f"parameter gradients: library {worst:.2e}, fp32 oracle {worst_ref:.2e}")
+
+
+def test_train_flow_matching_epoch_dropin(synth):
+    """train_flow_matching_epoch (mirror of flow_utils.py:103-156) for two batches in TRAINING mode (dropout 0.1) vs the same
+    loop written with stock PyTorch on a copy of the module: same seed -> same t, prior draw and dropout masks (both paths
+    consume torch's CUDA generator identically), so the losses and the updated parameters must agree to fp32 rounding."""
+    import copy
+    from oracle.unet_module import UNet
+    from ratio_guided_multimodal_fm_b200 import CFMSchedule
+    from ratio_guided_multimodal_fm_b200.fm_train import train_flow_matching_epoch
+    kind = "unet_mnist28"
+    model = UNet(kind)
+    model.load_state_dict(synth(kind, 12), strict=True)
+    model = model.to(DEV)
+    twin = copy.deepcopy(model)
+    g = torch.Generator().manual_seed(3)
+    data = [{"x": torch.randn(8, 1, 28, 28, generator=g), "y": torch.zeros(8, 1, 28, 28)} for _ in range(2)]
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    # TF32 off for the stock-PyTorch parts of BOTH loops (cuDNN's default lets its convs run in TF32)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(1234)
+        avg = train_flow_matching_epoch(model, data, opt, CFMSchedule(), DEV, modality="x")
+        # stock loop (flow_utils.py:127-153) on the twin
+        topt = torch.optim.SGD(twin.parameters(), lr=0.05)
+        twin.train()
+        torch.manual_seed(1234)
+        tot = 0.0
+        for batch in data:
+            x_1 = batch["x"].to(DEV)
+            t = torch.rand(x_1.shape[0], device=DEV)
+            x_0 = torch.randn_like(x_1)
+            tb = t.view(-1, 1, 1, 1)
+            x_t, u = (1 - tb) * x_0 + tb * x_1, x_1 - x_0
+            loss = torch.nn.functional.mse_loss(twin(x_t, t), u)
+            topt.zero_grad()
+            loss.backward()
+            topt.step()
+            tot += loss.item()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert abs(avg - tot / 2) <= 2e-5 * max(1.0, abs(tot / 2)), (avg, tot / 2)
+    for (k, p), (_, q) in zip(model.named_parameters(), twin.named_parameters()):
+        assert maxabs(p, q) <= 5e-5 * max(1.0, q.abs().max().item()), k
+    assert not any("forward" in c.__dict__ for c in model.modules())

@@ -108,3 +108,23 @@ def test_inverse_transforms_are_the_reference_pixel_permutations():
            "none": lambda t: t}
     for name, f in ref.items():
         assert torch.allclose(get_inverse_transform(name)(img), f(img), atol=0), name
+
+
+def test_library_convs_reroutes_exactly_the_3x3_convs_and_restores_them():
+    """fm_train.library_convs: host logic only (no CUDA call is made): the 3x3 / padding-1 convs of the module tree are
+    rerouted inside the block and back on nn.Conv2d.forward after it; 1x1 skip convs are left alone; CPU tensors are refused."""
+    import torch.nn as nn
+    from oracle.unet_module import UNet  # test infrastructure: the reference's module tree
+    from ratio_guided_multimodal_fm_b200 import fm_train, _lib
+    m = UNet("unet_mnist28")
+    n3 = sum(1 for c in m.modules() if isinstance(c, nn.Conv2d) and c.kernel_size == (3, 3))
+    n1 = sum(1 for c in m.modules() if isinstance(c, nn.Conv2d) and c.kernel_size == (1, 1))
+    assert n3 == 28 and n1 == 7  # input, 12 ResBlocks x 2, downsample, upsample, out; 7 channel-changing skips (1 encoder, 6 decoder)
+    with fm_train.library_convs(m) as count:
+        assert count == n3
+        assert all(("forward" in c.__dict__) == (c.kernel_size == (3, 3)) for c in m.modules() if isinstance(c, nn.Conv2d))
+        with pytest.raises(_lib.RgfmError):
+            m(torch.zeros(1, 1, 28, 28), torch.zeros(1))  # CPU tensors: no fallback
+    assert not any("forward" in c.__dict__ for c in m.modules())
+    v = m.eval()(torch.zeros(1, 1, 28, 28), torch.zeros(1))  # stock path works again
+    assert v.shape == (1, 1, 28, 28)

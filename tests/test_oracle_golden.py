@@ -132,3 +132,25 @@ def test_guidance_is_convex_blend_and_skipped_at_t0(synth):
     assert torch.allclose(a[0], b[0], atol=1e-5) and torch.allclose(a[1], b[1], atol=1e-5)
     assert torch.equal(c[0], b[0]) and torch.equal(c[1], b[1])
     assert torch.equal(one[0], one_plain[0])
+
+
+@pytest.mark.parametrize("kind", ["unet_mnist28", "unet_svhn"])
+def test_unet_module_restatement_matches_functional_oracle(kind, synth):
+    """oracle/unet_module.py (the module tree the flow-matching training tests reroute) against O.unet_forward, which
+    oracle/make_golden.py pins to the live reference: forward and every parameter gradient of the FM loss."""
+    from oracle.unet_module import UNet, fm_loss_and_grads
+    sd = synth(kind, 12)
+    m = UNet(kind).eval()
+    m.load_state_dict(sd, strict=True)
+    c, hw = (3, 32) if kind == "unet_svhn" else (1, 28)
+    g = torch.Generator().manual_seed(4)
+    x, t, u = torch.randn(2, c, hw, hw, generator=g), torch.rand(2, generator=g), torch.randn(2, c, hw, hw, generator=g)
+    v = m(x, t)
+    close(v.detach(), O.unet_forward(sd, kind, x, t))
+    loss = torch.nn.functional.mse_loss(v, u)
+    loss.backward()
+    oloss, ograds = fm_loss_and_grads(sd, kind, x, t, u)
+    close(loss.detach(), oloss)
+    assert set(ograds) == {k for k, _ in m.named_parameters()}
+    for k, p in m.named_parameters():
+        close(p.grad, ograds[k], tol=TOL * max(1.0, ograds[k].abs().max().item()))
