@@ -329,7 +329,65 @@ def train_step_numbers(dev):
         res[kind] = dict(loss_type=loss, e2e_ms=1e3 * e2e, device_ms=1e3 * s, pairs_per_s=TRAIN_B / e2e, loss=m["loss"],
                          finite=bool(np.isfinite(m["loss"])))
         plan.close()
+    res["flow_matching"] = fm_step_numbers(dev)
     return res
+
+
+def fm_step_numbers(dev):
+    """Flow-matching step of the U-Nets (flow_utils.py:127-153: t, add_noise, model, MSE, backward, Adam), batch 128, dropout
+    on: every 3x3 convolution (forward, input / weight / bias gradient) on the library's exact-fp32 kernels
+    (fm_train.fm_step), beside the same step in stock PyTorch on the same GPU (cuDNN, TF32 allowed = its default, and off)."""
+    import copy
+    import torch.nn.functional as F
+    from oracle import ref_loader  # the subject of both arms is the reference's OWN module when its tree travelled (oracle/_ref)
+    from ratio_guided_multimodal_fm_b200 import CFMSchedule, synthetic as S
+    from ratio_guided_multimodal_fm_b200.fm_train import fm_step
+    ns = ref_loader.load()
+
+    def make(kind):
+        if ns is not None:
+            return ns.classes[kind](), "reference class (oracle/_ref)"
+        from oracle.unet_module import UNet  # the same module tree restated (test infrastructure)
+        return UNet(kind), "oracle.unet_module restatement"
+    sched = CFMSchedule()
+    out = dict(workload=f"flow-matching step, batch {TRAIN_B}, Adam lr 1e-4, dropout 0.1; 3x3 convs on the library (exact fp32 CUDA-core "
+                        "kernels), GroupNorm / SiLU / 1x1 skips / time MLP stock PyTorch")
+    for kind in ("unet_mnist32", "unet_svhn"):
+        c = 3 if kind == "unet_svhn" else 1
+        base, what = make(kind)
+        base.load_state_dict(S.state_dict(kind, 12), strict=True)
+        x_1 = torch.randn(TRAIN_B, c, 32, 32, device=dev)
+        r = {"module": what}
+        tf32 = torch.backends.cudnn.allow_tf32
+        try:
+            for name in ("library_ms", "same_gpu_stock_pytorch_ms", "same_gpu_stock_pytorch_tf32_off_ms"):
+                m = copy.deepcopy(base).to(dev).train()
+                opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+                torch.backends.cudnn.allow_tf32 = name != "same_gpu_stock_pytorch_tf32_off_ms"
+
+                def step():
+                    opt.zero_grad()
+                    if name == "library_ms":
+                        loss = fm_step(m, x_1, sched)
+                    else:
+                        t = torch.rand(TRAIN_B, device=dev)
+                        x_t, u = sched.add_noise(x_1, t)
+                        loss = F.mse_loss(m(x_t, t), u)
+                        loss.backward()
+                    opt.step()
+                    return loss
+                for _ in range(3):
+                    loss = step()
+                sec, _ = _timed(step, reps=5)
+                r[name] = 1e3 * sec
+                if name == "library_ms":
+                    r["loss"] = float(loss.item())
+                    r["finite"] = bool(np.isfinite(r["loss"]))
+                    r["images_per_s"] = TRAIN_B / sec
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+        out[kind] = r
+    return out
 
 
 def other_configs(dev, world, rank, prec, dist, gather_pairs):

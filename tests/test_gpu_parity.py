@@ -1052,3 +1052,36 @@ def test_train_flow_matching_epoch_dropin(synth):
     for (k, p), (_, q) in zip(model.named_parameters(), twin.named_parameters()):
         assert maxabs(p, q) <= 5e-5 * max(1.0, q.abs().max().item()), k
     assert not any("forward" in c.__dict__ for c in model.modules())
+
+
+def test_fm_step_on_the_reference_module_object(synth):
+    """The same step on the UNMODIFIED reference class (FlowMatchingUNetSVHN from oracle/_ref, when the reference tree
+    travelled with the snapshot): library_convs reroutes its own nn.Conv2d children; gradients vs the float64 oracle."""
+    from oracle import ref_loader
+    from oracle.unet_module import fm_loss_and_grads
+    from ratio_guided_multimodal_fm_b200.fm_train import library_convs, fm_mse
+    ns = ref_loader.load()
+    if ns is None:
+        pytest.skip("no reference tree on this box (oracle/_ref is built by __graft_entry__.build() where /root/reference exists)")
+    kind = "unet_svhn"
+    sd = synth(kind, 12)
+    model = ns.classes[kind]()
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    g = torch.Generator().manual_seed(9)
+    x_t, t, u = torch.randn(4, 3, 32, 32, generator=g), torch.rand(4, generator=g), torch.randn(4, 3, 32, 32, generator=g)
+    old_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with library_convs(model) as nconv:
+            loss = fm_mse(model(x_t.to(DEV), t.to(DEV)), u.to(DEV))
+            loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    assert nconv == 40  # input, 17 ResBlocks x 2, 2 downsamplers, 2 upsamplers, out (SURVEY.md Appendix A.2)
+    eloss, egrads = fm_loss_and_grads(sd, kind, x_t, t, u, dtype=torch.float64)
+    assert abs(loss.item() - eloss.item()) <= 1e-5 * max(1.0, abs(eloss.item()))
+    for k, p in model.named_parameters():
+        rel = ((p.grad.cpu().double() - egrads[k]).norm() / egrads[k].norm().clamp_min(1e-30)).item()
+        assert rel <= 1e-4, (k, rel)
