@@ -598,8 +598,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_before();
   // the producer warp arrives without waiting (its barriers are its own work and it never touches TMEM); everybody else
   // needs the barriers and the TMEM address published
-  if (warp == 8) asm volatile("bar.arrive 0, %0;" ::"n"(TC_THREADS) : "memory");
-  else asm volatile("bar.sync 0, %0;" ::"n"(TC_THREADS) : "memory");
+  // (named barrier 5, not barrier 0: the kernel's closing __syncthreads() must never be able to count towards this one)
+  if (warp == 8) asm volatile("bar.arrive 5, %0;" ::"n"(TC_THREADS) : "memory");
+  else asm volatile("bar.sync 5, %0;" ::"n"(TC_THREADS) : "memory");
   tc_fence_after();
   const uint32_t tmem_d = warp == 8 ? 0u : tmem_slot;  // (the producer left the barrier early and never touches TMEM)
 #ifdef RGFM_TC_TRACE

@@ -361,6 +361,31 @@ def test_sm_split_between_the_chains_does_not_change_results(pair, synth, monkey
         assert torch.equal(x1, outs[0][0]) and torch.equal(y1, outs[0][1])
 
 
+def test_large_batch_chunking_does_not_change_results(synth):
+    """Batches of 2048 pairs and more run 2048 images per conv launch by default (1024 below): B = 2080 -- one full chunk and
+    a ragged one -- must give the same bits with chunk 1024 (three launches per layer) and the default, and rows of it must
+    match the same rows run alone (samples are independent given the bank)."""
+    sds = (synth("unet_mnist32", 12), synth("unet_svhn", 13), synth("ratio_mnist_svhn", 22))
+    B, N, steps = 2080, 32, 2
+    g = torch.Generator().manual_seed(27)
+    x0, y0 = torch.randn(B, 1, 32, 32, generator=g), torch.randn(B, 3, 32, 32, generator=g)
+    m0, n0 = torch.randn(N, 1, 32, 32, generator=g), torch.randn(N, 3, 32, 32, generator=g)
+    outs = []
+    for chunk in (0, 1024):
+        plan = _lib.SamplerPlan("mnist_svhn", *sds, guidance_method="mc_feng", guidance_strength=0.5, num_samples=B, num_steps=steps,
+                                mc_batch_size=N, precision="fp16", device=DEV, chunk=chunk)
+        x1, y1 = plan.run(x0.to(DEV), y0.to(DEV), m0.to(DEV), n0.to(DEV))
+        outs.append((x1.cpu(), y1.cpu()))
+        plan.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    rows = torch.tensor([0, 1023, 1024, 2047, 2048, 2079])
+    small = _lib.SamplerPlan("mnist_svhn", *sds, guidance_method="mc_feng", guidance_strength=0.5, num_samples=len(rows), num_steps=steps,
+                             mc_batch_size=N, precision="fp16", device=DEV)
+    xs, ys = small.run(x0[rows].to(DEV), y0[rows].to(DEV), m0.to(DEV), n0.to(DEV))
+    small.close()
+    assert maxabs(xs, outs[0][0][rows]) <= 5e-3 and maxabs(ys, outs[0][1][rows]) <= 5e-3  # same bank; tile placement differs (summation order of the statistics, then fp16 roundings)
+
+
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 @pytest.mark.parametrize("kind", ["unet_mnist32", "unet_svhn"])
 def test_unet_forward_bench_size(kind, prec, synth):
