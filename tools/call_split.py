@@ -1,5 +1,6 @@
 """Times one configs[1] sampler call and its main loop alone (bank reused) with CUDA events; used for same-box A/B of
-environment switches (RGFM_PDL, ...).   python tools/call_split.py [--batch 1024] [--nmc 256] [--reps 3]"""
+environment switches (RGFM_PDL, RGFM_SPLIT_PRE / _MAIN, ...) and of the plan options.
+  python tools/call_split.py [--pair mnist_svhn|pair28] [--batch 1024] [--nmc 256] [--chunk 0] [--reps 3]"""
 import argparse, os, sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
