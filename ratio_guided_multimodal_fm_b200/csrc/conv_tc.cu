@@ -886,8 +886,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int cC = p.coef_C[seg];
             const uint32_t sa = smem_base + as * p.a_slot;
             constexpr bool to_bf16 = XBF16;
+#ifdef RGFM_EXPERIMENTS  // accuracy experiment (exp build only): fp16 mode with the fp32-arithmetic transform (one rounding per operand)
+            const bool xf_fp32 = p.exp_no_xform == 3;
+#else
+            constexpr bool xf_fp32 = false;
+#endif
             if constexpr (DENSE) {
-              if (!to_bf16) {
+              if (!to_bf16 && !xf_fp32) {
                 // ---- row-dense tile, fp16 mode: the lean loop ----
                 // rstride (32 or 64 rows) is a multiple of the tile width, so a thread's rows all have the same pixel
                 // column w (threads of columns >= W idle) and its k-th row lies in tile image row a0 + k * da.  The rows of
@@ -964,7 +969,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 continue;
               }
             }
-            if (!to_bf16) {
+            if (!to_bf16 && !xf_fp32) {
               // ---- fp16 mode: packed half2 arithmetic, four rows in flight per thread ----
               // silu(z) = hz + hz * tanh(hz), hz = x * (scale / 2) + shift / 2: per PAIR of channels one HFMA2, one
               // MUFU.TANH (f16x2) and one HFMA2, no conversions (the fp32 path below spends ~4.5 instructions per element;
