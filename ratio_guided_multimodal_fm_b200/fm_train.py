@@ -123,9 +123,31 @@ def fm_mse(v, u):
     return _FmMse.apply(v.contiguous(), u.contiguous())
 
 
-def fm_step(model, x_1, schedule: CFMSchedule, t=None):
+def average_param_grads(params, group=None):
+    """Data-parallel exchange of a training step: the `.grad` tensors of `params` are averaged over the ranks of `group` with
+    ONE all-reduce over a flat buffer (NCCL on GPUs; 3.6 MB for the MNIST U-Nets, 24 MB for the SVHN one) and copied back in
+    place.  No process group, or a single rank: nothing happens.  The reference trains on one device; this is the multi-GPU
+    extension of its step (a collective only where the path has a real exchange)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    grads = [p.grad for p in params if p.grad is not None]
+    if world > 1 and grads:
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        o = 0
+        for g in grads:
+            g.copy_(flat[o:o + g.numel()].view_as(g))
+            o += g.numel()
+    return world
+
+
+def fm_step(model, x_1, schedule: CFMSchedule, t=None, data_parallel: bool = False, group=None):
     """One flow-matching loss evaluation with gradients left in `param.grad` (flow_utils.py:131-147 without the
-    optimiser): returns the loss tensor.  `t` defaults to `torch.rand(B)` drawn like the reference."""
+    optimiser): returns the loss tensor.  `t` defaults to `torch.rand(B)` drawn like the reference.
+    data_parallel=True: every rank calls this on its own shard of the batch; the gradients are averaged over `group`."""
     B = x_1.shape[0]
     if t is None:
         t = torch.rand(B, device=x_1.device)
@@ -134,12 +156,14 @@ def fm_step(model, x_1, schedule: CFMSchedule, t=None):
         v = model(x_t, t)
         loss = fm_mse(v, u)
         loss.backward()
+    if data_parallel:
+        average_param_grads(list(model.parameters()), group)
     return loss
 
 
-def train_flow_matching_epoch(model, dataloader, optimizer, schedule, device, modality='x'):
+def train_flow_matching_epoch(model, dataloader, optimizer, schedule, device, modality='x', data_parallel: bool = False, group=None):
     """Drop-in for flow_utils.py:103-156: same arguments, RNG draws (t, then the prior inside add_noise), loss and return
-    value; progress goes through tqdm when it is installed."""
+    value; progress goes through tqdm when it is installed.  data_parallel / group: see fm_step (extension)."""
     try:
         from tqdm import tqdm
     except ImportError:  # pragma: no cover
@@ -150,7 +174,7 @@ def train_flow_matching_epoch(model, dataloader, optimizer, schedule, device, mo
     for batch in tqdm(dataloader, desc=f"Training FM_{modality}"):
         x_1 = batch[modality].to(device)
         optimizer.zero_grad()
-        loss = fm_step(model, x_1, schedule)
+        loss = fm_step(model, x_1, schedule, data_parallel=data_parallel, group=group)
         optimizer.step()
         total_loss += loss.item()
         num_batches += 1

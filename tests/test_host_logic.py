@@ -79,6 +79,15 @@ def _worker(rank, world, port, n, q):
         flat = (2 * (mine @ w)[:, None] * mine).mean(0).clone()
         average_gradients(flat)
         ok = ok and torch.allclose(flat, full, atol=1e-6)
+        # the flow-matching step's exchange: .grad tensors of a parameter list averaged through ONE flat all-reduce, in place
+        from ratio_guided_multimodal_fm_b200.fm_train import average_param_grads
+        pa_, pb_ = torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5))
+        pc_ = torch.nn.Parameter(torch.zeros(2))  # no gradient: skipped
+        pa_.grad, pb_.grad = torch.full((3, 2), float(rank + 1)), torch.arange(5.0) * (rank + 1)
+        keep = pa_.grad
+        w2 = average_param_grads([pa_, pb_, pc_])
+        ok = ok and w2 == world and pa_.grad is keep and torch.allclose(pa_.grad, torch.full((3, 2), (world + 1) / 2.0))
+        ok = ok and torch.allclose(pb_.grad, torch.arange(5.0) * (world + 1) / 2.0) and pc_.grad is None
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
