@@ -351,7 +351,7 @@ def fm_step_numbers(dev):
         return UNet(kind), "oracle.unet_module restatement"
     sched = CFMSchedule()
     out = dict(workload=f"flow-matching step, batch {TRAIN_B}, Adam lr 1e-4, dropout 0.1; 3x3 convs on the library (exact fp32 CUDA-core "
-                        "kernels), GroupNorm / SiLU / 1x1 skips / time MLP stock PyTorch")
+                        "kernels), GroupNorm on the library in NHWC, SiLU / 1x1 skips / time MLP stock PyTorch")
     for kind in ("unet_mnist32", "unet_svhn"):
         c = 3 if kind == "unet_svhn" else 1
         base, what = make(kind)

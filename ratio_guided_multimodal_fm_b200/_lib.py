@@ -59,7 +59,7 @@ EXPORTS = [
     "rgfm_last_error", "rgfm_abi_version", "rgfm_sampler_create", "rgfm_sampler_run", "rgfm_sampler_run_host",
     "rgfm_sampler_set_strength", "rgfm_sampler_set_strength_schedule", "rgfm_sampler_run_reuse_bank", "rgfm_sampler_get_bank", "rgfm_sampler_profile_step", "rgfm_sampler_launch_count", "rgfm_sampler_destroy", "rgfm_net_create",
     "rgfm_unet_forward", "rgfm_unet_sample", "rgfm_ratio_log_ratio", "rgfm_ratio_grad_create", "rgfm_ratio_grad_create_prec", "rgfm_ratio_grad_log_ratio", "rgfm_coherence_matches", "rgfm_sampler_attach_evaluators", "rgfm_classifier_logits", "rgfm_net_destroy", "rgfm_mc_feng_step",
-    "rgfm_ratio_trainer_create", "rgfm_ratio_trainer_step", "rgfm_ratio_trainer_destroy", "rgfm_ratio_loss", "rgfm_cfm_add_noise", "rgfm_fm_mse_loss", "rgfm_conv3x3_forward", "rgfm_conv3x3_backward",
+    "rgfm_ratio_trainer_create", "rgfm_ratio_trainer_step", "rgfm_ratio_trainer_destroy", "rgfm_ratio_loss", "rgfm_cfm_add_noise", "rgfm_fm_mse_loss", "rgfm_conv3x3_forward", "rgfm_conv3x3_backward", "rgfm_groupnorm_nhwc_forward", "rgfm_groupnorm_nhwc_backward",
 ]
 
 
@@ -109,6 +109,8 @@ def lib() -> C.CDLL:
     L.rgfm_fm_mse_loss.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
     L.rgfm_conv3x3_forward.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, vp]
     L.rgfm_conv3x3_backward.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
+    L.rgfm_groupnorm_nhwc_forward.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_float, vp, vp, vp]
+    L.rgfm_groupnorm_nhwc_backward.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp]
     if L.rgfm_abi_version() != ABI_VERSION:
         raise RgfmError("librgfm.so ABI version mismatch; rebuild")
     _lib = L

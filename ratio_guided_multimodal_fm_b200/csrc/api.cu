@@ -30,6 +30,8 @@ void launch_cfm_interp(const float*, const float*, const float*, int, size_t, fl
 void launch_fm_mse(const float*, const float*, size_t, float*, float*, float*, cudaStream_t);
 void conv3x3_forward(const float*, int, int, int, int, const float*, const float*, int, int, float*, cudaStream_t);
 void conv3x3_backward(const float*, const float*, int, int, int, int, const float*, int, int, float*, float*, float*, cudaStream_t);
+void gn_nhwc_forward(const float*, int, int, int, int, const float*, const float*, float, float*, float*, cudaStream_t);
+void gn_nhwc_backward(const float*, const float*, int, int, int, int, const float*, const float*, float*, float*, float*, cudaStream_t);
 }  // namespace rgfm
 
 static thread_local std::string g_err;
@@ -388,6 +390,24 @@ int rgfm_conv3x3_backward(const float* x, const float* dy, int32_t n, int32_t H,
   RGFM_CHECK(dy, "rgfm_conv3x3_backward: null argument");
   set_device_of(dy);
   rgfm::conv3x3_backward(x, dy, n, H, W, Cin, w, Cout, stride, dx, dw, db, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_groupnorm_nhwc_forward(const float* x, int32_t n, int32_t hw, int32_t C, int32_t groups, const float* gamma, const float* beta,
+                                float eps, float* y, float* stats, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(x && gamma && beta && y && stats, "rgfm_groupnorm_nhwc_forward: null argument");
+  set_device_of(x);
+  rgfm::gn_nhwc_forward(x, n, hw, C, groups, gamma, beta, eps, y, stats, (cudaStream_t)stream);
+  RGFM_API_END
+}
+
+int rgfm_groupnorm_nhwc_backward(const float* x, const float* dy, int32_t n, int32_t hw, int32_t C, int32_t groups, const float* gamma,
+                                 const float* stats, float* dx, float* dgamma, float* dbeta, void* stream) {
+  RGFM_API_BEGIN
+  RGFM_CHECK(x && dy && gamma && stats, "rgfm_groupnorm_nhwc_backward: null argument");
+  set_device_of(x);
+  rgfm::gn_nhwc_backward(x, dy, n, hw, C, groups, gamma, stats, dx, dgamma, dbeta, (cudaStream_t)stream);
   RGFM_API_END
 }
 

@@ -1210,6 +1210,202 @@ void conv3x3_backward(const float* x, const float* dy, int n, int H, int W, int 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm on dense fp32 NHWC tensors, forward and backward, for the flow-matching training step (nn.GroupNorm(8, C) of
+// unet.py:54,64,209 / unet_flexible.py:51,61,196).  PyTorch's CUDA GroupNorm works in NCHW: on the channels_last tensors the
+// conv ops produce it converts its input and returns NCHW, which the next conv converts back (7 % of a step in copies).
+// Statistics: per (image, pixel slice, channel) partial sums in fp32, combined per group in double in a fixed order
+// (deterministic); stats[n][g] = {mean, rstd}.  Backward (x_hat = (x - mean) rstd, m = pixels x channels per group):
+//   dgamma_c = sum dy x_hat,  dbeta_c = sum dy,  dx = rstd (dy gamma - (x_hat A_g + B_g) / m),
+//   A_g = sum_{c in g} gamma_c sum_hw dy x_hat,  B_g = sum_{c in g} gamma_c sum_hw dy.
+// ------------------------------------------------------------------------------------------------
+// partial[n][slice][c][2]: MODE 0: {sum x, sum x^2}; MODE 1: {sum dy x_hat, sum dy}
+template <int MODE>
+__global__ void __launch_bounds__(256) gn_nhwc_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              const float* __restrict__ stats, int HW, int C, int groups, int slices,
+                                                              float* __restrict__ part) {
+  __shared__ float4 red[2][256];
+  const int n = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
+  const int Q = C >> 2, lanes = 256 / Q;  // channel quads, pixel lanes
+  const int q = tid % Q, pl = tid / Q;
+  const int per = (HW + slices - 1) / slices, p0 = sl * per, p1 = min(HW, p0 + per);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (pl < lanes) {
+    float mean = 0.f, rstd = 0.f;
+    if (MODE == 1) {
+      const int g = (q * 4) / (C / groups);
+      mean = stats[((size_t)n * groups + g) * 2];
+      rstd = stats[((size_t)n * groups + g) * 2 + 1];
+    }
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const size_t o = ((size_t)n * HW + p) * C + q * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + o));
+      if (MODE == 0) {
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
+      } else {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + o));
+        a.x = fmaf(d.x, (v.x - mean) * rstd, a.x); a.y = fmaf(d.y, (v.y - mean) * rstd, a.y);
+        a.z = fmaf(d.z, (v.z - mean) * rstd, a.z); a.w = fmaf(d.w, (v.w - mean) * rstd, a.w);
+        b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+      }
+    }
+  }
+  red[0][tid] = a;
+  red[1][tid] = b;
+  __syncthreads();
+  if (tid < Q) {  // pixel lanes in increasing order
+    float4 sa = red[0][tid], sb = red[1][tid];
+    for (int l = 1; l < lanes; ++l) {
+      const float4 ua = red[0][l * Q + tid], ub = red[1][l * Q + tid];
+      sa.x += ua.x; sa.y += ua.y; sa.z += ua.z; sa.w += ua.w;
+      sb.x += ub.x; sb.y += ub.y; sb.z += ub.z; sb.w += ub.w;
+    }
+    float* o = part + (((size_t)n * slices + sl) * C + tid * 4) * 2;
+    o[0] = sa.x; o[1] = sb.x; o[2] = sa.y; o[3] = sb.y; o[4] = sa.z; o[5] = sb.z; o[6] = sa.w; o[7] = sb.w;
+  }
+}
+// one block per image.  MODE 0: stats[n][g] = {mean, rstd}.  MODE 1: chan[n][c] = {sum dy x_hat, sum dy} and gsum[n][g] = {A_g, B_g}.
+template <int MODE>
+__global__ void __launch_bounds__(256) gn_nhwc_finish_kernel(const float* __restrict__ part, int HW, int C, int groups, int slices,
+                                                             const float* __restrict__ gamma, float eps, float* __restrict__ stats,
+                                                             float* __restrict__ chan) {
+  __shared__ double s0[1024], s1[1024];
+  const int n = blockIdx.x, cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double a = 0.0, b = 0.0;
+    for (int sl = 0; sl < slices; ++sl) {
+      const float* p = part + (((size_t)n * slices + sl) * C + c) * 2;
+      a += (double)p[0];
+      b += (double)p[1];
+    }
+    if (MODE == 1) {
+      chan[((size_t)n * C + c) * 2] = (float)a;
+      chan[((size_t)n * C + c) * 2 + 1] = (float)b;
+      a *= (double)gamma[c];
+      b *= (double)gamma[c];
+    }
+    s0[c] = a;
+    s1[c] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    double a = 0.0, b = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += s0[c];
+      b += s1[c];
+    }
+    float* o = stats + ((size_t)n * groups + g) * 2;
+    if (MODE == 0) {
+      const double m = (double)cpg * HW, mean = a / m;
+      double var = b / m - mean * mean;
+      if (var < 0.0) var = 0.0;
+      o[0] = (float)mean;
+      o[1] = (float)(1.0 / sqrt(var + (double)eps));
+    } else {
+      o[0] = (float)a;
+      o[1] = (float)b;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) gn_nhwc_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
+                                                            int groups, size_t total4, float* __restrict__ y) {
+  const int Q = C >> 2, cpg = C / groups;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Q);
+    const int n = (int)(i / ((size_t)Q * HW));
+    const int g = (q * 4) / cpg;
+    const float mean = stats[((size_t)n * groups + g) * 2], rstd = stats[((size_t)n * groups + g) * 2 + 1];
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + q), be = __ldg(reinterpret_cast<const float4*>(beta) + q);
+    float4 o;
+    o.x = fmaf((v.x - mean) * rstd, ga.x, be.x); o.y = fmaf((v.y - mean) * rstd, ga.y, be.y);
+    o.z = fmaf((v.z - mean) * rstd, ga.z, be.z); o.w = fmaf((v.w - mean) * rstd, ga.w, be.w);
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+}
+__global__ void __launch_bounds__(256) gn_nhwc_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                const float* __restrict__ stats, const float* __restrict__ gsum,
+                                                                const float* __restrict__ gamma, int HW, int C, int groups, size_t total4,
+                                                                float* __restrict__ dx) {
+  const int Q = C >> 2, cpg = C / groups;
+  const float inv_m = 1.0f / ((float)cpg * (float)HW);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Q);
+    const int n = (int)(i / ((size_t)Q * HW));
+    const int g = (q * 4) / cpg;
+    const size_t sg = ((size_t)n * groups + g) * 2;
+    const float mean = stats[sg], rstd = stats[sg + 1], A = gsum[sg] * inv_m, B = gsum[sg + 1] * inv_m;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i), d = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+    float4 o;
+    o.x = rstd * (d.x * ga.x - fmaf((v.x - mean) * rstd, A, B)); o.y = rstd * (d.y * ga.y - fmaf((v.y - mean) * rstd, A, B));
+    o.z = rstd * (d.z * ga.z - fmaf((v.z - mean) * rstd, A, B)); o.w = rstd * (d.w * ga.w - fmaf((v.w - mean) * rstd, A, B));
+    reinterpret_cast<float4*>(dx)[i] = o;
+  }
+}
+// dgamma[c] = sum_n chan[n][c][0], dbeta[c] = sum_n chan[n][c][1] (image order)
+__global__ void gn_nhwc_param_grad_kernel(const float* __restrict__ chan, int nimg, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int n = 0; n < nimg; ++n) {
+    a += (double)chan[((size_t)n * C + c) * 2];
+    b += (double)chan[((size_t)n * C + c) * 2 + 1];
+  }
+  if (dgamma) dgamma[c] = (float)a;
+  if (dbeta) dbeta[c] = (float)b;
+}
+
+namespace {
+inline int gn_slices(int n, int HW) { return std::max(1, std::min(std::max(1, HW / 64), (2 * 148 + n - 1) / n)); }
+inline void gn_check(int n, int HW, int C, int groups, const char* what) {
+  RGFM_CHECK(n >= 1 && HW >= 1 && groups >= 1 && groups <= 256 && C % groups == 0 && (C / groups) % 4 == 0 && C <= 1024,
+             std::string(what) + ": channels per group must be a multiple of 4, at most 1024 channels");
+}
+}  // namespace
+
+void gn_nhwc_forward(const float* x, int n, int HW, int C, int groups, const float* gamma, const float* beta, float eps, float* y,
+                     float* stats, cudaStream_t s) {
+  gn_check(n, HW, C, groups, "rgfm_groupnorm_nhwc_forward");
+  StreamScratch sc(s);
+  const int slices = gn_slices(n, HW);
+  float* part = sc.get((size_t)n * slices * C * 2);
+  gn_nhwc_partial_kernel<0><<<dim3(slices, n), 256, 0, s>>>(x, nullptr, nullptr, HW, C, groups, slices, part);
+  post_launch_t("gn_nhwc_partial");
+  gn_nhwc_finish_kernel<0><<<n, 256, 0, s>>>(part, HW, C, groups, slices, nullptr, eps, stats, nullptr);
+  post_launch_t("gn_nhwc_finish");
+  const size_t total4 = (size_t)n * HW * C / 4;
+  gn_nhwc_apply_kernel<<<blocks_for(total4), 256, 0, s>>>(x, stats, gamma, beta, HW, C, groups, total4, y);
+  post_launch_t("gn_nhwc_apply");
+}
+
+void gn_nhwc_backward(const float* x, const float* dy, int n, int HW, int C, int groups, const float* gamma, const float* stats,
+                      float* dx, float* dgamma, float* dbeta, cudaStream_t s) {
+  gn_check(n, HW, C, groups, "rgfm_groupnorm_nhwc_backward");
+  StreamScratch sc(s);
+  const int slices = gn_slices(n, HW);
+  float* part = sc.get((size_t)n * slices * C * 2);
+  float* chan = sc.get((size_t)n * C * 2);
+  float* gsum = sc.get((size_t)n * groups * 2);
+  gn_nhwc_partial_kernel<1><<<dim3(slices, n), 256, 0, s>>>(x, dy, stats, HW, C, groups, slices, part);
+  post_launch_t("gn_nhwc_partial");
+  gn_nhwc_finish_kernel<1><<<n, 256, 0, s>>>(part, HW, C, groups, slices, gamma, 0.f, gsum, chan);
+  post_launch_t("gn_nhwc_finish");
+  if (dgamma || dbeta) {
+    gn_nhwc_param_grad_kernel<<<(C + 127) / 128, 128, 0, s>>>(chan, n, C, dgamma, dbeta);
+    post_launch_t("gn_nhwc_param_grad");
+  }
+  if (dx) {
+    const size_t total4 = (size_t)n * HW * C / 4;
+    gn_nhwc_bwd_apply_kernel<<<blocks_for(total4), 256, 0, s>>>(x, dy, stats, gsum, gamma, HW, C, groups, total4, dx);
+    post_launch_t("gn_nhwc_bwd_apply");
+  }
+}
+
 }  // namespace rgfm
 
 // ---- C ABI (include/rgfm.h) ----

@@ -1033,7 +1033,8 @@ def test_flow_matching_step_grads(kind, synth):
           f"parameter gradients: library {worst:.2e}, fp32 oracle {worst_ref:.2e}")
 
 
-def test_train_flow_matching_epoch_dropin(synth):
+@pytest.mark.parametrize("library_norms", [False, True])
+def test_train_flow_matching_epoch_dropin(library_norms, synth):
     """train_flow_matching_epoch (mirror of flow_utils.py:103-156) for two batches in TRAINING mode (dropout 0.1) vs the same
     loop written with stock PyTorch on a copy of the module: same seed -> same t, prior draw and dropout masks (both paths
     consume torch's CUDA generator identically), so the losses and the updated parameters must agree to fp32 rounding."""
@@ -1042,7 +1043,10 @@ def test_train_flow_matching_epoch_dropin(synth):
     from ratio_guided_multimodal_fm_b200 import CFMSchedule
     from ratio_guided_multimodal_fm_b200.fm_train import train_flow_matching_epoch
     kind = "unet_mnist28"
-    model = UNet(kind)
+    # library_norms=False: GroupNorm stays stock, nn.Dropout sees the same NCHW tensors as in the stock loop -> identical masks
+    # with dropout 0.1.  library_norms=True: GroupNorm on the library in NHWC; dropout would assign the same draws in NHWC
+    # memory order (another mask of the same distribution), so that variant is compared with dropout off.
+    model = UNet(kind, dropout=0.0 if library_norms else 0.1)
     model.load_state_dict(synth(kind, 12), strict=True)
     model = model.to(DEV)
     twin = copy.deepcopy(model)
@@ -1054,7 +1058,7 @@ def test_train_flow_matching_epoch_dropin(synth):
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     try:
         torch.manual_seed(1234)
-        avg = train_flow_matching_epoch(model, data, opt, CFMSchedule(), DEV, modality="x")
+        avg = train_flow_matching_epoch(model, data, opt, CFMSchedule(), DEV, modality="x", library_norms=library_norms)
         # stock loop (flow_utils.py:127-153) on the twin
         topt = torch.optim.SGD(twin.parameters(), lr=0.05)
         twin.train()
@@ -1110,3 +1114,26 @@ def test_fm_step_on_the_reference_module_object(synth):
     for k, p in model.named_parameters():
         rel = ((p.grad.cpu().double() - egrads[k]).norm() / egrads[k].norm().clamp_min(1e-30)).item()
         assert rel <= 1e-4, (k, rel)
+
+
+@pytest.mark.parametrize("case", [(3, 32, 28, 28), (2, 96, 16, 16), (4, 192, 8, 8), (2, 64, 32, 32), (5, 256, 7, 7), (1, 128, 14, 14)])
+def test_groupnorm_nhwc_op_against_float64_autograd(case):
+    """rgfm_groupnorm_nhwc_forward / _backward (fm_train.group_norm_nhwc) vs F.group_norm + autograd in float64: output, input
+    gradient, gamma / beta gradients; 8 groups of 4 .. 32 channels (12 and 24: the concatenated decoder inputs), odd sizes."""
+    from ratio_guided_multimodal_fm_b200.fm_train import group_norm_nhwc
+    n, C, H, W = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n, C, H, W, generator=g) * 1.7 + 0.3
+    ga, be, dy = torch.randn(C, generator=g), torch.randn(C, generator=g), torch.randn(n, C, H, W, generator=g)
+    xd, gd, bd = (t.double().requires_grad_() for t in (x, ga, be))
+    yr = torch.nn.functional.group_norm(xd, 8, gd, bd, 1e-5)
+    yr.backward(dy.double())
+    xg, gg, bg = (t.to(DEV).requires_grad_() for t in (x, ga, be))
+    y = group_norm_nhwc(xg, 8, gg, bg, 1e-5)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    y.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    for name, got, ref in (("y", y, yr), ("dx", xg.grad, xd.grad), ("dgamma", gg.grad, gd.grad), ("dbeta", bg.grad, bd.grad)):
+        ref = ref.detach().float()
+        rel = ((got.detach().cpu().float() - ref).norm() / ref.norm()).item()
+        assert rel <= 3e-6, (case, name, rel)
