@@ -577,7 +577,17 @@ def run_gpu(args):
 
     if rank == 0:
         pk = peaks()
-        prof = plan.profile_step()
+        # Per-kernel CUDA-event profile of one eager Euler step, taken three times (each after a warm main loop) and the
+        # least-disturbed one kept (smallest conv total): a single pass right after the other legs of this script has read
+        # 7 % high on one box in five (clock / power state left by the preceding work), the graph step and the throughput not.
+        profs = []
+        for _ in range(3):
+            plan.run(dx0, dy0, reuse_bank=True)
+            torch.cuda.synchronize()
+            profs.append(plan.profile_step())
+        conv_total = lambda pr: sum(v["ms"] for k, v in pr.items() if k.startswith("conv"))
+        prof = min(profs, key=conv_total)
+        profile_runs = [round(conv_total(pr), 4) for pr in profs]
         graph_step_ms = prof.pop("graph_step", {"ms": None})["ms"]
         step_ms = sum(v["ms"] for v in prof.values())
         conv_kinds = [k for k in prof if k.startswith("conv")]
@@ -606,6 +616,7 @@ def run_gpu(args):
                                          frac=ua / pk["hbm"], share_of_step=upd["ms"] / step_ms)
         roof["per_kernel_ms_one_euler_step"] = {k: round(v["ms"], 4) for k, v in prof.items()}
         roof["graph_ms_one_euler_step"] = graph_step_ms
+        roof["conv_ms_of_the_three_profile_passes"] = profile_runs  # the smallest one is reported above
         total_flops = EULER_STEPS * (N_MC + B_PER_GPU) * (FLOPS_UNET_X + FLOPS_UNET_Y) + N_MC * FLOPS_RATIO
         # the CPU baseline is an N=1 number (rank 0, all host threads); multi-GPU lines carry null
         cpu_base = None
