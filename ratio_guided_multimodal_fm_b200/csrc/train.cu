@@ -1081,7 +1081,21 @@ namespace {
 struct StreamScratch {  // stream-ordered scratch of one op call
   cudaStream_t s;
   std::vector<void*> ptrs;
-  explicit StreamScratch(cudaStream_t st) : s(st) {}
+  explicit StreamScratch(cudaStream_t st) : s(st) {
+    // keep freed scratch in the device's default pool across synchronisations (the default release threshold of 0 hands it
+    // back to the driver at every sync -- a training loop synchronises once per step for loss.item())
+    thread_local int tuned_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != tuned_dev) {
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      tuned_dev = dev;
+    }
+  }
   float* get(size_t floats) {
     void* p = nullptr;
     RGFM_CUDA(cudaMallocAsync(&p, std::max<size_t>(floats, 4) * sizeof(float), s));
