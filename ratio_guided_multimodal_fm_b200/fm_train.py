@@ -137,6 +137,9 @@ def library_convs(model: nn.Module, norms: bool = True):
     patched, nconv = [], 0
     try:
         for m in model.modules():
+            if "forward" in m.__dict__:  # already rerouted (a nested block, or the caller's own instance-level forward): leave it
+                nconv += 1 if _is_lib_conv(m) and getattr(m.forward, "__func__", None) is not None and m.forward.__func__.__name__ == "fwd" else 0
+                continue
             if _is_lib_conv(m):
                 def fwd(self, x):
                     return conv3x3(x, self.weight, self.bias, self.stride[0])
@@ -153,7 +156,7 @@ def library_convs(model: nn.Module, norms: bool = True):
         yield nconv
     finally:
         for m in patched:
-            del m.forward  # back to the class's own forward
+            m.__dict__.pop("forward", None)  # back to the class's own forward
 
 
 class _FmMse(torch.autograd.Function):

@@ -137,3 +137,17 @@ def test_library_convs_reroutes_exactly_the_3x3_convs_and_restores_them():
     assert not any("forward" in c.__dict__ for c in m.modules())
     v = m.eval()(torch.zeros(1, 1, 28, 28), torch.zeros(1))  # stock path works again
     assert v.shape == (1, 1, 28, 28)
+
+
+def test_library_convs_nests():
+    """A nested library_convs block leaves the outer block's rerouting in place and only the outermost exit restores the modules."""
+    import torch.nn as nn
+    from oracle.unet_module import UNet
+    from ratio_guided_multimodal_fm_b200 import fm_train
+    m = UNet("unet_mnist28")
+    convs = [c for c in m.modules() if isinstance(c, nn.Conv2d) and c.kernel_size == (3, 3)]
+    with fm_train.library_convs(m) as outer:
+        with fm_train.library_convs(m) as inner:
+            assert outer == inner == len(convs)
+        assert all("forward" in c.__dict__ for c in convs)
+    assert not any("forward" in c.__dict__ for c in m.modules())
